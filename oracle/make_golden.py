@@ -1,0 +1,231 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (/root/reference) on seeded inputs.
+
+Runs only in the build container (the reference does not exist on the GPU box).  The reference module is
+imported as-is with MagicMock stand-ins for the simulator packages it imports transitively and no-op
+``.cuda()`` shims; it is put in ``eval()`` mode (SURVEY.md finding 0.3-1).
+Weights are ``rgbmanip_b200.weights.init_state_dict(seed)`` loaded with ``strict=True`` so every consumer
+can regenerate them; inputs come from ``rgbmanip_b200.synth``.
+
+    python oracle/make_golden.py            # writes tests/golden/{e2e,preprocess,units}.npz
+"""
+from __future__ import annotations
+
+import logging
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+import torch.nn as nn
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("RGBMANIP_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from rgbmanip_b200 import synth, weights  # noqa: E402
+
+
+def import_reference():
+    for m in ["sapien", "sapien.core", "sapien.core.renderer", "sapien.utils", "mplib", "gym", "gym.spaces",
+              "gym.vector", "gym.vector.utils", "gym.vector.utils.shared_memory", "ujson", "matplotlib",
+              "matplotlib.pyplot", "trimesh", "transforms3d"]:
+        sys.modules.setdefault(m, MagicMock())
+    torch.Tensor.cuda = lambda s, *a, **k: s
+    nn.Module.cuda = lambda s, *a, **k: s
+    from models.pose_estimator.AdaPose import interface_v5
+    from models.pose_estimator.AdaPose.lib import align, network_v5, rotation_utils, utils
+    return interface_v5, network_v5, rotation_utils, utils, align
+
+
+def build_reference_estimator(interface_v5, task="drawer", seed=0, direct_regression=True):
+    cfg = yaml.safe_load(open(f"{REF}/cfg/pose_estimator/adapose_{task}.yaml"))
+    cfg["load"] = False
+    cfg["direct_regression"] = direct_regression
+    est = interface_v5.AdaPoseEstimator_v5(None, cfg, logging.getLogger("golden"))
+    sd = weights.init_state_dict(seed, regress_pose=direct_regression)
+    est.estimator.load_state_dict({"module." + k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()},
+                                  strict=True)
+    est.estimator.eval()
+    return est, cfg, sd
+
+
+def golden_e2e(interface_v5, out_dir):
+    torch.manual_seed(0)
+    est, cfg, _ = build_reference_estimator(interface_v5)
+    batch = synth.make_batch(8, seed=0)
+    records = []
+    orig_prepare = est.prepare_model_input
+    orig_forward = est.estimator.module.forward
+    cur = {}
+
+    def prepare(rgb, mask, K, resize_size):
+        r = orig_prepare(rgb, mask, K, resize_size)
+        cur.setdefault("prep", []).append(r)
+        return r
+
+    def forward(*a, **k):
+        out = orig_forward(*a, **k)
+        cur["pred"] = {kk: v.detach().cpu().numpy() for kk, v in out.items()}
+        return out
+
+    est.prepare_model_input = prepare
+    est.estimator.module.forward = forward
+    feats = {}
+    est.estimator.module.img_extractor.register_forward_hook(
+        lambda m, i, o: feats.setdefault("f", []).append(o.detach().numpy().copy()))
+    est.estimator.module.cost_regularization.register_forward_hook(
+        lambda m, i, o: feats.setdefault("logits", []).append(o.detach().numpy().copy()))
+    np.random.seed(0)
+    boxes = []
+    for e in range(len(batch)):
+        cur.clear()
+        feats.clear()
+        b = batch.slice(e, e + 1)
+        boxes.append(est.predict(b.K[0], b.rgb1[0], b.mask1[0], b.E1[0], b.rgb2[0], b.mask2[0], b.E2[0]))
+        rec = {"valid": "pred" in cur}
+        if rec["valid"]:
+            (v1, ch1, _, K1), (v2, ch2, _, K2) = cur["prep"]
+            rec.update(choose1=ch1, choose2=ch2, K1=K1, K2=K2,
+                       view1_rgb_sub=v1.numpy()[:, ::8, ::8], view2_rgb_sub=v2.numpy()[:, ::8, ::8],
+                       feat1_sub=feats["f"][0][0, :, ::8, ::8], feat2_sub=feats["f"][1][0, :, ::8, ::8],
+                       logits1_sub=feats["logits"][0][0, 0, :, ::8, ::8])
+            for k in ("view1_nocs", "view1_depth", "view1_r", "view1_t", "view1_s",
+                      "view2_nocs", "view2_depth", "view2_r"):
+                rec[k] = cur["pred"][k][0]
+        records.append(rec)
+    out = {"boxes": np.asarray(boxes), "valid": np.array([r["valid"] for r in records])}
+    for e, r in enumerate(records):
+        for k, v in r.items():
+            if k != "valid":
+                out[f"env{e}_{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(out_dir, "e2e.npz"), **out)
+    print("e2e: valid", out["valid"], "boxes", out["boxes"].shape)
+
+
+def golden_branch_b(interface_v5, out_dir):
+    """direct_regression=False, use_depth=True -> RANSAC + Umeyama fit (interface_v5.py:322-338)."""
+    est, cfg, _ = build_reference_estimator(interface_v5, direct_regression=False)
+    batch = synth.make_batch(2, seed=3, special=False)
+    np.random.seed(5)
+    boxes = est.estimate(*batch.args())
+    np.savez_compressed(os.path.join(out_dir, "branch_b.npz"), boxes=boxes)
+    print("branch B boxes", boxes.shape, np.isfinite(boxes).all())
+
+
+def golden_preprocess(interface_v5, utils, out_dir):
+    est, cfg, _ = build_reference_estimator(interface_v5)
+    rng = np.random.default_rng(7)
+    K = synth.intrinsics()
+    out = {}
+    n = 0
+    for i in range(40):
+        dt = np.float64 if i % 3 == 0 else np.float32
+        rgb = rng.random((480, 640, 3)).astype(dt)
+        cx, cy = rng.uniform(0, 640), rng.uniform(0, 480)
+        ax, ay = rng.uniform(2, 260), rng.uniform(2, 200)
+        mask = synth._ellipse_mask(cx, cy, ax, ay)
+        if i % 5 == 0:
+            mask = mask.astype(np.float64)
+        if mask.sum() == 0:
+            continue
+        np.random.seed(100 + i)
+        v, ch, pts, Kp = est.prepare_model_input(rgb, mask, K, 224)
+        ys, xs = np.nonzero(mask)
+        win = utils.get_bbox([ys.min(), xs.min(), ys.max(), xs.max()])
+        out[f"c{n}_params"] = np.array([cx, cy, ax, ay, i], np.float64)
+        out[f"c{n}_window"] = np.array(win, np.int64)
+        out[f"c{n}_choose"] = ch
+        out[f"c{n}_pts2d_sub"] = pts[::16]
+        out[f"c{n}_K"] = Kp
+        out[f"c{n}_rgb_sub"] = v.numpy()[:, 3::8, 5::8].astype(np.float32)
+        out[f"c{n}_rgb_sum"] = np.array([float(v.double().sum()), float(v.double().abs().sum())])
+        n += 1
+    out["count"] = np.array(n)
+    # nearest-neighbour index tables for every window size the reference can produce
+    import cv2
+    for ws in range(40, 441, 40):
+        ramp = np.arange(ws, dtype=np.float32)[None].repeat(ws, 0)
+        out[f"nn_{ws}"] = cv2.resize(ramp, (224, 224), interpolation=cv2.INTER_NEAREST)[0].astype(np.int64)
+    np.savez_compressed(os.path.join(out_dir, "preprocess.npz"), **out)
+    print("preprocess cases:", n)
+
+
+def unit_inputs():
+    """Seeded inputs of the unit goldens (numpy PCG64: identical on every machine; not stored)."""
+    rng = np.random.default_rng(11)
+    f32 = lambda *s: rng.standard_normal(s, dtype=np.float32)
+    return {"warp_src": f32(1, 4, 224, 224), "cr_in": f32(1, 32, 8, 16, 24), "psp_in": f32(1, 3, 64, 96),
+            "r6": f32(5, 6)}
+
+
+def golden_units(network_v5, rotation_utils, utils, align, out_dir):
+    ui = {k: torch.from_numpy(v) for k, v in unit_inputs().items()}
+    out = {}
+    net = network_v5.StereoPoseNet_with_depth(n_cat=1, nv_pts=1024, regress_pose=True)
+    sd = weights.init_state_dict(1)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    net.eval()
+    with torch.no_grad():
+        # homo_warping on a small map with a realistic projection pair
+        b = synth.make_batch(1, seed=21, special=False)
+        from oracle import adapose_oracle as O
+        _, _, _, K1 = O.prepare_model_input(b.rgb1[0], b.mask1[0], b.K[0])
+        _, _, _, K2 = O.prepare_model_input(b.rgb2[0], b.mask2[0], b.K[0])
+        P1 = torch.from_numpy(O.projection(K1, b.E1[0])).float()[None]
+        P2 = torch.from_numpy(O.projection(K2, b.E2[0])).float()[None]
+        src = ui["warp_src"]
+        dv = torch.from_numpy(O.depth_hypotheses())[None]
+        warped = net.homo_warping(src, P2, P1, dv)
+        out.update(warp_P1=P1.numpy(), warp_P2=P2.numpy(), warp_out_sub=warped.numpy()[0, :, :, ::4, ::4])
+        # CostRegNet on a small volume
+        out.update(cr_out=net.cost_regularization(ui["cr_in"]).numpy())
+        # backbone on a small image
+        out.update(psp_out=net.img_extractor(ui["psp_in"]).numpy())
+        # 6-D -> rotation
+        r6 = ui["r6"]
+        out.update(r6_mat=rotation_utils.Ortho6d2Mat(r6[:, :3].contiguous(), r6[:, 3:].contiguous()).numpy())
+    # fit functions
+    rng = np.random.default_rng(5)
+    nocs = (rng.random((1024, 3)).astype(np.float32) - 0.5)
+    Rt = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    if np.linalg.det(Rt) < 0:
+        Rt[:, 0] *= -1
+    cam = (0.23 * (Rt @ nocs.T.astype(np.float64)).T + np.array([0.05, -0.02, 0.8])
+           + 0.004 * rng.standard_normal((1024, 3)))
+    out.update(fit_nocs=nocs, fit_cam=cam, fit_scale=np.array(utils.compute_scale(cam, nocs)))
+    depth = cam[:, 2].astype(np.float32)
+    choose = np.sort(rng.choice(224 * 224, 1024, replace=False))
+    Kp = np.array([[800.0, 0, 100.5], [0, 800.0, 120.25], [0, 0, 1]])
+    t, s = utils.compute_scale_and_translation(depth, nocs, choose, Kp, 224, Rt.astype(np.float32))
+    out.update(fit2_depth=depth, fit2_choose=choose, fit2_K=Kp, fit2_R=Rt.astype(np.float32), fit2_t=t,
+               fit2_s=np.array(s))
+    np.random.seed(9)
+    sc, R, tr, T = align.estimateSimilarityTransform(nocs, cam)
+    out.update(um_scale=np.array(sc), um_R=R, um_t=tr, um_T=T)
+    size = np.array([0.2, 0.4, 0.6])
+    out.update(bbox_size=size, bbox=utils.get_3d_bbox(size))
+    np.savez_compressed(os.path.join(out_dir, "units.npz"), **out)
+    print("units written")
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    interface_v5, network_v5, rotation_utils, utils, align = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b"]
+    if "units" in what:
+        golden_units(network_v5, rotation_utils, utils, align, out_dir)
+    if "preprocess" in what:
+        golden_preprocess(interface_v5, utils, out_dir)
+    if "e2e" in what:
+        golden_e2e(interface_v5, out_dir)
+    if "branch_b" in what:
+        golden_branch_b(interface_v5, out_dir)
+
+
+if __name__ == "__main__":
+    main()

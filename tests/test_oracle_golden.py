@@ -1,0 +1,153 @@
+"""The oracle (oracle/adapose_oracle.py) against vectors produced by the reference itself
+(oracle/make_golden.py, run in the build container against /root/reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import adapose_oracle as O
+from oracle.make_golden import unit_inputs
+from rgbmanip_b200 import synth, weights
+
+pytestmark = pytest.mark.filterwarnings("ignore")
+
+
+@pytest.fixture(scope="module")
+def units(golden_dir):
+    return np.load(os.path.join(golden_dir, "units.npz"))
+
+
+@pytest.fixture(scope="module")
+def sd1():
+    return weights.init_state_dict(1)
+
+
+def test_state_dict_matches_reference_table():
+    sd = weights.init_state_dict(0)
+    assert len(sd) == 150
+    assert sum(v.size for k, v in sd.items() if v.dtype == np.float32 and "running" not in k) == 24853130
+    weights.check_state_dict(sd)
+    assert len(weights.init_state_dict(0, regress_pose=False)) == 120
+
+
+def test_nearest_tables_match_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    for ws in range(40, 441, 40):
+        np.testing.assert_array_equal(O.nearest_src_index(224, ws), g[f"nn_{ws}"])
+
+
+def test_prepare_model_input(golden_dir):
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    rng = np.random.default_rng(7)
+    K = synth.intrinsics()
+    n = 0
+    for i in range(40):
+        dt = np.float64 if i % 3 == 0 else np.float32
+        rgb = rng.random((480, 640, 3)).astype(dt)
+        cx, cy = rng.uniform(0, 640), rng.uniform(0, 480)
+        ax, ay = rng.uniform(2, 260), rng.uniform(2, 200)
+        mask = synth._ellipse_mask(cx, cy, ax, ay)
+        if i % 5 == 0:
+            mask = mask.astype(np.float64)
+        if mask.sum() == 0:
+            continue
+        np.random.seed(100 + i)
+        v, ch, pts, Kp = O.prepare_model_input(rgb, mask, K)
+        ys, xs = np.nonzero(mask)
+        np.testing.assert_array_equal(O.get_bbox(ys.min(), xs.min(), ys.max(), xs.max()), g[f"c{n}_window"])
+        np.testing.assert_array_equal(ch, g[f"c{n}_choose"])          # integer work: bit exact
+        np.testing.assert_array_equal(Kp, g[f"c{n}_K"])
+        np.testing.assert_allclose(pts[::16], g[f"c{n}_pts2d_sub"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(v[:, 3::8, 5::8], g[f"c{n}_rgb_sub"], rtol=0, atol=2e-5)
+        assert abs(float(v.astype(np.float64).sum()) - g[f"c{n}_rgb_sum"][0]) < 0.05
+        n += 1
+    assert n == int(g["count"])
+
+
+def test_homo_warping(units):
+    src = torch.from_numpy(unit_inputs()["warp_src"])
+    out = O.homo_warping(src, torch.from_numpy(units["warp_P2"]), torch.from_numpy(units["warp_P1"]),
+                         torch.from_numpy(O.depth_hypotheses())[None])
+    np.testing.assert_allclose(out.numpy()[0, :, :, ::4, ::4], units["warp_out_sub"], rtol=0, atol=1e-5)
+
+
+def test_cost_reg_net(units, sd1):
+    with torch.no_grad():
+        out = O.cost_reg_net(sd1, torch.from_numpy(unit_inputs()["cr_in"]))
+    np.testing.assert_allclose(out.numpy(), units["cr_out"], rtol=1e-4, atol=1e-5)
+
+
+def test_pspnet(units, sd1):
+    with torch.no_grad():
+        out = O.pspnet(sd1, torch.from_numpy(unit_inputs()["psp_in"]))
+    np.testing.assert_allclose(out.numpy(), units["psp_out"], rtol=1e-4, atol=1e-4)
+
+
+def test_ortho6d(units):
+    r6 = torch.from_numpy(unit_inputs()["r6"])
+    m = O.ortho6d_to_mat(r6[:, :3].contiguous(), r6[:, 3:].contiguous()).numpy()
+    np.testing.assert_allclose(m, units["r6_mat"], rtol=0, atol=1e-6)
+
+
+def test_fit_functions(units):
+    assert O.compute_scale(units["fit_cam"], units["fit_nocs"]) == float(units["fit_scale"])
+    t, s = O.compute_scale_and_translation(units["fit2_depth"], units["fit_nocs"], units["fit2_choose"],
+                                           units["fit2_K"], 224, units["fit2_R"])
+    assert s == float(units["fit2_s"])
+    np.testing.assert_allclose(t, units["fit2_t"], rtol=0, atol=1e-12)
+    np.random.seed(9)
+    sc, R, tr, T = O.similarity_ransac(units["fit_nocs"], units["fit_cam"])
+    np.testing.assert_allclose(sc, float(units["um_scale"]), rtol=1e-12)
+    np.testing.assert_allclose(R, units["um_R"], atol=1e-12)
+    np.testing.assert_allclose(tr, units["um_t"], atol=1e-12)
+    np.testing.assert_array_equal(O.get_3d_bbox(units["bbox_size"]), units["bbox"])
+
+
+def test_end_to_end_against_reference(golden_dir):
+    """Full estimate() on 3 of the 8 golden envs (incl. the sentinel env) -- CPU time ~10 s."""
+    g = np.load(os.path.join(golden_dir, "e2e.npz"))
+    sd = weights.init_state_dict(0)
+    cfg = {"img_size": 224, "direct_regression": True, "use_depth": True}
+    batch = synth.make_batch(8, seed=0)
+    valid = g["valid"]
+    assert (~valid).any(), "golden batch must contain a sentinel env"
+    # replay the reference's global-RNG stream: envs must be visited in order
+    np.random.seed(0)
+    picked = {0, int(np.flatnonzero(~valid)[0])}
+    picked.add(max(picked) + 1 if max(picked) + 1 < 8 else 1)
+    last = max(picked)
+    for e in range(last + 1):
+        d = {}
+        if e in picked:
+            box = O.predict(sd, cfg, batch.K[e], batch.rgb1[e], batch.mask1[e], batch.E1[e],
+                            batch.rgb2[e], batch.mask2[e], batch.E2[e], details=d)
+        else:   # advance the RNG exactly like the reference without running the network
+            O.prepare_model_input(batch.rgb1[e], batch.mask1[e], batch.K[e])
+            O.prepare_model_input(batch.rgb2[e], batch.mask2[e], batch.K[e])
+            continue
+        if not valid[e]:
+            np.testing.assert_array_equal(box, O.DEFAULT_BBOX)
+            continue
+        np.testing.assert_array_equal(d["choose1"], g[f"env{e}_choose1"])
+        np.testing.assert_array_equal(d["choose2"], g[f"env{e}_choose2"])
+        np.testing.assert_allclose(d["pred"]["feat1"].numpy()[0, :, ::8, ::8], g[f"env{e}_feat1_sub"],
+                                   rtol=1e-3, atol=2e-3)
+        np.testing.assert_allclose(d["nocs"], g[f"env{e}_view1_nocs"], rtol=0, atol=2e-4)
+        np.testing.assert_allclose(d["depth"], g[f"env{e}_view1_depth"], rtol=0, atol=2e-4)
+        np.testing.assert_allclose(d["R"], g[f"env{e}_view1_r"], rtol=0, atol=1e-4)
+        px, deg, mm, cmm = O.parity_errors(box, g["boxes"][e], batch.K[e], batch.E1[e])
+        assert px < 0.05 and deg < 0.02 and mm < 0.1 and cmm < 0.2, (px, deg, mm, cmm)
+
+
+def test_branch_b_against_reference(golden_dir):
+    """direct_regression=False, use_depth=True: RANSAC + Umeyama branch (interface_v5.py:322-338)."""
+    g = np.load(os.path.join(golden_dir, "branch_b.npz"))
+    sd = weights.init_state_dict(0, regress_pose=False)
+    cfg = {"img_size": 224, "direct_regression": False, "use_depth": True}
+    batch = synth.make_batch(2, seed=3, special=False)
+    np.random.seed(5)
+    boxes = O.estimate(sd, cfg, *batch.args())
+    for e in range(2):
+        px, deg, mm, cmm = O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e])
+        assert px < 0.1 and deg < 0.05 and mm < 0.2, (px, deg, mm, cmm)
