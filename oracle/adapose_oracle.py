@@ -525,15 +525,21 @@ def rotation_angle_deg(Ra, Rb):
 
 
 def project_points(pts_world, K, E):
+    """Pin-hole projection; also returns the camera-frame depth of every point."""
     cam = (E[:3, :3] @ pts_world.T + E[:3, 3:4])
     uv = K @ cam
-    return (uv[:2] / uv[2]).T
+    return (uv[:2] / uv[2]).T, cam[2]
 
 
-def parity_errors(box_a, box_b, K, E1):
-    """(max corner reprojection error [px], rotation error [deg], centre error [mm], max corner error [mm])."""
+def parity_errors(box_a, box_b, K, E1, min_z=0.2):
+    """(max keypoint reprojection error [px], rotation error [deg], centre error [mm], max corner error [mm]).
+    Keypoints = the 8 box corners and the box centre projected into view 1; points closer than ``min_z``
+    metres to the camera plane (or behind it) are skipped because the projection is singular there."""
     ca, Ra, _ = box_pose(box_a)
     cb, Rb, _ = box_pose(box_b)
-    px = float(np.abs(project_points(box_a, K, E1) - project_points(box_b, K, E1)).max())
+    pa, za = project_points(np.vstack([box_a, ca[None]]), K, E1)
+    pb, zb = project_points(np.vstack([box_b, cb[None]]), K, E1)
+    ok = (za > min_z) & (zb > min_z)
+    px = float(np.abs(pa[ok] - pb[ok]).max()) if ok.any() else 0.0
     return (px, rotation_angle_deg(Ra, Rb), float(np.linalg.norm(ca - cb) * 1e3),
             float(np.linalg.norm(box_a - box_b, axis=1).max() * 1e3))

@@ -89,11 +89,19 @@ def param_table(regress_pose: bool = True):
     return ent
 
 
-def init_state_dict(seed: int = 0, regress_pose: bool = True, randomize_bn: bool = True):
+def init_state_dict(seed: int = 0, regress_pose: bool = True, randomize_bn: bool = True,
+                    nocs_gain: float = 16.0, prob_gain: float = 4.0):
     """Random-init weights of the AdaPose architecture as ``OrderedDict[str, np.ndarray]``.
 
     ``randomize_bn`` perturbs the BatchNorm3d affine parameters and running statistics so that BN
     folding is exercised (the constructor default 1/0/0/1 is the identity).
+
+    ``nocs_gain`` / ``prob_gain`` multiply the last NOCS layer's and the depth-logit conv's weights.  With
+    the plain constructor init (gains 1) the NOCS map is almost constant (std ~0.01, the very threshold of
+    the pair filter at utils.py:83) and the depth softmax is flat, so the scale fit divides by ~0 and
+    amplifies any rounding by 1/|dNOCS|: box-level parity would measure that conditioning, not the
+    kernels.  The default gains give NOCS a spread of a few tenths and a peaked depth distribution, like a
+    trained network, while staying a seeded random init of the same architecture.
     """
     rng = np.random.default_rng(seed)
     sd = OrderedDict()
@@ -122,6 +130,10 @@ def init_state_dict(seed: int = 0, regress_pose: bool = True, randomize_bn: bool
             w = np.zeros((), np.int64)
         else:  # pragma: no cover
             raise AssertionError(kind)
+        if name == "nocs_head.4.weight":
+            w = w * np.float32(nocs_gain)
+        elif name == "cost_regularization.prob.weight":
+            w = w * np.float32(prob_gain)
         sd[name] = w
     return sd
 
