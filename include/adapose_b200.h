@@ -1,0 +1,121 @@
+/* libadapose_b200.so -- C ABI of the B200-native AdaPose hot path.
+ *
+ * The reference (hyperplane-lab/RGBManip) is pure Python: it has no FFI for this path, the seam is the class
+ * models/pose_estimator/AdaPose/interface_v5.py:37 `AdaPoseEstimator_v5`, whose `estimate()` (:213-227) loops
+ * `predict()` (:229-374) over environments.  The entry points below are the device stages that replace the body
+ * of that loop; the Python host mirror (rgbmanip_b200/estimator.py) binds them with ctypes and keeps the
+ * reference's class/method surface.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure (adp_last_error() holds the
+ * message); pointers are raw CUDA device pointers unless named `host_*`; `stream` is a cudaStream_t passed as
+ * void*; nothing allocates device memory except adp_conv_tc_plan (a small descriptor object on the host) and
+ * nothing synchronises.  Activations are channels-last bf16 stored as a `hi` plane plus an optional `lo` plane
+ * (value = hi + lo, "bf16x3" split precision); fp32 tensors are plain channels-last.  No torch types appear.
+ */
+#ifndef ADAPOSE_B200_H
+#define ADAPOSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ADP_API __attribute__((visibility("default")))
+#else
+#define ADP_API
+#endif
+
+/* dtype codes for host-facing image inputs */
+#define ADP_DT_U8 0
+#define ADP_DT_F32 1
+#define ADP_DT_F64 2
+
+/* activation codes of a convolution epilogue */
+#define ADP_ACT_NONE 0
+#define ADP_ACT_RELU 1
+#define ADP_ACT_PRELU 2
+
+typedef struct adp_act {      /* channels-last activation [B, D, H, W, C]; D == 1 for 2-D maps */
+    void* hi;                 /* bf16 */
+    void* lo;                 /* bf16 or NULL */
+    int32_t B, D, H, W, C;
+} adp_act;
+
+typedef struct adp_epilogue { /* y = act(scale * acc + bias [+ res]) [+ res]  ->  out_hi/out_lo and/or out_f32 */
+    const float* scale;       /* [Cout] or NULL : folded BatchNorm3d scale (network_v5.py:19,240) */
+    const float* bias;        /* [Cout] or NULL : conv bias or folded BatchNorm shift */
+    float prelu;              /* slope for ADP_ACT_PRELU (pspnet.py:100-103) */
+    int32_t act;
+    int32_t res_after_act;    /* 0: residual joins before the activation (pspnet.py:27-29); 1: after (network_v5.py:287-289) */
+    const void* res_hi;       /* bf16 [.., Cout] or NULL */
+    const void* res_lo;
+    void* out_hi;             /* bf16 or NULL */
+    void* out_lo;
+    float* out_f32;           /* fp32 or NULL */
+} adp_epilogue;
+
+typedef struct adp_direct_conv {   /* generic CUDA-core convolution (strided / tiny-channel / transposed layers) */
+    const void* in_hi; const void* in_lo; const float* in_f32;   /* exactly one of in_hi / in_f32 */
+    int32_t B, Di, Hi, Wi, Cin;
+    int32_t Do, Ho, Wo, Cout;
+    int32_t kd, kh, kw, sd, sh, sw, pd, ph, pw, dil, transposed;
+    const float* w;           /* fp32 [taps][Cin][Cout] */
+    adp_epilogue ep;
+} adp_direct_conv;
+
+typedef struct adp_decode_weights {   /* fp32, each matrix transposed to [K][N]; names follow the reference state_dict */
+    const float *ic_w, *ic_b, *nh0_w, *nh0_b, *nh1_w, *nh1_b, *nh2_w, *nh2_b, *np0_w, *np0_b, *np1_w, *np1_b;
+    const float *pm0_w, *pm0_b, *pm1_w, *pm1_b, *q0_w, *q0_b, *q1_w, *q1_b, *r0_w, *r0_b, *r1_w, *r1_b, *r2_w, *r2_b;
+    const float* prob_w;      /* cost_regularization.prob.weight as [27][8] */
+} adp_decode_weights;
+
+typedef struct adp_conv_plan adp_conv_plan;   /* tcgen05 conv layer bound to fixed buffers (holds the TMA tensor maps) */
+
+ADP_API int adp_abi_version(void);
+ADP_API const char* adp_last_error(void);
+/* number of kernels launched by this library since load (bench.py reports it as gpu_launches) */
+ADP_API uint64_t adp_launch_count(void);
+ADP_API int adp_device_info(int device, int* num_sms, int* cc_major, int* cc_minor);
+
+/* --- preprocessing: interface_v5.py:58-170 (prepare_model_input), utils.py:10-38 (get_bbox) ------------------
+ * rgb [F,H,W,3] (f32|f64), mask [F,H,W] (u8|f32|f64), K [F,3,3] f64 (k_stride doubles between frames; 0 = shared).
+ * Outputs: win [F,4] = rmin,rmax,cmin,cmax; Kp [F,9] f64 crop intrinsics; valid [F]; crops [F,S,S,3] f32 normalised;
+ * choose [F,P] i32 (written when choose_mode == 0, read-only when 1 = caller-supplied); counts [F] foreground pixels. */
+ADP_API int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int mask_dtype, const double* K, int k_stride,
+                   int F, int H, int W, int S, int P, uint32_t seed, int choose_mode, int32_t* bbox_ws, int32_t* win,
+                   double* Kp, uint8_t* valid, float* crops, int32_t* choose, int32_t* counts, void* stream);
+
+/* --- backbone: pspnet.py:33-158 ------------------------------------------------------------------------------ */
+ADP_API int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, const void* w_lo, int cout, int kd,
+                     int ks, int dil, int npass, const adp_epilogue* ep, int num_sms);
+ADP_API int adp_conv_tc_run(adp_conv_plan* plan, int batch, int32_t* err_flag, void* stream);
+ADP_API void adp_conv_tc_free(adp_conv_plan* plan);
+ADP_API int adp_conv_direct(const adp_direct_conv* desc, int batch, void* stream);
+ADP_API int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, void* stream);                 /* pspnet.py:39 */
+ADP_API int adp_psp_priors(const adp_act* feat, const float* w, float* pooled, float* priors, int batch, void* stream); /* :84-90 */
+ADP_API int adp_psp_concat_up(const adp_act* feat, const float* priors, const adp_act* out, int batch, void* stream);   /* :92-94,105 */
+ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream);                   /* pspnet.py:105 */
+
+/* --- stereo volume: network_v5.py:378-416,429 ---------------------------------------------------------------- */
+ADP_API int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol,
+                     int B, int D, int H, int W, int C, void* stream);
+
+/* --- decode + heads: network_v5.py:432-465,486-499; rotation_utils.py:4-27 ----------------------------------- */
+ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
+               const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth,
+               float* pf1, float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused,
+               int B, int S, int D, int P, int regress_pose, void* stream);
+
+/* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
+ADP_API int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R,
+            const double* E, const uint8_t* valid, double* bbox, double* scale, double* trans, int B, int P, int S,
+            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,180 @@
+// extern "C" surface of libadapose_b200.so (see include/adapose_b200.h).
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/adapose_b200.h"
+#include "common.cuh"
+#include "direct_conv.cuh"
+#include "tc_conv.cuh"
+
+namespace adp {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// implemented in the stage translation units
+int maxpool3x3s2(const Act& in, const Act& out, int batch, cudaStream_t stream);
+int psp_priors(const Act& feat, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream);
+int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream);
+int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream);
+int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
+                   int S, int P, uint32_t seed, int choose_mode, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
+                   float* crops, int* choose, int* counts, cudaStream_t stream);
+int build_volume(const float* f_ref, const float* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
+                 int W, int C, cudaStream_t stream);
+int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
+            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, int B, int P, int S, cudaStream_t stream);
+
+struct DecodeWeights;
+struct DecodeArgs;
+int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
+                 const int* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth, float* pf1,
+                 float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P,
+                 int regress_pose, cudaStream_t stream);
+
+static Act to_act(const adp_act* a) {
+    Act r;
+    r.hi = reinterpret_cast<bf16*>(a->hi);
+    r.lo = reinterpret_cast<bf16*>(a->lo);
+    r.B = a->B; r.D = a->D; r.H = a->H; r.W = a->W; r.C = a->C;
+    return r;
+}
+
+}  // namespace adp
+
+struct adp_conv_plan {
+    adp::TcConvLayer layer;
+    int num_sms;
+};
+
+using namespace adp;
+
+extern "C" {
+
+int adp_abi_version(void) { return ADP_ABI_VERSION; }
+const char* adp_last_error(void) { return g_err; }
+uint64_t adp_launch_count(void) { return g_launches.load(); }
+
+int adp_device_info(int device, int* num_sms, int* cc_major, int* cc_minor) {
+    cudaDeviceProp prop;
+    ADP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (num_sms) *num_sms = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return ADP_OK;
+}
+
+int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int mask_dtype, const double* K, int k_stride, int F, int H,
+                   int W, int S, int P, uint32_t seed, int choose_mode, int32_t* bbox_ws, int32_t* win, double* Kp,
+                   uint8_t* valid, float* crops, int32_t* choose, int32_t* counts, void* stream) {
+    ADP_CHECK_ARG(rgb && mask && K && bbox_ws && win && Kp && valid && crops && choose && counts, "null pointer");
+    g_launches += 5;
+    return preprocess_run(rgb, rgb_dtype, mask, mask_dtype, K, k_stride, F, H, W, S, P, seed, choose_mode, bbox_ws, win, Kp,
+                          valid, crops, choose, counts, (cudaStream_t)stream);
+}
+
+int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, const void* w_lo, int cout, int kd, int ks,
+                     int dil, int npass, const adp_epilogue* ep, int num_sms) {
+    ADP_CHECK_ARG(plan && in && w_hi && ep, "null pointer");
+    ADP_CHECK_ARG(ep->out_hi || ep->out_f32, "epilogue has no output");
+    adp_conv_plan* pl = new adp_conv_plan();
+    int r = tc_conv_plan(&pl->layer, to_act(in), reinterpret_cast<const bf16*>(w_hi), reinterpret_cast<const bf16*>(w_lo), cout,
+                         kd, ks, dil, npass);
+    if (r != ADP_OK) {
+        delete pl;
+        return r;
+    }
+    TcConvParams& p = pl->layer.p;
+    p.bias = ep->bias; p.scale = ep->scale; p.prelu = ep->prelu; p.act = ep->act; p.res_after_act = ep->res_after_act;
+    p.res_hi = reinterpret_cast<const bf16*>(ep->res_hi); p.res_lo = reinterpret_cast<const bf16*>(ep->res_lo);
+    p.out_hi = reinterpret_cast<bf16*>(ep->out_hi); p.out_lo = reinterpret_cast<bf16*>(ep->out_lo);
+    p.out_f32 = ep->out_f32;
+    pl->num_sms = num_sms > 0 ? num_sms : 148;
+    *plan = pl;
+    return ADP_OK;
+}
+
+int adp_conv_tc_run(adp_conv_plan* plan, int batch, int32_t* err_flag, void* stream) {
+    ADP_CHECK_ARG(plan, "null plan");
+    plan->layer.p.err = err_flag;
+    g_launches += 1;
+    return tc_conv_launch(&plan->layer, batch, plan->num_sms, (cudaStream_t)stream);
+}
+
+void adp_conv_tc_free(adp_conv_plan* plan) { delete plan; }
+
+int adp_conv_direct(const adp_direct_conv* d, int batch, void* stream) {
+    ADP_CHECK_ARG(d, "null descriptor");
+    DirectConvParams p;
+    p.in_hi = reinterpret_cast<const bf16*>(d->in_hi); p.in_lo = reinterpret_cast<const bf16*>(d->in_lo); p.in_f32 = d->in_f32;
+    p.B = d->B; p.Di = d->Di; p.Hi = d->Hi; p.Wi = d->Wi; p.Cin = d->Cin;
+    p.Do = d->Do; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
+    p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
+    p.pd = d->pd; p.ph = d->ph; p.pw = d->pw; p.dil = d->dil; p.transposed = d->transposed;
+    p.w = d->w;
+    p.scale = d->ep.scale; p.bias = d->ep.bias; p.prelu = d->ep.prelu; p.act = d->ep.act; p.res_after_act = d->ep.res_after_act;
+    p.res_hi = reinterpret_cast<const bf16*>(d->ep.res_hi); p.res_lo = reinterpret_cast<const bf16*>(d->ep.res_lo);
+    p.out_hi = reinterpret_cast<bf16*>(d->ep.out_hi); p.out_lo = reinterpret_cast<bf16*>(d->ep.out_lo); p.out_f32 = d->ep.out_f32;
+    g_launches += 1;
+    return direct_conv_launch(p, batch, (cudaStream_t)stream);
+}
+
+int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, void* stream) {
+    ADP_CHECK_ARG(in && out, "null pointer");
+    g_launches += 1;
+    return maxpool3x3s2(to_act(in), to_act(out), batch, (cudaStream_t)stream);
+}
+
+int adp_psp_priors(const adp_act* feat, const float* w, float* pooled, float* priors, int batch, void* stream) {
+    ADP_CHECK_ARG(feat && w && pooled && priors, "null pointer");
+    g_launches += 2;
+    return psp_priors(to_act(feat), w, pooled, priors, batch, (cudaStream_t)stream);
+}
+
+int adp_psp_concat_up(const adp_act* feat, const float* priors, const adp_act* out, int batch, void* stream) {
+    ADP_CHECK_ARG(feat && priors && out, "null pointer");
+    g_launches += 1;
+    return psp_concat_up(to_act(feat), priors, to_act(out), batch, (cudaStream_t)stream);
+}
+
+int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream) {
+    ADP_CHECK_ARG(in && out, "null pointer");
+    g_launches += 1;
+    return upsample2x(to_act(in), to_act(out), batch, (cudaStream_t)stream);
+}
+
+int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol, int B, int D,
+                     int H, int W, int C, void* stream) {
+    ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && vol, "null pointer");
+    g_launches += 1;
+    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, (cudaStream_t)stream);
+}
+
+int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
+               const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth, float* pf1,
+               float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P,
+               int regress_pose, void* stream) {
+    ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && x11 && choose && w && nocs && depth && pf1 && gsum && psum && R,
+                  "null pointer");
+    g_launches += regress_pose ? 3 : 1;
+    return decode_run_c(feat_ref, feat_src, Mw, depths, x11, choose, valid, w, nocs, depth, pf1, gsum, psum, R, r6, dbg_logits,
+                        dbg_fused, B, S, D, P, regress_pose, (cudaStream_t)stream);
+}
+
+int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R, const double* E,
+            const uint8_t* valid, double* bbox, double* scale, double* trans, int B, int P, int S, void* stream) {
+    ADP_CHECK_ARG(nocs && depth && choose && Kp && R && E && bbox, "null pointer");
+    g_launches += 1;
+    return fit_run(nocs, depth, choose, Kp, R, E, valid, bbox, scale, trans, B, P, S, (cudaStream_t)stream);
+}
+
+}  // extern "C"

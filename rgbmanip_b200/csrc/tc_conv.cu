@@ -1,0 +1,495 @@
+// tcgen05 implicit-GEMM convolution -- see tc_conv.cuh for the scheme.
+#include "tc_conv.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace adp {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must end in a trapped kernel with a flag, never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// mbarrier arrives once all tcgen05 ops previously issued by this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+// ------------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major operand whose rows are KC*2 bytes (= the swizzle span).
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 (8-row group pitch)
+//   [46,48) version = 1 (sm_100) | [49,52) base offset = 0 (tiles are 1024B aligned) | [61,64) layout type
+template <int KC>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = (KC == 64) ? 2ull : (KC == 32) ? 4ull : 6ull;   // SWIZZLE_128B / 64B / 32B
+    constexpr uint64_t sbo = (uint64_t)(8 * KC * 2) >> 4;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// Instruction descriptor for kind::f16: D = fp32, A = B = bf16, both K-major, M = 128, N = BN.
+template <int BN>
+__device__ __forceinline__ uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+template <int BN, int KC>
+struct TcCfg {
+    static constexpr int A_BYTES = 128 * KC * 2;
+    static constexpr int B_BYTES = BN * KC * 2;
+    static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
+    static constexpr int STAGE_BYTES = A_BYTES + B_PAD;
+    static constexpr int STAGES = (STAGE_BYTES * 6 <= 196608) ? 6 : (196608 / STAGE_BYTES);
+    static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns per accumulator stage
+    static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : (2 * ACC_STRIDE <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+               const TcConvParams p, int batch) {
+    using Cfg = TcCfg<BN, KC>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t bar_base = ptx::smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA_hi);
+        ptx::prefetch_tmap(&tmW_hi);
+        if (p.npass > 1) {
+            ptx::prefetch_tmap(&tmA_lo);
+            ptx::prefetch_tmap(&tmW_lo);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int taps = p.kd * p.ks * p.ks;
+    const int k_iters = p.npass * taps * p.kchunks;
+    const int tiles_per_img = p.D * p.tiles_y * p.tiles_x * p.tiles_n;
+    const int total_tiles = batch * tiles_per_img;
+    const int rows_valid = p.TW * p.TH;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)(rows_valid * KC * 2 + Cfg::B_BYTES);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int nt = t % p.tiles_n; t /= p.tiles_n;
+                const int tx = t % p.tiles_x; t /= p.tiles_x;
+                const int ty = t % p.tiles_y; t /= p.tiles_y;
+                const int d = t % p.D;
+                const int b = t / p.D;
+                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
+                for (int pass = 0; pass < p.npass; ++pass) {
+                    const CUtensorMap* mapA = (pass == 1) ? &tmA_lo : &tmA_hi;
+                    const CUtensorMap* mapW = (pass == 2) ? &tmW_lo : &tmW_hi;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const int kx = tap % p.ks, ky = (tap / p.ks) % p.ks, kz = tap / (p.ks * p.ks);
+                        const int dx = (kx - p.ks / 2) * p.dil, dy = (ky - p.ks / 2) * p.dil, dz = kz - p.kd / 2;
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
+                            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                            ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+                            ptx::tma_load_5d(mapA, full_bar(stage), sa, kc * KC, x0 + dx, y0 + dy, d + dz, b);
+                            ptx::tma_load_3d(mapW, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, n0, tap);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        const uint32_t idesc = make_idesc<BN>();
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(tempty_bar(as), aphase ^ 1, p.err, 2);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE);
+            for (int it = 0; it < k_iters; ++it) {
+                ptx::mbar_wait(full_bar(stage), phase, p.err, 3);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t adesc = make_smem_desc<KC>(sa);
+                    const uint64_t bdesc = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the >>4 address field
+                        ptx::umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                       (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+                    if (it == k_iters - 1) ptx::umma_commit(tfull_bar(as));   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int ty_l = m / p.TW, tx_l = m - ty_l * p.TW;
+        int as = 0;
+        uint32_t aphase = 0;
+        constexpr int CH = (BN < 32) ? BN : 32;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int nt = t % p.tiles_n; t /= p.tiles_n;
+            const int tx = t % p.tiles_x; t /= p.tiles_x;
+            const int ty = t % p.tiles_y; t /= p.tiles_y;
+            const int d = t % p.D;
+            const int b = t / p.D;
+            const int x = tx * p.TW + tx_l, y = ty * p.TH + ty_l, n0 = nt * BN;
+            const bool valid = (m < rows_valid) && (x < p.W) && (y < p.H);
+            const size_t pix = (((size_t)b * p.D + d) * p.H + y) * p.W + x;
+            ptx::mbar_wait(tfull_bar(as), aphase, p.err, 4);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::ACC_STRIDE + c0);
+                ptx::tmem_ld16(taddr, r);
+                if (CH == 32) ptx::tmem_ld16(taddr + 16, r + 16);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    const int nbase = n0 + c0;
+                    if (nbase < p.Cout) {   // Cout may be padded up to BN (e.g. 8 -> 16)
+                        const int nvalid = min(CH, p.Cout - nbase);
+                        const size_t o = pix * p.Cout + nbase;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+                        if (p.scale) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] *= __ldg(p.scale + nbase + j);
+                        }
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nbase + j);
+                        }
+                        if (p.res_hi && !p.res_after_act) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act(p.res_hi, p.res_lo, o + j);
+                        }
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (p.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.prelu;
+                        }
+                        if (p.res_hi && p.res_after_act) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act(p.res_hi, p.res_lo, o + j);
+                        }
+                        if (p.out_f32) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
+                        }
+                        if (p.out_hi) {
+                            if (nvalid == CH && (CH % 8) == 0) {
+#pragma unroll
+                                for (int j = 0; j < CH; j += 8) {
+                                    uint32_t h[4], l[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const bf16 h0 = __float2bfloat16_rn(v[j + 2 * u]);
+                                        const bf16 h1 = __float2bfloat16_rn(v[j + 2 * u + 1]);
+                                        h[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                        const bf16 l0 = __float2bfloat16_rn(v[j + 2 * u] - __bfloat162float(h0));
+                                        const bf16 l1 = __float2bfloat16_rn(v[j + 2 * u + 1] - __bfloat162float(h1));
+                                        l[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                    }
+                                    *reinterpret_cast<uint4*>(p.out_hi + o + j) = make_uint4(h[0], h[1], h[2], h[3]);
+                                    if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + o + j) = make_uint4(l[0], l[1], l[2], l[3]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) if (j < nvalid) st_act(p.out_hi, p.out_lo, o + j, v[j]);
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int tc_conv_init_driver() {
+    if (g_encode) return ADP_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ADP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+        set_last_error("cuTensorMapEncodeTiled not available from the driver (query result %d)", (int)qres);
+        return ADP_ERR_CUDA;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return ADP_OK;
+}
+
+static CUtensorMapSwizzle swizzle_for(int KC) {
+    return KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+static int encode_act_map(CUtensorMap* tm, const bf16* ptr, const Act& a, int KC, int TW, int TH) {
+    cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2,
+                             (cuuint64_t)a.D * a.H * a.W * a.C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)TH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d D=%d B=%d box=%dx%dx%d) failed: %d", a.C, a.W, a.H,
+                       a.D, a.B, KC, TW, TH, (int)r);
+        return ADP_ERR_CUDA;
+    }
+    return ADP_OK;
+}
+
+static int encode_w_map(CUtensorMap* tm, const bf16* ptr, int Cin, int CoutPad, int taps, int KC, int BN) {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)CoutPad, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)CoutPad * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(weights Cin=%d Cout=%d taps=%d box=%dx%d) failed: %d", Cin, CoutPad, taps, KC,
+                       BN, (int)r);
+        return ADP_ERR_CUDA;
+    }
+    return ADP_OK;
+}
+
+void tc_pick_tile(int H, int W, int* TW, int* TH) {
+    // rectangle of <= 128 pixels; prefer exact divisors of the map so that no MMA rows are wasted
+    int tw = W;
+    if (W > 128) {
+        tw = 128;
+        for (int c = 128; c >= 8; --c) if (W % c == 0) { tw = c; break; }
+    }
+    int th = 128 / tw;
+    if (th < 1) th = 1;
+    if (th > H) th = H;
+    // when W divides into a smaller power of two with an exact row fit, prefer it (224 -> 32x4, 112 -> 16x8)
+    for (int c = 32; c >= 8; c >>= 1) {
+        if (W % c == 0 && H % (128 / c) == 0) { tw = c; th = 128 / c; break; }
+    }
+    *TW = tw;
+    *TH = th;
+}
+
+int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_lo, int Cout, int kd, int ks, int dil,
+                 int npass) {
+    ADP_TRY(tc_conv_init_driver());
+    int KC = in.C % 64 == 0 ? 64 : in.C % 32 == 0 ? 32 : in.C % 16 == 0 ? 16 : 0;
+    ADP_CHECK_ARG(KC != 0, "Cin must be a multiple of 16 for the tcgen05 path");
+    ADP_CHECK_ARG(npass == 1 || npass == 3, "npass");
+    ADP_CHECK_ARG(npass == 1 || (in.lo && w_lo), "split precision needs lo planes");
+    int coutPad = (Cout + 15) / 16 * 16;
+    int BN = coutPad % 256 == 0 ? 256 : coutPad % 128 == 0 ? 128 : coutPad % 64 == 0 ? 64 : coutPad % 32 == 0 ? 32 : 16;
+    if (KC < 64 && BN > 64) BN = 64;
+    TcConvParams& p = L->p;
+    p = TcConvParams{};
+    p.B = in.B; p.D = in.D; p.H = in.H; p.W = in.W;
+    p.Cin = in.C; p.Cout = Cout; p.kd = kd; p.ks = ks; p.dil = dil;
+    tc_pick_tile(in.H, in.W, &p.TW, &p.TH);
+    p.tiles_x = cdiv(in.W, p.TW);
+    p.tiles_y = cdiv(in.H, p.TH);
+    p.tiles_n = coutPad / BN;
+    p.kchunks = in.C / KC;
+    p.npass = npass;
+    L->BN = BN;
+    L->KC = KC;
+    ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH));
+    ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH));
+    ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, kd * ks * ks, KC, BN));
+    ADP_TRY(encode_w_map(&L->tmW_lo, w_lo ? w_lo : w_hi, in.C, coutPad, kd * ks * ks, KC, BN));
+    L->ready = true;
+    return ADP_OK;
+}
+
+template <int BN, int KC>
+static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
+    using Cfg = TcCfg<BN, KC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const TcConvParams& p = L->p;
+    long long total = (long long)batch * p.D * p.tiles_y * p.tiles_x * p.tiles_n;
+    int grid = (int)(total < num_sms ? total : num_sms);
+    if (grid <= 0) return ADP_OK;
+    tc_conv_kernel<BN, KC><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(L->tmA_hi, L->tmA_lo, L->tmW_hi, L->tmW_lo, p, batch);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
+    ADP_CHECK_ARG(L->ready, "layer not planned");
+    ADP_CHECK_ARG(batch <= L->p.B, "batch exceeds planned capacity");
+#define ADP_TC_CASE(bn, kc) if (L->BN == bn && L->KC == kc) return launch_impl<bn, kc>(L, batch, num_sms, stream)
+    ADP_TC_CASE(256, 64); ADP_TC_CASE(128, 64); ADP_TC_CASE(64, 64); ADP_TC_CASE(32, 64); ADP_TC_CASE(16, 64);
+    ADP_TC_CASE(64, 32); ADP_TC_CASE(32, 32); ADP_TC_CASE(16, 32);
+    ADP_TC_CASE(64, 16); ADP_TC_CASE(32, 16); ADP_TC_CASE(16, 16);
+#undef ADP_TC_CASE
+    set_last_error("no tcgen05 conv instantiation for BN=%d KC=%d", L->BN, L->KC);
+    return ADP_ERR_ARG;
+}
+
+}  // namespace adp

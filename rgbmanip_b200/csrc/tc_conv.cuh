@@ -1,0 +1,57 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for channels-last bf16 activations (sm_100a).
+//
+//   D[m, n] = sum_{tap, c} A[pixel(m) + offset(tap), c] * W[tap, n, c]
+//
+// m runs over a TH x TW rectangle of output pixels (<= 128 rows of the UMMA M=128 tile), n over BN output
+// channels, the K loop over (pass, tap, 64-channel chunk).  Each K step is one TMA box load of the shifted
+// activation rectangle (out-of-image coordinates are zero-filled by the TMA unit = the conv's zero padding)
+// and one box load of the weight slab, both landing in 128B-swizzled K-major shared memory, followed by
+// four tcgen05.mma (K = 16 each) accumulating into TMEM.  Stride-1 "same" convolutions only: 2-D with
+// D == 1, or 3-D where the depth axis is one more tensor-map dimension.
+//
+// Split precision ("bf16x3"): activations and weights are stored as hi + lo bf16 pairs and the K loop runs
+// three passes (A_hi W_hi, A_lo W_hi, A_hi W_lo) into the same fp32 accumulator, which restores ~16
+// mantissa bits -- see DESIGN.md "precision policy".
+#pragma once
+#include "common.cuh"
+
+namespace adp {
+
+struct TcConvParams {
+    int B, D, H, W;          // output == input extent (stride 1, same padding); D == 1 for 2-D
+    int Cin, Cout;
+    int kd, ks;              // taps along depth (1 or 3) and along y/x (1 or 3)
+    int dil;                 // dilation along y/x (depth dilation is 1)
+    int TW, TH;              // spatial tile; TW * TH <= 128
+    int tiles_x, tiles_y, tiles_n;
+    int kchunks;             // Cin / KC
+    int npass;               // 1 = bf16, 3 = bf16x3
+    // epilogue
+    const float* bias;       // [Cout] or nullptr (BatchNorm shift is passed here too)
+    const float* scale;      // [Cout] or nullptr (folded BatchNorm scale)
+    float prelu;             // slope for act == 2
+    int act;                 // 0 none, 1 relu, 2 prelu
+    int res_after_act;       // 0: act(acc + res)   1: act(acc) + res   (3-D U-Net skips)
+    const bf16* res_hi;
+    const bf16* res_lo;
+    bf16* out_hi;
+    bf16* out_lo;
+    float* out_f32;
+    int* err;                // device error flag (pipeline watchdog)
+};
+
+// Host side: build tensor maps + launch.  Returns ADP_OK or an error code (message via set_last_error).
+struct TcConvLayer {
+    CUtensorMap tmA_hi, tmA_lo, tmW_hi, tmW_lo;
+    TcConvParams p;
+    int BN;
+    int KC;                  // channels per K step (64 -> SWIZZLE_128B, 32 -> 64B, 16 -> 32B)
+    bool ready = false;
+};
+
+int tc_conv_init_driver();
+int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_lo, int Cout, int kd, int ks,
+                 int dil, int npass);
+int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream);
+
+}  // namespace adp
