@@ -101,6 +101,11 @@ ADP_API int adp_psp_concat_up(const adp_act* feat, const float* priors, const ad
 ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream);                   /* pspnet.py:105 */
 
 /* --- stereo volume: network_v5.py:378-416,429 ---------------------------------------------------------------- */
+/* Mw[b] = {rot 3x3 row-major, trans 3} of P_src inv(P_ref), P = [K' E[:3,:]; 0 0 0 1] (interface_v5.py:264-270);
+ * valid_env[b] = valid_ref[b] && valid_src[b] (an estimate needs both views, interface_v5.py:256-257). */
+ADP_API int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src,
+                              float* Mw, const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B,
+                              void* stream);
 ADP_API int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol,
                      int B, int D, int H, int W, int C, void* stream);
 

@@ -1,0 +1,104 @@
+"""ctypes binding of libadapose_b200.so (include/adapose_b200.h).  There is no fallback: if the CUDA library is
+missing or a call fails the product path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libadapose_b200.so")
+
+ADP_ABI_VERSION = 1
+DT_U8, DT_F32, DT_F64 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+
+vp = C.c_void_p
+i32 = C.c_int32
+
+
+class AdpError(RuntimeError):
+    pass
+
+
+class Act(C.Structure):
+    _fields_ = [("hi", vp), ("lo", vp), ("B", i32), ("D", i32), ("H", i32), ("W", i32), ("C", i32)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("scale", vp), ("bias", vp), ("prelu", C.c_float), ("act", i32), ("res_after_act", i32),
+                ("res_hi", vp), ("res_lo", vp), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp)]
+
+
+class DirectConv(C.Structure):
+    _fields_ = [("in_hi", vp), ("in_lo", vp), ("in_f32", vp),
+                ("B", i32), ("Di", i32), ("Hi", i32), ("Wi", i32), ("Cin", i32),
+                ("Do", i32), ("Ho", i32), ("Wo", i32), ("Cout", i32),
+                ("kd", i32), ("kh", i32), ("kw", i32), ("sd", i32), ("sh", i32), ("sw", i32),
+                ("pd", i32), ("ph", i32), ("pw", i32), ("dil", i32), ("transposed", i32),
+                ("w", vp), ("ep", Epilogue)]
+
+
+DECODE_FIELDS = ["ic_w", "ic_b", "nh0_w", "nh0_b", "nh1_w", "nh1_b", "nh2_w", "nh2_b", "np0_w", "np0_b", "np1_w", "np1_b",
+                 "pm0_w", "pm0_b", "pm1_w", "pm1_b", "q0_w", "q0_b", "q1_w", "q1_b", "r0_w", "r0_b", "r1_w", "r1_b",
+                 "r2_w", "r2_b", "prob_w"]
+
+
+class DecodeWeights(C.Structure):
+    _fields_ = [(n, vp) for n in DECODE_FIELDS]
+
+
+# name -> (restype, argtypes); the list doubles as the export check in tests/test_abi.py
+SIGNATURES = {
+    "adp_abi_version": (C.c_int, []),
+    "adp_last_error": (C.c_char_p, []),
+    "adp_launch_count": (C.c_uint64, []),
+    "adp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "adp_preprocess": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_uint32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "adp_conv_tc_plan": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(Epilogue), C.c_int]),
+    "adp_conv_tc_run": (C.c_int, [vp, C.c_int, vp, vp]),
+    "adp_conv_tc_free": (None, [vp]),
+    "adp_conv_direct": (C.c_int, [C.POINTER(DirectConv), C.c_int, vp]),
+    "adp_maxpool3x3s2": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
+    "adp_psp_priors": (C.c_int, [C.POINTER(Act), vp, vp, vp, C.c_int, vp]),
+    "adp_psp_concat_up": (C.c_int, [C.POINTER(Act), vp, C.POINTER(Act), C.c_int, vp]),
+    "adp_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
+    "adp_warp_matrices": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
+    "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_decode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DecodeWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is a separate, explicit step: ``python -m rgbmanip_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AdpError(f"{LIB_PATH} is missing: build it with `python -m rgbmanip_b200.build` "
+                       "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError -> the library does not match include/adapose_b200.h
+        fn.restype = res
+        fn.argtypes = args
+    if lib.adp_abi_version() != ADP_ABI_VERSION:
+        raise AdpError(f"ABI mismatch: library {lib.adp_abi_version()} vs binding {ADP_ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().adp_last_error()
+        raise AdpError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Raw device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -31,6 +31,8 @@ int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, c
                    float* crops, int* choose, int* counts, cudaStream_t stream);
 int build_volume(const float* f_ref, const float* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
                  int W, int C, cudaStream_t stream);
+int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
+                  const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream);
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
             const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, int B, int P, int S, cudaStream_t stream);
 
@@ -157,6 +159,13 @@ int adp_build_volume(const float* feat_ref, const float* feat_src, const float* 
     ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && vol, "null pointer");
     g_launches += 1;
     return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, (cudaStream_t)stream);
+}
+
+int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
+                      const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, void* stream) {
+    ADP_CHECK_ARG(Kp_ref && E_ref && Kp_src && E_src && Mw, "null pointer");
+    g_launches += 1;
+    return warp_matrices(Kp_ref, E_ref, Kp_src, E_src, Mw, valid_ref, valid_src, valid_env, B, (cudaStream_t)stream);
 }
 
 int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,

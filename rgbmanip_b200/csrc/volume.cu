@@ -67,4 +67,57 @@ int build_volume(const float* f_ref, const float* f_src, const float* Mw, const 
     return ADP_OK;
 }
 
+// M = P_src * inv(P_ref) with P = [K' E[:3,:]; 0 0 0 1] (ADA/interface_v5.py:264-270, network_v5.py:389-392), in fp64.
+// Mw[b] = {rot(9) row-major, trans(3)} as fp32.  Kp_* [B,9], E_* [B,16] row-major doubles.
+__global__ void warp_matrices_kernel(const double* __restrict__ Kp_ref, const double* __restrict__ E_ref,
+                                     const double* __restrict__ Kp_src, const double* __restrict__ E_src, float* __restrict__ Mw,
+                                     const uint8_t* __restrict__ valid_ref, const uint8_t* __restrict__ valid_src,
+                                     uint8_t* __restrict__ valid_env, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    // an estimate needs both views (interface_v5.py:256-257)
+    if (valid_env) valid_env[b] = (valid_ref ? valid_ref[b] : 1) && (valid_src ? valid_src[b] : 1);
+    double Pr[16], Ps[16];
+    for (int which = 0; which < 2; ++which) {
+        const double* K = (which ? Kp_src : Kp_ref) + 9 * b;
+        const double* E = (which ? E_src : E_ref) + 16 * b;
+        double* P = which ? Ps : Pr;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c) P[4 * r + c] = K[3 * r] * E[c] + K[3 * r + 1] * E[4 + c] + K[3 * r + 2] * E[8 + c];
+        P[12] = 0; P[13] = 0; P[14] = 0; P[15] = 1;
+    }
+    // Gauss-Jordan inverse of P_ref
+    double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) { a[r][c] = Pr[4 * r + c]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+        double best = fabs(a[col][col]);
+        for (int r = col + 1; r < 4; ++r) if (fabs(a[r][col]) > best) { best = fabs(a[r][col]); piv = r; }
+        if (piv != col) for (int c = 0; c < 8; ++c) { double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
+        const double d = 1.0 / a[col][col];
+        for (int c = 0; c < 8; ++c) a[col][c] *= d;
+        for (int r = 0; r < 4; ++r) if (r != col) {
+            const double f = a[r][col];
+            for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
+        }
+    }
+    float* out = Mw + 12 * b;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += Ps[4 * r + k] * a[k][4 + c];
+            if (c < 3) out[3 * r + c] = (float)s; else out[9 + r] = (float)s;
+        }
+    }
+}
+
+int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
+                  const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream) {
+    if (B == 0) return ADP_OK;
+    warp_matrices_kernel<<<cdiv(B, 64), 64, 0, stream>>>(Kp_ref, E_ref, Kp_src, E_src, Mw, valid_ref, valid_src, valid_env, B);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
 }  // namespace adp

@@ -1,0 +1,408 @@
+"""Device pipeline of the AdaPose hot path: weight packing, workspace, layer schedule.
+
+Everything numerical runs in libadapose_b200.so (hand-written sm_100a CUDA) through the C ABI of
+include/adapose_b200.h; torch is used for device memory, streams and host<->device copies only.
+
+Stage map (reference lines relative to models/pose_estimator/AdaPose):
+  preprocess   interface_v5.py:58-170          -> adp_preprocess
+  backbone     lib/pspnet.py:33-158            -> adp_conv_tc_* (tcgen05) / adp_conv_direct / adp_maxpool3x3s2 /
+                                                  adp_psp_priors / adp_psp_concat_up / adp_upsample2x
+  volume       lib/network_v5.py:378-430       -> adp_warp_matrices, adp_build_volume
+  cost reg.    lib/network_v5.py:260-291       -> adp_conv_tc_* (stride 1) / adp_conv_direct (stride 2, transposed)
+  decode       lib/network_v5.py:432-499       -> adp_decode (the `prob` conv is evaluated at the sampled pixels only)
+  fit + box    lib/utils.py:40-119, interface_v5.py:318-374 -> adp_fit
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import weights as W
+
+IMG_SIZE = 224
+N_PTS = 1024
+N_DEPTH = 24
+
+
+@dataclass
+class ActBuf:
+    hi: torch.Tensor
+    lo: torch.Tensor | None
+    B: int
+    D: int
+    H: int
+    W: int
+    Cn: int
+
+    @property
+    def c(self):
+        return L.Act(L.ptr(self.hi), L.ptr(self.lo), self.B, self.D, self.H, self.W, self.Cn)
+
+    def value(self, n=None):
+        """fp32 torch view [B,(D,)H,W,C] (debug / tests)."""
+        v = self.hi.float()
+        if self.lo is not None:
+            v = v + self.lo.float()
+        return v if n is None else v[:n]
+
+
+def _split_bf16(w: torch.Tensor):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+class Engine:
+    """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
+
+    def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="bf16x3", regress_pose=True, use_tc=True,
+                 use_tc_3d=True, debug=False, img_size=IMG_SIZE, n_pts=N_PTS):
+        if not torch.cuda.is_available():
+            raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.E = int(max_envs)
+        self.F = 2 * self.E
+        self.S = int(img_size)
+        self.P = int(n_pts)
+        self.split = precision == "bf16x3"
+        self.npass = 3 if self.split else 1
+        self.precision = precision
+        self.regress_pose = bool(regress_pose)
+        self.use_tc = use_tc
+        self.use_tc_3d = use_tc_3d
+        self.debug = debug
+        self._keep = []
+        self._plans = []
+        sms, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        L.check(self.lib.adp_device_info(self.device.index or 0, C.byref(sms), C.byref(maj), C.byref(mnr)), "device_info")
+        self.num_sms = sms.value
+        self.cc = (maj.value, mnr.value)
+        if self.cc[0] != 10:
+            raise L.AdpError(f"device compute capability {self.cc} is not sm_100: this library ships sm_100a code only")
+        sd = W.to_numpy_state_dict(state_dict)
+        W.check_state_dict(sd, self.regress_pose)
+        self.sd = sd
+        with torch.cuda.device(self.device):
+            self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._build_backbone()
+            self._build_stereo()
+            torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, a, dtype=torch.float32):
+        t = torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(self.device).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _act(self, B, H, Wd, Cn, D=1, split=None):
+        split = self.split if split is None else split
+        shape = (B, D, H, Wd, Cn) if D > 1 else (B, H, Wd, Cn)
+        hi = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
+        lo = torch.zeros(shape, dtype=torch.bfloat16, device=self.device) if split else None
+        return ActBuf(hi, lo, B, D, H, Wd, Cn)
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _epilogue(self, out: ActBuf | None, scale=None, bias=None, act=L.ACT_RELU, prelu=0.0, res: ActBuf | None = None,
+                  res_after_act=0, out_f32=None):
+        return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act, res_after_act,
+                          L.ptr(res.hi) if res else None, L.ptr(res.lo) if (res and res.lo is not None) else None,
+                          L.ptr(out.hi) if out else None, L.ptr(out.lo) if (out and out.lo is not None) else None,
+                          L.ptr(out_f32))
+
+    def _conv(self, w_np, x: ActBuf, out: ActBuf | None, *, stride=1, dil=1, transposed=False, npass=None, tc=None, **ep_kw):
+        """Returns a callable(batch) running the convolution x -> out.  w_np: torch layout
+        [Cout,Cin,(kd,)kh,kw] or, transposed, [Cin,Cout,kd,kh,kw]."""
+        w = torch.as_tensor(np.ascontiguousarray(w_np)).float()
+        three_d = w.dim() == 5
+        if transposed:
+            cin, cout = w.shape[0], w.shape[1]
+            w_tcin_cout = w.reshape(cin, cout, -1).permute(2, 0, 1).contiguous()        # [taps, Cin, Cout]
+        else:
+            cout, cin = w.shape[0], w.shape[1]
+            w_tcin_cout = w.reshape(cout, cin, -1).permute(2, 1, 0).contiguous()        # [taps, Cin, Cout]
+        kd = w.shape[2] if three_d else 1
+        ks = w.shape[-1]
+        assert cin == x.Cn
+        npass = self.npass if npass is None else npass
+        if tc is None:
+            tc = self.use_tc_3d if three_d else self.use_tc
+        can_tc = (tc and stride == 1 and not transposed and cin % 16 == 0 and ks in (1, 3)
+                  and (ks == w.shape[-2]) and (npass == 1 or x.lo is not None))
+        ep = self._epilogue(out, **ep_kw)
+        if can_tc:
+            cout_pad = (cout + 15) // 16 * 16
+            wt = w.reshape(cout, cin, -1).permute(2, 0, 1).contiguous()                   # [taps, Cout, Cin]
+            if cout_pad != cout:
+                wt = torch.cat([wt, torch.zeros(wt.shape[0], cout_pad - cout, cin)], 1).contiguous()
+            hi, lo = _split_bf16(wt)
+            hi, lo = hi.to(self.device).contiguous(), lo.to(self.device).contiguous()
+            self._keep += [hi, lo]
+            plan = C.c_void_p()
+            xa = x.c
+            L.check(self.lib.adp_conv_tc_plan(C.byref(plan), C.byref(xa), L.ptr(hi), L.ptr(lo) if npass == 3 else None,
+                                              cout, kd, ks, dil, npass, C.byref(ep), self.num_sms), "conv_tc_plan")
+            self._plans.append(plan)
+
+            def run(batch, plan=plan):
+                L.check(self.lib.adp_conv_tc_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv_tc_run")
+            run.kind = "tc"
+            return run
+        wd = w_tcin_cout.to(self.device).contiguous()
+        self._keep.append(wd)
+        if three_d:
+            Do, Ho, Wo = (x.D * 2, x.H * 2, x.W * 2) if transposed else ((x.D + stride - 1) // stride,
+                                                                        (x.H + stride - 1) // stride,
+                                                                        (x.W + stride - 1) // stride)
+            pd = 1
+        else:
+            Do, Ho, Wo = 1, (x.H + stride - 1) // stride, (x.W + stride - 1) // stride
+            pd = 0
+        pad = dil * (ks // 2)
+        d = L.DirectConv(L.ptr(x.hi), L.ptr(x.lo), None, x.B, x.D, x.H, x.W, cin, Do, Ho, Wo, cout,
+                         kd, ks, ks, stride if three_d else 1, stride, stride, pd, pad, pad, dil, 1 if transposed else 0,
+                         L.ptr(wd), ep)
+        if out is not None:
+            assert (out.D, out.H, out.W, out.Cn) == (Do, Ho, Wo, cout), ((out.D, out.H, out.W, out.Cn), (Do, Ho, Wo, cout))
+        self._keep.append(d)
+
+        def run(batch, d=d):
+            L.check(self.lib.adp_conv_direct(C.byref(d), batch, self.stream), "conv_direct")
+        run.kind = "direct"
+        return run
+
+    # ------------------------------------------------------------------ backbone (pspnet.py)
+    def _build_backbone(self):
+        sd, F, S = self.sd, self.F, self.S
+        ops = []
+        p = "img_extractor.feats"
+        self.crops = torch.zeros((F, S, S, 3), dtype=torch.float32, device=self.device)
+        # conv1 7x7/2 on the fp32 crop (Cin = 3: CUDA cores)
+        c1 = self._act(F, S // 2, S // 2, 64)
+        w = torch.as_tensor(sd[f"{p}.conv1.weight"]).float()
+        wd = w.reshape(64, 3, 49).permute(2, 1, 0).contiguous().to(self.device)
+        self._keep.append(wd)
+        d = L.DirectConv(None, None, L.ptr(self.crops), F, 1, S, S, 3, 1, S // 2, S // 2, 64, 1, 7, 7, 1, 2, 2, 0, 3, 3, 1, 0,
+                         L.ptr(wd), self._epilogue(c1, act=L.ACT_RELU))
+        self._keep.append(d)
+        ops.append(("conv1", lambda b, d=d: L.check(self.lib.adp_conv_direct(C.byref(d), b, self.stream), "conv1")))
+        mp = self._act(F, S // 4, S // 4, 64)
+        ops.append(("maxpool", lambda b, a=c1, o=mp: L.check(
+            self.lib.adp_maxpool3x3s2(C.byref(a.c), C.byref(o.c), b, self.stream), "maxpool")))
+        x = mp
+        self.taps = {"conv1": c1, "maxpool": mp}
+        for li, (planes, blocks, stride, dil) in enumerate(((64, 3, 1, 1), (128, 4, 2, 1), (256, 6, 1, 2), (512, 3, 1, 4)), 1):
+            Hn = x.H // stride
+            for bi in range(blocks):
+                pre = f"{p}.layer{li}.{bi}"
+                s_b = stride if bi == 0 else 1
+                d_b = 1 if bi == 0 else dil
+                t = self._act(F, Hn, Hn, planes)
+                ops.append((f"{pre}.conv1", self._conv(sd[f"{pre}.conv1.weight"], x, t, stride=s_b, dil=d_b, act=L.ACT_RELU)))
+                res = x
+                if f"{pre}.downsample.0.weight" in sd:
+                    res = self._act(F, Hn, Hn, planes)
+                    ops.append((f"{pre}.down", self._conv(sd[f"{pre}.downsample.0.weight"], x, res, stride=s_b, dil=1,
+                                                          act=L.ACT_NONE)))
+                o = self._act(F, Hn, Hn, planes)
+                ops.append((f"{pre}.conv2", self._conv(sd[f"{pre}.conv2.weight"], t, o, stride=1, dil=d_b, act=L.ACT_RELU,
+                                                       res=res)))
+                self.taps[pre] = o
+                x = o
+        # pyramid pooling + concat + first upsample
+        wpsp = torch.stack([torch.as_tensor(sd[f"img_extractor.psp.stages.{s}.1.weight"]).float().reshape(128, 512).t().contiguous()
+                            for s in range(4)]).contiguous().to(self.device)          # [4][512][128]
+        self._keep.append(wpsp)
+        self.pooled = torch.zeros((F, 50, 512), dtype=torch.float32, device=self.device)
+        self.priors = torch.zeros((F, 50, 128), dtype=torch.float32, device=self.device)
+        l4 = x
+        ops.append(("psp_priors", lambda b, a=l4: L.check(
+            self.lib.adp_psp_priors(C.byref(a.c), L.ptr(wpsp), L.ptr(self.pooled), L.ptr(self.priors), b, self.stream), "psp")))
+        u1 = self._act(F, 2 * l4.H, 2 * l4.W, 1024)
+        ops.append(("psp_concat_up", lambda b, a=l4, o=u1: L.check(
+            self.lib.adp_psp_concat_up(C.byref(a.c), L.ptr(self.priors), C.byref(o.c), b, self.stream), "psp_concat_up")))
+        x = u1
+        for nm, cout in (("up_1", 256), ("up_2", 64), ("up_3", 64)):
+            o = self._act(F, x.H, x.W, cout)
+            bias = self._dev(sd[f"img_extractor.{nm}.conv.0.bias"])
+            slope = float(np.asarray(sd[f"img_extractor.{nm}.conv.1.weight"]).reshape(-1)[0])
+            ops.append((nm, self._conv(sd[f"img_extractor.{nm}.conv.0.weight"], x, o, bias=bias, act=L.ACT_PRELU, prelu=slope)))
+            self.taps[nm] = o
+            if nm != "up_3":
+                u = self._act(F, 2 * o.H, 2 * o.W, cout)
+                ops.append((f"{nm}.upsample", lambda b, a=o, uu=u: L.check(
+                    self.lib.adp_upsample2x(C.byref(a.c), C.byref(uu.c), b, self.stream), "upsample")))
+                x = u
+            else:
+                x = o
+        self.feat = torch.zeros((F, S, S, 32), dtype=torch.float32, device=self.device)
+        fb = self._dev(sd["img_extractor.final.bias"])
+        ops.append(("final", self._conv(sd["img_extractor.final.weight"], x, None, bias=fb, act=L.ACT_NONE, out_f32=self.feat)))
+        self.backbone_ops = ops
+
+    def run_backbone(self, nframes):
+        for _, op in self.backbone_ops:
+            op(nframes)
+
+    # ------------------------------------------------------------------ stereo head (network_v5.py)
+    def _build_stereo(self):
+        sd, E, S, D = self.sd, self.E, self.S, N_DEPTH
+        dev = self.device
+        self.depths = self._dev(np.arange(0.1, 0.1 * (D - 0.5) + 0.1, 0.1, dtype=np.float32))
+        self.Mw = torch.zeros((E, 12), dtype=torch.float32, device=dev)
+        self.valid_env = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self.vol = self._act(E, S, S, 32, D=D, split=False)
+        cr = "cost_regularization"
+
+        def bn(name):
+            sc, sh = W.fold_bn(sd, f"{cr}.{name}.bn")
+            return self._dev(sc), self._dev(sh)
+
+        ops = []
+        dims = {0: (D, S), 1: (D // 2, S // 2), 2: (D // 4, S // 4), 3: (D // 8, S // 8)}
+
+        def act3(level, Cn):
+            d, s = dims[level]
+            return self._act(E, s, s, Cn, D=d, split=False)
+
+        c0 = act3(0, 8); c1 = act3(1, 16); c2 = act3(1, 16); c3 = act3(2, 32); c4 = act3(2, 32)
+        c5 = act3(3, 64); c6 = act3(3, 64); x7 = act3(2, 32); x9 = act3(1, 16); x11 = act3(0, 8)
+        chain = [("conv0", self.vol, c0, 1), ("conv1", c0, c1, 2), ("conv2", c1, c2, 1), ("conv3", c2, c3, 2),
+                 ("conv4", c3, c4, 1), ("conv5", c4, c5, 2), ("conv6", c5, c6, 1)]
+        for nm, xin, out, stride in chain:
+            sc, sh = bn(nm)
+            ops.append((f"cr.{nm}", self._conv(sd[f"{cr}.{nm}.conv.weight"], xin, out, stride=stride, npass=1, scale=sc, bias=sh,
+                                               act=L.ACT_RELU)))
+        for nm, xin, skip, out in (("conv7", c6, c4, x7), ("conv9", x7, c2, x9), ("conv11", x9, c0, x11)):
+            sc, sh = bn(nm)
+            ops.append((f"cr.{nm}", self._conv(sd[f"{cr}.{nm}.conv.weight"], xin, out, stride=2, transposed=True, npass=1,
+                                               scale=sc, bias=sh, act=L.ACT_RELU, res=skip, res_after_act=1)))
+        self.cr_ops = ops
+        self.cr_taps = {"conv0": c0, "conv1": c1, "conv2": c2, "conv3": c3, "conv4": c4, "conv5": c5, "conv6": c6,
+                        "conv7": x7, "conv9": x9, "conv11": x11}
+        self.x11 = x11
+        # decode weights, transposed to [K][N]
+        def tw(name):
+            w = torch.as_tensor(sd[name]).float()
+            return self._dev(w.reshape(w.shape[0], -1).t().contiguous())
+        dw = L.DecodeWeights()
+        names = {"ic": "instance_color.0", "nh0": "nocs_head.0", "nh1": "nocs_head.2", "nh2": "nocs_head.4"}
+        if self.regress_pose:
+            names.update({"np0": "nocs_pts_mlp.0", "np1": "nocs_pts_mlp.2", "pm0": "pose_mlp1.0", "pm1": "pose_mlp1.2",
+                          "q0": "pose_mlp2.0", "q1": "pose_mlp2.2", "r0": "rotation_estimator.0",
+                          "r1": "rotation_estimator.2", "r2": "rotation_estimator.4"})
+        for short, full in names.items():
+            setattr(dw, f"{short}_w", L.ptr(tw(f"{full}.weight")))
+            setattr(dw, f"{short}_b", L.ptr(self._dev(sd[f"{full}.bias"])))
+        pw = torch.as_tensor(sd[f"{cr}.prob.weight"]).float()[0].permute(1, 2, 3, 0).contiguous()    # [kz,ky,kx,c]
+        dw.prob_w = L.ptr(self._dev(pw.reshape(27, 8)))
+        self.dw = dw
+        P = self.P
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.nocs = torch.zeros((E, P, 3), **f32)
+        self.depth = torch.zeros((E, P), **f32)
+        self.pf1 = torch.zeros((E, P, 128), **f32)
+        self.gsum = torch.zeros((E, 128), **f32)
+        self.psum = torch.zeros((E, 256), **f32)
+        self.R = torch.zeros((E, 9), **f32)
+        self.r6 = torch.zeros((E, 6), **f32)
+        self.dbg_logits = torch.zeros((E, P, D), **f32) if self.debug else None
+        self.dbg_fused = torch.zeros((E, P, 32), **f32) if self.debug else None
+        # preprocess outputs (frames: [0,E) = view 1, [E,2E) = view 2)
+        F = self.F
+        self.bbox_ws = torch.zeros((F, 4), dtype=torch.int32, device=dev)
+        self.win = torch.zeros((F, 4), dtype=torch.int32, device=dev)
+        self.Kp = torch.zeros((F, 9), dtype=torch.float64, device=dev)
+        self.valid = torch.zeros(F, dtype=torch.uint8, device=dev)
+        self.choose = torch.zeros((F, P), dtype=torch.int32, device=dev)
+        self.counts = torch.zeros(F, dtype=torch.int32, device=dev)
+        self.bbox = torch.zeros((E, 8, 3), dtype=torch.float64, device=dev)
+        self.scale = torch.zeros(E, dtype=torch.float64, device=dev)
+        self.trans = torch.zeros((E, 3), dtype=torch.float64, device=dev)
+
+    # ------------------------------------------------------------------ stages
+    @staticmethod
+    def _dt(t, kinds):
+        code = {torch.uint8: L.DT_U8, torch.bool: L.DT_U8, torch.float32: L.DT_F32, torch.float64: L.DT_F64}.get(t.dtype)
+        if code is None or code not in kinds:
+            raise TypeError(f"unsupported dtype {t.dtype}")
+        return code
+
+    def preprocess(self, view, rgb, mask, K, n, seed=0, choose=None):
+        """view 0/1; rgb [n,H,W,3] f32|f64, mask [n,H,W] u8|bool|f32|f64, K [n,3,3] f64 -- device tensors."""
+        E = self.E
+        o = view * E
+        assert rgb.is_cuda and mask.is_cuda and K.is_cuda and K.dtype == torch.float64
+        assert rgb.is_contiguous() and mask.is_contiguous() and K.is_contiguous()
+        H, Wd = rgb.shape[1], rgb.shape[2]
+        mode = 0
+        if choose is not None:
+            self.choose[o:o + n].copy_(choose.to(torch.int32))
+            mode = 1
+        L.check(self.lib.adp_preprocess(
+            L.ptr(rgb), self._dt(rgb, (L.DT_F32, L.DT_F64)), L.ptr(mask), self._dt(mask, (L.DT_U8, L.DT_F32, L.DT_F64)),
+            L.ptr(K), 9, n, H, Wd, self.S, self.P, (seed * 2 + view) & 0xFFFFFFFF, mode,
+            L.ptr(self.bbox_ws[o:]), L.ptr(self.win[o:]), L.ptr(self.Kp[o:]), L.ptr(self.valid[o:]), L.ptr(self.crops[o:]),
+            L.ptr(self.choose[o:]), L.ptr(self.counts[o:]), self.stream), "preprocess")
+
+    def stereo(self, n, E1, E2):
+        """Frames [0,n) are view 1 and [E,E+n) view 2 of envs [0,n).  E1/E2 [n,4,4] f64 device tensors."""
+        E, S, D, P = self.E, self.S, N_DEPTH, self.P
+        lib, st = self.lib, self.stream
+        L.check(lib.adp_warp_matrices(L.ptr(self.Kp), L.ptr(E1), L.ptr(self.Kp[E:]), L.ptr(E2), L.ptr(self.Mw),
+                                      L.ptr(self.valid), L.ptr(self.valid[E:]), L.ptr(self.valid_env), n, st), "warp_matrices")
+        f1, f2 = self.feat, self.feat[E:]
+        L.check(lib.adp_build_volume(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.vol.hi), n, D, S, S,
+                                     32, st), "build_volume")
+        for _, op in self.cr_ops:
+            op(n)
+        L.check(lib.adp_decode(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi), L.ptr(self.choose),
+                               L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.pf1),
+                               L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
+                               L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, st), "decode")
+        L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
+                            L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans), n, P, S, st), "fit")
+
+    def run_chunk(self, K, rgb1, mask1, E1, rgb2, mask2, E2, seed=0, choose1=None, choose2=None):
+        """Device tensors for n <= max_envs environments -> self.bbox[:n] ([n,8,3] f64, world frame)."""
+        n = K.shape[0]
+        assert n <= self.E
+        if not self.regress_pose:
+            raise NotImplementedError("direct_regression=False (RANSAC/Umeyama, PnP branches) is not on the device path yet")
+        self.preprocess(0, rgb1, mask1, K, n, seed, choose1)
+        self.preprocess(1, rgb2, mask2, K, n, seed, choose2)
+        if n == self.E:
+            self.run_backbone(self.F)
+        else:   # the two views are not adjacent in the frame buffers: run them one after the other
+            self._backbone_partial(n)
+        self.stereo(n, E1, E2)
+        return self.bbox[:n]
+
+    def _backbone_partial(self, n):
+        # view-2 frames start at frame E; with n < E process frames [0, E + n) (the gap computes on stale crops, harmless)
+        self.run_backbone(self.E + n)
+
+    def check_error_flag(self):
+        v = int(self.err_flag.item())
+        if v:
+            raise L.AdpError(f"device pipeline watchdog tripped (code {v})")
+
+    def close(self):
+        for p in self._plans:
+            self.lib.adp_conv_tc_free(p)
+        self._plans = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,106 @@
+"""Drop-in for ``models.pose_estimator.AdaPose.interface_v5.AdaPoseEstimator_v5`` (RGBManip).
+
+Same constructor (``env, cfg, logger``), same ``estimate`` / ``predict`` signatures and return values
+(interface_v5.py:39-56,213-374): host numpy in, ``np.ndarray [num_envs, 8, 3]`` float64 world-frame box corners
+out, the ``unit cube + 10`` sentinel for environments whose mask is empty in either view or whose fit is not
+finite.  The per-env Python loop of the reference is replaced by chunked batches on the device pipeline
+(:class:`rgbmanip_b200.engine.Engine`); there is no CPU fallback.
+
+Deliberate deviations from the live reference, all documented in DESIGN.md:
+  * inference runs in eval mode (the reference never calls ``.eval()``: SURVEY.md finding 0.3-1);
+  * the random 1024-pixel subset is drawn by a counter-based hash on the device instead of the global numpy
+    RNG (same distribution; pass ``choose=`` to replay the reference's stream exactly);
+  * ``draw_result`` (interface_v5.py:364) and the view-2 decode branch are dead work and are not computed.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import weights as W
+from .engine import Engine
+
+try:  # inside an RGBManip checkout the real base class is importable; keep isinstance() relations intact
+    from models.pose_estimator.base_estimator import BasePoseEstimator  # type: ignore
+except Exception:  # pragma: no cover - stand-alone use
+    class BasePoseEstimator:  # mirrors models/pose_estimator/base_estimator.py:5-21
+        def __init__(self, env, cfg, logger):
+            self.env = env
+            self.cfg = cfg
+            self.logger = logger
+
+        def append_picture(self, pic, pose):
+            pass
+
+        def estimate(self):
+            pass
+
+
+DEFAULT_BBOX = np.asarray([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1],
+                           [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], dtype=np.float64) + 10.0
+
+
+class AdaPoseEstimator_v5(BasePoseEstimator):
+
+    def __init__(self, env, cfg, logger, state_dict=None, device=None, max_envs=None, precision=None, **engine_kw):
+        super().__init__(env, cfg, logger)
+        self.cfg = cfg
+        regress = bool(cfg.get("direct_regression", True))
+        if state_dict is None:
+            if cfg.get("load", False):
+                # same failure mode as the reference: a missing checkpoint raises from torch.load (interface_v5.py:55-56)
+                state_dict = W.load_checkpoint(cfg["checkpoint_path"], regress_pose=regress)
+            else:
+                state_dict = W.init_state_dict(int(cfg.get("seed", 0)), regress_pose=regress)
+        device = device or cfg.get("device", "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0")
+        self.device = torch.device(device)
+        self.estimator = Engine(state_dict, device=self.device, max_envs=int(max_envs or cfg.get("max_envs_per_chunk", 16)),
+                                precision=precision or cfg.get("precision", "bf16x3"), regress_pose=regress,
+                                img_size=int(cfg.get("img_size", 224)), **engine_kw)
+        self._seed = int(cfg.get("sample_seed", 0))
+        self._calls = 0
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _to_dev(self, a, dtype=None):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    # -- reference API ---------------------------------------------------------------------------
+    def estimate(self, camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
+                 rgb2_batch, view2_mask_batch, view2_extrinsic_batch, choose=None, return_tensor=False):
+        eng = self.estimator
+        N = len(camera_intrinsic_batch)
+        out = torch.empty((N, 8, 3), dtype=torch.float64, device=self.device)
+        self._calls += 1
+        with torch.cuda.device(self.device):
+            for lo in range(0, N, eng.E):
+                hi = min(N, lo + eng.E)
+                K = self._to_dev(camera_intrinsic_batch[lo:hi], torch.float64)
+                E1 = self._to_dev(view1_extrinsic_batch[lo:hi], torch.float64)
+                E2 = self._to_dev(view2_extrinsic_batch[lo:hi], torch.float64)
+                rgb1 = self._to_dev(rgb1_batch[lo:hi])
+                rgb2 = self._to_dev(rgb2_batch[lo:hi])
+                m1 = self._to_dev(view1_mask_batch[lo:hi])
+                m2 = self._to_dev(view2_mask_batch[lo:hi])
+                if rgb1.dtype not in (torch.float32, torch.float64):
+                    rgb1, rgb2 = rgb1.float(), rgb2.float()
+                c1 = c2 = None
+                if choose is not None:
+                    c1 = self._to_dev(choose[0][lo:hi], torch.int32)
+                    c2 = self._to_dev(choose[1][lo:hi], torch.int32)
+                box = eng.run_chunk(K, rgb1, m1, E1, rgb2, m2, E2, seed=self._seed + 7919 * self._calls + lo,
+                                    choose1=c1, choose2=c2)
+                out[lo:hi].copy_(box)
+            if return_tensor:
+                return out
+            res = out.cpu().numpy()
+        eng.check_error_flag()
+        return res
+
+    def predict(self, camera_intrinsic, rgb1, view1_mask, view1_extrinsic, rgb2, view2_mask, view2_extrinsic):
+        """Single environment (interface_v5.py:229-374) -> [8,3]."""
+        f = lambda a: (a if isinstance(a, torch.Tensor) else np.asarray(a))[None]
+        return self.estimate(f(camera_intrinsic), f(rgb1), f(view1_mask), f(view1_extrinsic),
+                             f(rgb2), f(view2_mask), f(view2_extrinsic))[0]

@@ -1,0 +1,132 @@
+"""Helpers for the -m gpu parity tests: raw calls through the C ABI on torch-allocated device buffers."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from rgbmanip_b200 import _lib as L
+
+DEV = "cuda:0"
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def split(x: torch.Tensor, with_lo=True):
+    """fp32 channels-last tensor -> (hi, lo) bf16 device planes."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16) if with_lo else None
+    return hi.to(DEV).contiguous(), (lo.to(DEV).contiguous() if with_lo else None)
+
+
+def act(hi, lo, B, D, H, W, Cn):
+    return L.Act(L.ptr(hi), L.ptr(lo), B, D, H, W, Cn)
+
+
+def val(hi, lo):
+    v = hi.float()
+    return (v + lo.float()) if lo is not None else v
+
+
+def to_cl(x):
+    """NCHW / NCDHW -> channels-last contiguous."""
+    if x.dim() == 4:
+        return x.permute(0, 2, 3, 1).contiguous()
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def from_cl(x):
+    if x.dim() == 4:
+        return x.permute(0, 3, 1, 2).contiguous()
+    return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def epilogue(out_hi=None, out_lo=None, out_f32=None, scale=None, bias=None, act_code=L.ACT_NONE, prelu=0.0, res_hi=None,
+             res_lo=None, res_after_act=0):
+    return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act_code, res_after_act, L.ptr(res_hi), L.ptr(res_lo),
+                      L.ptr(out_hi), L.ptr(out_lo), L.ptr(out_f32))
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def tc_conv(x_cl, w, *, dil=1, npass=3, bias=None, scale=None, act_code=L.ACT_NONE, prelu=0.0, res_cl=None, res_after_act=0,
+            batch=None):
+    """x_cl: fp32 [B,(D,)H,W,Cin] cpu; w: torch layout [Cout,Cin,(kd,)k,k].  Returns fp32 output (cpu, channels-last)."""
+    lib = L.load()
+    three_d = x_cl.dim() == 5
+    B = x_cl.shape[0]
+    D = x_cl.shape[1] if three_d else 1
+    H, Wd, Cin = x_cl.shape[-3], x_cl.shape[-2], x_cl.shape[-1]
+    Cout = w.shape[0]
+    kd = w.shape[2] if three_d else 1
+    ks = w.shape[-1]
+    xh, xl = split(x_cl, npass == 3)
+    cpad = (Cout + 15) // 16 * 16
+    wt = w.reshape(Cout, Cin, -1).permute(2, 0, 1).contiguous()
+    if cpad != Cout:
+        wt = torch.cat([wt, torch.zeros(wt.shape[0], cpad - Cout, Cin)], 1).contiguous()
+    wh, wl = split(wt, npass == 3)
+    out_f32 = torch.full(tuple(x_cl.shape[:-1]) + (Cout,), float("nan"), dtype=torch.float32, device=DEV)
+    out_hi = torch.zeros(out_f32.shape, dtype=torch.bfloat16, device=DEV)
+    out_lo = torch.zeros_like(out_hi)
+    rh = rl = None
+    if res_cl is not None:
+        rh, rl = split(res_cl, True)
+    b_d = bias.to(DEV) if bias is not None else None
+    s_d = scale.to(DEV) if scale is not None else None
+    ep = epilogue(out_hi, out_lo, out_f32, s_d, b_d, act_code, prelu, rh, rl, res_after_act)
+    a = act(xh, xl, B, D, H, Wd, Cin)
+    plan = C.c_void_p()
+    L.check(lib.adp_conv_tc_plan(C.byref(plan), C.byref(a), L.ptr(wh), L.ptr(wl), Cout, kd, ks, dil, npass, C.byref(ep), 148),
+            "plan")
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    L.check(lib.adp_conv_tc_run(plan, B if batch is None else batch, L.ptr(err), stream()), "run")
+    torch.cuda.synchronize()
+    lib.adp_conv_tc_free(plan)
+    assert int(err.item()) == 0, f"watchdog code {int(err.item())}"
+    return out_f32.cpu(), val(out_hi, out_lo).cpu()
+
+
+def direct_conv(x_cl, w, *, stride=1, dil=1, transposed=False, bias=None, scale=None, act_code=L.ACT_NONE, res_cl=None,
+                res_after_act=0, f32_input=False):
+    lib = L.load()
+    three_d = x_cl.dim() == 5
+    B = x_cl.shape[0]
+    D = x_cl.shape[1] if three_d else 1
+    H, Wd, Cin = x_cl.shape[-3], x_cl.shape[-2], x_cl.shape[-1]
+    if transposed:
+        Cout = w.shape[1]
+        wp = w.reshape(Cin, Cout, -1).permute(2, 0, 1).contiguous().to(DEV)
+        Do, Ho, Wo = 2 * D, 2 * H, 2 * Wd
+    else:
+        Cout = w.shape[0]
+        wp = w.reshape(Cout, Cin, -1).permute(2, 1, 0).contiguous().to(DEV)
+        Do = (D + stride - 1) // stride if three_d else 1
+        Ho, Wo = (H + stride - 1) // stride, (Wd + stride - 1) // stride
+    kd = w.shape[2] if three_d else 1
+    ks = w.shape[-1]
+    pad = dil * (ks // 2)
+    shape = (B, Do, Ho, Wo, Cout) if three_d else (B, Ho, Wo, Cout)
+    out_f32 = torch.full(shape, float("nan"), dtype=torch.float32, device=DEV)
+    rh = rl = None
+    if res_cl is not None:
+        rh, rl = split(res_cl, True)
+    b_d = bias.to(DEV) if bias is not None else None
+    s_d = scale.to(DEV) if scale is not None else None
+    ep = epilogue(None, None, out_f32, s_d, b_d, act_code, 0.0, rh, rl, res_after_act)
+    if f32_input:
+        xin = x_cl.to(DEV).contiguous()
+        xh = xl = None
+    else:
+        xin = None
+        xh, xl = split(x_cl, True)
+    d = L.DirectConv(L.ptr(xh), L.ptr(xl), L.ptr(xin), B, D, H, Wd, Cin, Do, Ho, Wo, Cout, kd, ks, ks,
+                     stride if three_d else 1, stride, stride, 1 if three_d else 0, pad, pad, dil, 1 if transposed else 0,
+                     L.ptr(wp), ep)
+    L.check(lib.adp_conv_direct(C.byref(d), B, stream()), "direct")
+    torch.cuda.synchronize()
+    return out_f32.cpu()

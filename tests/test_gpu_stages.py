@@ -1,0 +1,416 @@
+"""Stage-level parity on the B200: every CUDA stage, called through the C ABI, against the CPU oracle
+(oracle/adapose_oracle.py, itself pinned to the reference by tests/test_oracle_golden.py) on the same seeded inputs.
+
+Tolerances: integer/index work is bit exact; floating point stages state their bound next to the assert.  The
+tensor-core convolution is checked in both precision modes: "bf16x3" (split precision, fp32-grade) and plain
+"bf16" (one pass; bound = bf16 operand rounding)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import adapose_oracle as O
+from rgbmanip_b200 import _lib as L
+from rgbmanip_b200 import synth, weights
+
+pytestmark = [pytest.mark.gpu, pytest.mark.filterwarnings("ignore")]
+
+@pytest.fixture(scope="module")
+def G():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import importlib
+    L.load()
+    return importlib.import_module("gpu_util")
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _t(rng, *shape, scale=1.0):
+    return torch.from_numpy((rng.standard_normal(shape) * scale).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+TC2D_CASES = [
+    # (B, H, W, Cin, Cout, k, dil)
+    (2, 28, 28, 64, 64, 3, 1),
+    (1, 28, 28, 128, 256, 3, 2),
+    (2, 28, 28, 256, 512, 3, 4),
+    (1, 28, 28, 128, 256, 1, 1),
+    (1, 56, 56, 64, 64, 3, 1),
+    (1, 112, 112, 256, 64, 3, 1),
+    (1, 224, 224, 64, 64, 3, 1),
+    (1, 224, 224, 64, 32, 1, 1),
+    (3, 20, 12, 64, 128, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC2D_CASES, ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("npass", [3, 1])
+def test_tc_conv2d_matches_oracle(G, case, npass):
+    B, H, W, Cin, Cout, k, dil = case
+    rng = _rng(hash(case) % 2**31)
+    x = _t(rng, B, Cin, H, W)
+    w = _t(rng, Cout, Cin, k, k, scale=math.sqrt(2.0 / (k * k * Cin)))
+    bias = _t(rng, Cout)
+    res = _t(rng, B, Cout, H, W)
+    ref = F.relu(F.conv2d(x, w, bias, padding=dil * (k // 2), dilation=dil) + res)
+    out32, out16 = G.tc_conv(G.to_cl(x), w, dil=dil, npass=npass, bias=bias, act_code=L.ACT_RELU, res_cl=G.to_cl(res))
+    assert torch.isfinite(out32).all()
+    e = G.rel_err(G.from_cl(out32), ref)
+    # bf16x3 keeps ~16 mantissa bits of both operands; one bf16 pass keeps 8
+    assert e < (2e-4 if npass == 3 else 2e-2), e
+    assert G.rel_err(G.from_cl(out16), ref) < (2e-4 if npass == 3 else 2e-2)
+
+
+TC3D_CASES = [
+    # (B, D, H, W, Cin, Cout)
+    (1, 6, 28, 28, 32, 8),
+    (1, 5, 56, 56, 16, 16),
+    (2, 6, 28, 28, 32, 32),
+    (1, 3, 28, 28, 64, 64),
+    (1, 4, 224, 224, 32, 8),
+]
+
+
+@pytest.mark.parametrize("case", TC3D_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_tc_conv3d_matches_oracle(G, case):
+    B, D, H, W, Cin, Cout = case
+    rng = _rng(sum(case))
+    x = _t(rng, B, Cin, D, H, W).bfloat16().float()       # the volume stage stores bf16: make the input exactly representable
+    w = _t(rng, Cout, Cin, 3, 3, 3, scale=math.sqrt(1.0 / (27 * Cin)))
+    scale, shift = _t(rng, Cout).abs() + 0.5, _t(rng, Cout)
+    ref = F.relu(F.conv3d(x, w.bfloat16().float(), padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    out32, _ = G.tc_conv(G.to_cl(x), w, npass=1, bias=shift, scale=scale, act_code=L.ACT_RELU)
+    assert torch.isfinite(out32).all()
+    assert G.rel_err(G.from_cl(out32), ref) < 1e-4   # operands are exact bf16: only fp32 summation order differs
+
+
+DIRECT_CASES = [
+    # (dims, B, D, H, W, Cin, Cout, k, stride, dil, transposed)
+    (2, 2, 1, 32, 48, 3, 64, 7, 2, 1, False),
+    (2, 1, 1, 28, 28, 64, 128, 3, 2, 1, False),
+    (2, 1, 1, 28, 28, 64, 128, 1, 2, 1, False),
+    (2, 1, 1, 14, 14, 64, 64, 3, 1, 2, False),
+    (3, 1, 6, 16, 16, 8, 16, 3, 2, 1, False),
+    (3, 1, 6, 16, 16, 16, 32, 3, 2, 1, False),
+    (3, 1, 3, 8, 8, 64, 32, 3, 2, 1, True),
+    (3, 1, 6, 16, 16, 16, 8, 3, 2, 1, True),
+    (3, 1, 4, 12, 12, 32, 8, 3, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", DIRECT_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_direct_conv_matches_oracle(G, case):
+    dims, B, D, H, W, Cin, Cout, k, stride, dil, transposed = case
+    rng = _rng(sum(int(v) for v in case))
+    if dims == 2:
+        x = _t(rng, B, Cin, H, W)
+        w = _t(rng, Cout, Cin, k, k, scale=0.1)
+        ref = F.conv2d(x, w, stride=stride, padding=dil * (k // 2), dilation=dil)
+    elif transposed:
+        x = _t(rng, B, Cin, D, H, W)
+        w = _t(rng, Cin, Cout, 3, 3, 3, scale=0.1)
+        ref = F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1)
+    else:
+        x = _t(rng, B, Cin, D, H, W)
+        w = _t(rng, Cout, Cin, 3, 3, 3, scale=0.1)
+        ref = F.conv3d(x, w, stride=stride, padding=1)
+    out = G.direct_conv(G.to_cl(x), w, stride=stride, dil=dil, transposed=transposed, f32_input=(Cin == 3))
+    assert out.shape == G.to_cl(ref).shape
+    assert G.rel_err(G.from_cl(out), ref) < 2e-4    # input carried as hi+lo bf16 (~16 bits), fp32 weights
+
+
+# ------------------------------------------------------------------------------------------------ backbone helpers
+def test_maxpool_psp_upsample(G):
+    lib = L.load()
+    rng = _rng(3)
+    st = G.stream()
+    # max-pool
+    x = _t(rng, 2, 64, 30, 26)
+    xh, xl = G.split(G.to_cl(x))
+    oh = torch.zeros((2, 15, 13, 64), dtype=torch.bfloat16, device=G.DEV)
+    ol = torch.zeros_like(oh)
+    L.check(lib.adp_maxpool3x3s2(C.byref(G.act(xh, xl, 2, 1, 30, 26, 64)), C.byref(G.act(oh, ol, 2, 1, 15, 13, 64)), 2, st), "mp")
+    ref = F.max_pool2d(G.from_cl(G.val(xh, xl).cpu()), 3, 2, 1)
+    assert G.rel_err(G.from_cl(G.val(oh, ol).cpu()), ref) < 1e-5
+    # pyramid pooling + concat + x2 upsample against the oracle's psp_module + interpolate
+    sd = weights.init_state_dict(2)
+    f = _t(rng, 2, 512, 28, 28).abs()
+    fh, fl = G.split(G.to_cl(f))
+    wpsp = torch.stack([torch.from_numpy(sd[f"img_extractor.psp.stages.{s}.1.weight"]).reshape(128, 512).t().contiguous()
+                        for s in range(4)]).contiguous().to(G.DEV)
+    pooled = torch.zeros((2, 50, 512), device=G.DEV)
+    priors = torch.zeros((2, 50, 128), device=G.DEV)
+    fa = G.act(fh, fl, 2, 1, 28, 28, 512)
+    L.check(lib.adp_psp_priors(C.byref(fa), L.ptr(wpsp), L.ptr(pooled), L.ptr(priors), 2, st), "psp")
+    uh = torch.zeros((2, 56, 56, 1024), dtype=torch.bfloat16, device=G.DEV)
+    ul = torch.zeros_like(uh)
+    L.check(lib.adp_psp_concat_up(C.byref(fa), L.ptr(priors), C.byref(G.act(uh, ul, 2, 1, 56, 56, 1024)), 2, st), "cat")
+    fin = G.from_cl(G.val(fh, fl).cpu())
+    ref = F.interpolate(O.psp_module(sd, fin), scale_factor=2, mode="bilinear", align_corners=True)
+    assert G.rel_err(G.from_cl(G.val(uh, ul).cpu()), ref) < 5e-5
+    # plain x2 upsample
+    y = _t(rng, 1, 64, 12, 20)
+    yh, yl = G.split(G.to_cl(y))
+    zh = torch.zeros((1, 24, 40, 64), dtype=torch.bfloat16, device=G.DEV)
+    zl = torch.zeros_like(zh)
+    L.check(lib.adp_upsample2x(C.byref(G.act(yh, yl, 1, 1, 12, 20, 64)), C.byref(G.act(zh, zl, 1, 1, 24, 40, 64)), 1, st), "up")
+    ref = F.interpolate(G.from_cl(G.val(yh, yl).cpu()), scale_factor=2, mode="bilinear", align_corners=True)
+    assert G.rel_err(G.from_cl(G.val(zh, zl).cpu()), ref) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ preprocess
+def _preprocess(G, rgb, mask, K, choose=None, seed=0):
+    lib = L.load()
+    Fn = rgb.shape[0]
+    dev = G.DEV
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rgb_d, mask_d, K_d = t(rgb), t(mask), t(K.astype(np.float64))
+    dt = {torch.float32: L.DT_F32, torch.float64: L.DT_F64, torch.bool: L.DT_U8, torch.uint8: L.DT_U8}
+    out = dict(bbox=torch.zeros((Fn, 4), dtype=torch.int32, device=dev), win=torch.zeros((Fn, 4), dtype=torch.int32, device=dev),
+               Kp=torch.zeros((Fn, 9), dtype=torch.float64, device=dev), valid=torch.zeros(Fn, dtype=torch.uint8, device=dev),
+               crops=torch.zeros((Fn, 224, 224, 3), device=dev), choose=torch.zeros((Fn, 1024), dtype=torch.int32, device=dev),
+               counts=torch.zeros(Fn, dtype=torch.int32, device=dev))
+    mode = 0
+    if choose is not None:
+        out["choose"].copy_(torch.from_numpy(choose).to(torch.int32))
+        mode = 1
+    L.check(lib.adp_preprocess(L.ptr(rgb_d), dt[rgb_d.dtype], L.ptr(mask_d), dt[mask_d.dtype], L.ptr(K_d), 9, Fn, 480, 640, 224,
+                               1024, seed, mode, L.ptr(out["bbox"]), L.ptr(out["win"]), L.ptr(out["Kp"]), L.ptr(out["valid"]),
+                               L.ptr(out["crops"]), L.ptr(out["choose"]), L.ptr(out["counts"]), G.stream()), "preprocess")
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_preprocess_matches_oracle(G, dtype):
+    batch = synth.make_batch(16, seed=5, dtype=dtype)
+    mask = batch.mask1 if dtype == np.float32 else batch.mask1.astype(np.float64)
+    got = _preprocess(G, batch.rgb1, mask, batch.K)
+    n_checked = 0
+    for e in range(16):
+        ys, xs = np.nonzero(batch.mask1[e])
+        if len(ys) == 0:
+            assert got["valid"][e] == 0
+            continue
+        win = O.get_bbox(int(ys.min()), int(xs.min()), int(ys.max()), int(xs.max()))
+        np.testing.assert_array_equal(got["win"][e], win)                         # integer work: bit exact
+        np.random.seed(1)
+        v, ch, _, Kp = O.prepare_model_input(batch.rgb1[e], batch.mask1[e], batch.K[e])
+        nz = O.resize_nearest(batch.mask1[e][win[0]:win[1], win[2]:win[3]].astype(np.float32), 224).flatten().nonzero()[0]
+        assert got["counts"][e] == len(nz)
+        np.testing.assert_array_equal(got["Kp"][e].reshape(3, 3), Kp)
+        np.testing.assert_allclose(got["crops"][e].transpose(2, 0, 1), v, rtol=0, atol=2e-5)
+        c = got["choose"][e]
+        if len(nz) <= 1024:
+            np.testing.assert_array_equal(c, np.pad(nz, (0, 1024 - len(nz)), "wrap"))   # wrap padding: bit exact
+        else:                                                                      # device sampling: a sorted 1024-subset
+            assert len(np.unique(c)) == 1024 and (np.diff(c) > 0).all() and np.isin(c, nz).all()
+        n_checked += 1
+    assert n_checked >= 12
+
+
+def test_preprocess_sampling_is_uniform_and_seeded(G):
+    batch = synth.make_batch(4, seed=9, special=False)
+    a = _preprocess(G, batch.rgb1, batch.mask1, batch.K, seed=1)["choose"]
+    b = _preprocess(G, batch.rgb1, batch.mask1, batch.K, seed=1)["choose"]
+    c = _preprocess(G, batch.rgb1, batch.mask1, batch.K, seed=2)["choose"]
+    np.testing.assert_array_equal(a, b)
+    assert (a != c).any()
+    # selection probability must not depend on the position: compare the mean rank of the picks with n/2
+    win = None
+    for e in range(4):
+        ys, xs = np.nonzero(batch.mask1[e])
+        win = O.get_bbox(int(ys.min()), int(xs.min()), int(ys.max()), int(xs.max()))
+        nz = O.resize_nearest(batch.mask1[e][win[0]:win[1], win[2]:win[3]].astype(np.float32), 224).flatten().nonzero()[0]
+        if len(nz) > 4096:
+            ranks = np.searchsorted(nz, a[e])
+            assert abs(ranks.mean() / len(nz) - 0.5) < 0.04
+
+
+# ------------------------------------------------------------------------------------------------ volume / decode / fit
+def _stereo_inputs(seed=0):
+    batch = synth.make_batch(2, seed=seed, special=False)
+    np.random.seed(seed)
+    views = []
+    for e in range(2):
+        v1 = O.prepare_model_input(batch.rgb1[e], batch.mask1[e], batch.K[e])
+        v2 = O.prepare_model_input(batch.rgb2[e], batch.mask2[e], batch.K[e])
+        views.append((v1, v2))
+    return batch, views
+
+
+def test_warp_matrices_and_volume(G):
+    lib = L.load()
+    batch, views = _stereo_inputs(1)
+    rng = _rng(4)
+    dev = G.DEV
+    f1 = _t(rng, 2, 32, 224, 224)
+    f2 = _t(rng, 2, 32, 224, 224)
+    Kp1 = torch.from_numpy(np.stack([v[0][3] for v in views]).reshape(2, 9)).to(dev)
+    Kp2 = torch.from_numpy(np.stack([v[1][3] for v in views]).reshape(2, 9)).to(dev)
+    E1 = torch.from_numpy(batch.E1.reshape(2, 16)).to(dev)
+    E2 = torch.from_numpy(batch.E2.reshape(2, 16)).to(dev)
+    Mw = torch.zeros((2, 12), device=dev)
+    L.check(lib.adp_warp_matrices(L.ptr(Kp1), L.ptr(E1), L.ptr(Kp2), L.ptr(E2), L.ptr(Mw), None, None, None, 2, G.stream()), "wm")
+    P1 = np.stack([O.projection(views[e][0][3], batch.E1[e]) for e in range(2)])
+    P2 = np.stack([O.projection(views[e][1][3], batch.E2[e]) for e in range(2)])
+    M = P2 @ np.linalg.inv(P1)
+    want = np.concatenate([M[:, :3, :3].reshape(2, 9), M[:, :3, 3]], 1)
+    np.testing.assert_allclose(Mw.cpu().numpy(), want, rtol=2e-6, atol=1e-6)
+    depths = torch.from_numpy(O.depth_hypotheses()).to(dev)
+    vol = torch.zeros((2, 24, 224, 224, 32), dtype=torch.bfloat16, device=dev)
+    f1d, f2d = G.to_cl(f1).to(dev), G.to_cl(f2).to(dev)
+    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), 2, 24, 224, 224, 32, G.stream()), "vol")
+    torch.cuda.synchronize()
+    ref = f1[:, :, None] + O.homo_warping(f2, torch.from_numpy(P2).float(), torch.from_numpy(P1).float(),
+                                          torch.from_numpy(O.depth_hypotheses())[None].repeat(2, 1))
+    got = vol.float().cpu().permute(0, 4, 1, 2, 3)
+    diff = (got - ref).abs()
+    # bf16 storage (2^-9 relative) plus sample positions that agree to ~1e-4 px; a handful of voxels sit on a
+    # bilinear cell boundary or the zero-padding edge where that flips a corner
+    assert float(diff.mean()) < 6e-3
+    assert float((diff > 0.05).float().mean()) < 2e-4
+
+
+def _run_costreg_decode(G, sd, eng_kw):
+    from rgbmanip_b200.engine import Engine
+    eng = Engine(sd, device=G.DEV, max_envs=2, debug=True, **eng_kw)
+    return eng
+
+
+def test_costreg_and_decode_match_oracle(G):
+    """Feed oracle feature maps into the device volume/cost-regularisation/decode stages."""
+    from rgbmanip_b200.engine import Engine
+    sd = weights.init_state_dict(0)
+    batch, views = _stereo_inputs(2)
+    eng = Engine(sd, device=G.DEV, max_envs=2, debug=True)
+    dev = G.DEV
+    with torch.no_grad():
+        img1 = torch.from_numpy(np.stack([v[0][0] for v in views])).float()
+        img2 = torch.from_numpy(np.stack([v[1][0] for v in views])).float()
+        f1, f2 = O.pspnet(sd, img1), O.pspnet(sd, img2)
+    eng.feat[:2].copy_(G.to_cl(f1))
+    eng.feat[2:4].copy_(G.to_cl(f2))
+    ch1 = np.stack([v[0][1] for v in views])
+    eng.choose[:2].copy_(torch.from_numpy(ch1).to(torch.int32))
+    eng.Kp[:2].copy_(torch.from_numpy(np.stack([v[0][3] for v in views]).reshape(2, 9)))
+    eng.Kp[2:4].copy_(torch.from_numpy(np.stack([v[1][3] for v in views]).reshape(2, 9)))
+    eng.valid.fill_(1)
+    E1 = torch.from_numpy(batch.E1).to(dev)
+    E2 = torch.from_numpy(batch.E2).to(dev)
+    eng.stereo(2, E1, E2)
+    torch.cuda.synchronize()
+    eng.check_error_flag()
+    P1 = torch.from_numpy(np.stack([O.projection(views[e][0][3], batch.E1[e]) for e in range(2)])).float()
+    P2 = torch.from_numpy(np.stack([O.projection(views[e][1][3], batch.E2[e]) for e in range(2)])).float()
+    dv = torch.from_numpy(O.depth_hypotheses())[None].repeat(2, 1)
+    tap = O.Taps(record=True)
+    with torch.no_grad():
+        fused = f1[:, :, None] + O.homo_warping(f2, P2, P1, dv)
+        logits_vol = O.cost_reg_net(sd, fused, tap)
+        ref = O.decode_view(sd, f1, fused, logits_vol, torch.from_numpy(ch1), dv, True, tap)
+    # U-Net stages: bf16 storage of every activation -> a few 1e-3 of the activation scale
+    for nm in ("conv0", "conv2", "conv4", "conv6", "conv7", "conv9", "conv11"):
+        got = G.from_cl(eng.cr_taps[nm].value().cpu())
+        want = tap.store[f"cr.{nm}"]
+        assert G.rel_err(got, want) < 2e-2, nm
+        assert float((got - want).abs().mean() / want.abs().mean()) < 4e-3, nm
+    logits = eng.dbg_logits.cpu().permute(0, 2, 1)
+    assert float((logits - tap.store["logits"]).abs().max()) < 0.08          # logits span ~ +-10
+    np.testing.assert_allclose(eng.nocs.cpu().numpy(), ref["nocs"].numpy(), rtol=0, atol=2e-5)      # fp32 MLP on fp32 features
+    assert float((eng.depth.cpu() - ref["depth"]).abs().max()) < 6e-3         # per-pixel depth, metres (bf16 U-Net)
+    assert float((eng.depth.cpu() - ref["depth"]).abs().mean()) < 8e-4
+    assert float((eng.dbg_fused.cpu().permute(0, 2, 1) - tap.store["fused_pts"]).abs().max()) < 2e-2
+    Rg = eng.R.cpu().numpy().reshape(2, 3, 3)
+    for e in range(2):
+        assert O.rotation_angle_deg(Rg[e], ref["r"][e].numpy()) < 0.05        # degrees
+    # fit on the device outputs vs the oracle's fit on the same numbers (fp32 vs fp64 arithmetic only)
+    box = eng.bbox.cpu().numpy()
+    for e in range(2):
+        t, s = O.compute_scale_and_translation(eng.depth[e].cpu().numpy(), eng.nocs[e].cpu().numpy(), ch1[e], views[e][0][3], 224, Rg[e])
+        assert abs(float(eng.scale[e]) - s) / s < 2e-6
+        np.testing.assert_allclose(eng.trans[e].cpu().numpy(), t, rtol=0, atol=2e-6)
+        want = O.box_from_fit(eng.nocs[e].cpu().numpy(), s, Rg[e], t, batch.E1[e])
+        np.testing.assert_allclose(box[e], want, rtol=0, atol=5e-6)
+    eng.close()
+
+
+def test_fit_median_is_exact_and_sentinel(G):
+    lib = L.load()
+    dev = G.DEV
+    rng = _rng(12)
+    B, P = 4, 1024
+    nocs = (rng.random((B, P, 3)).astype(np.float32) - 0.5)
+    nocs[2] *= 0.001                                  # no pair passes |dn| > 0.01 -> NaN scale -> sentinel box
+    depth = (0.8 + 0.05 * rng.standard_normal((B, P))).astype(np.float32)
+    choose = np.stack([np.sort(rng.choice(224 * 224, P, replace=False)) for _ in range(B)]).astype(np.int32)
+    Kp = np.tile(np.array([[800.0, 0, 100.5], [0, 800.0, 120.25], [0, 0, 1]]).reshape(1, 9), (B, 1))
+    R = np.tile(np.eye(3, dtype=np.float32).reshape(1, 9), (B, 1))
+    E = np.tile(np.eye(4).reshape(1, 16), (B, 1))
+    E[1, 3] = 0.3
+    valid = np.array([1, 1, 1, 0], np.uint8)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    bbox = torch.zeros((B, 8, 3), dtype=torch.float64, device=dev)
+    scale = torch.zeros(B, dtype=torch.float64, device=dev)
+    trans = torch.zeros((B, 3), dtype=torch.float64, device=dev)
+    args = [t(nocs), t(depth), t(choose), t(Kp), t(R), t(E), t(valid)]
+    L.check(lib.adp_fit(*[L.ptr(a) for a in args], L.ptr(bbox), L.ptr(scale), L.ptr(trans), B, P, 224, G.stream()), "fit")
+    torch.cuda.synchronize()
+    for e in (0, 1):
+        cam = O.back_project(depth[e], choose[e], Kp[e].reshape(3, 3))
+        s = O.compute_scale(cam, nocs[e])
+        assert abs(float(scale[e]) - s) / s < 1e-6     # exact order statistic; fp32 vs fp64 distance arithmetic
+    np.testing.assert_array_equal(bbox[2].cpu().numpy(), O.DEFAULT_BBOX)
+    np.testing.assert_array_equal(bbox[3].cpu().numpy(), O.DEFAULT_BBOX)
+
+
+# ------------------------------------------------------------------------------------------------ backbone end to end
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 2e-3), ("bf16", 6e-2)])
+def test_backbone_matches_oracle(G, precision, tol):
+    from rgbmanip_b200.engine import Engine
+    sd = weights.init_state_dict(0)
+    rng = _rng(21)
+    img = _t(rng, 2, 3, 224, 224)
+    eng = Engine(sd, device=G.DEV, max_envs=1, precision=precision)
+    eng.crops.copy_(G.to_cl(img))
+    eng.run_backbone(2)
+    torch.cuda.synchronize()
+    eng.check_error_flag()
+    tap = O.Taps(record=True)
+    with torch.no_grad():
+        ref = O.pspnet(sd, img, tap)
+    errs = {}
+    for nm, buf in eng.taps.items():
+        key = nm if nm in tap.store else nm
+        errs[nm] = G.rel_err(G.from_cl(buf.value(2).cpu()), tap.store[key])
+    got = G.from_cl(eng.feat[:2].cpu())
+    errs["feat"] = G.rel_err(got, ref)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, (bad, errs)
+    kinds = [getattr(op, "kind", None) for _, op in eng.backbone_ops]
+    assert kinds.count("tc") >= 30, kinds                 # the tcgen05 kernel really is the one that ran
+    eng.close()
+
+
+def test_tc_and_direct_backbones_agree(G):
+    """The tensor-core path against the CUDA-core path of the same library (fp32 weights, fp32 accumulate)."""
+    from rgbmanip_b200.engine import Engine
+    sd = weights.init_state_dict(3)
+    rng = _rng(22)
+    img = _t(rng, 1, 3, 224, 224)
+    outs = []
+    for use_tc in (True, False):
+        eng = Engine(sd, device=G.DEV, max_envs=1, precision="bf16x3", use_tc=use_tc)
+        eng.crops[:1].copy_(G.to_cl(img))
+        eng.run_backbone(1)
+        torch.cuda.synchronize()
+        outs.append(eng.feat[:1].cpu())
+        eng.close()
+    assert G.rel_err(outs[0], outs[1]) < 2e-3
