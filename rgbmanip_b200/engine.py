@@ -106,7 +106,9 @@ class Engine:
         shape = (B, D, H, Wd, Cn) if D > 1 else (B, H, Wd, Cn)
         hi = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
         lo = torch.zeros(shape, dtype=torch.bfloat16, device=self.device) if split else None
-        return ActBuf(hi, lo, B, D, H, Wd, Cn)
+        buf = ActBuf(hi, lo, B, D, H, Wd, Cn)
+        self._keep.append(buf)   # layer plans hold raw pointers: the tensors must outlive them
+        return buf
 
     @property
     def stream(self):

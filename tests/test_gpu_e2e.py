@@ -124,4 +124,4 @@ def test_four_task_configs_share_the_path():
         outs.append(est.estimate(*batch.args()))
         est.estimator.close()
     for o in outs[1:]:
-        np.testing.assert_array_equal(o, outs[0])       # same weights, same seed -> deterministic, identical
+        np.testing.assert_allclose(o, outs[0], rtol=0, atol=1e-5)   # same weights/seed; only atomicAdd order differs

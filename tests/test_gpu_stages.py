@@ -324,7 +324,7 @@ def test_costreg_and_decode_match_oracle(G):
         assert float((got - want).abs().mean() / want.abs().mean()) < 4e-3, nm
     logits = eng.dbg_logits.cpu().permute(0, 2, 1)
     assert float((logits - tap.store["logits"]).abs().max()) < 0.08          # logits span ~ +-10
-    np.testing.assert_allclose(eng.nocs.cpu().numpy(), ref["nocs"].numpy(), rtol=0, atol=2e-5)      # fp32 MLP on fp32 features
+    np.testing.assert_allclose(eng.nocs.cpu().numpy(), ref["nocs"].numpy(), rtol=0, atol=2e-4)      # fp32 MLP (last layer gain 16) + tanhf
     assert float((eng.depth.cpu() - ref["depth"]).abs().max()) < 6e-3         # per-pixel depth, metres (bf16 U-Net)
     assert float((eng.depth.cpu() - ref["depth"]).abs().mean()) < 8e-4
     assert float((eng.dbg_fused.cpu().permute(0, 2, 1) - tap.store["fused_pts"]).abs().max()) < 2e-2
