@@ -40,10 +40,21 @@ extern "C" {
 #define ADP_ACT_PRELU 2
 
 typedef struct adp_act {      /* channels-last activation [B, D, H, W, C]; D == 1 for 2-D maps */
-    void* hi;                 /* bf16 */
+    void* hi;                 /* bf16 (or IEEE half when f16 != 0) */
     void* lo;                 /* bf16 or NULL */
     int32_t B, D, H, W, C;
+    int32_t f16;              /* 1: 16-bit planes are IEEE half (3-D cost-regularisation stage), no lo plane */
 } adp_act;
+
+typedef struct adp_tc_geom {  /* non-default geometry of a tcgen05 conv: explicit tap table and grid mapping */
+    int32_t ntaps;            /* <= 28 */
+    int8_t dz[32], dy[32], dx[32], wt[32];   /* input offset of each tap (after in_mul scaling) and its weight slab */
+    int32_t in_mul;           /* input coord = tile coord * in_mul + offset: 2 for stride-2 convs */
+    int32_t out_mul, out_oz, out_oy, out_ox; /* output coord = tile coord * out_mul + offset: 2 / parity for transposed convs */
+    int32_t gD, gH, gW;       /* tile-space grid */
+    int32_t oD, oH, oW;       /* output grid */
+    int32_t w_taps;           /* tap slabs in the packed weights */
+} adp_tc_geom;
 
 typedef struct adp_epilogue { /* y = act(scale * acc + bias [+ res]) [+ res]  ->  out_hi/out_lo and/or out_f32 */
     const float* scale;       /* [Cout] or NULL : folded BatchNorm3d scale (network_v5.py:19,240) */
@@ -63,6 +74,7 @@ typedef struct adp_direct_conv {   /* generic CUDA-core convolution (strided / t
     int32_t B, Di, Hi, Wi, Cin;
     int32_t Do, Ho, Wo, Cout;
     int32_t kd, kh, kw, sd, sh, sw, pd, ph, pw, dil, transposed;
+    int32_t f16;              /* 16-bit planes (in/res/out) are IEEE half instead of bf16 */
     const float* w;           /* fp32 [taps][Cin][Cout] */
     adp_epilogue ep;
 } adp_direct_conv;
@@ -91,7 +103,7 @@ ADP_API int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int
 
 /* --- backbone: pspnet.py:33-158 ------------------------------------------------------------------------------ */
 ADP_API int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, const void* w_lo, int cout, int kd,
-                     int ks, int dil, int npass, const adp_epilogue* ep, int num_sms);
+                     int ks, int dil, int npass, const adp_epilogue* ep, const adp_tc_geom* geom, int num_sms);
 ADP_API int adp_conv_tc_run(adp_conv_plan* plan, int batch, int32_t* err_flag, void* stream);
 ADP_API void adp_conv_tc_free(adp_conv_plan* plan);
 ADP_API int adp_conv_direct(const adp_direct_conv* desc, int batch, void* stream);
@@ -107,13 +119,13 @@ ADP_API int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const d
                               float* Mw, const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B,
                               void* stream);
 ADP_API int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol,
-                     int B, int D, int H, int W, int C, void* stream);
+                     int B, int D, int H, int W, int C, int f16, void* stream);
 
 /* --- decode + heads: network_v5.py:432-465,486-499; rotation_utils.py:4-27 ----------------------------------- */
 ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth,
                float* pf1, float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused,
-               int B, int S, int D, int P, int regress_pose, void* stream);
+               int B, int S, int D, int P, int regress_pose, int x11_f16, void* stream);
 
 /* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
 ADP_API int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R,

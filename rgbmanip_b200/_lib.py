@@ -21,7 +21,13 @@ class AdpError(RuntimeError):
 
 
 class Act(C.Structure):
-    _fields_ = [("hi", vp), ("lo", vp), ("B", i32), ("D", i32), ("H", i32), ("W", i32), ("C", i32)]
+    _fields_ = [("hi", vp), ("lo", vp), ("B", i32), ("D", i32), ("H", i32), ("W", i32), ("C", i32), ("f16", i32)]
+
+
+class TcGeom(C.Structure):
+    _fields_ = [("ntaps", i32), ("dz", C.c_int8 * 32), ("dy", C.c_int8 * 32), ("dx", C.c_int8 * 32), ("wt", C.c_int8 * 32),
+                ("in_mul", i32), ("out_mul", i32), ("out_oz", i32), ("out_oy", i32), ("out_ox", i32),
+                ("gD", i32), ("gH", i32), ("gW", i32), ("oD", i32), ("oH", i32), ("oW", i32), ("w_taps", i32)]
 
 
 class Epilogue(C.Structure):
@@ -34,7 +40,7 @@ class DirectConv(C.Structure):
                 ("B", i32), ("Di", i32), ("Hi", i32), ("Wi", i32), ("Cin", i32),
                 ("Do", i32), ("Ho", i32), ("Wo", i32), ("Cout", i32),
                 ("kd", i32), ("kh", i32), ("kw", i32), ("sd", i32), ("sh", i32), ("sw", i32),
-                ("pd", i32), ("ph", i32), ("pw", i32), ("dil", i32), ("transposed", i32),
+                ("pd", i32), ("ph", i32), ("pw", i32), ("dil", i32), ("transposed", i32), ("f16", i32),
                 ("w", vp), ("ep", Epilogue)]
 
 
@@ -56,7 +62,7 @@ SIGNATURES = {
     "adp_preprocess": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_uint32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     "adp_conv_tc_plan": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                   C.POINTER(Epilogue), C.c_int]),
+                                   C.POINTER(Epilogue), C.POINTER(TcGeom), C.c_int]),
     "adp_conv_tc_run": (C.c_int, [vp, C.c_int, vp, vp]),
     "adp_conv_tc_free": (None, [vp]),
     "adp_conv_direct": (C.c_int, [C.POINTER(DirectConv), C.c_int, vp]),
@@ -65,9 +71,9 @@ SIGNATURES = {
     "adp_psp_concat_up": (C.c_int, [C.POINTER(Act), vp, C.POINTER(Act), C.c_int, vp]),
     "adp_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
     "adp_warp_matrices": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
-    "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_decode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DecodeWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }
 

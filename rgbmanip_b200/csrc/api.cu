@@ -30,7 +30,7 @@ int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, c
                    int S, int P, uint32_t seed, int choose_mode, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream);
 int build_volume(const float* f_ref, const float* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, cudaStream_t stream);
+                 int W, int C, int f16, cudaStream_t stream);
 int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
                   const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream);
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
@@ -41,13 +41,13 @@ struct DecodeArgs;
 int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                  const int* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth, float* pf1,
                  float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P,
-                 int regress_pose, cudaStream_t stream);
+                 int regress_pose, int x11_f16, cudaStream_t stream);
 
 static Act to_act(const adp_act* a) {
     Act r;
     r.hi = reinterpret_cast<bf16*>(a->hi);
     r.lo = reinterpret_cast<bf16*>(a->lo);
-    r.B = a->B; r.D = a->D; r.H = a->H; r.W = a->W; r.C = a->C;
+    r.B = a->B; r.D = a->D; r.H = a->H; r.W = a->W; r.C = a->C; r.f16 = a->f16;
     return r;
 }
 
@@ -85,12 +85,19 @@ int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int mask_dt
 }
 
 int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, const void* w_lo, int cout, int kd, int ks,
-                     int dil, int npass, const adp_epilogue* ep, int num_sms) {
+                     int dil, int npass, const adp_epilogue* ep, const adp_tc_geom* geom, int num_sms) {
     ADP_CHECK_ARG(plan && in && w_hi && ep, "null pointer");
     ADP_CHECK_ARG(ep->out_hi || ep->out_f32, "epilogue has no output");
     adp_conv_plan* pl = new adp_conv_plan();
+    TcGeom g;
+    if (geom) {
+        g.ntaps = geom->ntaps;
+        for (int t = 0; t < 32; ++t) { g.dz[t] = geom->dz[t]; g.dy[t] = geom->dy[t]; g.dx[t] = geom->dx[t]; g.wt[t] = geom->wt[t]; }
+        g.in_mul = geom->in_mul; g.out_mul = geom->out_mul; g.out_oz = geom->out_oz; g.out_oy = geom->out_oy; g.out_ox = geom->out_ox;
+        g.gD = geom->gD; g.gH = geom->gH; g.gW = geom->gW; g.oD = geom->oD; g.oH = geom->oH; g.oW = geom->oW; g.w_taps = geom->w_taps;
+    }
     int r = tc_conv_plan(&pl->layer, to_act(in), reinterpret_cast<const bf16*>(w_hi), reinterpret_cast<const bf16*>(w_lo), cout,
-                         kd, ks, dil, npass);
+                         kd, ks, dil, npass, geom ? &g : nullptr, in->f16);
     if (r != ADP_OK) {
         delete pl;
         return r;
@@ -121,7 +128,7 @@ int adp_conv_direct(const adp_direct_conv* d, int batch, void* stream) {
     p.B = d->B; p.Di = d->Di; p.Hi = d->Hi; p.Wi = d->Wi; p.Cin = d->Cin;
     p.Do = d->Do; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
     p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
-    p.pd = d->pd; p.ph = d->ph; p.pw = d->pw; p.dil = d->dil; p.transposed = d->transposed;
+    p.pd = d->pd; p.ph = d->ph; p.pw = d->pw; p.dil = d->dil; p.transposed = d->transposed; p.f16 = d->f16;
     p.w = d->w;
     p.scale = d->ep.scale; p.bias = d->ep.bias; p.prelu = d->ep.prelu; p.act = d->ep.act; p.res_after_act = d->ep.res_after_act;
     p.res_hi = reinterpret_cast<const bf16*>(d->ep.res_hi); p.res_lo = reinterpret_cast<const bf16*>(d->ep.res_lo);
@@ -155,10 +162,10 @@ int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* strea
 }
 
 int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol, int B, int D,
-                     int H, int W, int C, void* stream) {
+                     int H, int W, int C, int f16, void* stream) {
     ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && vol, "null pointer");
     g_launches += 1;
-    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, (cudaStream_t)stream);
+    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, f16, (cudaStream_t)stream);
 }
 
 int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
@@ -171,12 +178,12 @@ int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* K
 int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth, float* pf1,
                float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P,
-               int regress_pose, void* stream) {
+               int regress_pose, int x11_f16, void* stream) {
     ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && x11 && choose && w && nocs && depth && pf1 && gsum && psum && R,
                   "null pointer");
     g_launches += regress_pose ? 3 : 1;
     return decode_run_c(feat_ref, feat_src, Mw, depths, x11, choose, valid, w, nocs, depth, pf1, gsum, psum, R, r6, dbg_logits,
-                        dbg_fused, B, S, D, P, regress_pose, (cudaStream_t)stream);
+                        dbg_fused, B, S, D, P, regress_pose, x11_f16, (cudaStream_t)stream);
 }
 
 int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R, const double* E,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -48,6 +49,7 @@ struct Act {
     bf16* hi = nullptr;
     bf16* lo = nullptr;   // nullptr -> single bf16
     int B = 0, D = 1, H = 0, W = 0, C = 0;
+    int f16 = 0;          // 1: the planes hold IEEE half instead of bf16 (3-D stage; no lo plane)
     size_t numel() const { return (size_t)B * D * H * W * C; }
 };
 
@@ -61,6 +63,16 @@ __device__ __forceinline__ void st_act(bf16* __restrict__ hi, bf16* __restrict__
     bf16 h = __float2bfloat16_rn(v);
     hi[i] = h;
     if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// 16-bit storage that is either bf16 (f16 == 0) or IEEE half (f16 == 1); the pointer type stays bf16* for brevity
+__device__ __forceinline__ float ld_act16(const bf16* __restrict__ hi, const bf16* __restrict__ lo, size_t i, int f16) {
+    if (f16) return __half2float(reinterpret_cast<const __half*>(hi)[i]);
+    return ld_act(hi, lo, i);
+}
+__device__ __forceinline__ void st_act16(bf16* __restrict__ hi, bf16* __restrict__ lo, size_t i, float v, int f16) {
+    if (f16) reinterpret_cast<__half*>(hi)[i] = __float2half_rn(v);
+    else st_act(hi, lo, i, v);
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

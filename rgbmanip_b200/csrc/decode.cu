@@ -82,6 +82,7 @@ struct DecodeArgs {
     float* dbg_logits;       // [B,P,D] or nullptr
     float* dbg_fused;        // [B,P,32] or nullptr
     int B, S, D, P;
+    int x11_f16;             // x11 holds IEEE half instead of bf16
 };
 
 __global__ void __launch_bounds__(DEC_THREADS)
@@ -122,8 +123,16 @@ decode_points_kernel(const DecodeArgs a, const DecodeWeights w) {
                     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        acc = fmaf(__uint_as_float(u[q] << 16), wt[2 * q], acc);
-                        acc = fmaf(__uint_as_float(u[q] & 0xffff0000u), wt[2 * q + 1], acc);
+                        float lo16, hi16;
+                        if (a.x11_f16) {
+                            lo16 = __half2float(__ushort_as_half((unsigned short)(u[q] & 0xffffu)));
+                            hi16 = __half2float(__ushort_as_half((unsigned short)(u[q] >> 16)));
+                        } else {
+                            lo16 = __uint_as_float(u[q] << 16);
+                            hi16 = __uint_as_float(u[q] & 0xffff0000u);
+                        }
+                        acc = fmaf(lo16, wt[2 * q], acc);
+                        acc = fmaf(hi16, wt[2 * q + 1], acc);
                     }
                 }
             }
@@ -336,7 +345,7 @@ int decode_run(const DecodeArgs& a, const DecodeWeights& w, float* psum, float* 
 int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                  const int* choose, const uint8_t* valid, const adp_decode_weights* cw, float* nocs, float* depth, float* pf1,
                  float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P,
-                 int regress_pose, cudaStream_t stream) {
+                 int regress_pose, int x11_f16, cudaStream_t stream) {
     DecodeWeights w;
     w.ic_w = cw->ic_w; w.ic_b = cw->ic_b; w.nh0_w = cw->nh0_w; w.nh0_b = cw->nh0_b; w.nh1_w = cw->nh1_w; w.nh1_b = cw->nh1_b;
     w.nh2_w = cw->nh2_w; w.nh2_b = cw->nh2_b; w.np0_w = cw->np0_w; w.np0_b = cw->np0_b; w.np1_w = cw->np1_w; w.np1_b = cw->np1_b;
@@ -346,7 +355,7 @@ int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, 
     DecodeArgs a;
     a.feat_ref = feat_ref; a.feat_src = feat_src; a.Mw = Mw; a.depths = depths; a.x11 = reinterpret_cast<const bf16*>(x11);
     a.choose = choose; a.valid = valid; a.nocs = nocs; a.depth = depth; a.pf1 = pf1; a.gsum = gsum;
-    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P;
+    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16;
     return decode_run(a, w, psum, R, r6, regress_pose, stream);
 }
 

@@ -62,7 +62,7 @@ direct_conv_kernel(const DirectConvParams p, int batch) {
                     }
                     if (ok && iz >= 0 && iz < p.Di && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) {
                         const size_t idx = ((((size_t)b * p.Di + iz) * p.Hi + iy) * p.Wi + ix) * p.Cin + c;
-                        v = p.in_f32 ? p.in_f32[idx] : ld_act(p.in_hi, p.in_lo, idx);
+                        v = p.in_f32 ? p.in_f32[idx] : ld_act16(p.in_hi, p.in_lo, idx, p.f16);
                     }
                 }
                 As[k][i] = v;
@@ -104,12 +104,12 @@ direct_conv_kernel(const DirectConvParams p, int batch) {
             const size_t o = pix * p.Cout + n;
             if (p.scale) v *= p.scale[n];
             if (p.bias) v += p.bias[n];
-            if (p.res_hi && !p.res_after_act) v += ld_act(p.res_hi, p.res_lo, o);
+            if (p.res_hi && !p.res_after_act) v += ld_act16(p.res_hi, p.res_lo, o, p.f16);
             if (p.act == 1) v = fmaxf(v, 0.f);
             else if (p.act == 2) v = v > 0.f ? v : v * p.prelu;
-            if (p.res_hi && p.res_after_act) v += ld_act(p.res_hi, p.res_lo, o);
+            if (p.res_hi && p.res_after_act) v += ld_act16(p.res_hi, p.res_lo, o, p.f16);
             if (p.out_f32) p.out_f32[o] = v;
-            if (p.out_hi) st_act(p.out_hi, p.out_lo, o, v);
+            if (p.out_hi) st_act16(p.out_hi, p.out_lo, o, v, p.f16);
         }
     }
 }

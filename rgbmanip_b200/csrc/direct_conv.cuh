@@ -18,6 +18,7 @@ struct DirectConvParams {
     int pd = 0, ph = 0, pw = 0;
     int dil = 1;             // dilation along h/w
     int transposed = 0;      // 1: ConvTranspose (gather form o = i*s - p + k)
+    int f16 = 0;             // 16-bit planes are IEEE half
     const float* w = nullptr;   // [taps][Cin][Cout]
     const float* scale = nullptr;
     const float* bias = nullptr;

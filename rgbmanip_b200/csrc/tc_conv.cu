@@ -119,8 +119,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor for kind::f16: D = fp32, A = B = bf16, both K-major, M = 128, N = BN.
 template <int BN>
-__device__ __forceinline__ uint32_t make_idesc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int f16) {
+    const uint32_t fmt = f16 ? 0u : 1u;   // F16 = 0, BF16 = 1
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,7 +189,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int taps = p.kd * p.ks * p.ks;
+    const int taps = p.ntaps;
     const int k_iters = p.npass * taps * p.kchunks;
     const int tiles_per_img = p.D * p.tiles_y * p.tiles_x * p.tiles_n;
     const int total_tiles = batch * tiles_per_img;
@@ -212,14 +213,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const CUtensorMap* mapA = (pass == 1) ? &tmA_lo : &tmA_hi;
                     const CUtensorMap* mapW = (pass == 2) ? &tmW_lo : &tmW_hi;
                     for (int tap = 0; tap < taps; ++tap) {
-                        const int kx = tap % p.ks, ky = (tap / p.ks) % p.ks, kz = tap / (p.ks * p.ks);
-                        const int dx = (kx - p.ks / 2) * p.dil, dy = (ky - p.ks / 2) * p.dil, dz = kz - p.kd / 2;
+                        const int cx = x0 * p.in_mul + p.tdx[tap], cy = y0 * p.in_mul + p.tdy[tap];
+                        const int cz = d * p.in_mul + p.tdz[tap], wt = p.twt[tap];
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
                             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                             ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-                            ptx::tma_load_5d(mapA, full_bar(stage), sa, kc * KC, x0 + dx, y0 + dy, d + dz, b);
-                            ptx::tma_load_3d(mapW, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, n0, tap);
+                            ptx::tma_load_5d(mapA, full_bar(stage), sa, kc * KC, cx, cy, cz, b);
+                            ptx::tma_load_3d(mapW, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, n0, wt);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -232,7 +233,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint32_t phase = 0;
         int as = 0;
         uint32_t aphase = 0;
-        const uint32_t idesc = make_idesc<BN>();
+        const uint32_t idesc = make_idesc<BN>(p.f16);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             ptx::mbar_wait(tempty_bar(as), aphase ^ 1, p.err, 2);
             ptx::tc_fence_after();
@@ -275,7 +276,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int b = t / p.D;
             const int x = tx * p.TW + tx_l, y = ty * p.TH + ty_l, n0 = nt * BN;
             const bool valid = (m < rows_valid) && (x < p.W) && (y < p.H);
-            const size_t pix = (((size_t)b * p.D + d) * p.H + y) * p.W + x;
+            const size_t pix = (((size_t)b * p.oD + (d * p.out_mul + p.out_oz)) * p.oH + (y * p.out_mul + p.out_oy)) * p.oW +
+                               (x * p.out_mul + p.out_ox);
             ptx::mbar_wait(tfull_bar(as), aphase, p.err, 4);
             ptx::tc_fence_after();
 #pragma unroll 1
@@ -303,7 +305,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         }
                         if (p.res_hi && !p.res_after_act) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act(p.res_hi, p.res_lo, o + j);
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, o + j, p.f16);
                         }
                         if (p.act == 1) {
 #pragma unroll
@@ -314,14 +316,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         }
                         if (p.res_hi && p.res_after_act) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act(p.res_hi, p.res_lo, o + j);
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, o + j, p.f16);
                         }
                         if (p.out_f32) {
 #pragma unroll
                             for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
                         }
                         if (p.out_hi) {
-                            if (nvalid == CH && (CH % 8) == 0) {
+                            if (p.f16) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) if (j < nvalid) st_act16(p.out_hi, p.out_lo, o + j, v[j], 1);
+                            } else if (nvalid == CH && (CH % 8) == 0) {
 #pragma unroll
                                 for (int j = 0; j < CH; j += 8) {
                                     uint32_t h[4], l[4];
@@ -382,13 +387,14 @@ static CUtensorMapSwizzle swizzle_for(int KC) {
     return KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
-static int encode_act_map(CUtensorMap* tm, const bf16* ptr, const Act& a, int KC, int TW, int TH) {
+static int encode_act_map(CUtensorMap* tm, const bf16* ptr, const Act& a, int KC, int TW, int TH, int in_mul, int f16) {
     cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B};
     cuuint64_t strides[4] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2,
                              (cuuint64_t)a.D * a.H * a.W * a.C * 2};
-    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)TH, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(ptr), dims, strides, box, estr,
+    // with an element stride s the unit loads ceil(box / s) elements: a box of (T-1)*s+1 yields exactly T
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)((TW - 1) * in_mul + 1), (cuuint32_t)((TH - 1) * in_mul + 1), 1, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)in_mul, (cuuint32_t)in_mul, (cuuint32_t)(a.D > 1 ? in_mul : 1), 1};
+    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -399,12 +405,12 @@ static int encode_act_map(CUtensorMap* tm, const bf16* ptr, const Act& a, int KC
     return ADP_OK;
 }
 
-static int encode_w_map(CUtensorMap* tm, const bf16* ptr, int Cin, int CoutPad, int taps, int KC, int BN) {
+static int encode_w_map(CUtensorMap* tm, const bf16* ptr, int Cin, int CoutPad, int taps, int KC, int BN, int f16) {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)CoutPad, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)CoutPad * Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -434,7 +440,7 @@ void tc_pick_tile(int H, int W, int* TW, int* TH) {
 }
 
 int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_lo, int Cout, int kd, int ks, int dil,
-                 int npass) {
+                 int npass, const TcGeom* geom, int f16) {
     ADP_TRY(tc_conv_init_driver());
     int KC = in.C % 64 == 0 ? 64 : in.C % 32 == 0 ? 32 : in.C % 16 == 0 ? 16 : 0;
     ADP_CHECK_ARG(KC != 0, "Cin must be a multiple of 16 for the tcgen05 path");
@@ -445,20 +451,44 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     if (KC < 64 && BN > 64) BN = 64;
     TcConvParams& p = L->p;
     p = TcConvParams{};
-    p.B = in.B; p.D = in.D; p.H = in.H; p.W = in.W;
-    p.Cin = in.C; p.Cout = Cout; p.kd = kd; p.ks = ks; p.dil = dil;
-    tc_pick_tile(in.H, in.W, &p.TW, &p.TH);
-    p.tiles_x = cdiv(in.W, p.TW);
-    p.tiles_y = cdiv(in.H, p.TH);
+    p.B = in.B;
+    p.Cin = in.C; p.Cout = Cout; p.f16 = f16;
+    int w_taps;
+    if (geom) {
+        ADP_CHECK_ARG(geom->ntaps >= 1 && geom->ntaps <= kTcMaxTaps, "tap count");
+        p.D = geom->gD; p.H = geom->gH; p.W = geom->gW;
+        p.ntaps = geom->ntaps;
+        for (int t = 0; t < geom->ntaps; ++t) { p.tdz[t] = geom->dz[t]; p.tdy[t] = geom->dy[t]; p.tdx[t] = geom->dx[t]; p.twt[t] = geom->wt[t]; }
+        p.in_mul = geom->in_mul; p.out_mul = geom->out_mul;
+        p.out_oz = geom->out_oz; p.out_oy = geom->out_oy; p.out_ox = geom->out_ox;
+        p.oD = geom->oD; p.oH = geom->oH; p.oW = geom->oW;
+        w_taps = geom->w_taps;
+    } else {
+        p.D = in.D; p.H = in.H; p.W = in.W;
+        p.ntaps = kd * ks * ks;
+        ADP_CHECK_ARG(p.ntaps <= kTcMaxTaps, "tap count");
+        for (int t = 0; t < p.ntaps; ++t) {
+            const int kx = t % ks, ky = (t / ks) % ks, kz = t / (ks * ks);
+            p.tdx[t] = (signed char)((kx - ks / 2) * dil); p.tdy[t] = (signed char)((ky - ks / 2) * dil);
+            p.tdz[t] = (signed char)(kz - kd / 2); p.twt[t] = (signed char)t;
+        }
+        p.in_mul = 1; p.out_mul = 1; p.out_oz = p.out_oy = p.out_ox = 0;
+        p.oD = in.D; p.oH = in.H; p.oW = in.W;
+        w_taps = p.ntaps;
+    }
+    ADP_CHECK_ARG(p.in_mul == 1 || p.in_mul == 2, "in_mul");
+    tc_pick_tile(p.H, p.W, &p.TW, &p.TH);
+    p.tiles_x = cdiv(p.W, p.TW);
+    p.tiles_y = cdiv(p.H, p.TH);
     p.tiles_n = coutPad / BN;
     p.kchunks = in.C / KC;
     p.npass = npass;
     L->BN = BN;
     L->KC = KC;
-    ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH));
-    ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH));
-    ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, kd * ks * ks, KC, BN));
-    ADP_TRY(encode_w_map(&L->tmW_lo, w_lo ? w_lo : w_hi, in.C, coutPad, kd * ks * ks, KC, BN));
+    ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
+    ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
+    ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, w_taps, KC, BN, f16));
+    ADP_TRY(encode_w_map(&L->tmW_lo, w_lo ? w_lo : w_hi, in.C, coutPad, w_taps, KC, BN, f16));
     L->ready = true;
     return ADP_OK;
 }

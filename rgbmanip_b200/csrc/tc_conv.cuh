@@ -17,11 +17,20 @@
 
 namespace adp {
 
+constexpr int kTcMaxTaps = 28;
+
 struct TcConvParams {
-    int B, D, H, W;          // output == input extent (stride 1, same padding); D == 1 for 2-D
+    int B, D, H, W;          // tile-space extent: the grid the M tiles walk over (output grid for convs, input grid for
+                             // the parity classes of a transposed conv); D == 1 for 2-D
     int Cin, Cout;
-    int kd, ks;              // taps along depth (1 or 3) and along y/x (1 or 3)
-    int dil;                 // dilation along y/x (depth dilation is 1)
+    // tap table: input coordinate = tile coordinate * in_mul + (dz, dy, dx); weight slab index wt
+    int ntaps;
+    signed char tdz[kTcMaxTaps], tdy[kTcMaxTaps], tdx[kTcMaxTaps], twt[kTcMaxTaps];
+    int in_mul;              // 1, or 2 for stride-2 convs (TMA element stride 2)
+    // output coordinate = tile coordinate * out_mul + (out_oz, out_oy, out_ox), inside an [oD, oH, oW] grid
+    int out_mul, out_oz, out_oy, out_ox;
+    int oD, oH, oW;
+    int f16;                 // 0: bf16 operands/activations, 1: fp16
     int TW, TH;              // spatial tile; TW * TH <= 128
     int tiles_x, tiles_y, tiles_n;
     int kchunks;             // Cin / KC
@@ -50,8 +59,18 @@ struct TcConvLayer {
 };
 
 int tc_conv_init_driver();
+struct TcGeom {             // non-standard geometries (NULL = stride-1 "same" conv with a kd x ks x ks window)
+    int ntaps;
+    signed char dz[32], dy[32], dx[32], wt[32];
+    int in_mul;
+    int out_mul, out_oz, out_oy, out_ox;
+    int gD, gH, gW;
+    int oD, oH, oW;
+    int w_taps;             // number of tap slabs in the packed weight tensor
+};
+
 int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_lo, int Cout, int kd, int ks,
-                 int dil, int npass);
+                 int dil, int npass, const TcGeom* geom, int f16);
 int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream);
 
 }  // namespace adp

@@ -11,7 +11,7 @@ namespace adp {
 // one thread = one voxel x 8 channels (C == 32 -> 4 threads per voxel, 128 B coalesced per corner)
 __global__ void __launch_bounds__(256)
 build_volume_kernel(const float* __restrict__ f_ref, const float* __restrict__ f_src, const float* __restrict__ Mw,
-                    const float* __restrict__ depths, bf16* __restrict__ vol, int B, int D, int H, int W) {
+                    const float* __restrict__ depths, bf16* __restrict__ vol, int B, int D, int H, int W, int f16) {
     constexpr int C = 32;
     const size_t total = (size_t)B * D * H * W * 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -47,8 +47,11 @@ build_volume_kernel(const float* __restrict__ f_ref, const float* __restrict__ f
         uint32_t o[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            o[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u])) |
-                   ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u + 1])) << 16);
+            if (f16)
+                o[u] = (uint32_t)__half_as_ushort(__float2half_rn(v[2 * u])) | ((uint32_t)__half_as_ushort(__float2half_rn(v[2 * u + 1])) << 16);
+            else
+                o[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u])) |
+                       ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u + 1])) << 16);
         }
         *reinterpret_cast<uint4*>(vol + ((((size_t)b * D + d) * H + y) * W + x) * C + cg * 8) =
             make_uint4(o[0], o[1], o[2], o[3]);
@@ -56,13 +59,13 @@ build_volume_kernel(const float* __restrict__ f_ref, const float* __restrict__ f
 }
 
 int build_volume(const float* f_ref, const float* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, cudaStream_t stream) {
+                 int W, int C, int f16, cudaStream_t stream) {
     ADP_CHECK_ARG(C == 32, "feature channels must be 32");
     size_t total = (size_t)B * D * H * W * 4;
     if (total == 0) return ADP_OK;
     size_t blocks = (total + 255) / 256;
     int grid = (int)(blocks < (size_t)148 * 32 ? blocks : (size_t)148 * 32);
-    build_volume_kernel<<<grid, 256, 0, stream>>>(f_ref, f_src, Mw, depths, vol, B, D, H, W);
+    build_volume_kernel<<<grid, 256, 0, stream>>>(f_ref, f_src, Mw, depths, vol, B, D, H, W, f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

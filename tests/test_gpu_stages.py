@@ -91,6 +91,53 @@ def test_tc_conv3d_matches_oracle(G, case):
     assert G.rel_err(G.from_cl(out32), ref) < 1e-4   # operands are exact bf16: only fp32 summation order differs
 
 
+TC_GEOM_CASES = [
+    # (dims, B, D, H, W, Cin, Cout, k, stride, transposed, f16)
+    (2, 2, 1, 56, 56, 64, 128, 3, 2, False, 0),
+    (2, 1, 1, 56, 56, 64, 128, 1, 2, False, 0),
+    (3, 1, 12, 112, 112, 16, 32, 3, 2, False, 1),
+    (3, 1, 6, 56, 56, 32, 64, 3, 2, False, 1),
+    (3, 1, 6, 56, 56, 32, 64, 3, 2, False, 0),
+    (3, 1, 3, 28, 28, 64, 32, 3, 2, True, 1),
+    (3, 1, 6, 56, 56, 32, 16, 3, 2, True, 1),
+    (3, 2, 4, 28, 28, 16, 8, 3, 2, True, 1),
+    (3, 1, 4, 28, 28, 16, 8, 3, 2, True, 0),
+    (3, 1, 5, 56, 56, 32, 8, 3, 1, False, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_GEOM_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_tc_conv_strided_transposed_fp16(G, case):
+    """Stride-2 convs (TMA element stride), transposed convs (8 output-parity classes) and fp16 operands on tcgen05."""
+    dims, B, D, H, W, Cin, Cout, k, stride, transposed, f16 = case
+    rng = _rng(sum(int(v) for v in case) + 77)
+    q = (lambda t: t.half().float()) if f16 else (lambda t: t.bfloat16().float())
+    if dims == 2:
+        x = q(_t(rng, B, Cin, H, W))
+        w = q(_t(rng, Cout, Cin, k, k, scale=math.sqrt(1.0 / (k * k * Cin))))
+        ref = F.conv2d(x, w, stride=stride, padding=k // 2)
+        res = q(_t(rng, *ref.shape))
+        ref = F.relu(ref) + res
+    elif transposed:
+        x = q(_t(rng, B, Cin, D, H, W))
+        w = q(_t(rng, Cin, Cout, 3, 3, 3, scale=math.sqrt(1.0 / (8 * Cin))))
+        ref = F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1)
+        res = q(_t(rng, *ref.shape))
+        ref = F.relu(ref) + res
+    else:
+        x = q(_t(rng, B, Cin, D, H, W))
+        w = q(_t(rng, Cout, Cin, 3, 3, 3, scale=math.sqrt(1.0 / (27 * Cin))))
+        ref = F.conv3d(x, w, stride=stride, padding=1)
+        res = q(_t(rng, *ref.shape))
+        ref = F.relu(ref) + res
+    out32, out16 = G.tc_conv(G.to_cl(x), w, npass=1, act_code=L.ACT_RELU, res_cl=G.to_cl(res), res_after_act=1, stride=stride,
+                             transposed=bool(transposed), f16=f16)
+    assert out32.shape == G.to_cl(ref).shape
+    assert torch.isfinite(out32).all()
+    assert G.rel_err(G.from_cl(out32), ref) < 1e-4        # operands exactly representable: fp32 summation order only
+    assert G.rel_err(G.from_cl(out16), ref) < (2e-3 if f16 else 1.2e-2)   # 16-bit output rounding
+
+
 DIRECT_CASES = [
     # (dims, B, D, H, W, Cin, Cout, k, stride, dil, transposed)
     (2, 2, 1, 32, 48, 3, 64, 7, 2, 1, False),
@@ -267,7 +314,7 @@ def test_warp_matrices_and_volume(G):
     depths = torch.from_numpy(O.depth_hypotheses()).to(dev)
     vol = torch.zeros((2, 24, 224, 224, 32), dtype=torch.bfloat16, device=dev)
     f1d, f2d = G.to_cl(f1).to(dev), G.to_cl(f2).to(dev)
-    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), 2, 24, 224, 224, 32, G.stream()), "vol")
+    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), 2, 24, 224, 224, 32, 0, G.stream()), "vol")
     torch.cuda.synchronize()
     ref = f1[:, :, None] + O.homo_warping(f2, torch.from_numpy(P2).float(), torch.from_numpy(P1).float(),
                                           torch.from_numpy(O.depth_hypotheses())[None].repeat(2, 1))
