@@ -64,6 +64,7 @@ typedef struct adp_epilogue { /* y = act(scale * acc + bias [+ res]) [+ res]  ->
     int32_t res_after_act;    /* 0: residual joins before the activation (pspnet.py:27-29); 1: after (network_v5.py:287-289) */
     const void* res_hi;       /* bf16 [.., Cout] or NULL */
     const void* res_lo;
+    int32_t res_cstride;      /* channel pitch of the residual tensor (0 = Cout); lets a channel-padded tensor be the skip */
     void* out_hi;             /* bf16 or NULL */
     void* out_lo;
     float* out_f32;           /* fp32 or NULL */
@@ -111,6 +112,9 @@ ADP_API int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, v
 ADP_API int adp_psp_priors(const adp_act* feat, const float* w, float* pooled, float* priors, int batch, void* stream); /* :84-90 */
 ADP_API int adp_psp_concat_up(const adp_act* feat, const float* priors, const adp_act* out, int batch, void* stream);   /* :92-94,105 */
 ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream);                   /* pspnet.py:105 */
+/* fp32 crops [F,S,S,3] -> space-to-depth(2) activation [F,S/2,S/2,16] (channel = (py*2+px)*3 + c, 12 used): the 7x7/2
+ * stem conv (pspnet.py:37) then is a 4x4 stride-1 conv over 16 channels and runs on the tcgen05 kernel. */
+ADP_API int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream);
 
 /* --- stereo volume: network_v5.py:378-416,429 ---------------------------------------------------------------- */
 /* Mw[b] = {rot 3x3 row-major, trans 3} of P_src inv(P_ref), P = [K' E[:3,:]; 0 0 0 1] (interface_v5.py:264-270);

@@ -32,7 +32,7 @@ class TcGeom(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("scale", vp), ("bias", vp), ("prelu", C.c_float), ("act", i32), ("res_after_act", i32),
-                ("res_hi", vp), ("res_lo", vp), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp)]
+                ("res_hi", vp), ("res_lo", vp), ("res_cstride", i32), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp)]
 
 
 class DirectConv(C.Structure):
@@ -70,6 +70,7 @@ SIGNATURES = {
     "adp_psp_priors": (C.c_int, [C.POINTER(Act), vp, vp, vp, C.c_int, vp]),
     "adp_psp_concat_up": (C.c_int, [C.POINTER(Act), vp, C.POINTER(Act), C.c_int, vp]),
     "adp_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
+    "adp_pack_s2d": (C.c_int, [vp, C.POINTER(Act), C.c_int, C.c_int, vp]),
     "adp_warp_matrices": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
     "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_decode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DecodeWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp,

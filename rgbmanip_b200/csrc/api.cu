@@ -26,6 +26,7 @@ int maxpool3x3s2(const Act& in, const Act& out, int batch, cudaStream_t stream);
 int psp_priors(const Act& feat, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream);
 int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream);
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream);
+int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t stream);
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
                    int S, int P, uint32_t seed, int choose_mode, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream);
@@ -105,6 +106,7 @@ int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, 
     TcConvParams& p = pl->layer.p;
     p.bias = ep->bias; p.scale = ep->scale; p.prelu = ep->prelu; p.act = ep->act; p.res_after_act = ep->res_after_act;
     p.res_hi = reinterpret_cast<const bf16*>(ep->res_hi); p.res_lo = reinterpret_cast<const bf16*>(ep->res_lo);
+    p.res_cs = ep->res_cstride ? ep->res_cstride : cout;
     p.out_hi = reinterpret_cast<bf16*>(ep->out_hi); p.out_lo = reinterpret_cast<bf16*>(ep->out_lo);
     p.out_f32 = ep->out_f32;
     pl->num_sms = num_sms > 0 ? num_sms : 148;
@@ -132,6 +134,7 @@ int adp_conv_direct(const adp_direct_conv* d, int batch, void* stream) {
     p.w = d->w;
     p.scale = d->ep.scale; p.bias = d->ep.bias; p.prelu = d->ep.prelu; p.act = d->ep.act; p.res_after_act = d->ep.res_after_act;
     p.res_hi = reinterpret_cast<const bf16*>(d->ep.res_hi); p.res_lo = reinterpret_cast<const bf16*>(d->ep.res_lo);
+    p.res_cs = d->ep.res_cstride;
     p.out_hi = reinterpret_cast<bf16*>(d->ep.out_hi); p.out_lo = reinterpret_cast<bf16*>(d->ep.out_lo); p.out_f32 = d->ep.out_f32;
     g_launches += 1;
     return direct_conv_launch(p, batch, (cudaStream_t)stream);
@@ -159,6 +162,12 @@ int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* strea
     ADP_CHECK_ARG(in && out, "null pointer");
     g_launches += 1;
     return upsample2x(to_act(in), to_act(out), batch, (cudaStream_t)stream);
+}
+
+int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream) {
+    ADP_CHECK_ARG(crops && out, "null pointer");
+    g_launches += 1;
+    return pack_s2d(crops, to_act(out), batch, S, (cudaStream_t)stream);
 }
 
 int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol, int B, int D,

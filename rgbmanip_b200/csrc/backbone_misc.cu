@@ -5,19 +5,54 @@
 
 namespace adp {
 
+// 8 consecutive channels (16 B per plane) <-> fp32 registers
+__device__ __forceinline__ void ld8(const bf16* __restrict__ hi, const bf16* __restrict__ lo, size_t i, float* v) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + i));
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        v[2 * u] = __uint_as_float(hw[u] << 16);
+        v[2 * u + 1] = __uint_as_float(hw[u] & 0xffff0000u);
+    }
+    if (lo) {
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + i));
+        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[2 * u] += __uint_as_float(lw[u] << 16);
+            v[2 * u + 1] += __uint_as_float(lw[u] & 0xffff0000u);
+        }
+    }
+}
+__device__ __forceinline__ void st8(bf16* __restrict__ hi, bf16* __restrict__ lo, size_t i, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const bf16 h0 = __float2bfloat16_rn(v[2 * u]), h1 = __float2bfloat16_rn(v[2 * u + 1]);
+        h[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        const bf16 l0 = __float2bfloat16_rn(v[2 * u] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * u + 1] - __bfloat162float(h1));
+        l[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + i) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + i) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // max-pool 3x3 stride 2 pad 1 (pspnet.py:39,69)
 // ---------------------------------------------------------------------------------------------
 __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
                                     bf16* __restrict__ out_lo, int B, int Hi, int Wi, int Ho, int Wo, int C) {
-    const size_t total = (size_t)B * Ho * Wo * C;
+    const int C8 = C >> 3;
+    const size_t total = (size_t)B * Ho * Wo * C8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        size_t t = i / C;
+        const int c = (int)(i % C8) * 8;
+        size_t t = i / C8;
         const int ox = (int)(t % Wo); t /= Wo;
         const int oy = (int)(t % Ho);
         const int b = (int)(t / Ho);
-        float m = -INFINITY;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * 2 - 1 + ky;
@@ -26,16 +61,19 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in_hi, const bf16* 
             for (int kx = 0; kx < 3; ++kx) {
                 const int ix = ox * 2 - 1 + kx;
                 if (ix < 0 || ix >= Wi) continue;
-                m = fmaxf(m, ld_act(in_hi, in_lo, (((size_t)b * Hi + iy) * Wi + ix) * C + c));
+                float v[8];
+                ld8(in_hi, in_lo, (((size_t)b * Hi + iy) * Wi + ix) * C + c, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
             }
         }
-        st_act(out_hi, out_lo, i, m);
+        st8(out_hi, out_lo, (((size_t)b * Ho + oy) * Wo + ox) * C + c, m);
     }
 }
 
 int maxpool3x3s2(const Act& in, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(in.C == out.C && out.H == (in.H + 1) / 2 && out.W == (in.W + 1) / 2, "maxpool shapes");
-    size_t total = (size_t)batch * out.H * out.W * out.C;
+    ADP_CHECK_ARG(in.C == out.C && out.H == (in.H + 1) / 2 && out.W == (in.W + 1) / 2 && in.C % 8 == 0, "maxpool shapes");
+    size_t total = (size_t)batch * out.H * out.W * (out.C / 8);
     int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (grid == 0) return ADP_OK;
     maxpool3x3s2_kernel<<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, batch, in.H, in.W, out.H, out.W, in.C);
@@ -126,11 +164,11 @@ __device__ __forceinline__ float prior_at(const float* __restrict__ pr, int bins
 __global__ void psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* __restrict__ f_lo,
                                      const float* __restrict__ priors, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
                                      int B, int H, int W, int C) {
-    const int Ho = 2 * H, Wo = 2 * W, Ct = C + 512;
-    const size_t total = (size_t)B * Ho * Wo * Ct;
+    const int Ho = 2 * H, Wo = 2 * W, Ct = C + 512, C8 = Ct >> 3;
+    const size_t total = (size_t)B * Ho * Wo * C8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Ct);
-        size_t t = i / Ct;
+        const int c = (int)(i % C8) * 8;
+        size_t t = i / C8;
         const int X = (int)(t % Wo); t /= Wo;
         const int Y = (int)(t % Ho);
         const int b = (int)(t / Ho);
@@ -138,31 +176,59 @@ __global__ void psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* 
         float wy, wx;
         lin_coord(Y, H, Ho, &y0, &y1, &wy);
         lin_coord(X, W, Wo, &x0, &x1, &wx);
-        float v00, v01, v10, v11;
+        float v00[8], v01[8], v10[8], v11[8], o[8];
         if (c < C) {
             const size_t base = (size_t)b * H * W;
-            v00 = ld_act(f_hi, f_lo, (base + (size_t)y0 * W + x0) * C + c);
-            v01 = ld_act(f_hi, f_lo, (base + (size_t)y0 * W + x1) * C + c);
-            v10 = ld_act(f_hi, f_lo, (base + (size_t)y1 * W + x0) * C + c);
-            v11 = ld_act(f_hi, f_lo, (base + (size_t)y1 * W + x1) * C + c);
+            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x0) * C + c, v00);
+            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x1) * C + c, v01);
+            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x0) * C + c, v10);
+            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x1) * C + c, v11);
         } else {
-            const int s = (c - C) / 128, n = (c - C) % 128;
+            const int s = (c - C) / 128, n0 = (c - C) % 128;
             const int bins = s == 0 ? 1 : s == 1 ? 2 : s == 2 ? 3 : 6;
             const int off = s == 0 ? 0 : s == 1 ? 1 : s == 2 ? 5 : 14;
-            const float* pr = priors + ((size_t)b * 50 + off) * 128;
-            v00 = prior_at(pr, bins, y0, x0, H, W, n);
-            v01 = prior_at(pr, bins, y0, x1, H, W, n);
-            v10 = prior_at(pr, bins, y1, x0, H, W, n);
-            v11 = prior_at(pr, bins, y1, x1, H, W, n);
+            const float* pr = priors + ((size_t)b * 50 + off) * 128 + n0;
+            // prior map value at the four (H x W)-grid corners: each is itself a bilinear read of the bins x bins map
+            const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+            int py0[2], py1[2], px0[2], px1[2];
+            float pwy[2], pwx[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                lin_coord(ys[q], bins, H, &py0[q], &py1[q], &pwy[q]);
+                lin_coord(xs[q], bins, W, &px0[q], &px1[q], &pwx[q]);
+            }
+            float* dst[4] = {v00, v01, v10, v11};
+#pragma unroll
+            for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                for (int qx = 0; qx < 2; ++qx) {
+                    const float* a00 = pr + (py0[qy] * bins + px0[qx]) * 128;
+                    const float* a01 = pr + (py0[qy] * bins + px1[qx]) * 128;
+                    const float* a10 = pr + (py1[qy] * bins + px0[qx]) * 128;
+                    const float* a11 = pr + (py1[qy] * bins + px1[qx]) * 128;
+                    const float wy_ = pwy[qy], wx_ = pwx[qx];
+                    float* d = dst[qy * 2 + qx];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 4) {
+                        const float4 p00 = __ldg(reinterpret_cast<const float4*>(a00 + j)), p01 = __ldg(reinterpret_cast<const float4*>(a01 + j));
+                        const float4 p10 = __ldg(reinterpret_cast<const float4*>(a10 + j)), p11 = __ldg(reinterpret_cast<const float4*>(a11 + j));
+                        d[j + 0] = (1.f - wy_) * ((1.f - wx_) * p00.x + wx_ * p01.x) + wy_ * ((1.f - wx_) * p10.x + wx_ * p11.x);
+                        d[j + 1] = (1.f - wy_) * ((1.f - wx_) * p00.y + wx_ * p01.y) + wy_ * ((1.f - wx_) * p10.y + wx_ * p11.y);
+                        d[j + 2] = (1.f - wy_) * ((1.f - wx_) * p00.z + wx_ * p01.z) + wy_ * ((1.f - wx_) * p10.z + wx_ * p11.z);
+                        d[j + 3] = (1.f - wy_) * ((1.f - wx_) * p00.w + wx_ * p01.w) + wy_ * ((1.f - wx_) * p10.w + wx_ * p11.w);
+                    }
+                }
         }
-        const float v = (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
-        st_act(out_hi, out_lo, i, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o[j] = (1.f - wy) * ((1.f - wx) * v00[j] + wx * v01[j]) + wy * ((1.f - wx) * v10[j] + wx * v11[j]);
+        st8(out_hi, out_lo, i * 8, o);
     }
 }
 
 int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(out.C == feat.C + 512 && out.H == 2 * feat.H && out.W == 2 * feat.W, "psp concat shapes");
-    size_t total = (size_t)batch * out.H * out.W * out.C;
+    ADP_CHECK_ARG(out.C == feat.C + 512 && out.H == 2 * feat.H && out.W == 2 * feat.W && feat.C % 8 == 0, "psp concat shapes");
+    size_t total = (size_t)batch * out.H * out.W * (out.C / 8);
     if (total == 0) return ADP_OK;
     int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
     psp_concat_up_kernel<<<grid, 256, 0, stream>>>(feat.hi, feat.lo, priors, out.hi, out.lo, batch, feat.H, feat.W, feat.C);
@@ -175,11 +241,11 @@ int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batc
 // ---------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
                                   bf16* __restrict__ out_lo, int B, int H, int W, int C) {
-    const int Ho = 2 * H, Wo = 2 * W;
-    const size_t total = (size_t)B * Ho * Wo * C;
+    const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;
+    const size_t total = (size_t)B * Ho * Wo * C8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        size_t t = i / C;
+        const int c = (int)(i % C8) * 8;
+        size_t t = i / C8;
         const int X = (int)(t % Wo); t /= Wo;
         const int Y = (int)(t % Ho);
         const int b = (int)(t / Ho);
@@ -188,20 +254,62 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __
         lin_coord(Y, H, Ho, &y0, &y1, &wy);
         lin_coord(X, W, Wo, &x0, &x1, &wx);
         const size_t base = (size_t)b * H * W;
-        const float v00 = ld_act(in_hi, in_lo, (base + (size_t)y0 * W + x0) * C + c);
-        const float v01 = ld_act(in_hi, in_lo, (base + (size_t)y0 * W + x1) * C + c);
-        const float v10 = ld_act(in_hi, in_lo, (base + (size_t)y1 * W + x0) * C + c);
-        const float v11 = ld_act(in_hi, in_lo, (base + (size_t)y1 * W + x1) * C + c);
-        st_act(out_hi, out_lo, i, (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11));
+        float v00[8], v01[8], v10[8], v11[8], o[8];
+        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x0) * C + c, v00);
+        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x1) * C + c, v01);
+        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x0) * C + c, v10);
+        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x1) * C + c, v11);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o[j] = (1.f - wy) * ((1.f - wx) * v00[j] + wx * v01[j]) + wy * ((1.f - wx) * v10[j] + wx * v11[j]);
+        st8(out_hi, out_lo, i * 8, o);
     }
 }
 
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(out.C == in.C && out.H == 2 * in.H && out.W == 2 * in.W, "upsample shapes");
-    size_t total = (size_t)batch * out.H * out.W * out.C;
+    ADP_CHECK_ARG(out.C == in.C && out.H == 2 * in.H && out.W == 2 * in.W && in.C % 8 == 0, "upsample shapes");
+    size_t total = (size_t)batch * out.H * out.W * (out.C / 8);
     if (total == 0) return ADP_OK;
     int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
     upsample2x_kernel<<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, batch, in.H, in.W, in.C);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 crops [F,S,S,3] -> space-to-depth(2) [F,S/2,S/2,16]: channel (py*2+px)*3 + c, channels 12..15 zero
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_s2d_kernel(const float* __restrict__ crops, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int S) {
+    const int Hs = S / 2;
+    const size_t total = (size_t)B * Hs * Hs * 2;     // two 8-channel halves per s2d pixel
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int half = (int)(i & 1);
+        size_t t = i >> 1;
+        const int x = (int)(t % Hs); t /= Hs;
+        const int y = (int)(t % Hs);
+        const int b = (int)(t / Hs);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = half * 8 + j;
+            float val = 0.f;
+            if (ch < 12) {
+                const int pp = ch / 3, c = ch - pp * 3;
+                const int py = pp >> 1, px = pp & 1;
+                val = crops[(((size_t)b * S + 2 * y + py) * S + 2 * x + px) * 3 + c];
+            }
+            v[j] = val;
+        }
+        st8(out_hi, out_lo, i * 8, v);
+    }
+}
+
+int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t stream) {
+    ADP_CHECK_ARG(out.C == 16 && out.H == S / 2 && out.W == S / 2 && S % 2 == 0, "s2d shapes");
+    size_t total = (size_t)batch * out.H * out.W * 2;
+    if (total == 0) return ADP_OK;
+    int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    pack_s2d_kernel<<<grid, 256, 0, stream>>>(crops, out.hi, out.lo, batch, S);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

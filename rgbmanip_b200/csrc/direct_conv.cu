@@ -102,12 +102,13 @@ direct_conv_kernel(const DirectConvParams p, int batch) {
             if (n >= p.Cout) continue;
             float v = acc[i][j];
             const size_t o = pix * p.Cout + n;
+            const size_t ro = pix * (p.res_cs ? p.res_cs : p.Cout) + n;
             if (p.scale) v *= p.scale[n];
             if (p.bias) v += p.bias[n];
-            if (p.res_hi && !p.res_after_act) v += ld_act16(p.res_hi, p.res_lo, o, p.f16);
+            if (p.res_hi && !p.res_after_act) v += ld_act16(p.res_hi, p.res_lo, ro, p.f16);
             if (p.act == 1) v = fmaxf(v, 0.f);
             else if (p.act == 2) v = v > 0.f ? v : v * p.prelu;
-            if (p.res_hi && p.res_after_act) v += ld_act16(p.res_hi, p.res_lo, o, p.f16);
+            if (p.res_hi && p.res_after_act) v += ld_act16(p.res_hi, p.res_lo, ro, p.f16);
             if (p.out_f32) p.out_f32[o] = v;
             if (p.out_hi) st_act16(p.out_hi, p.out_lo, o, v, p.f16);
         }

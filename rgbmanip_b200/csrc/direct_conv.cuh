@@ -27,6 +27,7 @@ struct DirectConvParams {
     int res_after_act = 0;
     const bf16* res_hi = nullptr;
     const bf16* res_lo = nullptr;
+    int res_cs = 0;
     bf16* out_hi = nullptr;
     bf16* out_lo = nullptr;
     float* out_f32 = nullptr;

@@ -292,6 +292,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     if (nbase < p.Cout) {   // Cout may be padded up to BN (e.g. 8 -> 16)
                         const int nvalid = min(CH, p.Cout - nbase);
                         const size_t o = pix * p.Cout + nbase;
+                        const size_t ro = pix * p.res_cs + nbase;
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
@@ -305,7 +306,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         }
                         if (p.res_hi && !p.res_after_act) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, o + j, p.f16);
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
                         }
                         if (p.act == 1) {
 #pragma unroll
@@ -316,7 +317,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         }
                         if (p.res_hi && p.res_after_act) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, o + j, p.f16);
+                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
                         }
                         if (p.out_f32) {
 #pragma unroll

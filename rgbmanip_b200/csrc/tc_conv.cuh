@@ -43,6 +43,7 @@ struct TcConvParams {
     int res_after_act;       // 0: act(acc + res)   1: act(acc) + res   (3-D U-Net skips)
     const bf16* res_hi;
     const bf16* res_lo;
+    int res_cs;              // channel pitch of the residual tensor
     bf16* out_hi;
     bf16* out_lo;
     float* out_f32;

@@ -127,8 +127,34 @@ class Engine:
                   res_after_act=0, out_f32=None):
         return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act, res_after_act,
                           L.ptr(res.hi) if res else None, L.ptr(res.lo) if (res and res.lo is not None) else None,
+                          res.Cn if res else 0,
                           L.ptr(out.hi) if out else None, L.ptr(out.lo) if (out and out.lo is not None) else None,
                           L.ptr(out_f32))
+
+    def _tc_plans(self, x: ActBuf, wt, cout, kd, ks, dil, npass, ep, geoms):
+        """wt: fp32 [taps, CoutPad, Cin] packed weights -> callable(batch) launching one tcgen05 conv per geometry."""
+        if x.f16:
+            hi, lo = wt.to(torch.float16), None
+        else:
+            hi, lo = _split_bf16(wt)
+            lo = lo.to(self.device).contiguous()
+        hi = hi.to(self.device).contiguous()
+        self._keep += [hi, lo]
+        plans = []
+        xa = x.c
+        for g in geoms:
+            plan = C.c_void_p()
+            L.check(self.lib.adp_conv_tc_plan(C.byref(plan), C.byref(xa), L.ptr(hi), L.ptr(lo) if npass == 3 else None,
+                                              cout, kd, ks, dil, npass, C.byref(ep), C.byref(g) if g is not None else None,
+                                              self.num_sms), "conv_tc_plan")
+            self._plans.append(plan)
+            plans.append(plan)
+
+        def run(batch, plans=plans):
+            for plan in plans:
+                L.check(self.lib.adp_conv_tc_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv_tc_run")
+        run.kind = "tc"
+        return run
 
     def _conv(self, w_np, x: ActBuf, out: ActBuf | None, *, stride=1, dil=1, transposed=False, npass=None, tc=None, **ep_kw):
         """Returns a callable(batch) running the convolution x -> out.  w_np: torch layout
@@ -166,34 +192,13 @@ class Engine:
             wt = w_tcout_cin
             if cout_pad != cout:
                 wt = torch.cat([wt, torch.zeros(wt.shape[0], cout_pad - cout, cin)], 1).contiguous()
-            if x.f16:
-                hi, lo = wt.to(torch.float16), None
-            else:
-                hi, lo = _split_bf16(wt)
-                lo = lo.to(self.device).contiguous()
-            hi = hi.to(self.device).contiguous()
-            self._keep += [hi, lo]
             if transposed:
                 geoms = G.transposed_classes(x.D, x.H, x.W)
             elif stride == 2:
                 geoms = [G.strided(three_d, x.D, x.H, x.W, ks, 2)]
             else:
                 geoms = [None]
-            plans = []
-            xa = x.c
-            for g in geoms:
-                plan = C.c_void_p()
-                L.check(self.lib.adp_conv_tc_plan(C.byref(plan), C.byref(xa), L.ptr(hi), L.ptr(lo) if npass == 3 else None,
-                                                  cout, kd, ks, dil, npass, C.byref(ep), C.byref(g) if g is not None else None,
-                                                  self.num_sms), "conv_tc_plan")
-                self._plans.append(plan)
-                plans.append(plan)
-
-            def run(batch, plans=plans):
-                for plan in plans:
-                    L.check(self.lib.adp_conv_tc_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv_tc_run")
-            run.kind = "tc"
-            return run
+            return self._tc_plans(x, wt, cout, kd, ks, dil, npass, ep, geoms)
         wd = w_tcin_cout.to(self.device).contiguous()
         self._keep.append(wd)
         pd = 1 if three_d else 0
@@ -217,12 +222,20 @@ class Engine:
         # conv1 7x7/2 on the fp32 crop (Cin = 3: CUDA cores)
         c1 = self._act(F, S // 2, S // 2, 64)
         w = torch.as_tensor(sd[f"{p}.conv1.weight"]).float()
-        wd = w.reshape(64, 3, 49).permute(2, 1, 0).contiguous().to(self.device)
-        self._keep.append(wd)
-        d = L.DirectConv(None, None, L.ptr(self.crops), F, 1, S, S, 3, 1, S // 2, S // 2, 64, 1, 7, 7, 1, 2, 2, 0, 3, 3, 1, 0,
-                         0, L.ptr(wd), self._epilogue(c1, act=L.ACT_RELU))
-        self._keep.append(d)
-        ops.append(("conv1", lambda b, d=d: L.check(self.lib.adp_conv_direct(C.byref(d), b, self.stream), "conv1")))
+        if self.use_tc:
+            # stem on tensor cores: space-to-depth(2) repack of the crop, then a 4x4 stride-1 window over 16 channels
+            s2d = self._act(F, S // 2, S // 2, 16)
+            ops.append(("pack_s2d", lambda b, o=s2d: L.check(
+                self.lib.adp_pack_s2d(L.ptr(self.crops), C.byref(o.c), b, S, self.stream), "pack_s2d")))
+            ops.append(("conv1", self._tc_plans(s2d, G.stem_s2d_weights(w), 64, 1, 4, 1, self.npass,
+                                                self._epilogue(c1, act=L.ACT_RELU), [G.stem_s2d(S)])))
+        else:
+            wd = w.reshape(64, 3, 49).permute(2, 1, 0).contiguous().to(self.device)
+            self._keep.append(wd)
+            d = L.DirectConv(None, None, L.ptr(self.crops), F, 1, S, S, 3, 1, S // 2, S // 2, 64, 1, 7, 7, 1, 2, 2, 0, 3, 3, 1, 0,
+                             0, L.ptr(wd), self._epilogue(c1, act=L.ACT_RELU))
+            self._keep.append(d)
+            ops.append(("conv1", lambda b, d=d: L.check(self.lib.adp_conv_direct(C.byref(d), b, self.stream), "conv1")))
         mp = self._act(F, S // 4, S // 4, 64)
         ops.append(("maxpool", lambda b, a=c1, o=mp: L.check(
             self.lib.adp_maxpool3x3s2(C.byref(a.c), C.byref(o.c), b, self.stream), "maxpool")))
@@ -302,14 +315,20 @@ class Engine:
             d, s = dims[level]
             return self._act(E, s, s, Cn, D=d, split=False, f16=self.vol_f16)
 
-        c0 = act3(0, 8); c1 = act3(1, 16); c2 = act3(1, 16); c3 = act3(2, 32); c4 = act3(2, 32)
+        pad0 = 16 if self.use_tc_3d else 8    # conv0's output carries 8 zero channels so that conv1 (Cin = 8) fits the K=16 MMA
+        c0 = act3(0, pad0); c1 = act3(1, 16); c2 = act3(1, 16); c3 = act3(2, 32); c4 = act3(2, 32)
         c5 = act3(3, 64); c6 = act3(3, 64); x7 = act3(2, 32); x9 = act3(1, 16); x11 = act3(0, 8)
         chain = [("conv0", self.vol, c0, 1), ("conv1", c0, c1, 2), ("conv2", c1, c2, 1), ("conv3", c2, c3, 2),
                  ("conv4", c3, c4, 1), ("conv5", c4, c5, 2), ("conv6", c5, c6, 1)]
         for nm, xin, out, stride in chain:
             sc, sh = bn(nm)
-            ops.append((f"cr.{nm}", self._conv(sd[f"{cr}.{nm}.conv.weight"], xin, out, stride=stride, npass=1, scale=sc, bias=sh,
-                                               act=L.ACT_RELU)))
+            wgt = torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float()
+            if nm == "conv0" and pad0 == 16:      # zero output channels 8..15
+                wgt = torch.cat([wgt, torch.zeros(8, *wgt.shape[1:])], 0)
+                sc = self._dev(torch.cat([sc.cpu(), torch.zeros(8)])); sh = self._dev(torch.cat([sh.cpu(), torch.zeros(8)]))
+            if nm == "conv1" and pad0 == 16:      # zero input channels 8..15
+                wgt = torch.cat([wgt, torch.zeros(wgt.shape[0], 8, 3, 3, 3)], 1)
+            ops.append((f"cr.{nm}", self._conv(wgt.numpy(), xin, out, stride=stride, npass=1, scale=sc, bias=sh, act=L.ACT_RELU)))
         for nm, xin, skip, out in (("conv7", c6, c4, x7), ("conv9", x7, c2, x9), ("conv11", x9, c0, x11)):
             sc, sh = bn(nm)
             ops.append((f"cr.{nm}", self._conv(sd[f"{cr}.{nm}.conv.weight"], xin, out, stride=2, transposed=True, npass=1,

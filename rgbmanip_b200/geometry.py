@@ -49,3 +49,32 @@ def transposed_classes(D, H, W):
                 g.w_taps = 27
                 out.append(g)
     return out
+
+
+def stem_s2d(S):
+    """The 7x7 stride-2 pad-3 stem conv (pspnet.py:37) over a space-to-depth(2) input: output o reads pixels 2o+k-3,
+    i.e. s2d cells o-2..o+1 -> a 4x4 stride-1 window over [S/2, S/2, 16] (see adp_pack_s2d)."""
+    taps = [(0, ty - 2, tx - 2, ty * 4 + tx) for ty in range(4) for tx in range(4)]
+    g = _fill(L.TcGeom(), taps)
+    g.in_mul = g.out_mul = 1
+    g.out_oz = g.out_oy = g.out_ox = 0
+    g.gD, g.gH, g.gW = 1, S // 2, S // 2
+    g.oD, g.oH, g.oW = 1, S // 2, S // 2
+    g.w_taps = 16
+    return g
+
+
+def stem_s2d_weights(w):
+    """[64,3,7,7] torch weights -> [16 taps, 64, 16 ch] with ch = (py*2+px)*3 + c (zeros where the 7x7 window ends)."""
+    import torch
+    cout = w.shape[0]
+    out = torch.zeros(16, cout, 16)
+    for ty in range(4):
+        for tx in range(4):
+            for py in range(2):
+                for px in range(2):
+                    ky, kx = 2 * (ty - 2) + py + 3, 2 * (tx - 2) + px + 3
+                    if 0 <= ky < 7 and 0 <= kx < 7:
+                        for c in range(3):
+                            out[ty * 4 + tx, :, (py * 2 + px) * 3 + c] = w[:, c, ky, kx]
+    return out

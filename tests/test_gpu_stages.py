@@ -367,6 +367,9 @@ def test_costreg_and_decode_match_oracle(G):
     for nm in ("conv0", "conv2", "conv4", "conv6", "conv7", "conv9", "conv11"):
         got = G.from_cl(eng.cr_taps[nm].value().cpu())
         want = tap.store[f"cr.{nm}"]
+        if got.shape[1] != want.shape[1]:          # conv0's output carries 8 zero pad channels
+            assert float(got[:, want.shape[1]:].abs().max()) == 0.0
+            got = got[:, :want.shape[1]]
         assert G.rel_err(got, want) < 2e-2, nm
         assert float((got - want).abs().mean() / want.abs().mean()) < 4e-3, nm
     logits = eng.dbg_logits.cpu().permute(0, 2, 1)
@@ -442,7 +445,7 @@ def test_backbone_matches_oracle(G, precision, tol):
     bad = {k: v for k, v in errs.items() if not v < tol}
     assert not bad, (bad, errs)
     kinds = [getattr(op, "kind", None) for _, op in eng.backbone_ops]
-    assert kinds.count("tc") >= 30, kinds                 # the tcgen05 kernel really is the one that ran
+    assert kinds.count("tc") >= 40 and kinds.count("direct") == 0, kinds   # every backbone conv ran on the tcgen05 kernel
     eng.close()
 
 
