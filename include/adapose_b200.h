@@ -132,9 +132,10 @@ ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float
                int B, int S, int D, int P, int regress_pose, int x11_f16, void* stream);
 
 /* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
+/* scratch: B * P*(P-1)/2 floats (the pair ratios are evaluated once and parked there for the exact-median select). */
 ADP_API int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R,
-            const double* E, const uint8_t* valid, double* bbox, double* scale, double* trans, int B, int P, int S,
-            void* stream);
+            const double* E, const uint8_t* valid, double* bbox, double* scale, double* trans, float* scratch, int B, int P,
+            int S, void* stream);
 
 #ifdef __cplusplus
 }

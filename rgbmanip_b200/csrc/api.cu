@@ -35,7 +35,8 @@ int build_volume(const float* f_ref, const float* f_src, const float* Mw, const 
 int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
                   const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream);
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
-            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, int B, int P, int S, cudaStream_t stream);
+            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, float* scratch, int B, int P, int S,
+            cudaStream_t stream);
 
 struct DecodeWeights;
 struct DecodeArgs;
@@ -196,10 +197,10 @@ int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, co
 }
 
 int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R, const double* E,
-            const uint8_t* valid, double* bbox, double* scale, double* trans, int B, int P, int S, void* stream) {
-    ADP_CHECK_ARG(nocs && depth && choose && Kp && R && E && bbox, "null pointer");
+            const uint8_t* valid, double* bbox, double* scale, double* trans, float* scratch, int B, int P, int S, void* stream) {
+    ADP_CHECK_ARG(nocs && depth && choose && Kp && R && E && bbox && scratch, "null pointer");
     g_launches += 1;
-    return fit_run(nocs, depth, choose, Kp, R, E, valid, bbox, scale, trans, B, P, S, (cudaStream_t)stream);
+    return fit_run(nocs, depth, choose, Kp, R, E, valid, bbox, scale, trans, scratch, B, P, S, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -8,7 +8,7 @@
 
 namespace adp {
 
-constexpr int FIT_THREADS = 512;
+constexpr int FIT_THREADS = 1024;
 constexpr int FIT_MAXP = 1024;
 
 __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
@@ -61,12 +61,23 @@ __device__ bool invert4x4(const double* m, double* inv) {
     return true;
 }
 
+// warp-aggregated shared-memory histogram increment (most keys of a pass share a handful of bins)
+__device__ __forceinline__ void hist_add(unsigned int* hist, unsigned int bin, bool active) {
+    const unsigned int act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned int peers = __match_any_sync(act, bin);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned int)__popc(peers));
+}
+
+constexpr int FIT_BINS = 2048;   // 11 + 11 + 10 bit radix passes over the positive-float bit pattern
+
 __global__ void __launch_bounds__(FIT_THREADS)
 fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, const int* __restrict__ choose,
            const double* __restrict__ Kp, const float* __restrict__ R, const double* __restrict__ E, const uint8_t* __restrict__ valid,
-           double* __restrict__ bbox, double* __restrict__ scale_out, double* __restrict__ trans_out, int P, int S) {
+           double* __restrict__ bbox, double* __restrict__ scale_out, double* __restrict__ trans_out, float* __restrict__ scratch,
+           int P, int S) {
     __shared__ float cx[FIT_MAXP], cy[FIT_MAXP], cz[FIT_MAXP], nx[FIT_MAXP], ny[FIT_MAXP], nz[FIT_MAXP];
-    __shared__ unsigned int hist[256];
+    __shared__ unsigned int hist[FIT_BINS];
     __shared__ float red[FIT_THREADS / 32];
     __shared__ unsigned long long s_cnt;
     __shared__ unsigned int s_sel[4];
@@ -92,19 +103,25 @@ fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, cons
     if (tid == 0) s_cnt = 0ull;
     __syncthreads();
 
-    // unordered pairs (i < j): the reference's ordered-pair list holds every ratio twice, which leaves the median unchanged
-    const long long npairs = (long long)P * (P - 1) / 2;
-    // ---- pass 0: count the valid pairs
+    // unordered pairs (i < j): the reference's ordered-pair list holds every ratio twice, which leaves the median unchanged.
+    // pass 0: evaluate every pair once, park the ratio (negative = filtered out) in the per-env scratch row, count the valid ones
+    const size_t npairs = (size_t)P * (P - 1) / 2;
+    float* rat = scratch + (size_t)b * npairs;
     {
         unsigned int c = 0;
-        for (int i = 0; i < P; ++i)
-            for (int j = i + 1 + tid; j < P; j += FIT_THREADS) c += pair_ratio(cx, cy, cz, nx, ny, nz, i, j) >= 0.f;
+        for (int i = 0; i < P - 1; ++i) {
+            const size_t row0 = (size_t)i * (2 * P - i - 1) / 2;      // index of pair (i, i+1)
+            for (int j = i + 1 + tid; j < P; j += FIT_THREADS) {
+                const float r = pair_ratio(cx, cy, cz, nx, ny, nz, i, j);
+                rat[row0 + (j - i - 1)] = r;
+                c += r >= 0.f;
+            }
+        }
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if ((tid & 31) == 0) atomicAdd(&s_cnt, (unsigned long long)c);
     }
     __syncthreads();
     const long long m = (long long)s_cnt;
-    (void)npairs;
     double scale = nan("");
     if (m > 0) {
         // rank (0-based) of the upper middle element among the m sorted ratios; the lower one is rank (m-1)/2
@@ -112,31 +129,47 @@ fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, cons
         const long long k_lo = (m - 1) / 2;
         unsigned int prefix = 0, pmask = 0;
         long long need = k_hi + 1;      // find the (k_hi+1)-th smallest
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int i = tid; i < 256; i += FIT_THREADS) hist[i] = 0;
+        const int shifts[3] = {21, 10, 0};
+        const int widths[3] = {11, 11, 10};
+        const size_t npad = (npairs + FIT_THREADS - 1) / FIT_THREADS * FIT_THREADS;
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = shifts[pass];
+            const unsigned int bmask = (1u << widths[pass]) - 1u;
+            for (int i = tid; i < FIT_BINS; i += FIT_THREADS) hist[i] = 0;
             __syncthreads();
-            for (int i = 0; i < P; ++i)
-                for (int j = i + 1 + tid; j < P; j += FIT_THREADS) {
-                    const float r = pair_ratio(cx, cy, cz, nx, ny, nz, i, j);
-                    if (r >= 0.f) {
-                        const unsigned int key = __float_as_uint(r);
-                        if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
+            for (size_t q = tid; q < npad; q += FIT_THREADS) {
+                const float r = q < npairs ? rat[q] : -1.f;
+                const unsigned int key = __float_as_uint(r);
+                const bool act = (r >= 0.f) && ((key & pmask) == prefix);
+                hist_add(hist, (key >> shift) & bmask, act);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // warp 0 scans the histogram: each lane sums a contiguous slice, then the slices are walked in order
+                const int per = FIT_BINS / 32;
+                long long part = 0;
+                for (int q = 0; q < per; ++q) part += hist[tid * per + q];
+                long long incl = part;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += y;
+                }
+                const long long excl = incl - part;
+                const bool mine = (excl < need) && (need <= incl);
+                if (mine) {
+                    long long acc = excl;
+                    int bsel = tid * per;
+                    for (; bsel < tid * per + per; ++bsel) {
+                        if (acc + (long long)hist[bsel] >= need) break;
+                        acc += hist[bsel];
                     }
+                    s_sel[0] = (unsigned int)bsel;
+                    s_sel[1] = (unsigned int)(need - acc);
                 }
-            __syncthreads();
-            if (tid == 0) {
-                long long acc = 0;
-                int bsel = 0;
-                for (; bsel < 256; ++bsel) {
-                    if (acc + (long long)hist[bsel] >= need) break;
-                    acc += hist[bsel];
-                }
-                s_sel[0] = (unsigned int)bsel;
-                s_sel[1] = (unsigned int)(need - acc);
             }
             __syncthreads();
             prefix |= s_sel[0] << shift;
-            pmask |= 0xffu << shift;
+            pmask |= bmask << shift;
             need = (long long)s_sel[1];
             __syncthreads();
         }
@@ -146,11 +179,10 @@ fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, cons
         if (k_lo < k_hi) {
             unsigned int less = 0;
             float mx = -1.f;
-            for (int i = 0; i < P; ++i)
-                for (int j = i + 1 + tid; j < P; j += FIT_THREADS) {
-                    const float r = pair_ratio(cx, cy, cz, nx, ny, nz, i, j);
-                    if (r >= 0.f && r < v_hi) { ++less; mx = fmaxf(mx, r); }
-                }
+            for (size_t q = tid; q < npairs; q += FIT_THREADS) {
+                const float r = rat[q];
+                if (r >= 0.f && r < v_hi) { ++less; mx = fmaxf(mx, r); }
+            }
             if (tid == 0) s_cnt = 0ull;
             __syncthreads();
             for (int o = 16; o > 0; o >>= 1) less += __shfl_xor_sync(0xffffffffu, less, o);
@@ -208,10 +240,12 @@ fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, cons
 }
 
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
-            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, int B, int P, int S, cudaStream_t stream) {
+            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, float* scratch, int B, int P, int S,
+            cudaStream_t stream) {
     ADP_CHECK_ARG(P <= FIT_MAXP, "at most 1024 points per env");
+    ADP_CHECK_ARG(scratch != nullptr, "scratch of B * P*(P-1)/2 floats");
     if (B == 0) return ADP_OK;
-    fit_kernel<<<B, FIT_THREADS, 0, stream>>>(nocs, depth, choose, Kp, R, E, valid, bbox, scale_out, trans_out, P, S);
+    fit_kernel<<<B, FIT_THREADS, 0, stream>>>(nocs, depth, choose, Kp, R, E, valid, bbox, scale_out, trans_out, scratch, P, S);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

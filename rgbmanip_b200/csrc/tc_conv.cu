@@ -135,14 +135,17 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * KC * 2;
     static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
     static constexpr int STAGE_BYTES = A_BYTES + B_PAD;
-    static constexpr int STAGES = (STAGE_BYTES * 6 <= 196608) ? 6 : (196608 / STAGE_BYTES);
+    // small-N layers are latency bound per tile: fewer stages -> several CTAs per SM overlap their pipelines
+    static constexpr int CTAS_PER_SM = BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
+    static constexpr int SMEM_BUDGET = 196608 / CTAS_PER_SM;
+    static constexpr int STAGES = (STAGE_BYTES * 6 <= SMEM_BUDGET) ? 6 : (SMEM_BUDGET / STAGE_BYTES);
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns per accumulator stage
     static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : (2 * ACC_STRIDE <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, int KC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, TcCfg<BN, KC>::CTAS_PER_SM)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                const TcConvParams p, int batch) {
@@ -504,7 +507,8 @@ static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_
     }
     const TcConvParams& p = L->p;
     long long total = (long long)batch * p.D * p.tiles_y * p.tiles_x * p.tiles_n;
-    int grid = (int)(total < num_sms ? total : num_sms);
+    const long long slots = (long long)num_sms * Cfg::CTAS_PER_SM;
+    int grid = (int)(total < slots ? total : slots);
     if (grid <= 0) return ADP_OK;
     tc_conv_kernel<BN, KC><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(L->tmA_hi, L->tmA_lo, L->tmW_hi, L->tmW_lo, p, batch);
     ADP_CUDA(cudaGetLastError());

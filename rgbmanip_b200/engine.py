@@ -375,6 +375,7 @@ class Engine:
         self.bbox = torch.zeros((E, 8, 3), dtype=torch.float64, device=dev)
         self.scale = torch.zeros(E, dtype=torch.float64, device=dev)
         self.trans = torch.zeros((E, 3), dtype=torch.float64, device=dev)
+        self.fit_scratch = torch.zeros((E, P * (P - 1) // 2), dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ stages
     @staticmethod
@@ -401,23 +402,30 @@ class Engine:
             L.ptr(self.bbox_ws[o:]), L.ptr(self.win[o:]), L.ptr(self.Kp[o:]), L.ptr(self.valid[o:]), L.ptr(self.crops[o:]),
             L.ptr(self.choose[o:]), L.ptr(self.counts[o:]), self.stream), "preprocess")
 
-    def stereo(self, n, E1, E2):
-        """Frames [0,n) are view 1 and [E,E+n) view 2 of envs [0,n).  E1/E2 [n,4,4] f64 device tensors."""
+    def stereo(self, n, E1, E2, mark=None):
+        """Frames [0,n) are view 1 and [E,E+n) view 2 of envs [0,n).  E1/E2 [n,4,4] f64 device tensors.
+        ``mark(name)`` (optional) is called after each stage, e.g. to record CUDA events."""
         E, S, D, P = self.E, self.S, N_DEPTH, self.P
         lib, st = self.lib, self.stream
+        mark = mark or (lambda name: None)
         L.check(lib.adp_warp_matrices(L.ptr(self.Kp), L.ptr(E1), L.ptr(self.Kp[E:]), L.ptr(E2), L.ptr(self.Mw),
                                       L.ptr(self.valid), L.ptr(self.valid[E:]), L.ptr(self.valid_env), n, st), "warp_matrices")
         f1, f2 = self.feat, self.feat[E:]
         L.check(lib.adp_build_volume(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.vol.hi), n, D, S, S,
                                      32, self.vol_f16, st), "build_volume")
-        for _, op in self.cr_ops:
+        mark("volume")
+        for name, op in self.cr_ops:
             op(n)
+            mark(name)
         L.check(lib.adp_decode(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi), L.ptr(self.choose),
                                L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.pf1),
                                L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
                                L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.vol_f16, st), "decode")
+        mark("decode")
         L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
-                            L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans), n, P, S, st), "fit")
+                            L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans), L.ptr(self.fit_scratch),
+                            n, P, S, st), "fit")
+        mark("fit")
 
     def run_chunk(self, K, rgb1, mask1, E1, rgb2, mask2, E2, seed=0, choose1=None, choose2=None):
         """Device tensors for n <= max_envs environments -> self.bbox[:n] ([n,8,3] f64, world frame)."""

@@ -42,6 +42,13 @@ for prec in ("bf16x3", "bf16"):
         eng.run_backbone(2 * N); marks[2].record()
         eng.stereo(N, E1, E2); marks[3].record()
         torch.cuda.synchronize()
+    evs = [("start", ev())]
+    evs[0][1].record()
+    def mark(name):
+        e = ev(); e.record(); evs.append((name, e))
+    eng.stereo(N, E1, E2, mark=mark)
+    torch.cuda.synchronize()
+    lines.append(f"{prec} stereo stages ms: " + ", ".join(f"{evs[i][0]}={evs[i-1][1].elapsed_time(evs[i][1]):.3f}" for i in range(1, len(evs))))
     lines.append(f"{prec} timing N={N}: preprocess {marks[0].elapsed_time(marks[1]):.2f} ms, backbone({2*N} frames) {marks[1].elapsed_time(marks[2]):.2f} ms, stereo {marks[2].elapsed_time(marks[3]):.2f} ms")
     # per-op timing
     for group, ops in (("backbone", eng.backbone_ops), ("costreg", eng.cr_ops)):
