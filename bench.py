@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--unique", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
@@ -287,7 +288,7 @@ def main():
     kernels["volume_decode_fit_ms"] = dec_ms
 
     if rank == 0:
-        cpu_rate, threads, cpu_dt = cpu_oracle_rate(args.cpu_sample)
+        cpu_rate, threads, cpu_dt = (0.0, 0, 0.0) if args.no_cpu else cpu_oracle_rate(args.cpu_sample)
         line = {"metric": "pose estimates/sec at num_envs=1024", "value": value, "unit": "estimates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": f"synthetic ({args.unique} seeded envs tiled to {N})",

@@ -116,6 +116,14 @@ ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, voi
  * stem conv (pspnet.py:37) then is a 4x4 stride-1 conv over 16 channels and runs on the tcgen05 kernel. */
 ADP_API int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream);
 
+/* conv0 of the cost-regularisation U-Net (network_v5.py:263,283) as a depth-ring tcgen05 kernel: vol [B,D,H,W,32] ->
+ * out [B,D,H,W,16] (8 channels + 8 zero), folded BatchNorm + ReLU.  w: 16-bit [9 (ky,kx)][4 chunks][32 (kz,co)][8]. */
+typedef struct adp_conv0_plan adp_conv0_plan;
+ADP_API int adp_conv0_plan_create(adp_conv0_plan** plan, const adp_act* vol, const void* w_packed, const float* scale,
+                                  const float* shift, void* out, int num_sms);
+ADP_API int adp_conv0_run(adp_conv0_plan* plan, int batch, int32_t* err_flag, void* stream);
+ADP_API void adp_conv0_free(adp_conv0_plan* plan);
+
 /* --- stereo volume: network_v5.py:378-416,429 ---------------------------------------------------------------- */
 /* Mw[b] = {rot 3x3 row-major, trans 3} of P_src inv(P_ref), P = [K' E[:3,:]; 0 0 0 1] (interface_v5.py:264-270);
  * valid_env[b] = valid_ref[b] && valid_src[b] (an estimate needs both views, interface_v5.py:256-257). */

@@ -38,6 +38,13 @@ int fit_run(const float* nocs, const float* depth, const int* choose, const doub
             const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, float* scratch, int B, int P, int S,
             cudaStream_t stream);
 
+struct Conv0Plan;
+Conv0Plan* conv0_alloc();
+void conv0_release(Conv0Plan* p);
+int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const float* scale, const float* shift, uint16_t* out,
+               int num_sms);
+int conv0_run(Conv0Plan* pl, int batch, int* err_flag, cudaStream_t stream);
+
 struct DecodeWeights;
 struct DecodeArgs;
 int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
@@ -164,6 +171,28 @@ int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* strea
     g_launches += 1;
     return upsample2x(to_act(in), to_act(out), batch, (cudaStream_t)stream);
 }
+
+int adp_conv0_plan_create(adp_conv0_plan** plan, const adp_act* vol, const void* w_packed, const float* scale, const float* shift,
+                          void* out, int num_sms) {
+    ADP_CHECK_ARG(plan && vol && w_packed && scale && shift && out, "null pointer");
+    Conv0Plan* pl = conv0_alloc();
+    int r = conv0_plan(pl, to_act(vol), reinterpret_cast<const uint16_t*>(w_packed), scale, shift, reinterpret_cast<uint16_t*>(out),
+                       num_sms);
+    if (r != ADP_OK) {
+        conv0_release(pl);
+        return r;
+    }
+    *plan = reinterpret_cast<adp_conv0_plan*>(pl);
+    return ADP_OK;
+}
+
+int adp_conv0_run(adp_conv0_plan* plan, int batch, int32_t* err_flag, void* stream) {
+    ADP_CHECK_ARG(plan, "null plan");
+    g_launches += 1;
+    return conv0_run(reinterpret_cast<Conv0Plan*>(plan), batch, err_flag, (cudaStream_t)stream);
+}
+
+void adp_conv0_free(adp_conv0_plan* plan) { conv0_release(reinterpret_cast<Conv0Plan*>(plan)); }
 
 int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream) {
     ADP_CHECK_ARG(crops && out, "null pointer");

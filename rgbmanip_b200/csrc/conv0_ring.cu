@@ -1,0 +1,274 @@
+// conv0 of the cost-regularisation U-Net (ADA/lib/network_v5.py:263,283): 3x3x3, 32 -> 8 channels over the full
+// [24, 224, 224] plane-sweep volume -- 68 % of the U-Net's FLOPs with only 8 output channels.
+//
+// A plain implicit GEMM (M = pixels, N = 8) re-reads the volume 27 times and leaves the MMA N dimension nearly empty.
+// This kernel instead walks the depth axis sequentially and folds the depth taps into N:
+//
+//   P[d'][pixel, (kz, co)] = sum_{ky,kx,c} In[d', y+ky-1, x+kx-1, c] * W[co, c, kz, ky, kx]      (N = 3 x 8 = 24 of 32)
+//   out[d][pixel, co]      = P[d-1][kz=0] + P[d][kz=1] + P[d+1][kz=2]
+//
+// One work unit = one image row segment of 112 pixels (M = 128 rows of the UMMA tile) for all 24 depths.  For each
+// input plane d' the three rows y-1, y, y+1 (with a one-pixel halo in x) are brought in by TMA in the canonical
+// NO-SWIZZLE K-major layout ([16-byte channel chunk][pixel][8 channels]), in which the x taps are plain +16-byte
+// shifts of the shared-memory descriptor start address, so every volume row is read 3 times (once per ky) instead
+// of 27.  P[d'] accumulates in one of four 32-column TMEM slots (a ring over depth); the epilogue warps add the three
+// lane-aligned column groups of three consecutive slots, apply the folded BatchNorm + ReLU and store 16 channels
+// (8 real + 8 zero: conv1 needs Cin = 16 for the K = 16 MMA).
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace adp {
+
+constexpr int C0_THREADS = 192;
+constexpr int C0_SEG = 112;                 // pixels per unit (224 = 2 x 112)
+constexpr int C0_PIXPITCH = 136;            // pixels per channel-chunk plane in smem (halo + M = 128 tile overhang; 128 B aligned)
+constexpr int C0_CHUNK_BYTES = C0_PIXPITCH * 16;          // 2176: LBO of the A descriptor
+constexpr int C0_ROW_BYTES = 4 * C0_CHUNK_BYTES;          // 32 channels = 4 chunks of 8
+constexpr int C0_STAGE_BYTES = 3 * C0_ROW_BYTES;          // rows y-1, y, y+1 of one depth plane
+constexpr int C0_STAGES = 3;
+constexpr int C0_W_BYTES = 9 * 4 * 32 * 16;               // [tap][chunk][n = 32][8 ch] 16-bit
+constexpr int C0_SLOTS = 4;
+constexpr int C0_SMEM = C0_STAGES * C0_STAGE_BYTES + C0_W_BYTES + 1024 + 256;
+
+struct Conv0Params {
+    int B, D, H, W;
+    int f16;
+    const uint16_t* w;        // packed weights, C0_W_BYTES
+    const float* scale;       // [8] folded BatchNorm
+    const float* shift;       // [8]
+    uint16_t* out;            // [B, D, H, W, 16]
+    int* err;
+};
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = byte distance between the two 16-byte K chunks of one MMA,
+// SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(C0_THREADS, 2)
+conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p, int batch) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* wsm = smem + C0_STAGES * C0_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + C0_W_BYTES);
+    // bars: [0,S) full, [S,2S) empty, [2S,2S+4) tmem_full, [2S+4,2S+8) tmem_empty, then the TMEM base
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C0_STAGES + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t w_base = ptx::smem_u32(wsm);
+    const uint32_t bar_base = ptx::smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C0_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C0_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C0_STAGES + 4 + s); };
+
+    // weights -> smem (generic proxy), made visible to the tensor core's async proxy by the fence below
+    for (int i = threadIdx.x; i < C0_W_BYTES / 16; i += C0_THREADS)
+        reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.w) + i);
+    // the overhang pixels (beyond the 114 loaded ones) are read by MMA rows >= 112 only; keep them finite
+    for (int i = threadIdx.x; i < C0_STAGES * C0_STAGE_BYTES / 16; i += C0_THREADS)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmIn);
+        for (int s = 0; s < C0_STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < C0_SLOTS; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 128);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int segs = p.W / C0_SEG;
+    const int units = batch * p.H * segs;
+    const int D = p.D;
+
+    if (warp == 0) {
+        // ===================== TMA producer: 3 rows x 4 channel chunks per depth plane =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int seg = u % segs, y = (u / segs) % p.H, b = u / (segs * p.H);
+                const int x0 = seg * C0_SEG - 1;
+                for (int d = 0; d < D; ++d) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 11);
+                    const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), 12u * (C0_SEG + 2) * 16u);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc)
+                            ptx::tma_load_5d(&tmIn, full_bar(stage), sa + ky * C0_ROW_BYTES + kc * C0_CHUNK_BYTES, kc * 8, x0,
+                                             y + ky - 1, d, b);
+                    if (++stage == C0_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: 9 (ky,kx) taps x 2 K steps per plane into TMEM slot g % 4 =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t idesc = make_idesc_n(32, p.f16);
+        unsigned g = 0;   // running plane counter (D % 4 == 0 keeps slot == depth % 4)
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            for (int d = 0; d < D; ++d, ++g) {
+                const int slot = g & 3;
+                ptx::mbar_wait(tempty_bar(slot), ((g >> 2) & 1) ^ 1, p.err, 12);
+                ptx::mbar_wait(full_bar(stage), phase, p.err, 13);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(slot * 32);
+                    int first = 1;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint64_t adesc = make_desc_noswz(sa + ky * C0_ROW_BYTES + (2 * ks) * C0_CHUNK_BYTES + kx * 16,
+                                                                       C0_CHUNK_BYTES, 128);
+                                const uint64_t bdesc = make_desc_noswz(w_base + ((ky * 3 + kx) * 4 + 2 * ks) * 512, 512, 128);
+                                ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                    ptx::umma_commit(empty_bar(stage));
+                    ptx::umma_commit(tfull_bar(slot));
+                }
+                __syncwarp();
+                if (++stage == C0_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: out[d] = P[d-1][kz=0] + P[d][kz=1] + P[d+1][kz=2] =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = p.scale[j]; sh[j] = p.shift[j]; }
+        unsigned g0 = 0;   // plane counter at the start of the unit
+        for (int u = blockIdx.x; u < units; u += gridDim.x, g0 += (unsigned)D) {
+            const int seg = u % segs, y = (u / segs) % p.H, b = u / (segs * p.H);
+            const int x = seg * C0_SEG + m;
+            const bool valid = m < C0_SEG;
+            for (int d = 0; d < D; ++d) {
+                // planes complete in order: waiting for plane d+1 (or d at the last depth) covers d-1 and d
+                const unsigned gl = g0 + (unsigned)(d + 1 < D ? d + 1 : d);
+                ptx::mbar_wait(tfull_bar(gl & 3), (gl >> 2) & 1, p.err, 14);
+                ptx::tc_fence_after();
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+                for (int kz = 0; kz < 3; ++kz) {
+                    const int dp = d + kz - 1;
+                    if (dp < 0 || dp >= D) continue;
+                    uint32_t r[8];
+                    tmem_ld8(lane_addr + (uint32_t)(((g0 + dp) & 3) * 32 + kz * 8), r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(r[j]);
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                // plane d-1 is no longer needed once out[d] has been formed; the last step also frees plane D-1
+                if (lane == 0) {
+                    if (d >= 1) ptx::mbar_arrive(tempty_bar((g0 + d - 1) & 3));
+                    if (d == D - 1) ptx::mbar_arrive(tempty_bar((g0 + d) & 3));
+                }
+                if (valid) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float v0 = fmaxf(fmaf(acc[2 * j], sc[2 * j], sh[2 * j]), 0.f);
+                        const float v1 = fmaxf(fmaf(acc[2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]), 0.f);
+                        if (p.f16)
+                            o[j] = (uint32_t)__half_as_ushort(__float2half_rn(v0)) | ((uint32_t)__half_as_ushort(__float2half_rn(v1)) << 16);
+                        else
+                            o[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) |
+                                   ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + ((((size_t)b * D + d) * p.H + y) * p.W + x) * 16);
+                    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_uint4(0, 0, 0, 0);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+struct Conv0Plan {
+    CUtensorMap tmIn;
+    Conv0Params p;
+    int num_sms;
+};
+
+int tc_conv_init_driver();
+extern PFN_cuTensorMapEncodeTiled_v12000 g_encode_shared;
+
+Conv0Plan* conv0_alloc() { return new Conv0Plan(); }
+void conv0_release(Conv0Plan* p) { delete p; }
+
+int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const float* scale, const float* shift, uint16_t* out,
+               int num_sms) {
+    ADP_TRY(tc_conv_init_driver());
+    ADP_CHECK_ARG(in.C == 32 && in.W % C0_SEG == 0 && in.D % 4 == 0 && in.D >= 4, "conv0 ring kernel: C = 32, W % 112 == 0, D % 4 == 0");
+    cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.D, (cuuint64_t)in.B};
+    cuuint64_t strides[4] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2,
+                             (cuuint64_t)in.D * in.H * in.W * in.C * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)(C0_SEG + 2), 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode_shared(&pl->tmIn, in.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, in.hi, dims,
+                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(conv0 volume) failed: %d", (int)r);
+        return ADP_ERR_CUDA;
+    }
+    pl->p.B = in.B; pl->p.D = in.D; pl->p.H = in.H; pl->p.W = in.W; pl->p.f16 = in.f16;
+    pl->p.w = w_packed; pl->p.scale = scale; pl->p.shift = shift; pl->p.out = out; pl->p.err = nullptr;
+    pl->num_sms = num_sms > 0 ? num_sms : 148;
+    return ADP_OK;
+}
+
+int conv0_run(Conv0Plan* pl, int batch, int* err_flag, cudaStream_t stream) {
+    ADP_CHECK_ARG(batch <= pl->p.B, "batch exceeds planned capacity");
+    static bool attr = false;
+    if (!attr) {
+        ADP_CUDA(cudaFuncSetAttribute(conv0_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM));
+        attr = true;
+    }
+    pl->p.err = err_flag;
+    const int units = batch * pl->p.H * (pl->p.W / C0_SEG);
+    if (units == 0) return ADP_OK;
+    const int slots = pl->num_sms * 2;
+    const int grid = units < slots ? units : slots;
+    conv0_ring_kernel<<<grid, C0_THREADS, C0_SMEM, stream>>>(pl->tmIn, pl->p, batch);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+}  // namespace adp

@@ -62,8 +62,8 @@ class Engine:
     """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
 
     def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="bf16x3", regress_pose=True, use_tc=True,
-                 use_tc_3d=True, tc_strided=True, tc_transposed=True, volume_dtype="fp16", debug=False, img_size=IMG_SIZE,
-                 n_pts=N_PTS):
+                 use_tc_3d=True, tc_strided=True, tc_transposed=True, conv0_ring=True, volume_dtype="fp16", debug=False,
+                 img_size=IMG_SIZE, n_pts=N_PTS):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
         if precision not in ("bf16", "bf16x3"):
@@ -82,6 +82,8 @@ class Engine:
         self.use_tc_3d = use_tc_3d
         self.tc_strided = tc_strided
         self.tc_transposed = tc_transposed
+        self.conv0_ring = conv0_ring and use_tc_3d
+        self._conv0_plans = []
         if volume_dtype not in ("fp16", "bf16"):
             raise ValueError("volume_dtype must be 'fp16' or 'bf16'")
         self.vol_f16 = 1 if volume_dtype == "fp16" else 0
@@ -328,6 +330,21 @@ class Engine:
                 sc = self._dev(torch.cat([sc.cpu(), torch.zeros(8)])); sh = self._dev(torch.cat([sh.cpu(), torch.zeros(8)]))
             if nm == "conv1" and pad0 == 16:      # zero input channels 8..15
                 wgt = torch.cat([wgt, torch.zeros(wgt.shape[0], 8, 3, 3, 3)], 1)
+            if nm == "conv0" and self.conv0_ring and S % 112 == 0 and pad0 == 16:
+                w16 = G.conv0_ring_weights(torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float())
+                w16 = w16.to(torch.float16 if self.vol_f16 else torch.bfloat16).to(self.device).contiguous()
+                self._keep.append(w16)
+                plan = C.c_void_p()
+                va = xin.c
+                L.check(self.lib.adp_conv0_plan_create(C.byref(plan), C.byref(va), L.ptr(w16), L.ptr(sc), L.ptr(sh), L.ptr(out.hi),
+                                                       self.num_sms), "conv0_plan")
+                self._conv0_plans.append(plan)
+
+                def run0(batch, plan=plan):
+                    L.check(self.lib.adp_conv0_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv0_run")
+                run0.kind = "tc"
+                ops.append((f"cr.{nm}", run0))
+                continue
             ops.append((f"cr.{nm}", self._conv(wgt.numpy(), xin, out, stride=stride, npass=1, scale=sc, bias=sh, act=L.ACT_RELU)))
         for nm, xin, skip, out in (("conv7", c6, c4, x7), ("conv9", x7, c2, x9), ("conv11", x9, c0, x11)):
             sc, sh = bn(nm)
@@ -455,6 +472,9 @@ class Engine:
         for p in self._plans:
             self.lib.adp_conv_tc_free(p)
         self._plans = []
+        for p in self._conv0_plans:
+            self.lib.adp_conv0_free(p)
+        self._conv0_plans = []
 
     def __del__(self):
         try:

@@ -78,3 +78,15 @@ def stem_s2d_weights(w):
                         for c in range(3):
                             out[ty * 4 + tx, :, (py * 2 + px) * 3 + c] = w[:, c, ky, kx]
     return out
+
+
+def conv0_ring_weights(w):
+    """[8,32,3,3,3] torch weights -> [9 (ky,kx)][4 chunks][32 n = kz*8+co][8 ch] for adp_conv0_run (rows 24..31 zero)."""
+    import torch
+    out = torch.zeros(9, 4, 32, 8)
+    for ky in range(3):
+        for kx in range(3):
+            for kz in range(3):
+                blk = w[:, :, kz, ky, kx]                       # [co, c]
+                out[ky * 3 + kx, :, kz * 8:(kz + 1) * 8, :] = blk.reshape(8, 4, 8).permute(1, 0, 2)
+    return out.contiguous()

@@ -138,6 +138,37 @@ def test_tc_conv_strided_transposed_fp16(G, case):
     assert G.rel_err(G.from_cl(out16), ref) < (2e-3 if f16 else 1.2e-2)   # 16-bit output rounding
 
 
+@pytest.mark.parametrize("f16", [1, 0])
+def test_conv0_depth_ring_kernel(G, f16):
+    """conv0 (3x3x3, 32 -> 8) as the depth-ring tcgen05 kernel (csrc/conv0_ring.cu) against F.conv3d."""
+    from rgbmanip_b200 import geometry
+    lib = L.load()
+    rng = _rng(31 + f16)
+    B, D, H, W = 2, 8, 12, 224
+    dt = torch.float16 if f16 else torch.bfloat16
+    x = _t(rng, B, 32, D, H, W).to(dt).float()
+    w = _t(rng, 8, 32, 3, 3, 3, scale=math.sqrt(1.0 / (27 * 32))).to(dt).float()
+    scale, shift = _t(rng, 8).abs() + 0.5, _t(rng, 8)
+    ref = F.relu(F.conv3d(x, w, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    xd = G.to_cl(x).to(dt).to(G.DEV).contiguous()
+    wd = geometry.conv0_ring_weights(w).to(dt).to(G.DEV).contiguous()
+    sc = torch.cat([scale, torch.zeros(8)]).to(G.DEV)
+    sh = torch.cat([shift, torch.zeros(8)]).to(G.DEV)
+    out = torch.full((B, D, H, W, 16), float("nan"), dtype=dt, device=G.DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=G.DEV)
+    plan = C.c_void_p()
+    a = G.act(xd, None, B, D, H, W, 32, f16)
+    L.check(lib.adp_conv0_plan_create(C.byref(plan), C.byref(a), L.ptr(wd), L.ptr(sc), L.ptr(sh), L.ptr(out), 148), "plan")
+    L.check(lib.adp_conv0_run(plan, B, L.ptr(err), G.stream()), "run")
+    torch.cuda.synchronize()
+    lib.adp_conv0_free(plan)
+    assert int(err.item()) == 0
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert float(got[..., 8:].abs().max()) == 0.0
+    assert G.rel_err(G.from_cl(got[..., :8].contiguous()), ref) < (2e-3 if f16 else 1.2e-2)   # 16-bit output rounding
+
+
 DIRECT_CASES = [
     # (dims, B, D, H, W, Cin, Cout, k, stride, dil, transposed)
     (2, 2, 1, 32, 48, 3, 64, 7, 2, 1, False),
