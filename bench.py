@@ -185,8 +185,8 @@ def main():
     torch.cuda.set_device(dev)
     lib = _lib.load()
     N = args.num_envs
-    per = (N + world - 1) // world
-    lo, hi = rank * per, min(N, (rank + 1) * per)
+    from rgbmanip_b200.dist import shard_range
+    lo, hi, per = shard_range(N, rank, world)
     n_loc = hi - lo
     # synthetic inputs: `unique` distinct envs tiled over this rank's shard, resident in HBM and mirrored in pinned host memory
     base = synth.make_batch(args.unique, seed=100 + rank, special=True)

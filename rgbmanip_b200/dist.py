@@ -1,0 +1,39 @@
+"""Env-sharded data parallelism: one process per GPU, contiguous blocks of environments per rank, one all-gather of the
+per-env boxes.  Environments are independent (eval-mode BatchNorm is folded, nothing couples
+them), so the only exchange is the [N, 8, 3] result -- 192 KiB at N = 1024.
+
+The reference's single-process ``nn.DataParallel`` wrapper (interface_v5.py:48) degenerates to one replica because
+``estimate`` calls the network with batch 1; this module replaces it.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of rank ``rank``; every rank's block has ceil(n / world) slots, the tail may be short/empty."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per), per
+
+
+def estimate_sharded(estimate_fn, args, n: int, group=None, device=None):
+    """Run ``estimate_fn(*shard_of_args) -> tensor [n_loc, 8, 3]`` on this rank's block and all-gather the boxes.
+
+    ``args``: sequences/tensors indexed by environment along dim 0.  Returns a [n, 8, 3] float64 tensor on every rank
+    (NCCL for CUDA tensors, gloo for CPU tensors)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi, per = shard_range(n, rank, world)
+    local = estimate_fn(*[a[lo:hi] for a in args]) if hi > lo else None
+    if device is None:
+        device = local.device if local is not None else torch.device("cpu")
+    if world == 1:
+        return local
+    pad = torch.zeros((per, 8, 3), dtype=torch.float64, device=device)
+    if local is not None:
+        pad[: hi - lo].copy_(local)
+    out = torch.empty((world * per, 8, 3), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out[:n]
