@@ -99,6 +99,10 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         eng.check_error_flag()
         return res
 
+    def estimate_tensor(self, *args, **kw):
+        """Same as :meth:`estimate` but returns the [N,8,3] float64 CUDA tensor without the device->host copy."""
+        return self.estimate(*args, return_tensor=True, **kw)
+
     def predict(self, camera_intrinsic, rgb1, view1_mask, view1_extrinsic, rgb2, view2_mask, view2_extrinsic):
         """Single environment (interface_v5.py:229-374) -> [8,3]."""
         f = lambda a: (a if isinstance(a, torch.Tensor) else np.asarray(a))[None]
