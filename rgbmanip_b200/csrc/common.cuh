@@ -75,6 +75,42 @@ __device__ __forceinline__ void st_act16(bf16* __restrict__ hi, bf16* __restrict
     else st_act(hi, lo, i, v);
 }
 
+// 8 consecutive 16-bit values (one 128-bit access) <-> fp32
+__device__ __forceinline__ void ld8_16(const bf16* __restrict__ p, size_t i, int f16, float* v, bool accumulate) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float a, b;
+        if (f16) {
+            a = __half2float(__ushort_as_half((unsigned short)(w[q] & 0xffffu)));
+            b = __half2float(__ushort_as_half((unsigned short)(w[q] >> 16)));
+        } else {
+            a = __uint_as_float(w[q] << 16);
+            b = __uint_as_float(w[q] & 0xffff0000u);
+        }
+        if (accumulate) { v[2 * q] += a; v[2 * q + 1] += b; } else { v[2 * q] = a; v[2 * q + 1] = b; }
+    }
+}
+// stores hi (and lo = v - hi for bf16 split precision)
+__device__ __forceinline__ void st8_16(bf16* __restrict__ hi, bf16* __restrict__ lo, size_t i, int f16, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (f16) {
+            h[q] = (uint32_t)__half_as_ushort(__float2half_rn(v[2 * q])) | ((uint32_t)__half_as_ushort(__float2half_rn(v[2 * q + 1])) << 16);
+            l[q] = 0;
+        } else {
+            const bf16 h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
+            h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            const bf16 l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
+            l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+    }
+    *reinterpret_cast<uint4*>(hi + i) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo && !f16) *reinterpret_cast<uint4*>(lo + i) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace adp

@@ -37,7 +37,7 @@ struct TcCfg {
     static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
     static constexpr int STAGE_BYTES = A_BYTES + B_PAD;
     // small-N layers are latency bound per tile: fewer stages -> several CTAs per SM overlap their pipelines
-    static constexpr int CTAS_PER_SM = BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
+    static constexpr int CTAS_PER_SM = (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
     static constexpr int SMEM_BUDGET = 196608 / CTAS_PER_SM;
     static constexpr int STAGES = (STAGE_BYTES * 6 <= SMEM_BUDGET) ? 6 : (SMEM_BUDGET / STAGE_BYTES);
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns per accumulator stage
@@ -208,9 +208,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nbase + j);
                         }
+                        const bool vec_ok = ((p.Cout | p.res_cs) & 7) == 0;   // 128-bit accesses stay aligned
                         if (p.res_hi && !p.res_after_act) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
+                            for (int j0 = 0; j0 < CH; j0 += 8) {
+                                if (vec_ok && j0 + 8 <= nvalid) {
+                                    ld8_16(p.res_hi, ro + j0, p.f16, v + j0, true);
+                                    if (p.res_lo && !p.f16) ld8_16(p.res_lo, ro + j0, 0, v + j0, true);
+                                } else {
+#pragma unroll
+                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
+                                }
+                            }
                         }
                         if (p.act == 1) {
 #pragma unroll
@@ -221,35 +230,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         }
                         if (p.res_hi && p.res_after_act) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
+                            for (int j0 = 0; j0 < CH; j0 += 8) {
+                                if (vec_ok && j0 + 8 <= nvalid) {
+                                    ld8_16(p.res_hi, ro + j0, p.f16, v + j0, true);
+                                    if (p.res_lo && !p.f16) ld8_16(p.res_lo, ro + j0, 0, v + j0, true);
+                                } else {
+#pragma unroll
+                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
+                                }
+                            }
                         }
                         if (p.out_f32) {
 #pragma unroll
                             for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
                         }
                         if (p.out_hi) {
-                            if (p.f16) {
 #pragma unroll
-                                for (int j = 0; j < CH; ++j) if (j < nvalid) st_act16(p.out_hi, p.out_lo, o + j, v[j], 1);
-                            } else if (nvalid == CH && (CH % 8) == 0) {
+                            for (int j0 = 0; j0 < CH; j0 += 8) {
+                                if (vec_ok && j0 + 8 <= nvalid) {
+                                    st8_16(p.out_hi, p.out_lo, o + j0, p.f16, v + j0);
+                                } else {
 #pragma unroll
-                                for (int j = 0; j < CH; j += 8) {
-                                    uint32_t h[4], l[4];
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        const bf16 h0 = __float2bfloat16_rn(v[j + 2 * u]);
-                                        const bf16 h1 = __float2bfloat16_rn(v[j + 2 * u + 1]);
-                                        h[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                        const bf16 l0 = __float2bfloat16_rn(v[j + 2 * u] - __bfloat162float(h0));
-                                        const bf16 l1 = __float2bfloat16_rn(v[j + 2 * u + 1] - __bfloat162float(h1));
-                                        l[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                                    }
-                                    *reinterpret_cast<uint4*>(p.out_hi + o + j) = make_uint4(h[0], h[1], h[2], h[3]);
-                                    if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + o + j) = make_uint4(l[0], l[1], l[2], l[3]);
+                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) st_act16(p.out_hi, p.out_lo, o + j, v[j], p.f16);
                                 }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < CH; ++j) if (j < nvalid) st_act(p.out_hi, p.out_lo, o + j, v[j]);
                             }
                         }
                     }

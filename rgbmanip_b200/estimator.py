@@ -59,6 +59,7 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
                                 img_size=int(cfg.get("img_size", 224)), **engine_kw)
         self._seed = int(cfg.get("sample_seed", 0))
         self._calls = 0
+        self._copy_stream = None
 
     # -- helpers ---------------------------------------------------------------------------------
     def _to_dev(self, a, dtype=None):
@@ -68,30 +69,49 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         return t.to(self.device, non_blocking=True).contiguous()
 
     # -- reference API ---------------------------------------------------------------------------
+    def _stage_chunk(self, batches, choose, lo, hi, stream):
+        """Issue the host->device copies of envs [lo, hi) on ``stream`` (no-ops for tensors already on the device)."""
+        K_b, rgb1_b, m1_b, E1_b, rgb2_b, m2_b, E2_b = batches
+        with torch.cuda.stream(stream):
+            t = dict(K=self._to_dev(K_b[lo:hi], torch.float64), E1=self._to_dev(E1_b[lo:hi], torch.float64),
+                     E2=self._to_dev(E2_b[lo:hi], torch.float64), rgb1=self._to_dev(rgb1_b[lo:hi]),
+                     rgb2=self._to_dev(rgb2_b[lo:hi]), m1=self._to_dev(m1_b[lo:hi]), m2=self._to_dev(m2_b[lo:hi]))
+            if t["rgb1"].dtype not in (torch.float32, torch.float64):
+                t["rgb1"], t["rgb2"] = t["rgb1"].float(), t["rgb2"].float()
+            t["c1"] = t["c2"] = None
+            if choose is not None:
+                t["c1"] = self._to_dev(choose[0][lo:hi], torch.int32)
+                t["c2"] = self._to_dev(choose[1][lo:hi], torch.int32)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return t, ev
+
     def estimate(self, camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
                  rgb2_batch, view2_mask_batch, view2_extrinsic_batch, choose=None, return_tensor=False):
         eng = self.estimator
         N = len(camera_intrinsic_batch)
         out = torch.empty((N, 8, 3), dtype=torch.float64, device=self.device)
         self._calls += 1
+        batches = (camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
+                   rgb2_batch, view2_mask_batch, view2_extrinsic_batch)
         with torch.cuda.device(self.device):
-            for lo in range(0, N, eng.E):
-                hi = min(N, lo + eng.E)
-                K = self._to_dev(camera_intrinsic_batch[lo:hi], torch.float64)
-                E1 = self._to_dev(view1_extrinsic_batch[lo:hi], torch.float64)
-                E2 = self._to_dev(view2_extrinsic_batch[lo:hi], torch.float64)
-                rgb1 = self._to_dev(rgb1_batch[lo:hi])
-                rgb2 = self._to_dev(rgb2_batch[lo:hi])
-                m1 = self._to_dev(view1_mask_batch[lo:hi])
-                m2 = self._to_dev(view2_mask_batch[lo:hi])
-                if rgb1.dtype not in (torch.float32, torch.float64):
-                    rgb1, rgb2 = rgb1.float(), rgb2.float()
-                c1 = c2 = None
-                if choose is not None:
-                    c1 = self._to_dev(choose[0][lo:hi], torch.int32)
-                    c2 = self._to_dev(choose[1][lo:hi], torch.int32)
-                box = eng.run_chunk(K, rgb1, m1, E1, rgb2, m2, E2, seed=self._seed + 7919 * self._calls + lo,
-                                    choose1=c1, choose2=c2)
+            compute = torch.cuda.current_stream(self.device)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            copy = self._copy_stream
+            copy.wait_stream(compute)
+            bounds = [(lo, min(N, lo + eng.E)) for lo in range(0, N, eng.E)]
+            nxt = self._stage_chunk(batches, choose, *bounds[0], copy) if bounds else None
+            for i, (lo, hi) in enumerate(bounds):
+                t, ev = nxt
+                compute.wait_event(ev)
+                for v in t.values():          # allocated on the copy stream, consumed on the compute stream
+                    if isinstance(v, torch.Tensor) and v.is_cuda:
+                        v.record_stream(compute)
+                # the next chunk's upload overlaps this chunk's kernels
+                nxt = self._stage_chunk(batches, choose, *bounds[i + 1], copy) if i + 1 < len(bounds) else None
+                box = eng.run_chunk(t["K"], t["rgb1"], t["m1"], t["E1"], t["rgb2"], t["m2"], t["E2"],
+                                    seed=self._seed + 7919 * self._calls + lo, choose1=t["c1"], choose2=t["c2"])
                 out[lo:hi].copy_(box)
             if return_tensor:
                 return out
