@@ -145,6 +145,12 @@ ADP_API int adp_fit(const float* nocs, const float* depth, const int32_t* choose
             const double* E, const uint8_t* valid, double* bbox, double* scale, double* trans, float* scratch, int B, int P,
             int S, void* stream);
 
+/* --- pose fit, branch B: align.py:44-102 (RANSAC + Umeyama), interface_v5.py:322-338 --------------------------
+ * rand_idx: [B,128,5] sample indices (NULL = counter-based hash of `seed`); rot [B,9], trans [B,3], scale [B] optional. */
+ADP_API int adp_fit_umeyama(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const double* E,
+                    const uint8_t* valid, const int32_t* rand_idx, uint32_t seed, double* bbox, double* scale, double* rot,
+                    double* trans, int B, int P, int S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,7 @@ SIGNATURES = {
     "adp_decode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DecodeWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp,
                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_fit_umeyama": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }
 
 _lib = None

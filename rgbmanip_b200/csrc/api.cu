@@ -38,6 +38,9 @@ int fit_run(const float* nocs, const float* depth, const int* choose, const doub
             const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, float* scratch, int B, int P, int S,
             cudaStream_t stream);
 
+int fit_umeyama_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const double* E, const uint8_t* valid,
+                    const int* rand_idx, uint32_t seed, double* bbox, double* scale_out, double* rot_out, double* trans_out, int B,
+                    int P, int S, cudaStream_t stream);
 struct Conv0Plan;
 Conv0Plan* conv0_alloc();
 void conv0_release(Conv0Plan* p);
@@ -230,6 +233,14 @@ int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const 
     ADP_CHECK_ARG(nocs && depth && choose && Kp && R && E && bbox && scratch, "null pointer");
     g_launches += 1;
     return fit_run(nocs, depth, choose, Kp, R, E, valid, bbox, scale, trans, scratch, B, P, S, (cudaStream_t)stream);
+}
+
+int adp_fit_umeyama(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const double* E,
+                    const uint8_t* valid, const int32_t* rand_idx, uint32_t seed, double* bbox, double* scale, double* rot,
+                    double* trans, int B, int P, int S, void* stream) {
+    ADP_CHECK_ARG(nocs && depth && choose && Kp && E && bbox, "null pointer");
+    g_launches += 1;
+    return fit_umeyama_run(nocs, depth, choose, Kp, E, valid, rand_idx, seed, bbox, scale, rot, trans, B, P, S, (cudaStream_t)stream);
 }
 
 }  // extern "C"

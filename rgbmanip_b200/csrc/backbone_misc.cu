@@ -161,24 +161,27 @@ __device__ __forceinline__ float prior_at(const float* __restrict__ pr, int bins
     return (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
 }
 
-__global__ void psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* __restrict__ f_lo,
-                                     const float* __restrict__ priors, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
-                                     int B, int H, int W, int C) {
+// one block = one output row of one frame; the frame's 50 x 128 prior table sits in shared memory
+__global__ void __launch_bounds__(256)
+psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* __restrict__ f_lo, const float* __restrict__ priors,
+                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int H, int W, int C) {
+    __shared__ __align__(16) float spr[50 * 128];
     const int Ho = 2 * H, Wo = 2 * W, Ct = C + 512, C8 = Ct >> 3;
-    const size_t total = (size_t)B * Ho * Wo * C8;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C8) * 8;
-        size_t t = i / C8;
-        const int X = (int)(t % Wo); t /= Wo;
-        const int Y = (int)(t % Ho);
-        const int b = (int)(t / Ho);
-        int y0, y1, x0, x1;
-        float wy, wx;
-        lin_coord(Y, H, Ho, &y0, &y1, &wy);
+    const int b = blockIdx.y, Y = blockIdx.x;
+    for (int i = threadIdx.x; i < 50 * 128 / 4; i += blockDim.x)
+        reinterpret_cast<float4*>(spr)[i] = __ldg(reinterpret_cast<const float4*>(priors + (size_t)b * 50 * 128) + i);
+    __syncthreads();
+    int y0, y1;
+    float wy;
+    lin_coord(Y, H, Ho, &y0, &y1, &wy);
+    const size_t base = (size_t)b * H * W;
+    for (int it = threadIdx.x; it < Wo * C8; it += blockDim.x) {
+        const int X = it / C8, c = (it - X * C8) * 8;
+        int x0, x1;
+        float wx;
         lin_coord(X, W, Wo, &x0, &x1, &wx);
         float v00[8], v01[8], v10[8], v11[8], o[8];
         if (c < C) {
-            const size_t base = (size_t)b * H * W;
             ld8(f_hi, f_lo, (base + (size_t)y0 * W + x0) * C + c, v00);
             ld8(f_hi, f_lo, (base + (size_t)y0 * W + x1) * C + c, v01);
             ld8(f_hi, f_lo, (base + (size_t)y1 * W + x0) * C + c, v10);
@@ -187,7 +190,7 @@ __global__ void psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* 
             const int s = (c - C) / 128, n0 = (c - C) % 128;
             const int bins = s == 0 ? 1 : s == 1 ? 2 : s == 2 ? 3 : 6;
             const int off = s == 0 ? 0 : s == 1 ? 1 : s == 2 ? 5 : 14;
-            const float* pr = priors + ((size_t)b * 50 + off) * 128 + n0;
+            const float* pr = spr + off * 128 + n0;
             // prior map value at the four (H x W)-grid corners: each is itself a bilinear read of the bins x bins map
             const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
             int py0[2], py1[2], px0[2], px1[2];
@@ -210,8 +213,8 @@ __global__ void psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* 
                     float* d = dst[qy * 2 + qx];
 #pragma unroll
                     for (int j = 0; j < 8; j += 4) {
-                        const float4 p00 = __ldg(reinterpret_cast<const float4*>(a00 + j)), p01 = __ldg(reinterpret_cast<const float4*>(a01 + j));
-                        const float4 p10 = __ldg(reinterpret_cast<const float4*>(a10 + j)), p11 = __ldg(reinterpret_cast<const float4*>(a11 + j));
+                        const float4 p00 = *reinterpret_cast<const float4*>(a00 + j), p01 = *reinterpret_cast<const float4*>(a01 + j);
+                        const float4 p10 = *reinterpret_cast<const float4*>(a10 + j), p11 = *reinterpret_cast<const float4*>(a11 + j);
                         d[j + 0] = (1.f - wy_) * ((1.f - wx_) * p00.x + wx_ * p01.x) + wy_ * ((1.f - wx_) * p10.x + wx_ * p11.x);
                         d[j + 1] = (1.f - wy_) * ((1.f - wx_) * p00.y + wx_ * p01.y) + wy_ * ((1.f - wx_) * p10.y + wx_ * p11.y);
                         d[j + 2] = (1.f - wy_) * ((1.f - wx_) * p00.z + wx_ * p01.z) + wy_ * ((1.f - wx_) * p10.z + wx_ * p11.z);
@@ -222,16 +225,14 @@ __global__ void psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* 
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             o[j] = (1.f - wy) * ((1.f - wx) * v00[j] + wx * v01[j]) + wy * ((1.f - wx) * v10[j] + wx * v11[j]);
-        st8(out_hi, out_lo, i * 8, o);
+        st8(out_hi, out_lo, (((size_t)b * Ho + Y) * Wo + X) * Ct + c, o);
     }
 }
 
 int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream) {
     ADP_CHECK_ARG(out.C == feat.C + 512 && out.H == 2 * feat.H && out.W == 2 * feat.W && feat.C % 8 == 0, "psp concat shapes");
-    size_t total = (size_t)batch * out.H * out.W * (out.C / 8);
-    if (total == 0) return ADP_OK;
-    int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    psp_concat_up_kernel<<<grid, 256, 0, stream>>>(feat.hi, feat.lo, priors, out.hi, out.lo, batch, feat.H, feat.W, feat.C);
+    if (batch == 0) return ADP_OK;
+    psp_concat_up_kernel<<<dim3(out.H, batch), 256, 0, stream>>>(feat.hi, feat.lo, priors, out.hi, out.lo, feat.H, feat.W, feat.C);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

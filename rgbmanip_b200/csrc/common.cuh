@@ -111,6 +111,28 @@ __device__ __forceinline__ void st8_16(bf16* __restrict__ hi, bf16* __restrict__
     if (lo && !f16) *reinterpret_cast<uint4*>(lo + i) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// general 4x4 inverse (Gauss-Jordan with partial pivoting), fp64: np.linalg.inv(view1_extrinsic) at interface_v5.py:369
+__device__ inline bool invert4x4(const double* m, double* inv) {
+    double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) { a[r][c] = m[4 * r + c]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+        double best = fabs(a[col][col]);
+        for (int r = col + 1; r < 4; ++r) if (fabs(a[r][col]) > best) { best = fabs(a[r][col]); piv = r; }
+        if (!(best > 0.0)) return false;
+        if (piv != col) for (int c = 0; c < 8; ++c) { double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
+        const double d = 1.0 / a[col][col];
+        for (int c = 0; c < 8; ++c) a[col][c] *= d;
+        for (int r = 0; r < 4; ++r) if (r != col) {
+            const double f = a[r][col];
+            if (f != 0.0) for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
+        }
+    }
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) inv[4 * r + c] = a[r][4 + c];
+    return true;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace adp

@@ -83,6 +83,7 @@ struct DecodeArgs {
     float* dbg_fused;        // [B,P,32] or nullptr
     int B, S, D, P;
     int x11_f16;             // x11 holds IEEE half instead of bf16
+    int regress;             // 0: stop after NOCS + depth (no pose heads: direct_regression = False)
 };
 
 __global__ void __launch_bounds__(DEC_THREADS)
@@ -215,6 +216,7 @@ decode_points_kernel(const DecodeArgs a, const DecodeWeights w) {
         a.nocs[((size_t)b * a.P + p0 + r) * 3 + n] = t;
     }
     __syncthreads();
+    if (!a.regress) return;
     // ---- (e) nocs_pts_mlp 3 -> 32 -> 64, concat with fused (B[:, 0:32]) -> pose_mlp1 96 -> 128 -> 128
     mlp_layer<32>(bufA, 3, w.np0_w, w.np0_b, bufA, 32, true);           // A[:, 32:64]
     __syncthreads();
@@ -355,7 +357,7 @@ int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, 
     DecodeArgs a;
     a.feat_ref = feat_ref; a.feat_src = feat_src; a.Mw = Mw; a.depths = depths; a.x11 = reinterpret_cast<const bf16*>(x11);
     a.choose = choose; a.valid = valid; a.nocs = nocs; a.depth = depth; a.pf1 = pf1; a.gsum = gsum;
-    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16;
+    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16; a.regress = regress_pose;
     return decode_run(a, w, psum, R, r6, regress_pose, stream);
 }
 

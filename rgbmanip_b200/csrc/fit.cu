@@ -40,27 +40,6 @@ __device__ __forceinline__ float pair_ratio(const float* cx, const float* cy, co
     return (dn > 0.01f && dc < 0.3f) ? dc / dn : -1.f;
 }
 
-__device__ bool invert4x4(const double* m, double* inv) {
-    double a[4][8];
-    for (int r = 0; r < 4; ++r)
-        for (int c = 0; c < 4; ++c) { a[r][c] = m[4 * r + c]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
-    for (int col = 0; col < 4; ++col) {
-        int piv = col;
-        double best = fabs(a[col][col]);
-        for (int r = col + 1; r < 4; ++r) if (fabs(a[r][col]) > best) { best = fabs(a[r][col]); piv = r; }
-        if (!(best > 0.0)) return false;
-        if (piv != col) for (int c = 0; c < 8; ++c) { double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
-        const double d = 1.0 / a[col][col];
-        for (int c = 0; c < 8; ++c) a[col][c] *= d;
-        for (int r = 0; r < 4; ++r) if (r != col) {
-            const double f = a[r][col];
-            if (f != 0.0) for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
-        }
-    }
-    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) inv[4 * r + c] = a[r][4 + c];
-    return true;
-}
-
 // warp-aggregated shared-memory histogram increment (most keys of a pass share a handful of bins)
 __device__ __forceinline__ void hist_add(unsigned int* hist, unsigned int bin, bool active) {
     const unsigned int act = __ballot_sync(0xffffffffu, active);

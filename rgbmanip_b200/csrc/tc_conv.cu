@@ -241,8 +241,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             }
                         }
                         if (p.out_f32) {
+                            if (nvalid == CH && (p.Cout & 3) == 0) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
+                                for (int j = 0; j < CH; j += 4)
+                                    *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
+                            }
                         }
                         if (p.out_hi) {
 #pragma unroll

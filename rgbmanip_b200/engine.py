@@ -393,6 +393,7 @@ class Engine:
         self.scale = torch.zeros(E, dtype=torch.float64, device=dev)
         self.trans = torch.zeros((E, 3), dtype=torch.float64, device=dev)
         self.fit_scratch = torch.zeros((E, P * (P - 1) // 2), dtype=torch.float32, device=dev)
+        self.rot64 = torch.zeros((E, 9), dtype=torch.float64, device=dev)
 
     # ------------------------------------------------------------------ stages
     @staticmethod
@@ -419,7 +420,7 @@ class Engine:
             L.ptr(self.bbox_ws[o:]), L.ptr(self.win[o:]), L.ptr(self.Kp[o:]), L.ptr(self.valid[o:]), L.ptr(self.crops[o:]),
             L.ptr(self.choose[o:]), L.ptr(self.counts[o:]), self.stream), "preprocess")
 
-    def stereo(self, n, E1, E2, mark=None):
+    def stereo(self, n, E1, E2, mark=None, ransac_idx=None, seed=0):
         """Frames [0,n) are view 1 and [E,E+n) view 2 of envs [0,n).  E1/E2 [n,4,4] f64 device tensors.
         ``mark(name)`` (optional) is called after each stage, e.g. to record CUDA events."""
         E, S, D, P = self.E, self.S, N_DEPTH, self.P
@@ -439,24 +440,27 @@ class Engine:
                                L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
                                L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.vol_f16, st), "decode")
         mark("decode")
-        L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
-                            L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans), L.ptr(self.fit_scratch),
-                            n, P, S, st), "fit")
+        if self.regress_pose:
+            L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
+                                L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans),
+                                L.ptr(self.fit_scratch), n, P, S, st), "fit")
+        else:   # direct_regression = False, use_depth = True: RANSAC + Umeyama (interface_v5.py:322-338)
+            L.check(lib.adp_fit_umeyama(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(E1),
+                                        L.ptr(self.valid_env), L.ptr(ransac_idx), seed & 0xFFFFFFFF, L.ptr(self.bbox),
+                                        L.ptr(self.scale), L.ptr(self.rot64), L.ptr(self.trans), n, P, S, st), "fit_umeyama")
         mark("fit")
 
-    def run_chunk(self, K, rgb1, mask1, E1, rgb2, mask2, E2, seed=0, choose1=None, choose2=None):
+    def run_chunk(self, K, rgb1, mask1, E1, rgb2, mask2, E2, seed=0, choose1=None, choose2=None, ransac_idx=None):
         """Device tensors for n <= max_envs environments -> self.bbox[:n] ([n,8,3] f64, world frame)."""
         n = K.shape[0]
         assert n <= self.E
-        if not self.regress_pose:
-            raise NotImplementedError("direct_regression=False (RANSAC/Umeyama, PnP branches) is not on the device path yet")
         self.preprocess(0, rgb1, mask1, K, n, seed, choose1)
         self.preprocess(1, rgb2, mask2, K, n, seed, choose2)
         if n == self.E:
             self.run_backbone(self.F)
         else:   # the two views are not adjacent in the frame buffers: run them one after the other
             self._backbone_partial(n)
-        self.stereo(n, E1, E2)
+        self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed)
         return self.bbox[:n]
 
     def _backbone_partial(self, n):

@@ -46,6 +46,9 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         super().__init__(env, cfg, logger)
         self.cfg = cfg
         regress = bool(cfg.get("direct_regression", True))
+        if not regress and not cfg.get("use_depth", True):
+            # branch C (interface_v5.py:339-349) lives inside OpenCV (triangulatePoints / solvePnPRansac): parity unpinned
+            raise NotImplementedError("direct_regression=False with use_depth=False (NOCS matching + cv2 PnP) is not supported")
         if state_dict is None:
             if cfg.get("load", False):
                 # same failure mode as the reference: a missing checkpoint raises from torch.load (interface_v5.py:55-56)
@@ -87,7 +90,7 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         return t, ev
 
     def estimate(self, camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
-                 rgb2_batch, view2_mask_batch, view2_extrinsic_batch, choose=None, return_tensor=False):
+                 rgb2_batch, view2_mask_batch, view2_extrinsic_batch, choose=None, return_tensor=False, ransac_idx=None):
         eng = self.estimator
         N = len(camera_intrinsic_batch)
         out = torch.empty((N, 8, 3), dtype=torch.float64, device=self.device)
@@ -110,8 +113,11 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
                         v.record_stream(compute)
                 # the next chunk's upload overlaps this chunk's kernels
                 nxt = self._stage_chunk(batches, choose, *bounds[i + 1], copy) if i + 1 < len(bounds) else None
+                ridx = None
+                if ransac_idx is not None:      # [N,128,5] sample indices of the RANSAC fit (branch B parity replay)
+                    ridx = self._to_dev(ransac_idx[lo:hi], torch.int32)
                 box = eng.run_chunk(t["K"], t["rgb1"], t["m1"], t["E1"], t["rgb2"], t["m2"], t["E2"],
-                                    seed=self._seed + 7919 * self._calls + lo, choose1=t["c1"], choose2=t["c2"])
+                                    seed=self._seed + 7919 * self._calls + lo, choose1=t["c1"], choose2=t["c2"], ransac_idx=ridx)
                 out[lo:hi].copy_(box)
             if return_tensor:
                 return out

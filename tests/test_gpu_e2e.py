@@ -130,3 +130,45 @@ def test_four_task_configs_share_the_path():
         est.estimator.close()
     for o in outs[1:]:
         np.testing.assert_allclose(o, outs[0], rtol=0, atol=1e-5)   # same weights/seed; only atomicAdd order differs
+
+
+def test_branch_b_matches_reference_golden(golden_dir):
+    """direct_regression=False, use_depth=True (RANSAC + Umeyama fit on the device) against the reference's boxes.
+    The reference consumes the global numpy stream (pixel subsets and RANSAC draws interleaved, early exits included);
+    the CPU oracle replays it here to recover the exact draws, which are then handed to the device path."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200.estimator import AdaPoseEstimator_v5
+    g = np.load(os.path.join(golden_dir, "branch_b.npz"))
+    sd = weights.init_state_dict(0, regress_pose=False)
+    cfg = {"img_size": 224, "direct_regression": False, "use_depth": True, "load": False}
+    batch = synth.make_batch(2, seed=3, special=False)
+
+    class Recorder:                      # np.random facade that logs the randint draws
+        def __init__(self):
+            self.draws = []
+        def shuffle(self, a):
+            np.random.shuffle(a)
+        def randint(self, n, size):
+            r = np.random.randint(n, size=size)
+            self.draws.append(r)
+            return r
+
+    np.random.seed(5)
+    chooses, tables = [], []
+    for e in range(2):
+        rec = Recorder()
+        d = {}
+        O.predict(sd, cfg, batch.K[e], batch.rgb1[e], batch.mask1[e], batch.E1[e], batch.rgb2[e], batch.mask2[e], batch.E2[e],
+                  rng=rec, details=d)
+        tab = np.zeros((128, 5), np.int32)
+        tab[:len(rec.draws)] = np.stack(rec.draws)
+        chooses.append((d["choose1"], d["choose2"]))
+        tables.append(tab)
+    est = AdaPoseEstimator_v5(None, cfg, None, state_dict=sd, max_envs=2)
+    choose = (np.stack([c[0] for c in chooses]).astype(np.int32), np.stack([c[1] for c in chooses]).astype(np.int32))
+    boxes = est.estimate(*batch.args(), choose=choose, ransac_idx=np.stack(tables))
+    for e in range(2):
+        px, deg, mm, cmm = O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e], min_z=MIN_Z)
+        assert px < TOL_PX and deg < TOL_DEG and mm < TOL_MM and cmm < TOL_MM, (e, px, deg, mm, cmm)
+    est.estimator.close()

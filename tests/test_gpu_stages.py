@@ -496,3 +496,49 @@ def test_tc_and_direct_backbones_agree(G):
         outs.append(eng.feat[:1].cpu())
         eng.close()
     assert G.rel_err(outs[0], outs[1]) < 2e-3
+
+
+def test_fit_umeyama_ransac_matches_oracle(G):
+    """Branch B (align.py:44-102): same 128 x 5 sample table on both sides -> same similarity transform and box."""
+    lib = L.load()
+    dev = G.DEV
+    rng = _rng(44)
+    B, P = 3, 1024
+    nocs = (rng.random((B, P, 3)).astype(np.float32) - 0.5)
+    Kp = np.tile(np.array([[400.0, 0, 112.0], [0, 400.0, 112.0], [0, 0, 1]]).reshape(1, 9), (B, 1))
+    choose = np.zeros((B, P), np.int32)
+    depth = np.zeros((B, P), np.float32)
+    E = np.tile(np.eye(4).reshape(1, 16), (B, 1))
+    E[1, 3] = 0.2
+    for b in range(B):
+        Rt = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        if np.linalg.det(Rt) < 0:
+            Rt[:, 0] *= -1
+        cam = 0.2 * (Rt @ nocs[b].T.astype(np.float64)).T + np.array([0.02, -0.01, 0.8])
+        px = np.clip(np.rint(400.0 * cam[:, 0] / cam[:, 2] + 112.0), 0, 223).astype(np.int32)    # the pixel the point lands on
+        py = np.clip(np.rint(400.0 * cam[:, 1] / cam[:, 2] + 112.0), 0, 223).astype(np.int32)
+        choose[b] = py * 224 + px
+        depth[b] = (cam[:, 2] + 0.002 * rng.standard_normal(P)).astype(np.float32)
+    depth[2, ::2] += 0.3                                                               # half the points are gross outliers
+    depth[1, :] = rng.random(P).astype(np.float32) + 0.3                                # env 1: no consistent model at all
+    ridx = rng.integers(0, P, size=(B, 128, 5)).astype(np.int32)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    bbox = torch.zeros((B, 8, 3), dtype=torch.float64, device=dev)
+    scale = torch.zeros(B, dtype=torch.float64, device=dev)
+    rot = torch.zeros((B, 9), dtype=torch.float64, device=dev)
+    trans = torch.zeros((B, 3), dtype=torch.float64, device=dev)
+    args = [t(nocs), t(depth), t(choose), t(Kp), t(E), None, t(ridx)]
+    L.check(lib.adp_fit_umeyama(*[L.ptr(a) for a in args], 0, L.ptr(bbox), L.ptr(scale), L.ptr(rot), L.ptr(trans), B, P, 224,
+                                G.stream()), "fit_umeyama")
+    torch.cuda.synchronize()
+    for b in range(B):
+        cam = O.back_project(depth[b], choose[b], Kp[b].reshape(3, 3))
+        s, R, tr, _ = O.similarity_ransac(nocs[b], cam, rand_idx=ridx[b])
+        if s is None:                                   # inlier ratio < 0.1 -> the reference returns None -> sentinel box
+            np.testing.assert_array_equal(bbox[b].cpu().numpy(), O.DEFAULT_BBOX)
+            continue
+        assert abs(float(scale[b]) - s) / s < 1e-9
+        np.testing.assert_allclose(rot[b].cpu().numpy().reshape(3, 3), R, atol=1e-9)
+        np.testing.assert_allclose(trans[b].cpu().numpy(), tr, atol=1e-9)
+        want = O.box_from_fit(nocs[b], s, R, tr, E[b].reshape(4, 4))
+        np.testing.assert_allclose(bbox[b].cpu().numpy(), want, rtol=0, atol=1e-7)
