@@ -30,14 +30,16 @@ __device__ __forceinline__ uint32_t make_idesc(int f16) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
-template <int BN, int KC>
+// FUSED: split-precision layers whose tiles are L2-bound (small N) keep A_hi, A_lo, W_hi, W_lo of one (tap, K chunk) in
+// the same stage and issue the three MMA groups (hi*hi, lo*hi, hi*lo) from it: 2x the bytes of a single pass instead of 3x.
+template <int BN, int KC, bool FUSED = false>
 struct TcCfg {
     static constexpr int A_BYTES = 128 * KC * 2;
     static constexpr int B_BYTES = BN * KC * 2;
     static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
-    static constexpr int STAGE_BYTES = A_BYTES + B_PAD;
+    static constexpr int STAGE_BYTES = (FUSED ? 2 : 1) * (A_BYTES + B_PAD);
     // small-N layers are latency bound per tile: fewer stages -> several CTAs per SM overlap their pipelines
-    static constexpr int CTAS_PER_SM = (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
+    static constexpr int CTAS_PER_SM = FUSED ? (BN <= 64 ? 2 : 1) : (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
     static constexpr int SMEM_BUDGET = 196608 / CTAS_PER_SM;
     static constexpr int STAGES = (STAGE_BYTES * 6 <= SMEM_BUDGET) ? 6 : (SMEM_BUDGET / STAGE_BYTES);
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns per accumulator stage
@@ -45,12 +47,12 @@ struct TcCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int KC>
-__global__ void __launch_bounds__(kTcThreads, TcCfg<BN, KC>::CTAS_PER_SM)
+template <int BN, int KC, bool FUSED>
+__global__ void __launch_bounds__(kTcThreads, TcCfg<BN, KC, FUSED>::CTAS_PER_SM)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                const TcConvParams p, int batch) {
-    using Cfg = TcCfg<BN, KC>;
+    using Cfg = TcCfg<BN, KC, FUSED>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,7 +96,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     const int taps = p.ntaps;
-    const int k_iters = p.npass * taps * p.kchunks;
+    const int npass_loop = FUSED ? 1 : p.npass;
+    const int k_iters = npass_loop * taps * p.kchunks;
     const int tiles_per_img = p.D * p.tiles_y * p.tiles_x * p.tiles_n;
     const int total_tiles = batch * tiles_per_img;
     const int rows_valid = p.TW * p.TH;
@@ -104,7 +107,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(rows_valid * KC * 2 + Cfg::B_BYTES);
+            const uint32_t tx_bytes = (uint32_t)((FUSED ? 2 : 1) * (rows_valid * KC * 2 + Cfg::B_BYTES));
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int t = tile;
                 const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -113,7 +116,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int d = t % p.D;
                 const int b = t / p.D;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
-                for (int pass = 0; pass < p.npass; ++pass) {
+                for (int pass = 0; pass < npass_loop; ++pass) {
                     const CUtensorMap* mapA = (pass == 1) ? &tmA_lo : &tmA_hi;
                     const CUtensorMap* mapW = (pass == 2) ? &tmW_lo : &tmW_hi;
                     for (int tap = 0; tap < taps; ++tap) {
@@ -123,8 +126,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
                             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                             ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-                            ptx::tma_load_5d(mapA, full_bar(stage), sa, kc * KC, cx, cy, cz, b);
-                            ptx::tma_load_3d(mapW, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, n0, wt);
+                            if (FUSED) {   // [A_hi | A_lo | W_hi | W_lo]
+                                ptx::tma_load_5d(&tmA_hi, full_bar(stage), sa, kc * KC, cx, cy, cz, b);
+                                ptx::tma_load_5d(&tmA_lo, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, cx, cy, cz, b);
+                                ptx::tma_load_3d(&tmW_hi, full_bar(stage), sa + 2 * Cfg::A_BYTES, kc * KC, n0, wt);
+                                ptx::tma_load_3d(&tmW_lo, full_bar(stage), sa + 2 * Cfg::A_BYTES + Cfg::B_PAD, kc * KC, n0, wt);
+                            } else {
+                                ptx::tma_load_5d(mapA, full_bar(stage), sa, kc * KC, cx, cy, cz, b);
+                                ptx::tma_load_3d(mapW, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, n0, wt);
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -147,13 +157,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 ptx::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint64_t adesc = make_smem_desc<KC>(sa);
-                    const uint64_t bdesc = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+                    if (FUSED) {
+                        const uint64_t ah = make_smem_desc<KC>(sa), al = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+                        const uint64_t wh = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES);
+                        const uint64_t wl = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES + Cfg::B_PAD);
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the >>4 address field
-                        ptx::umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                       (it > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < KC / 16; ++k) {
+                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            ptx::umma_bf16(tmem_d, al + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, 1u);
+                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u);
+                        }
+                    } else {
+                        const uint64_t adesc = make_smem_desc<KC>(sa);
+                        const uint64_t bdesc = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k) {
+                            // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the >>4 address field
+                            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                           (it > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     ptx::umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
                     if (it == k_iters - 1) ptx::umma_commit(tfull_bar(as));   // accumulator complete
@@ -283,6 +305,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // host side
 // ------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static bool g_fuse_128 = false;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_shared = nullptr;   // for the other tcgen05 translation units
 
 int tc_conv_init_driver() {
@@ -401,6 +424,7 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     p.npass = npass;
     L->BN = BN;
     L->KC = KC;
+    L->fused = (npass == 3) && (BN <= 64 || (BN == 128 && g_fuse_128));
     ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, w_taps, KC, BN, f16));
@@ -409,12 +433,12 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     return ADP_OK;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, bool FUSED = false>
 static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
-    using Cfg = TcCfg<BN, KC>;
+    using Cfg = TcCfg<BN, KC, FUSED>;
     static bool attr_set = false;
     if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        ADP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, KC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const TcConvParams& p = L->p;
@@ -422,7 +446,7 @@ static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_
     const long long slots = (long long)num_sms * Cfg::CTAS_PER_SM;
     int grid = (int)(total < slots ? total : slots);
     if (grid <= 0) return ADP_OK;
-    tc_conv_kernel<BN, KC><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(L->tmA_hi, L->tmA_lo, L->tmW_hi, L->tmW_lo, p, batch);
+    tc_conv_kernel<BN, KC, FUSED><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(L->tmA_hi, L->tmA_lo, L->tmW_hi, L->tmW_lo, p, batch);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }
@@ -430,6 +454,12 @@ static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_
 int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
     ADP_CHECK_ARG(L->ready, "layer not planned");
     ADP_CHECK_ARG(batch <= L->p.B, "batch exceeds planned capacity");
+    if (L->p.npass == 3 && L->fused) {   // split precision, small N: one stage carries hi and lo operands
+        if (L->BN == 64 && L->KC == 64) return launch_impl<64, 64, true>(L, batch, num_sms, stream);
+        if (L->BN == 32 && L->KC == 64) return launch_impl<32, 64, true>(L, batch, num_sms, stream);
+        if (L->BN == 64 && L->KC == 16) return launch_impl<64, 16, true>(L, batch, num_sms, stream);
+        if (L->BN == 128 && L->KC == 64) return launch_impl<128, 64, true>(L, batch, num_sms, stream);
+    }
 #define ADP_TC_CASE(bn, kc) if (L->BN == bn && L->KC == kc) return launch_impl<bn, kc>(L, batch, num_sms, stream)
     ADP_TC_CASE(256, 64); ADP_TC_CASE(128, 64); ADP_TC_CASE(64, 64); ADP_TC_CASE(32, 64); ADP_TC_CASE(16, 64);
     ADP_TC_CASE(64, 32); ADP_TC_CASE(32, 32); ADP_TC_CASE(16, 32);

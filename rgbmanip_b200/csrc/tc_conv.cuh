@@ -56,6 +56,7 @@ struct TcConvLayer {
     TcConvParams p;
     int BN;
     int KC;                  // channels per K step (64 -> SWIZZLE_128B, 32 -> 64B, 16 -> 32B)
+    bool fused = false;      // split precision with hi and lo operands sharing a pipeline stage
     bool ready = false;
 };
 
