@@ -3,6 +3,7 @@
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace adp {
 
@@ -305,7 +306,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // host side
 // ------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-static bool g_fuse_128 = false;
+static int g_fuse_max_bn = -1;   // split-precision layers with BN <= this share hi/lo stages (ADP_FUSE_MAXBN overrides)
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_shared = nullptr;   // for the other tcgen05 translation units
 
 int tc_conv_init_driver() {
@@ -424,7 +425,11 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     p.npass = npass;
     L->BN = BN;
     L->KC = KC;
-    L->fused = (npass == 3) && (BN <= 64 || (BN == 128 && g_fuse_128));
+    if (g_fuse_max_bn < 0) {
+        const char* e = getenv("ADP_FUSE_MAXBN");
+        g_fuse_max_bn = e ? atoi(e) : 256;
+    }
+    L->fused = (npass == 3) && (BN <= g_fuse_max_bn) && KC >= 16;
     ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, w_taps, KC, BN, f16));
@@ -459,6 +464,7 @@ int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t st
         if (L->BN == 32 && L->KC == 64) return launch_impl<32, 64, true>(L, batch, num_sms, stream);
         if (L->BN == 64 && L->KC == 16) return launch_impl<64, 16, true>(L, batch, num_sms, stream);
         if (L->BN == 128 && L->KC == 64) return launch_impl<128, 64, true>(L, batch, num_sms, stream);
+        if (L->BN == 256 && L->KC == 64) return launch_impl<256, 64, true>(L, batch, num_sms, stream);
     }
 #define ADP_TC_CASE(bn, kc) if (L->BN == bn && L->KC == kc) return launch_impl<bn, kc>(L, batch, num_sms, stream)
     ADP_TC_CASE(256, 64); ADP_TC_CASE(128, 64); ADP_TC_CASE(64, 64); ADP_TC_CASE(32, 64); ADP_TC_CASE(16, 64);
