@@ -68,6 +68,7 @@ typedef struct adp_epilogue { /* y = act(scale * acc + bias [+ res]) [+ res]  ->
     void* out_hi;             /* bf16 or NULL */
     void* out_lo;
     float* out_f32;           /* fp32 or NULL */
+    void* out_h16;            /* optional extra IEEE-half copy of the output (feature map for the volume builder) or NULL */
 } adp_epilogue;
 
 typedef struct adp_direct_conv {   /* generic CUDA-core convolution (strided / tiny-channel / transposed layers) */
@@ -124,14 +125,24 @@ ADP_API int adp_conv0_plan_create(adp_conv0_plan** plan, const adp_act* vol, con
 ADP_API int adp_conv0_run(adp_conv0_plan* plan, int batch, int32_t* err_flag, void* stream);
 ADP_API void adp_conv0_free(adp_conv0_plan* plan);
 
+/* ConvTranspose3d(k3, s2, p1, op1) + folded BN + ReLU + skip (network_v5.py:217-258,274-278,287-289) with all 8 output
+ * parity classes in one tcgen05 kernel.  in [B,D,H,W,Cin] (Cin 16|32, single 16-bit plane), w 16-bit [27][pad16(Cout)][Cin],
+ * res [B,2D,2H,2W,res_cstride] or NULL, out [B,2D,2H,2W,Cout]. */
+typedef struct adp_tconv_plan adp_tconv_plan;
+ADP_API int adp_tconv_plan_create(adp_tconv_plan** plan, const adp_act* in, const void* w, int cout, const float* scale,
+                                  const float* bias, const void* res, int res_cstride, void* out, int num_sms);
+ADP_API int adp_tconv_run(adp_tconv_plan* plan, int batch, int32_t* err_flag, void* stream);
+ADP_API void adp_tconv_free(adp_tconv_plan* plan);
+
 /* --- stereo volume: network_v5.py:378-416,429 ---------------------------------------------------------------- */
 /* Mw[b] = {rot 3x3 row-major, trans 3} of P_src inv(P_ref), P = [K' E[:3,:]; 0 0 0 1] (interface_v5.py:264-270);
  * valid_env[b] = valid_ref[b] && valid_src[b] (an estimate needs both views, interface_v5.py:256-257). */
 ADP_API int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src,
                               float* Mw, const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B,
                               void* stream);
-ADP_API int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol,
-                     int B, int D, int H, int W, int C, int f16, void* stream);
+/* feat_*: [B,H,W,32] fp32, or IEEE half when feat_f16 != 0 */
+ADP_API int adp_build_volume(const void* feat_ref, const void* feat_src, const float* Mw, const float* depths, void* vol,
+                     int B, int D, int H, int W, int C, int f16, int feat_f16, void* stream);
 
 /* --- decode + heads: network_v5.py:432-465,486-499; rotation_utils.py:4-27 ----------------------------------- */
 ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,

@@ -32,7 +32,7 @@ class TcGeom(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("scale", vp), ("bias", vp), ("prelu", C.c_float), ("act", i32), ("res_after_act", i32),
-                ("res_hi", vp), ("res_lo", vp), ("res_cstride", i32), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp)]
+                ("res_hi", vp), ("res_lo", vp), ("res_cstride", i32), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp), ("out_h16", vp)]
 
 
 class DirectConv(C.Structure):
@@ -74,8 +74,11 @@ SIGNATURES = {
     "adp_conv0_plan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, vp, vp, C.c_int]),
     "adp_conv0_run": (C.c_int, [vp, C.c_int, vp, vp]),
     "adp_conv0_free": (None, [vp]),
+    "adp_tconv_plan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int]),
+    "adp_tconv_run": (C.c_int, [vp, C.c_int, vp, vp]),
+    "adp_tconv_free": (None, [vp]),
     "adp_warp_matrices": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
-    "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_decode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DecodeWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp,
                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),

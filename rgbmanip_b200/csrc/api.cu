@@ -30,8 +30,8 @@ int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t 
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
                    int S, int P, uint32_t seed, int choose_mode, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream);
-int build_volume(const float* f_ref, const float* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, int f16, cudaStream_t stream);
+int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
+                 int W, int C, int f16, int feat_f16, cudaStream_t stream);
 int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
                   const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream);
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
@@ -47,6 +47,13 @@ void conv0_release(Conv0Plan* p);
 int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const float* scale, const float* shift, uint16_t* out,
                int num_sms);
 int conv0_run(Conv0Plan* pl, int batch, int* err_flag, cudaStream_t stream);
+
+struct TconvPlan;
+TconvPlan* tconv_alloc();
+void tconv_release(TconvPlan* p);
+int tconv_plan(TconvPlan* pl, const Act& in, const bf16* w, int Cout, const float* scale, const float* bias, const bf16* res,
+               int res_cs, bf16* out, int num_sms);
+int tconv_run(TconvPlan* pl, int batch, int* err_flag, cudaStream_t stream);
 
 struct DecodeWeights;
 struct DecodeArgs;
@@ -120,6 +127,7 @@ int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, 
     p.res_cs = ep->res_cstride ? ep->res_cstride : cout;
     p.out_hi = reinterpret_cast<bf16*>(ep->out_hi); p.out_lo = reinterpret_cast<bf16*>(ep->out_lo);
     p.out_f32 = ep->out_f32;
+    p.out_h16 = reinterpret_cast<__half*>(ep->out_h16);
     pl->num_sms = num_sms > 0 ? num_sms : 148;
     *plan = pl;
     return ADP_OK;
@@ -197,17 +205,39 @@ int adp_conv0_run(adp_conv0_plan* plan, int batch, int32_t* err_flag, void* stre
 
 void adp_conv0_free(adp_conv0_plan* plan) { conv0_release(reinterpret_cast<Conv0Plan*>(plan)); }
 
+int adp_tconv_plan_create(adp_tconv_plan** plan, const adp_act* in, const void* w, int cout, const float* scale, const float* bias,
+                          const void* res, int res_cstride, void* out, int num_sms) {
+    ADP_CHECK_ARG(plan && in && w && scale && bias && out, "null pointer");
+    TconvPlan* pl = tconv_alloc();
+    int r = tconv_plan(pl, to_act(in), reinterpret_cast<const bf16*>(w), cout, scale, bias, reinterpret_cast<const bf16*>(res),
+                       res_cstride, reinterpret_cast<bf16*>(out), num_sms);
+    if (r != ADP_OK) {
+        tconv_release(pl);
+        return r;
+    }
+    *plan = reinterpret_cast<adp_tconv_plan*>(pl);
+    return ADP_OK;
+}
+
+int adp_tconv_run(adp_tconv_plan* plan, int batch, int32_t* err_flag, void* stream) {
+    ADP_CHECK_ARG(plan, "null plan");
+    g_launches += 1;
+    return tconv_run(reinterpret_cast<TconvPlan*>(plan), batch, err_flag, (cudaStream_t)stream);
+}
+
+void adp_tconv_free(adp_tconv_plan* plan) { tconv_release(reinterpret_cast<TconvPlan*>(plan)); }
+
 int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream) {
     ADP_CHECK_ARG(crops && out, "null pointer");
     g_launches += 1;
     return pack_s2d(crops, to_act(out), batch, S, (cudaStream_t)stream);
 }
 
-int adp_build_volume(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, void* vol, int B, int D,
-                     int H, int W, int C, int f16, void* stream) {
+int adp_build_volume(const void* feat_ref, const void* feat_src, const float* Mw, const float* depths, void* vol, int B, int D,
+                     int H, int W, int C, int f16, int feat_f16, void* stream) {
     ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && vol, "null pointer");
     g_launches += 1;
-    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, f16, (cudaStream_t)stream);
+    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, f16, feat_f16, (cudaStream_t)stream);
 }
 
 int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,

@@ -273,6 +273,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                                 for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
                             }
                         }
+                        if (p.out_h16) {
+#pragma unroll
+                            for (int j0 = 0; j0 < CH; j0 += 8) {
+                                if (vec_ok && j0 + 8 <= nvalid) st8_16(reinterpret_cast<bf16*>(p.out_h16), nullptr, o + j0, 1, v + j0);
+                                else {
+#pragma unroll
+                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) p.out_h16[o + j] = __float2half_rn(v[j]);
+                                }
+                            }
+                        }
                         if (p.out_hi) {
 #pragma unroll
                             for (int j0 = 0; j0 < CH; j0 += 8) {

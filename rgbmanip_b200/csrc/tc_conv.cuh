@@ -47,6 +47,7 @@ struct TcConvParams {
     bf16* out_hi;
     bf16* out_lo;
     float* out_f32;
+    __half* out_h16;         // optional extra fp16 copy
     int* err;                // device error flag (pipeline watchdog)
 };
 

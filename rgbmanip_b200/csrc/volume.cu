@@ -8,9 +8,26 @@
 
 namespace adp {
 
-// one thread = one voxel x 8 channels (C == 32 -> 4 threads per voxel, 128 B coalesced per corner)
+// 8 consecutive feature channels as fp32, from an fp32 or an fp16 feature map
+template <typename FT> __device__ __forceinline__ void ld_feat8(const FT* p, float* v);
+template <> __device__ __forceinline__ void ld_feat8<float>(const float* p, float* v) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld_feat8<__half>(const __half* p, float* v) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[2 * q] = __half2float(__ushort_as_half((unsigned short)(w[q] & 0xffffu)));
+        v[2 * q + 1] = __half2float(__ushort_as_half((unsigned short)(w[q] >> 16)));
+    }
+}
+
+// one thread = one voxel x 8 channels (C == 32 -> 4 threads per voxel, coalesced 64/128 B per corner)
+template <typename FT>
 __global__ void __launch_bounds__(256)
-build_volume_kernel(const float* __restrict__ f_ref, const float* __restrict__ f_src, const float* __restrict__ Mw,
+build_volume_kernel(const FT* __restrict__ f_ref, const FT* __restrict__ f_src, const float* __restrict__ Mw,
                     const float* __restrict__ depths, bf16* __restrict__ vol, int B, int D, int H, int W, int f16) {
     constexpr int C = 32;
     const size_t total = (size_t)B * D * H * W * 4;
@@ -24,23 +41,19 @@ build_volume_kernel(const float* __restrict__ f_ref, const float* __restrict__ f
         float ix, iy;
         warp_coords(Mw + 12 * b, (float)x, (float)y, depths[d], W, H, &ix, &iy);
         const Bilin bl = bilin_setup(ix, iy, W, H);
-        const float* ref = f_ref + (((size_t)b * H + y) * W + x) * C + cg * 8;
-        float4 a0 = *reinterpret_cast<const float4*>(ref), a1 = *reinterpret_cast<const float4*>(ref + 4);
-        float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float v[8];
+        ld_feat8<FT>(f_ref + (((size_t)b * H + y) * W + x) * C + cg * 8, v);
         if (bl.any) {
-            const float* src = f_src + (size_t)b * H * W * C + cg * 8;
+            const FT* src = f_src + (size_t)b * H * W * C + cg * 8;
             const float wts[4] = {bl.w00, bl.w01, bl.w10, bl.w11};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (wts[k] != 0.f) {
                     const int yy = bl.y0 + (k >> 1), xx = bl.x0 + (k & 1);
-                    const float* p = src + ((size_t)yy * W + xx) * C;
-                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p));
-                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-                    v[0] = fmaf(wts[k], s0.x, v[0]); v[1] = fmaf(wts[k], s0.y, v[1]);
-                    v[2] = fmaf(wts[k], s0.z, v[2]); v[3] = fmaf(wts[k], s0.w, v[3]);
-                    v[4] = fmaf(wts[k], s1.x, v[4]); v[5] = fmaf(wts[k], s1.y, v[5]);
-                    v[6] = fmaf(wts[k], s1.z, v[6]); v[7] = fmaf(wts[k], s1.w, v[7]);
+                    float s8[8];
+                    ld_feat8<FT>(src + ((size_t)yy * W + xx) * C, s8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(wts[k], s8[j], v[j]);
                 }
             }
         }
@@ -58,14 +71,19 @@ build_volume_kernel(const float* __restrict__ f_ref, const float* __restrict__ f
     }
 }
 
-int build_volume(const float* f_ref, const float* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, int f16, cudaStream_t stream) {
+int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
+                 int W, int C, int f16, int feat_f16, cudaStream_t stream) {
     ADP_CHECK_ARG(C == 32, "feature channels must be 32");
     size_t total = (size_t)B * D * H * W * 4;
     if (total == 0) return ADP_OK;
     size_t blocks = (total + 255) / 256;
     int grid = (int)(blocks < (size_t)148 * 32 ? blocks : (size_t)148 * 32);
-    build_volume_kernel<<<grid, 256, 0, stream>>>(f_ref, f_src, Mw, depths, vol, B, D, H, W, f16);
+    if (feat_f16)
+        build_volume_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(f_ref), reinterpret_cast<const __half*>(f_src),
+                                                              Mw, depths, vol, B, D, H, W, f16);
+    else
+        build_volume_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(f_ref), reinterpret_cast<const float*>(f_src),
+                                                             Mw, depths, vol, B, D, H, W, f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

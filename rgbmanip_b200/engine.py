@@ -62,7 +62,7 @@ class Engine:
     """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
 
     def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="bf16x3", regress_pose=True, use_tc=True,
-                 use_tc_3d=True, tc_strided=True, tc_transposed=True, conv0_ring=True, volume_dtype="fp16", debug=False,
+                 use_tc_3d=True, tc_strided=True, tc_transposed=True, conv0_ring=True, tconv_fused=True, volume_dtype="fp16", debug=False,
                  img_size=IMG_SIZE, n_pts=N_PTS):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
@@ -83,7 +83,9 @@ class Engine:
         self.tc_strided = tc_strided
         self.tc_transposed = tc_transposed
         self.conv0_ring = conv0_ring and use_tc_3d
+        self.tconv_fused = tconv_fused and use_tc_3d and tc_transposed
         self._conv0_plans = []
+        self._tconv_plans = []
         if volume_dtype not in ("fp16", "bf16"):
             raise ValueError("volume_dtype must be 'fp16' or 'bf16'")
         self.vol_f16 = 1 if volume_dtype == "fp16" else 0
@@ -126,12 +128,12 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _epilogue(self, out: ActBuf | None, scale=None, bias=None, act=L.ACT_RELU, prelu=0.0, res: ActBuf | None = None,
-                  res_after_act=0, out_f32=None):
+                  res_after_act=0, out_f32=None, out_h16=None):
         return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act, res_after_act,
                           L.ptr(res.hi) if res else None, L.ptr(res.lo) if (res and res.lo is not None) else None,
                           res.Cn if res else 0,
                           L.ptr(out.hi) if out else None, L.ptr(out.lo) if (out and out.lo is not None) else None,
-                          L.ptr(out_f32))
+                          L.ptr(out_f32), L.ptr(out_h16))
 
     def _tc_plans(self, x: ActBuf, wt, cout, kd, ks, dil, npass, ep, geoms):
         """wt: fp32 [taps, CoutPad, Cin] packed weights -> callable(batch) launching one tcgen05 conv per geometry."""
@@ -288,8 +290,11 @@ class Engine:
             else:
                 x = o
         self.feat = torch.zeros((F, S, S, 32), dtype=torch.float32, device=self.device)
+        # fp16 twin of the feature map for the plane-sweep volume builder (the volume itself is fp16; halves its gather traffic)
+        self.feat16 = torch.zeros((F, S, S, 32), dtype=torch.float16, device=self.device) if (self.vol_f16 and self.use_tc) else None
         fb = self._dev(sd["img_extractor.final.bias"])
-        ops.append(("final", self._conv(sd["img_extractor.final.weight"], x, None, bias=fb, act=L.ACT_NONE, out_f32=self.feat)))
+        ops.append(("final", self._conv(sd["img_extractor.final.weight"], x, None, bias=fb, act=L.ACT_NONE, out_f32=self.feat,
+                                        out_h16=self.feat16)))
         self.backbone_ops = ops
 
     def run_backbone(self, nframes):
@@ -348,6 +353,26 @@ class Engine:
             ops.append((f"cr.{nm}", self._conv(wgt.numpy(), xin, out, stride=stride, npass=1, scale=sc, bias=sh, act=L.ACT_RELU)))
         for nm, xin, skip, out in (("conv7", c6, c4, x7), ("conv9", x7, c2, x9), ("conv11", x9, c0, x11)):
             sc, sh = bn(nm)
+            if self.tconv_fused and xin.Cn in (16, 32) and xin.lo is None:
+                wgt = torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float()            # [Cin, Cout, 3,3,3]
+                cin, cout = wgt.shape[0], wgt.shape[1]
+                bn_pad = 16 if cout <= 16 else 32
+                wt = wgt.reshape(cin, cout, 27).permute(2, 1, 0).contiguous()            # [27, Cout, Cin]
+                if bn_pad != cout:
+                    wt = torch.cat([wt, torch.zeros(27, bn_pad - cout, cin)], 1).contiguous()
+                w16 = wt.to(torch.float16 if xin.f16 else torch.bfloat16).to(self.device).contiguous()
+                self._keep.append(w16)
+                plan = C.c_void_p()
+                xa = xin.c
+                L.check(self.lib.adp_tconv_plan_create(C.byref(plan), C.byref(xa), L.ptr(w16), cout, L.ptr(sc), L.ptr(sh),
+                                                       L.ptr(skip.hi), skip.Cn, L.ptr(out.hi), self.num_sms), "tconv_plan")
+                self._tconv_plans.append(plan)
+
+                def runt(batch, plan=plan):
+                    L.check(self.lib.adp_tconv_run(plan, batch, L.ptr(self.err_flag), self.stream), "tconv_run")
+                runt.kind = "tc"
+                ops.append((f"cr.{nm}", runt))
+                continue
             ops.append((f"cr.{nm}", self._conv(sd[f"{cr}.{nm}.conv.weight"], xin, out, stride=2, transposed=True, npass=1,
                                                scale=sc, bias=sh, act=L.ACT_RELU, res=skip, res_after_act=1)))
         self.cr_ops = ops
@@ -429,8 +454,12 @@ class Engine:
         L.check(lib.adp_warp_matrices(L.ptr(self.Kp), L.ptr(E1), L.ptr(self.Kp[E:]), L.ptr(E2), L.ptr(self.Mw),
                                       L.ptr(self.valid), L.ptr(self.valid[E:]), L.ptr(self.valid_env), n, st), "warp_matrices")
         f1, f2 = self.feat, self.feat[E:]
-        L.check(lib.adp_build_volume(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.vol.hi), n, D, S, S,
-                                     32, self.vol_f16, st), "build_volume")
+        if self.feat16 is not None and not getattr(self, "force_f32_volume_feats", False):
+            L.check(lib.adp_build_volume(L.ptr(self.feat16), L.ptr(self.feat16[E:]), L.ptr(self.Mw), L.ptr(self.depths),
+                                         L.ptr(self.vol.hi), n, D, S, S, 32, self.vol_f16, 1, st), "build_volume")
+        else:
+            L.check(lib.adp_build_volume(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.vol.hi), n, D, S, S,
+                                         32, self.vol_f16, 0, st), "build_volume")
         mark("volume")
         for name, op in self.cr_ops:
             op(n)
@@ -479,6 +508,9 @@ class Engine:
         for p in self._conv0_plans:
             self.lib.adp_conv0_free(p)
         self._conv0_plans = []
+        for p in self._tconv_plans:
+            self.lib.adp_tconv_free(p)
+        self._tconv_plans = []
 
     def __del__(self):
         try:

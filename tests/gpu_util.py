@@ -45,7 +45,7 @@ def from_cl(x):
 def epilogue(out_hi=None, out_lo=None, out_f32=None, scale=None, bias=None, act_code=L.ACT_NONE, prelu=0.0, res_hi=None,
              res_lo=None, res_after_act=0):
     return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act_code, res_after_act, L.ptr(res_hi), L.ptr(res_lo), 0,
-                      L.ptr(out_hi), L.ptr(out_lo), L.ptr(out_f32))
+                      L.ptr(out_hi), L.ptr(out_lo), L.ptr(out_f32), None)
 
 
 def rel_err(a, b):

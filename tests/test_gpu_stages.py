@@ -169,6 +169,44 @@ def test_conv0_depth_ring_kernel(G, f16):
     assert G.rel_err(G.from_cl(got[..., :8].contiguous()), ref) < (2e-3 if f16 else 1.2e-2)   # 16-bit output rounding
 
 
+@pytest.mark.parametrize("case", [(2, 4, 28, 28, 16, 8, 1), (1, 3, 56, 56, 32, 16, 1), (1, 4, 28, 28, 16, 8, 0), (1, 5, 20, 12, 32, 16, 1)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_tconv_fused_kernel(G, case):
+    """Transposed conv + BN + ReLU + skip with the 8 parity classes fused in one tcgen05 kernel (csrc/tconv_fused.cu)."""
+    lib = L.load()
+    B, D, H, W, Cin, Cout, f16 = case
+    rng = _rng(sum(case) + 5)
+    dt = torch.float16 if f16 else torch.bfloat16
+    x = _t(rng, B, Cin, D, H, W).to(dt).float()
+    w = _t(rng, Cin, Cout, 3, 3, 3, scale=math.sqrt(1.0 / (8 * Cin))).to(dt).float()
+    scale, shift = _t(rng, Cout).abs() + 0.5, _t(rng, Cout)
+    res_c = 16 if Cout == 8 else Cout                               # the conv0 skip tensor is channel padded
+    res = _t(rng, B, res_c, 2 * D, 2 * H, 2 * W).to(dt).float()
+    ref = F.relu(F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1) * scale.view(1, -1, 1, 1, 1)
+                 + shift.view(1, -1, 1, 1, 1)) + res[:, :Cout]
+    xd = G.to_cl(x).to(dt).to(G.DEV).contiguous()
+    wt = w.reshape(Cin, Cout, 27).permute(2, 1, 0).contiguous()
+    bn = 16 if Cout <= 16 else 32
+    if bn != Cout:
+        wt = torch.cat([wt, torch.zeros(27, bn - Cout, Cin)], 1).contiguous()
+    wd = wt.to(dt).to(G.DEV).contiguous()
+    rd = G.to_cl(res).to(dt).to(G.DEV).contiguous()
+    out = torch.full((B, 2 * D, 2 * H, 2 * W, Cout), float("nan"), dtype=dt, device=G.DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=G.DEV)
+    plan = C.c_void_p()
+    a = G.act(xd, None, B, D, H, W, Cin, f16)
+    sc, sh = scale.to(G.DEV), shift.to(G.DEV)
+    L.check(lib.adp_tconv_plan_create(C.byref(plan), C.byref(a), L.ptr(wd), Cout, L.ptr(sc), L.ptr(sh), L.ptr(rd), res_c, L.ptr(out),
+                                      148), "plan")
+    L.check(lib.adp_tconv_run(plan, B, L.ptr(err), G.stream()), "run")
+    torch.cuda.synchronize()
+    lib.adp_tconv_free(plan)
+    assert int(err.item()) == 0
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert G.rel_err(G.from_cl(got), ref) < (2e-3 if f16 else 1.2e-2)       # 16-bit output rounding
+
+
 DIRECT_CASES = [
     # (dims, B, D, H, W, Cin, Cout, k, stride, dil, transposed)
     (2, 2, 1, 32, 48, 3, 64, 7, 2, 1, False),
@@ -345,7 +383,7 @@ def test_warp_matrices_and_volume(G):
     depths = torch.from_numpy(O.depth_hypotheses()).to(dev)
     vol = torch.zeros((2, 24, 224, 224, 32), dtype=torch.bfloat16, device=dev)
     f1d, f2d = G.to_cl(f1).to(dev), G.to_cl(f2).to(dev)
-    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), 2, 24, 224, 224, 32, 0, G.stream()), "vol")
+    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), 2, 24, 224, 224, 32, 0, 0, G.stream()), "vol")
     torch.cuda.synchronize()
     ref = f1[:, :, None] + O.homo_warping(f2, torch.from_numpy(P2).float(), torch.from_numpy(P1).float(),
                                           torch.from_numpy(O.depth_hypotheses())[None].repeat(2, 1))
@@ -376,6 +414,7 @@ def test_costreg_and_decode_match_oracle(G):
         f1, f2 = O.pspnet(sd, img1), O.pspnet(sd, img2)
     eng.feat[:2].copy_(G.to_cl(f1))
     eng.feat[2:4].copy_(G.to_cl(f2))
+    eng.feat16.copy_(eng.feat)           # the volume builder reads the fp16 twin written by the `final` conv
     ch1 = np.stack([v[0][1] for v in views])
     eng.choose[:2].copy_(torch.from_numpy(ch1).to(torch.int32))
     eng.Kp[:2].copy_(torch.from_numpy(np.stack([v[0][3] for v in views]).reshape(2, 9)))
