@@ -118,10 +118,11 @@ ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, voi
 ADP_API int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream);
 
 /* conv0 of the cost-regularisation U-Net (network_v5.py:263,283) as a depth-ring tcgen05 kernel: vol [B,D,H,W,32] ->
- * out [B,D,H,W,16] (8 channels + 8 zero), folded BatchNorm + ReLU.  w: 16-bit [9 (ky,kx)][4 chunks][32 (kz,co)][8]. */
+ * out [B,D,H,W,16] (8 channels + 8 zero), folded BatchNorm + ReLU.  w: 16-bit [9 (ky,kx)][4 chunks][32 (kz,co)][8].
+ * vol_planar != 0: the volume is stored [B,D,H,4,W,8] (adp_build_volume planar) and a row arrives in one TMA box. */
 typedef struct adp_conv0_plan adp_conv0_plan;
 ADP_API int adp_conv0_plan_create(adp_conv0_plan** plan, const adp_act* vol, const void* w_packed, const float* scale,
-                                  const float* shift, void* out, int num_sms);
+                                  const float* shift, void* out, int vol_planar, int num_sms);
 ADP_API int adp_conv0_run(adp_conv0_plan* plan, int batch, int32_t* err_flag, void* stream);
 ADP_API void adp_conv0_free(adp_conv0_plan* plan);
 
@@ -140,9 +141,10 @@ ADP_API void adp_tconv_free(adp_tconv_plan* plan);
 ADP_API int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src,
                               float* Mw, const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B,
                               void* stream);
-/* feat_*: [B,H,W,32] fp32, or IEEE half when feat_f16 != 0 */
+/* feat_*: [B,H,W,32] fp32, or IEEE half when feat_f16 != 0.  vol: [B,D,H,W,32], or the channel-chunk-planar layout
+ * [B,D,H,4,W,8] when planar != 0 (what adp_conv0_run reads: one contiguous 16-byte-per-pixel run per chunk and row). */
 ADP_API int adp_build_volume(const void* feat_ref, const void* feat_src, const float* Mw, const float* depths, void* vol,
-                     int B, int D, int H, int W, int C, int f16, int feat_f16, void* stream);
+                     int B, int D, int H, int W, int C, int f16, int feat_f16, int planar, void* stream);
 
 /* --- decode + heads: network_v5.py:432-465,486-499; rotation_utils.py:4-27 ----------------------------------- */
 ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,

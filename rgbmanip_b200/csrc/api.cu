@@ -31,7 +31,7 @@ int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, c
                    int S, int P, uint32_t seed, int choose_mode, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream);
 int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, int f16, int feat_f16, cudaStream_t stream);
+                 int W, int C, int f16, int feat_f16, int planar, cudaStream_t stream);
 int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
                   const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream);
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
@@ -45,7 +45,7 @@ struct Conv0Plan;
 Conv0Plan* conv0_alloc();
 void conv0_release(Conv0Plan* p);
 int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const float* scale, const float* shift, uint16_t* out,
-               int num_sms);
+               int planar, int num_sms);
 int conv0_run(Conv0Plan* pl, int batch, int* err_flag, cudaStream_t stream);
 
 struct TconvPlan;
@@ -184,11 +184,11 @@ int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* strea
 }
 
 int adp_conv0_plan_create(adp_conv0_plan** plan, const adp_act* vol, const void* w_packed, const float* scale, const float* shift,
-                          void* out, int num_sms) {
+                          void* out, int vol_planar, int num_sms) {
     ADP_CHECK_ARG(plan && vol && w_packed && scale && shift && out, "null pointer");
     Conv0Plan* pl = conv0_alloc();
     int r = conv0_plan(pl, to_act(vol), reinterpret_cast<const uint16_t*>(w_packed), scale, shift, reinterpret_cast<uint16_t*>(out),
-                       num_sms);
+                       vol_planar, num_sms);
     if (r != ADP_OK) {
         conv0_release(pl);
         return r;
@@ -234,10 +234,10 @@ int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void*
 }
 
 int adp_build_volume(const void* feat_ref, const void* feat_src, const float* Mw, const float* depths, void* vol, int B, int D,
-                     int H, int W, int C, int f16, int feat_f16, void* stream) {
+                     int H, int W, int C, int f16, int feat_f16, int planar, void* stream) {
     ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && vol, "null pointer");
     g_launches += 1;
-    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, f16, feat_f16, (cudaStream_t)stream);
+    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, f16, feat_f16, planar, (cudaStream_t)stream);
 }
 
 int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,

@@ -26,15 +26,17 @@ constexpr int C0_SEG = 112;                 // pixels per unit (224 = 2 x 112)
 constexpr int C0_PIXPITCH = 136;            // pixels per channel-chunk plane in smem (halo + M = 128 tile overhang; 128 B aligned)
 constexpr int C0_CHUNK_BYTES = C0_PIXPITCH * 16;          // 2176: LBO of the A descriptor
 constexpr int C0_ROW_BYTES = 4 * C0_CHUNK_BYTES;          // 32 channels = 4 chunks of 8
-constexpr int C0_STAGE_BYTES = 3 * C0_ROW_BYTES;          // rows y-1, y, y+1 of one depth plane
+constexpr int C0_R = 4;                                   // output rows per unit: rows y0-1 .. y0+R are loaded once for R outputs
+constexpr int C0_STAGE_BYTES = (C0_R + 2) * C0_ROW_BYTES; // one depth plane of the unit
 constexpr int C0_STAGES = 3;
 constexpr int C0_W_BYTES = 9 * 4 * 32 * 16;               // [tap][chunk][n = 32][8 ch] 16-bit
-constexpr int C0_SLOTS = 4;
+constexpr int C0_SLOTS = 4;                               // depth ring; TMEM column = (row * 4 + slot) * 32
 constexpr int C0_SMEM = C0_STAGES * C0_STAGE_BYTES + C0_W_BYTES + 1024 + 256;
 
 struct Conv0Params {
     int B, D, H, W;
     int f16;
+    int planar;               // volume layout [B,D,H,4,W,8]: one TMA box per row
     const uint16_t* w;        // packed weights, C0_W_BYTES
     const float* scale;       // [8] folded BatchNorm
     const float* shift;       // [8]
@@ -54,7 +56,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr));
 }
 
-__global__ void __launch_bounds__(C0_THREADS, 2)
+__global__ void __launch_bounds__(C0_THREADS, 1)
 conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p, int batch) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,7 +87,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 128);
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 128 * C0_R);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -94,7 +96,8 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     const uint32_t tmem_base = *tmem_slot;
 
     const int segs = p.W / C0_SEG;
-    const int units = batch * p.H * segs;
+    const int ygroups = p.H / C0_R;
+    const int units = batch * ygroups * segs;
     const int D = p.D;
 
     if (warp == 0) {
@@ -103,18 +106,27 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
             int stage = 0;
             uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int seg = u % segs, y = (u / segs) % p.H, b = u / (segs * p.H);
+                const int seg = u % segs, y = ((u / segs) % ygroups) * C0_R, b = u / (segs * ygroups);
                 const int x0 = seg * C0_SEG - 1;
                 for (int d = 0; d < D; ++d) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 11);
                     const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), 12u * (C0_SEG + 2) * 16u);
+                    if (p.planar) {
+                        // tensor map dims (8, W, 4, H, B*D), box (8, 136, 4, 1, 1): a whole row with all four channel
+                        // chunks in one instruction, already in the smem layout of the A operand
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(C0_R + 2) * C0_ROW_BYTES);
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
+                        for (int ky = 0; ky < C0_R + 2; ++ky)
+                            ptx::tma_load_5d(&tmIn, full_bar(stage), sa + ky * C0_ROW_BYTES, 0, x0, 0, y + ky - 1, b * D + d);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(C0_R + 2) * 4u * (C0_SEG + 2) * 16u);
 #pragma unroll
-                        for (int kc = 0; kc < 4; ++kc)
-                            ptx::tma_load_5d(&tmIn, full_bar(stage), sa + ky * C0_ROW_BYTES + kc * C0_CHUNK_BYTES, kc * 8, x0,
-                                             y + ky - 1, d, b);
+                        for (int ky = 0; ky < C0_R + 2; ++ky)
+#pragma unroll
+                            for (int kc = 0; kc < 4; ++kc)
+                                ptx::tma_load_5d(&tmIn, full_bar(stage), sa + ky * C0_ROW_BYTES + kc * C0_CHUNK_BYTES, kc * 8, x0,
+                                                 y + ky - 1, d, b);
+                    }
                     if (++stage == C0_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -133,20 +145,23 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                 ptx::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(slot * 32);
-                    int first = 1;
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
+                    for (int r = 0; r < C0_R; ++r) {
+                        const uint32_t tmem_d = tmem_base + (uint32_t)((r * C0_SLOTS + slot) * 32);
+                        int first = 1;
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx)
+                        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint64_t adesc = make_desc_noswz(sa + ky * C0_ROW_BYTES + (2 * ks) * C0_CHUNK_BYTES + kx * 16,
-                                                                       C0_CHUNK_BYTES, 128);
-                                const uint64_t bdesc = make_desc_noswz(w_base + ((ky * 3 + kx) * 4 + 2 * ks) * 512, 512, 128);
-                                ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-                                first = 0;
-                            }
+                            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                                for (int ks = 0; ks < 2; ++ks) {
+                                    const uint64_t adesc = make_desc_noswz(sa + (r + ky) * C0_ROW_BYTES + (2 * ks) * C0_CHUNK_BYTES + kx * 16,
+                                                                           C0_CHUNK_BYTES, 128);
+                                    const uint64_t bdesc = make_desc_noswz(w_base + ((ky * 3 + kx) * 4 + 2 * ks) * 512, 512, 128);
+                                    ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+                                    first = 0;
+                                }
+                    }
                     ptx::umma_commit(empty_bar(stage));
                     ptx::umma_commit(tfull_bar(slot));
                 }
@@ -164,7 +179,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
         for (int j = 0; j < 8; ++j) { sc[j] = p.scale[j]; sh[j] = p.shift[j]; }
         unsigned g0 = 0;   // plane counter at the start of the unit
         for (int u = blockIdx.x; u < units; u += gridDim.x, g0 += (unsigned)D) {
-            const int seg = u % segs, y = (u / segs) % p.H, b = u / (segs * p.H);
+            const int seg = u % segs, y0 = ((u / segs) % ygroups) * C0_R, b = u / (segs * ygroups);
             const int x = seg * C0_SEG + m;
             const bool valid = m < C0_SEG;
             for (int d = 0; d < D; ++d) {
@@ -172,18 +187,21 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                 const unsigned gl = g0 + (unsigned)(d + 1 < D ? d + 1 : d);
                 ptx::mbar_wait(tfull_bar(gl & 3), (gl >> 2) & 1, p.err, 14);
                 ptx::tc_fence_after();
-                float acc[8];
+                float acc[C0_R][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+                for (int r = 0; r < C0_R; ++r) {
 #pragma unroll
-                for (int kz = 0; kz < 3; ++kz) {
-                    const int dp = d + kz - 1;
-                    if (dp < 0 || dp >= D) continue;
-                    uint32_t r[8];
-                    tmem_ld8(lane_addr + (uint32_t)(((g0 + dp) & 3) * 32 + kz * 8), r);
-                    ptx::tmem_ld_wait();
+                    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(r[j]);
+                    for (int kz = 0; kz < 3; ++kz) {
+                        const int dp = d + kz - 1;
+                        if (dp < 0 || dp >= D) continue;
+                        uint32_t rr[8];
+                        tmem_ld8(lane_addr + (uint32_t)((r * C0_SLOTS + ((g0 + dp) & 3)) * 32 + kz * 8), rr);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[r][j] += __uint_as_float(rr[j]);
+                    }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -193,11 +211,14 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                     if (d == D - 1) ptx::mbar_arrive(tempty_bar((g0 + d) & 3));
                 }
                 if (valid) {
+#pragma unroll
+                  for (int r = 0; r < C0_R; ++r) {
+                    const int y = y0 + r;
                     uint32_t o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float v0 = fmaxf(fmaf(acc[2 * j], sc[2 * j], sh[2 * j]), 0.f);
-                        const float v1 = fmaxf(fmaf(acc[2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]), 0.f);
+                        const float v0 = fmaxf(fmaf(acc[r][2 * j], sc[2 * j], sh[2 * j]), 0.f);
+                        const float v1 = fmaxf(fmaf(acc[r][2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]), 0.f);
                         if (p.f16)
                             o[j] = (uint32_t)__half_as_ushort(__float2half_rn(v0)) | ((uint32_t)__half_as_ushort(__float2half_rn(v1)) << 16);
                         else
@@ -207,6 +228,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                     uint4* dst = reinterpret_cast<uint4*>(p.out + ((((size_t)b * D + d) * p.H + y) * p.W + x) * 16);
                     dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
                     dst[1] = make_uint4(0, 0, 0, 0);
+                  }
                 }
             }
         }
@@ -215,7 +237,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 128);
+        ptx::tmem_dealloc(tmem_base, 128 * C0_R);
     }
 }
 
@@ -233,14 +255,20 @@ Conv0Plan* conv0_alloc() { return new Conv0Plan(); }
 void conv0_release(Conv0Plan* p) { delete p; }
 
 int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const float* scale, const float* shift, uint16_t* out,
-               int num_sms) {
+               int planar, int num_sms) {
     ADP_TRY(tc_conv_init_driver());
-    ADP_CHECK_ARG(in.C == 32 && in.W % C0_SEG == 0 && in.D % 4 == 0 && in.D >= 4, "conv0 ring kernel: C = 32, W % 112 == 0, D % 4 == 0");
+    ADP_CHECK_ARG(in.C == 32 && in.W % C0_SEG == 0 && in.D % 4 == 0 && in.D >= 4 && in.H % C0_R == 0,
+                  "conv0 ring kernel: C = 32, W % 112 == 0, D % 4 == 0, H % 4 == 0");
     cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.D, (cuuint64_t)in.B};
     cuuint64_t strides[4] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2,
                              (cuuint64_t)in.D * in.H * in.W * in.C * 2};
     cuuint32_t box[5] = {8, (cuuint32_t)(C0_SEG + 2), 1, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (planar) {   // [B*D][H][4][W][8]
+        dims[0] = 8; dims[1] = (cuuint64_t)in.W; dims[2] = 4; dims[3] = (cuuint64_t)in.H; dims[4] = (cuuint64_t)in.B * in.D;
+        strides[0] = 16; strides[1] = (cuuint64_t)in.W * 16; strides[2] = (cuuint64_t)in.W * 64; strides[3] = (cuuint64_t)in.H * in.W * 64;
+        box[1] = C0_PIXPITCH; box[2] = 4;
+    }
     CUresult r = g_encode_shared(&pl->tmIn, in.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, in.hi, dims,
                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -248,7 +276,7 @@ int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const flo
         set_last_error("cuTensorMapEncodeTiled(conv0 volume) failed: %d", (int)r);
         return ADP_ERR_CUDA;
     }
-    pl->p.B = in.B; pl->p.D = in.D; pl->p.H = in.H; pl->p.W = in.W; pl->p.f16 = in.f16;
+    pl->p.B = in.B; pl->p.D = in.D; pl->p.H = in.H; pl->p.W = in.W; pl->p.f16 = in.f16; pl->p.planar = planar;
     pl->p.w = w_packed; pl->p.scale = scale; pl->p.shift = shift; pl->p.out = out; pl->p.err = nullptr;
     pl->num_sms = num_sms > 0 ? num_sms : 148;
     return ADP_OK;
@@ -262,9 +290,9 @@ int conv0_run(Conv0Plan* pl, int batch, int* err_flag, cudaStream_t stream) {
         attr = true;
     }
     pl->p.err = err_flag;
-    const int units = batch * pl->p.H * (pl->p.W / C0_SEG);
+    const int units = batch * (pl->p.H / C0_R) * (pl->p.W / C0_SEG);
     if (units == 0) return ADP_OK;
-    const int slots = pl->num_sms * 2;
+    const int slots = pl->num_sms;
     const int grid = units < slots ? units : slots;
     conv0_ring_kernel<<<grid, C0_THREADS, C0_SMEM, stream>>>(pl->tmIn, pl->p, batch);
     ADP_CUDA(cudaGetLastError());

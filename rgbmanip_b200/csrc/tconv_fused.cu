@@ -42,13 +42,13 @@ struct TfCfg {
     static constexpr int W_SLOT = (BN * KC * 2 + 1023) / 1024 * 1024;
     static constexpr int W_BYTES = 27 * W_SLOT;
     static constexpr int STAGES = 6;
-    static constexpr int REGION = BN < 32 ? 32 : BN;          // TMEM columns per parity class
+    static constexpr int REGION = BN;                         // TMEM columns per parity class
     static constexpr int TMEM_COLS = 2 * 8 * REGION;          // two accumulator sets
     static constexpr int SMEM = STAGES * A_BYTES + W_BYTES + 1024 + 256;
 };
 
 template <int KC, int BN>
-__global__ void __launch_bounds__(TF_THREADS, 1)
+__global__ void __launch_bounds__(TF_THREADS, 2)
 tconv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TconvParams p, int batch) {
     using Cfg = TfCfg<KC, BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -263,7 +263,8 @@ static int tconv_launch(TconvPlan* pl, int batch, cudaStream_t stream) {
     }
     const long long total = (long long)batch * pl->p.D * pl->p.tiles_y * pl->p.tiles_x;
     if (total == 0) return ADP_OK;
-    const int grid = (int)(total < pl->num_sms ? total : pl->num_sms);
+    const long long slots = 2LL * pl->num_sms;
+    const int grid = (int)(total < slots ? total : slots);
     tconv_fused_kernel<KC, BN><<<grid, TF_THREADS, Cfg::SMEM, stream>>>(pl->tmA, pl->tmW, pl->p, batch);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;

@@ -28,13 +28,19 @@ template <> __device__ __forceinline__ void ld_feat8<__half>(const __half* p, fl
 template <typename FT>
 __global__ void __launch_bounds__(256)
 build_volume_kernel(const FT* __restrict__ f_ref, const FT* __restrict__ f_src, const float* __restrict__ Mw,
-                    const float* __restrict__ depths, bf16* __restrict__ vol, int B, int D, int H, int W, int f16) {
+                    const float* __restrict__ depths, bf16* __restrict__ vol, int B, int D, int H, int W, int f16, int planar) {
     constexpr int C = 32;
     const size_t total = (size_t)B * D * H * W * 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int cg = (int)(i & 3);
-        size_t t = i >> 2;
-        const int x = (int)(t % W); t /= W;
+        int cg, x;
+        size_t t;
+        if (planar) {      // consecutive threads = consecutive x of one channel chunk (coalesced 16 B stores per chunk plane)
+            x = (int)(i % W); t = i / W;
+            cg = (int)(t & 3); t >>= 2;
+        } else {
+            cg = (int)(i & 3); t = i >> 2;
+            x = (int)(t % W); t /= W;
+        }
         const int y = (int)(t % H); t /= H;
         const int d = (int)(t % D);
         const int b = (int)(t / D);
@@ -66,13 +72,14 @@ build_volume_kernel(const FT* __restrict__ f_ref, const FT* __restrict__ f_src, 
                 o[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u])) |
                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u + 1])) << 16);
         }
-        *reinterpret_cast<uint4*>(vol + ((((size_t)b * D + d) * H + y) * W + x) * C + cg * 8) =
-            make_uint4(o[0], o[1], o[2], o[3]);
+        const size_t off = planar ? (((((size_t)b * D + d) * H + y) * 4 + cg) * W + x) * 8
+                                  : ((((size_t)b * D + d) * H + y) * W + x) * C + cg * 8;
+        *reinterpret_cast<uint4*>(vol + off) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
 int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, int f16, int feat_f16, cudaStream_t stream) {
+                 int W, int C, int f16, int feat_f16, int planar, cudaStream_t stream) {
     ADP_CHECK_ARG(C == 32, "feature channels must be 32");
     size_t total = (size_t)B * D * H * W * 4;
     if (total == 0) return ADP_OK;
@@ -80,10 +87,10 @@ int build_volume(const void* f_ref, const void* f_src, const float* Mw, const fl
     int grid = (int)(blocks < (size_t)148 * 32 ? blocks : (size_t)148 * 32);
     if (feat_f16)
         build_volume_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(f_ref), reinterpret_cast<const __half*>(f_src),
-                                                              Mw, depths, vol, B, D, H, W, f16);
+                                                              Mw, depths, vol, B, D, H, W, f16, planar);
     else
         build_volume_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(f_ref), reinterpret_cast<const float*>(f_src),
-                                                             Mw, depths, vol, B, D, H, W, f16);
+                                                             Mw, depths, vol, B, D, H, W, f16, planar);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

@@ -309,6 +309,7 @@ class Engine:
         self.Mw = torch.zeros((E, 12), dtype=torch.float32, device=dev)
         self.valid_env = torch.zeros(E, dtype=torch.uint8, device=dev)
         self.vol = self._act(E, S, S, 32, D=D, split=False, f16=self.vol_f16)
+        self.vol_planar = 0     # set when conv0 runs as the depth-ring kernel, which reads the chunk-planar layout
         cr = "cost_regularization"
 
         def bn(name):
@@ -341,8 +342,9 @@ class Engine:
                 self._keep.append(w16)
                 plan = C.c_void_p()
                 va = xin.c
+                self.vol_planar = 1 if getattr(self, 'want_planar_volume', False) else 0
                 L.check(self.lib.adp_conv0_plan_create(C.byref(plan), C.byref(va), L.ptr(w16), L.ptr(sc), L.ptr(sh), L.ptr(out.hi),
-                                                       self.num_sms), "conv0_plan")
+                                                       self.vol_planar, self.num_sms), "conv0_plan")
                 self._conv0_plans.append(plan)
 
                 def run0(batch, plan=plan):
@@ -456,10 +458,10 @@ class Engine:
         f1, f2 = self.feat, self.feat[E:]
         if self.feat16 is not None and not getattr(self, "force_f32_volume_feats", False):
             L.check(lib.adp_build_volume(L.ptr(self.feat16), L.ptr(self.feat16[E:]), L.ptr(self.Mw), L.ptr(self.depths),
-                                         L.ptr(self.vol.hi), n, D, S, S, 32, self.vol_f16, 1, st), "build_volume")
+                                         L.ptr(self.vol.hi), n, D, S, S, 32, self.vol_f16, 1, self.vol_planar, st), "build_volume")
         else:
             L.check(lib.adp_build_volume(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.vol.hi), n, D, S, S,
-                                         32, self.vol_f16, 0, st), "build_volume")
+                                         32, self.vol_f16, 0, self.vol_planar, st), "build_volume")
         mark("volume")
         for name, op in self.cr_ops:
             op(n)

@@ -138,8 +138,9 @@ def test_tc_conv_strided_transposed_fp16(G, case):
     assert G.rel_err(G.from_cl(out16), ref) < (2e-3 if f16 else 1.2e-2)   # 16-bit output rounding
 
 
+@pytest.mark.parametrize("planar", [0, 1])
 @pytest.mark.parametrize("f16", [1, 0])
-def test_conv0_depth_ring_kernel(G, f16):
+def test_conv0_depth_ring_kernel(G, f16, planar):
     """conv0 (3x3x3, 32 -> 8) as the depth-ring tcgen05 kernel (csrc/conv0_ring.cu) against F.conv3d."""
     from rgbmanip_b200 import geometry
     lib = L.load()
@@ -151,6 +152,8 @@ def test_conv0_depth_ring_kernel(G, f16):
     scale, shift = _t(rng, 8).abs() + 0.5, _t(rng, 8)
     ref = F.relu(F.conv3d(x, w, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
     xd = G.to_cl(x).to(dt).to(G.DEV).contiguous()
+    if planar:      # [B,D,H,W,32] -> [B,D,H,4,W,8]
+        xd = xd.reshape(B, D, H, W, 4, 8).permute(0, 1, 2, 4, 3, 5).contiguous()
     wd = geometry.conv0_ring_weights(w).to(dt).to(G.DEV).contiguous()
     sc = torch.cat([scale, torch.zeros(8)]).to(G.DEV)
     sh = torch.cat([shift, torch.zeros(8)]).to(G.DEV)
@@ -158,7 +161,7 @@ def test_conv0_depth_ring_kernel(G, f16):
     err = torch.zeros(1, dtype=torch.int32, device=G.DEV)
     plan = C.c_void_p()
     a = G.act(xd, None, B, D, H, W, 32, f16)
-    L.check(lib.adp_conv0_plan_create(C.byref(plan), C.byref(a), L.ptr(wd), L.ptr(sc), L.ptr(sh), L.ptr(out), 148), "plan")
+    L.check(lib.adp_conv0_plan_create(C.byref(plan), C.byref(a), L.ptr(wd), L.ptr(sc), L.ptr(sh), L.ptr(out), planar, 148), "plan")
     L.check(lib.adp_conv0_run(plan, B, L.ptr(err), G.stream()), "run")
     torch.cuda.synchronize()
     lib.adp_conv0_free(plan)
@@ -383,7 +386,7 @@ def test_warp_matrices_and_volume(G):
     depths = torch.from_numpy(O.depth_hypotheses()).to(dev)
     vol = torch.zeros((2, 24, 224, 224, 32), dtype=torch.bfloat16, device=dev)
     f1d, f2d = G.to_cl(f1).to(dev), G.to_cl(f2).to(dev)
-    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), 2, 24, 224, 224, 32, 0, 0, G.stream()), "vol")
+    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), 2, 24, 224, 224, 32, 0, 0, 0, G.stream()), "vol")
     torch.cuda.synchronize()
     ref = f1[:, :, None] + O.homo_warping(f2, torch.from_numpy(P2).float(), torch.from_numpy(P1).float(),
                                           torch.from_numpy(O.depth_hypotheses())[None].repeat(2, 1))
