@@ -39,6 +39,11 @@ CFG = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "
        "n_pts": 1024, "direct_regression": True, "real_world": False}
 
 
+def workload_name(n):
+    return (f"adapose_v5 estimate(), num_envs={n}, 2 views/env, 480x640 fp32 RGB + u8 mask -> [N,8,3] world boxes "
+            "(BASELINE configs[3]; all four adapose_* yamls share this architecture)")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -126,7 +131,7 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in vals) / len(vals),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"adapose_v5 estimate(), num_envs={args.num_envs}, 2 views/env, 480x640 RGB -> [N,8,3] boxes",
+            "config": {"workload": workload_name(args.num_envs),
                        "note": "reference's per-env CPU loop (oracle port, torch CPU fp32 eval mode); cost is linear in num_envs"},
             "cpu_baseline": {"value": rate, "unit": "estimates/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} envs per step of the {args.num_envs}-env workload (per-env loop, linear)"},
@@ -292,8 +297,7 @@ def main():
         line = {"metric": "pose estimates/sec at num_envs=1024", "value": value, "unit": "estimates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": f"synthetic ({args.unique} seeded envs tiled to {N})",
-                "config": {"workload": f"adapose_v5 estimate(), num_envs={N}, 2 views/env, 480x640 fp32 RGB + u8 mask -> [N,8,3] world boxes "
-                                       "(BASELINE configs[3]; all four adapose_* yamls share this architecture)",
+                "config": {"workload": workload_name(N),
                            "precision": eng.precision, "chunk_envs": eng.E, "sharding": f"env-sharded dp{world}, NCCL all-gather of poses",
                            "l2": "inputs (>= 8 GB per step) exceed the 126 MB L2; no explicit flush needed",
                            "sampling": "device hash sampler for the 1024-pixel subset"},

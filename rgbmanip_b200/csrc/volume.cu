@@ -78,11 +78,59 @@ build_volume_kernel(const FT* __restrict__ f_ref, const FT* __restrict__ f_src, 
     }
 }
 
+// one block = one volume row (b, d, y), one thread = one voxel with all 32 channels: the homography is evaluated once per
+// voxel and the row index needs no per-thread division (the 4-threads-per-voxel kernel above is issue bound on exactly that)
+__global__ void __launch_bounds__(256)
+build_volume_row_kernel(const __half* __restrict__ f_ref, const __half* __restrict__ f_src, const float* __restrict__ Mw,
+                        const float* __restrict__ depths, bf16* __restrict__ vol, int D, int H, int W, int f16) {
+    constexpr int C = 32;
+    const int row = blockIdx.x;
+    const int y = row % H, d = (row / H) % D, b = row / (H * D);
+    const float dep = depths[d];
+    const float* M = Mw + 12 * b;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        float ix, iy;
+        warp_coords(M, (float)x, (float)y, dep, W, H, &ix, &iy);
+        const Bilin bl = bilin_setup(ix, iy, W, H);
+        float v[C];
+        const __half* ref = f_ref + (((size_t)b * H + y) * W + x) * C;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ld_feat8<__half>(ref + 8 * q, v + 8 * q);
+        if (bl.any) {
+            const __half* src = f_src + (size_t)b * H * W * C;
+            const float wts[4] = {bl.w00, bl.w01, bl.w10, bl.w11};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (wts[k] != 0.f) {
+                    const __half* p = src + ((size_t)(bl.y0 + (k >> 1)) * W + bl.x0 + (k & 1)) * C;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float s8[8];
+                        ld_feat8<__half>(p + 8 * q, s8);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[8 * q + j] = fmaf(wts[k], s8[j], v[8 * q + j]);
+                    }
+                }
+            }
+        }
+        bf16* dst = vol + ((((size_t)b * D + d) * H + y) * W + x) * C;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st8_16(dst, nullptr, 8 * q, f16, v + 8 * q);
+    }
+}
+
 int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
                  int W, int C, int f16, int feat_f16, int planar, cudaStream_t stream) {
     ADP_CHECK_ARG(C == 32, "feature channels must be 32");
     size_t total = (size_t)B * D * H * W * 4;
     if (total == 0) return ADP_OK;
+    if (feat_f16 && !planar) {
+        build_volume_row_kernel<<<B * D * H, W <= 128 ? 128 : 256, 0, stream>>>(reinterpret_cast<const __half*>(f_ref),
+                                                                               reinterpret_cast<const __half*>(f_src), Mw, depths, vol, D,
+                                                                               H, W, f16);
+        ADP_CUDA(cudaGetLastError());
+        return ADP_OK;
+    }
     size_t blocks = (total + 255) / 256;
     int grid = (int)(blocks < (size_t)148 * 32 ? blocks : (size_t)148 * 32);
     if (feat_f16)
