@@ -35,6 +35,9 @@ GF_BACKBONE_PER_FRAME = 57.0177e9       # SURVEY.md A.3 (2 * MACs of every conv 
 GF_BACKBONE_TC_PER_FRAME = 57.0177e9 - 0.2360e9 - 0.1156e9 - 0.0128e9 - 0.0066e9   # minus conv1, layer2.0 strided convs, psp
 GF_COSTREG_PER_VIEW = 24.4506e9
 DECODE_BYTES_PER_VIEW = 1708092
+# ncu capture of the 40 tc_conv_kernel launches of one backbone pass (128 frames, bf16x3): profiles/r01_backbone_tc_summary.csv
+NCU_TC_DRAM_BYTES_PER_FRAME = 18958.8e6 / 128
+NCU_TC_TENSOR_ACTIVE = 0.712            # time-weighted sm__pipe_tensor_cycles_active over those launches
 CFG = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
        "n_pts": 1024, "direct_regression": True, "real_world": False}
 
@@ -279,7 +282,11 @@ def main():
     if tc_ms > 0:
         ach = tc_flops / (tc_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "tc_conv_kernel (tcgen05 implicit-GEMM, backbone 2-D convs)", "achieved": ach,
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": NCU_TC_DRAM_BYTES_PER_FRAME * frames if eng.precision == "bf16x3" else None,
+                "traffic_note": "dram__bytes_read+write summed over the launch group, ncu capture at 128 frames scaled to this chunk "
+                                "(profiles/r01_backbone_tc_summary.csv)",
+                "tensor_pipe_active_ncu": NCU_TC_TENSOR_ACTIVE if eng.precision == "bf16x3" else None,
                 "peak_source": pk["src"] + " (sustained: timed inside a long step)",
                 "algorithmic_flops_per_launch_group": tc_flops, "launches": classes["tc"]["launches"],
                 "tensor_pipe_work_frac": ach * npass / pk["tf_sustained"],
