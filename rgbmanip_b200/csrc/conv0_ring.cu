@@ -18,17 +18,18 @@
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace adp {
 
 constexpr int C0_THREADS = 192;
 constexpr int C0_SEG = 112;                 // pixels per unit (224 = 2 x 112)
-constexpr int C0_PIXPITCH = 136;            // pixels per channel-chunk plane in smem (halo + M = 128 tile overhang; 128 B aligned)
-constexpr int C0_CHUNK_BYTES = C0_PIXPITCH * 16;          // 2176: LBO of the A descriptor
-constexpr int C0_ROW_BYTES = 4 * C0_CHUNK_BYTES;          // 32 channels = 4 chunks of 8
 constexpr int C0_R = 4;                                   // output rows per unit: rows y0-1 .. y0+R are loaded once for R outputs
-constexpr int C0_STAGE_BYTES = (C0_R + 2) * C0_ROW_BYTES; // one depth plane of the unit
-constexpr int C0_STAGES = 3;
+constexpr int C0_PIXPITCH = 120;                          // pixels per slab row in smem (112 + halo, padded so that a row is a 128-byte multiple)
+constexpr int C0_ROWPITCH = C0_PIXPITCH * 16;             // 1920 bytes
+constexpr int C0_CHUNK_BYTES = (C0_R + 2) * C0_ROWPITCH;  // one 8-channel chunk plane [row][pixel][16 B] = ONE TMA box; LBO of the A descriptor
+constexpr int C0_STAGE_BYTES = 4 * C0_CHUNK_BYTES + 512;  // one depth plane of the unit (+ slack: the M = 128 tile overhangs the last slab row)
+constexpr int C0_STAGES = 4;
 constexpr int C0_W_BYTES = 9 * 4 * 32 * 16;               // [tap][chunk][n = 32][8 ch] 16-bit
 constexpr int C0_SLOTS = 4;                               // depth ring; TMEM column = (row * 4 + slot) * 32
 constexpr int C0_SMEM = C0_STAGES * C0_STAGE_BYTES + C0_W_BYTES + 1024 + 256;
@@ -36,7 +37,6 @@ constexpr int C0_SMEM = C0_STAGES * C0_STAGE_BYTES + C0_W_BYTES + 1024 + 256;
 struct Conv0Params {
     int B, D, H, W;
     int f16;
-    int planar;               // volume layout [B,D,H,4,W,8]: one TMA box per row
     const uint16_t* w;        // packed weights, C0_W_BYTES
     const float* scale;       // [8] folded BatchNorm
     const float* shift;       // [8]
@@ -101,7 +101,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     const int D = p.D;
 
     if (warp == 0) {
-        // ===================== TMA producer: 3 rows x 4 channel chunks per depth plane =====================
+        // ===================== TMA producer: one box per 8-channel chunk = (R + 2) rows x 120 pixels x 16 bytes =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -111,22 +111,10 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                 for (int d = 0; d < D; ++d) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 11);
                     const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
-                    if (p.planar) {
-                        // tensor map dims (8, W, 4, H, B*D), box (8, 136, 4, 1, 1): a whole row with all four channel
-                        // chunks in one instruction, already in the smem layout of the A operand
-                        ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(C0_R + 2) * C0_ROW_BYTES);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), 4u * C0_CHUNK_BYTES);
 #pragma unroll
-                        for (int ky = 0; ky < C0_R + 2; ++ky)
-                            ptx::tma_load_5d(&tmIn, full_bar(stage), sa + ky * C0_ROW_BYTES, 0, x0, 0, y + ky - 1, b * D + d);
-                    } else {
-                        ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(C0_R + 2) * 4u * (C0_SEG + 2) * 16u);
-#pragma unroll
-                        for (int ky = 0; ky < C0_R + 2; ++ky)
-#pragma unroll
-                            for (int kc = 0; kc < 4; ++kc)
-                                ptx::tma_load_5d(&tmIn, full_bar(stage), sa + ky * C0_ROW_BYTES + kc * C0_CHUNK_BYTES, kc * 8, x0,
-                                                 y + ky - 1, d, b);
-                    }
+                    for (int kc = 0; kc < 4; ++kc)
+                        ptx::tma_load_5d(&tmIn, full_bar(stage), sa + kc * C0_CHUNK_BYTES, kc * 8, x0, y - 1, d, b);
                     if (++stage == C0_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -155,7 +143,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
                                 for (int ks = 0; ks < 2; ++ks) {
-                                    const uint64_t adesc = make_desc_noswz(sa + (r + ky) * C0_ROW_BYTES + (2 * ks) * C0_CHUNK_BYTES + kx * 16,
+                                    const uint64_t adesc = make_desc_noswz(sa + (2 * ks) * C0_CHUNK_BYTES + (r + ky) * C0_ROWPITCH + kx * 16,
                                                                            C0_CHUNK_BYTES, 128);
                                     const uint64_t bdesc = make_desc_noswz(w_base + ((ky * 3 + kx) * 4 + 2 * ks) * 512, 512, 128);
                                     ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
@@ -187,6 +175,17 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                 const unsigned gl = g0 + (unsigned)(d + 1 < D ? d + 1 : d);
                 ptx::mbar_wait(tfull_bar(gl & 3), (gl >> 2) & 1, p.err, 14);
                 ptx::tc_fence_after();
+                // issue every TMEM load of this depth first, wait once: the loads overlap instead of paying 12 round trips
+                uint32_t rr[C0_R][3][8];
+#pragma unroll
+                for (int r = 0; r < C0_R; ++r)
+#pragma unroll
+                    for (int kz = 0; kz < 3; ++kz) {
+                        const int dp = d + kz - 1;
+                        const int dpc = dp < 0 ? 0 : (dp >= D ? D - 1 : dp);     // clamped (masked below): keeps the loads uniform
+                        tmem_ld8(lane_addr + (uint32_t)((r * C0_SLOTS + ((g0 + dpc) & 3)) * 32 + kz * 8), rr[r][kz]);
+                    }
+                ptx::tmem_ld_wait();
                 float acc[C0_R][8];
 #pragma unroll
                 for (int r = 0; r < C0_R; ++r) {
@@ -196,11 +195,8 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                     for (int kz = 0; kz < 3; ++kz) {
                         const int dp = d + kz - 1;
                         if (dp < 0 || dp >= D) continue;
-                        uint32_t rr[8];
-                        tmem_ld8(lane_addr + (uint32_t)((r * C0_SLOTS + ((g0 + dp) & 3)) * 32 + kz * 8), rr);
-                        ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[r][j] += __uint_as_float(rr[j]);
+                        for (int j = 0; j < 8; ++j) acc[r][j] += __uint_as_float(rr[r][kz][j]);
                     }
                 }
                 ptx::tc_fence_before();
@@ -262,21 +258,18 @@ int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const flo
     cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.D, (cuuint64_t)in.B};
     cuuint64_t strides[4] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2,
                              (cuuint64_t)in.D * in.H * in.W * in.C * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)(C0_SEG + 2), 1, 1, 1};
+    cuuint32_t box[5] = {8, (cuuint32_t)C0_PIXPITCH, (cuuint32_t)(C0_R + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    if (planar) {   // [B*D][H][4][W][8]
-        dims[0] = 8; dims[1] = (cuuint64_t)in.W; dims[2] = 4; dims[3] = (cuuint64_t)in.H; dims[4] = (cuuint64_t)in.B * in.D;
-        strides[0] = 16; strides[1] = (cuuint64_t)in.W * 16; strides[2] = (cuuint64_t)in.W * 64; strides[3] = (cuuint64_t)in.H * in.W * 64;
-        box[1] = C0_PIXPITCH; box[2] = 4;
-    }
-    CUresult r = g_encode_shared(&pl->tmIn, in.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, in.hi, dims,
+    ADP_CHECK_ARG(!planar, "the depth-ring kernel reads the channels-last volume");
+    const int rank = 5;
+    CUresult r = g_encode_shared(&pl->tmIn, in.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, in.hi, dims,
                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(conv0 volume) failed: %d", (int)r);
         return ADP_ERR_CUDA;
     }
-    pl->p.B = in.B; pl->p.D = in.D; pl->p.H = in.H; pl->p.W = in.W; pl->p.f16 = in.f16; pl->p.planar = planar;
+    pl->p.B = in.B; pl->p.D = in.D; pl->p.H = in.H; pl->p.W = in.W; pl->p.f16 = in.f16;
     pl->p.w = w_packed; pl->p.scale = scale; pl->p.shift = shift; pl->p.out = out; pl->p.err = nullptr;
     pl->num_sms = num_sms > 0 ? num_sms : 148;
     return ADP_OK;

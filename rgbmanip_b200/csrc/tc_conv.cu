@@ -29,6 +29,88 @@ __device__ __forceinline__ uint32_t make_idesc(int f16) {
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
+// Epilogue of one accumulator chunk: r[0..CH) fp32 accumulators of output pixel `pix`, channels [nbase, nbase + CH)
+template <int CH>
+__device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase) {
+                            const int nvalid = min(CH, p.Cout - nbase);
+                            const size_t o = pix * p.Cout + nbase;
+                            const size_t ro = pix * p.res_cs + nbase;
+                            float v[32];
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+                            if (p.scale) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] *= __ldg(p.scale + nbase + j);
+                            }
+                            if (p.bias) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nbase + j);
+                            }
+                            const bool vec_ok = ((p.Cout | p.res_cs) & 7) == 0;   // 128-bit accesses stay aligned
+                            if (p.res_hi && !p.res_after_act) {
+#pragma unroll
+                                for (int j0 = 0; j0 < CH; j0 += 8) {
+                                    if (vec_ok && j0 + 8 <= nvalid) {
+                                        ld8_16(p.res_hi, ro + j0, p.f16, v + j0, true);
+                                        if (p.res_lo && !p.f16) ld8_16(p.res_lo, ro + j0, 0, v + j0, true);
+                                    } else {
+#pragma unroll
+                                        for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
+                                    }
+                                }
+                            }
+                            if (p.act == 1) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+                            } else if (p.act == 2) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.prelu;
+                            }
+                            if (p.res_hi && p.res_after_act) {
+#pragma unroll
+                                for (int j0 = 0; j0 < CH; j0 += 8) {
+                                    if (vec_ok && j0 + 8 <= nvalid) {
+                                        ld8_16(p.res_hi, ro + j0, p.f16, v + j0, true);
+                                        if (p.res_lo && !p.f16) ld8_16(p.res_lo, ro + j0, 0, v + j0, true);
+                                    } else {
+#pragma unroll
+                                        for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
+                                    }
+                                }
+                            }
+                            if (p.out_f32) {
+                                if (nvalid == CH && (p.Cout & 3) == 0) {
+#pragma unroll
+                                    for (int j = 0; j < CH; j += 4)
+                                        *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
+                                }
+                            }
+                            if (p.out_h16) {
+#pragma unroll
+                                for (int j0 = 0; j0 < CH; j0 += 8) {
+                                    if (vec_ok && j0 + 8 <= nvalid) st8_16(reinterpret_cast<bf16*>(p.out_h16), nullptr, o + j0, 1, v + j0);
+                                    else {
+#pragma unroll
+                                        for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) p.out_h16[o + j] = __float2half_rn(v[j]);
+                                    }
+                                }
+                            }
+                            if (p.out_hi) {
+#pragma unroll
+                                for (int j0 = 0; j0 < CH; j0 += 8) {
+                                    if (vec_ok && j0 + 8 <= nvalid) {
+                                        st8_16(p.out_hi, p.out_lo, o + j0, p.f16, v + j0);
+                                    } else {
+#pragma unroll
+                                        for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) st_act16(p.out_hi, p.out_lo, o + j, v[j], p.f16);
+                                    }
+                                }
+                            }
+}
+
 constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 // FUSED: split-precision layers whose tiles are L2-bound (small N) keep A_hi, A_lo, W_hi, W_lo of one (tap, K chunk) in
@@ -217,83 +299,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (valid) {
                     const int nbase = n0 + c0;
                     if (nbase < p.Cout) {   // Cout may be padded up to BN (e.g. 8 -> 16)
-                        const int nvalid = min(CH, p.Cout - nbase);
-                        const size_t o = pix * p.Cout + nbase;
-                        const size_t ro = pix * p.res_cs + nbase;
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-                        if (p.scale) {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] *= __ldg(p.scale + nbase + j);
-                        }
-                        if (p.bias) {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nbase + j);
-                        }
-                        const bool vec_ok = ((p.Cout | p.res_cs) & 7) == 0;   // 128-bit accesses stay aligned
-                        if (p.res_hi && !p.res_after_act) {
-#pragma unroll
-                            for (int j0 = 0; j0 < CH; j0 += 8) {
-                                if (vec_ok && j0 + 8 <= nvalid) {
-                                    ld8_16(p.res_hi, ro + j0, p.f16, v + j0, true);
-                                    if (p.res_lo && !p.f16) ld8_16(p.res_lo, ro + j0, 0, v + j0, true);
-                                } else {
-#pragma unroll
-                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
-                                }
-                            }
-                        }
-                        if (p.act == 1) {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-                        } else if (p.act == 2) {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.prelu;
-                        }
-                        if (p.res_hi && p.res_after_act) {
-#pragma unroll
-                            for (int j0 = 0; j0 < CH; j0 += 8) {
-                                if (vec_ok && j0 + 8 <= nvalid) {
-                                    ld8_16(p.res_hi, ro + j0, p.f16, v + j0, true);
-                                    if (p.res_lo && !p.f16) ld8_16(p.res_lo, ro + j0, 0, v + j0, true);
-                                } else {
-#pragma unroll
-                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) v[j] += ld_act16(p.res_hi, p.res_lo, ro + j, p.f16);
-                                }
-                            }
-                        }
-                        if (p.out_f32) {
-                            if (nvalid == CH && (p.Cout & 3) == 0) {
-#pragma unroll
-                                for (int j = 0; j < CH; j += 4)
-                                    *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < CH; ++j) if (j < nvalid) p.out_f32[o + j] = v[j];
-                            }
-                        }
-                        if (p.out_h16) {
-#pragma unroll
-                            for (int j0 = 0; j0 < CH; j0 += 8) {
-                                if (vec_ok && j0 + 8 <= nvalid) st8_16(reinterpret_cast<bf16*>(p.out_h16), nullptr, o + j0, 1, v + j0);
-                                else {
-#pragma unroll
-                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) p.out_h16[o + j] = __float2half_rn(v[j]);
-                                }
-                            }
-                        }
-                        if (p.out_hi) {
-#pragma unroll
-                            for (int j0 = 0; j0 < CH; j0 += 8) {
-                                if (vec_ok && j0 + 8 <= nvalid) {
-                                    st8_16(p.out_hi, p.out_lo, o + j0, p.f16, v + j0);
-                                } else {
-#pragma unroll
-                                    for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) st_act16(p.out_hi, p.out_lo, o + j, v[j], p.f16);
-                                }
-                            }
-                        }
+                        tc_epilogue_chunk<CH>(p, r, pix, nbase);
                     }
                 }
             }

@@ -82,7 +82,7 @@ build_volume_kernel(const FT* __restrict__ f_ref, const FT* __restrict__ f_src, 
 // voxel and the row index needs no per-thread division (the 4-threads-per-voxel kernel above is issue bound on exactly that)
 __global__ void __launch_bounds__(256)
 build_volume_row_kernel(const __half* __restrict__ f_ref, const __half* __restrict__ f_src, const float* __restrict__ Mw,
-                        const float* __restrict__ depths, bf16* __restrict__ vol, int D, int H, int W, int f16) {
+                        const float* __restrict__ depths, bf16* __restrict__ vol, int D, int H, int W, int f16, int planar) {
     constexpr int C = 32;
     const int row = blockIdx.x;
     const int y = row % H, d = (row / H) % D, b = row / (H * D);
@@ -113,9 +113,15 @@ build_volume_row_kernel(const __half* __restrict__ f_ref, const __half* __restri
                 }
             }
         }
-        bf16* dst = vol + ((((size_t)b * D + d) * H + y) * W + x) * C;
+        if (planar) {     // [B,D,H,4,W,8]: consecutive threads write consecutive 16-byte pieces of each chunk plane
+            bf16* dst = vol + ((((size_t)b * D + d) * H + y) * 4 * W + x) * 8;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) st8_16(dst, nullptr, 8 * q, f16, v + 8 * q);
+            for (int q = 0; q < 4; ++q) st8_16(dst, nullptr, (size_t)q * W * 8, f16, v + 8 * q);
+        } else {
+            bf16* dst = vol + ((((size_t)b * D + d) * H + y) * W + x) * C;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st8_16(dst, nullptr, 8 * q, f16, v + 8 * q);
+        }
     }
 }
 
@@ -124,10 +130,10 @@ int build_volume(const void* f_ref, const void* f_src, const float* Mw, const fl
     ADP_CHECK_ARG(C == 32, "feature channels must be 32");
     size_t total = (size_t)B * D * H * W * 4;
     if (total == 0) return ADP_OK;
-    if (feat_f16 && !planar) {
+    if (feat_f16) {
         build_volume_row_kernel<<<B * D * H, W <= 128 ? 128 : 256, 0, stream>>>(reinterpret_cast<const __half*>(f_ref),
                                                                                reinterpret_cast<const __half*>(f_src), Mw, depths, vol, D,
-                                                                               H, W, f16);
+                                                                               H, W, f16, planar);
         ADP_CUDA(cudaGetLastError());
         return ADP_OK;
     }

@@ -342,7 +342,7 @@ class Engine:
                 self._keep.append(w16)
                 plan = C.c_void_p()
                 va = xin.c
-                self.vol_planar = 1 if getattr(self, 'want_planar_volume', False) else 0
+                self.vol_planar = 0
                 L.check(self.lib.adp_conv0_plan_create(C.byref(plan), C.byref(va), L.ptr(w16), L.ptr(sc), L.ptr(sh), L.ptr(out.hi),
                                                        self.vol_planar, self.num_sms), "conv0_plan")
                 self._conv0_plans.append(plan)

@@ -138,9 +138,8 @@ def test_tc_conv_strided_transposed_fp16(G, case):
     assert G.rel_err(G.from_cl(out16), ref) < (2e-3 if f16 else 1.2e-2)   # 16-bit output rounding
 
 
-@pytest.mark.parametrize("planar", [0, 1])
 @pytest.mark.parametrize("f16", [1, 0])
-def test_conv0_depth_ring_kernel(G, f16, planar):
+def test_conv0_depth_ring_kernel(G, f16, planar=0):
     """conv0 (3x3x3, 32 -> 8) as the depth-ring tcgen05 kernel (csrc/conv0_ring.cu) against F.conv3d."""
     from rgbmanip_b200 import geometry
     lib = L.load()
