@@ -183,3 +183,36 @@ def test_branch_b_matches_reference_golden(golden_dir):
         px, deg, mm, cmm = O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e], min_z=MIN_Z)
         assert deg < TOL_DEG and mm < 5.0 and cmm < 8.0, (e, px, deg, mm, cmm)
     est.estimator.close()
+
+
+def test_size_independent_properties_at_scale(golden):
+    """num_envs = 256 (BASELINE configs[2] size): properties that do not need the oracle at that size --
+    (i) tiling the 8 golden envs gives 32 identical copies of the 8 golden boxes (independence of environments, chunk
+    boundaries and buffer reuse), (ii) a permutation of the environments permutes the boxes, (iii) the chunk size does not
+    matter, (iv) sentinel envs stay sentinels.  Tolerance 2e-5 m: only the atomicAdd order of the per-env means differs."""
+    g = golden
+    base = synth.make_batch(8, seed=0)
+    N = 256
+    idx = np.arange(N) % 8
+    args = [a[idx] for a in base.args()]
+    c1, c2 = _golden_choose(g, 8)
+    choose = (c1[idx], c2[idx])
+    est = _make(max_envs=48)          # 256 = 5 * 48 + 16: exercises the partial last chunk
+    boxes = est.estimate(*args, choose=choose)
+    assert boxes.shape == (N, 8, 3)
+    for e in range(8):
+        same = boxes[idx == e]
+        np.testing.assert_allclose(same, np.broadcast_to(same[0], same.shape), rtol=0, atol=2e-5)
+        if not g["valid"][e]:
+            np.testing.assert_array_equal(same[0], O.DEFAULT_BBOX)
+        else:
+            px, deg, mm, cmm = O.parity_errors(same[0], g["boxes"][e], base.K[e], base.E1[e], min_z=MIN_Z)
+            assert px < TOL_PX and deg < TOL_DEG and mm < TOL_MM and cmm < TOL_MM
+    perm = np.random.default_rng(3).permutation(N)
+    boxes_p = est.estimate(*[a[perm] for a in args], choose=(choose[0][perm], choose[1][perm]))
+    np.testing.assert_allclose(boxes_p, boxes[perm], rtol=0, atol=2e-5)
+    est.estimator.close()
+    est2 = _make(max_envs=7)
+    boxes_c = est2.estimate(*[a[:40] for a in args], choose=(choose[0][:40], choose[1][:40]))
+    np.testing.assert_allclose(boxes_c, boxes[:40], rtol=0, atol=2e-5)
+    est2.estimator.close()
