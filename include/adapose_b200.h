@@ -38,6 +38,7 @@ extern "C" {
 #define ADP_ACT_NONE 0
 #define ADP_ACT_RELU 1
 #define ADP_ACT_PRELU 2
+#define ADP_ACT_TANH 3
 
 typedef struct adp_act {      /* channels-last activation [B, D, H, W, C]; D == 1 for 2-D maps */
     void* hi;                 /* bf16 (or IEEE half when f16 != 0) */
@@ -69,6 +70,9 @@ typedef struct adp_epilogue { /* y = act(scale * acc + bias [+ res]) [+ res]  ->
     void* out_lo;
     float* out_f32;           /* fp32 or NULL */
     void* out_h16;            /* optional extra IEEE-half copy of the output (feature map for the volume builder) or NULL */
+    int32_t out_cstride;      /* channel pitch of out_hi/out_lo (0 = Cout): lets a layer write a column range of a wider tensor */
+    int32_t out_coff;         /* first channel of that range (torch.cat of network_v5.py:488 without a copy) */
+    int32_t bias_per_batch;   /* 1: bias is [B, Cout] (the per-env global feature term of pose_mlp2, network_v5.py:491-493) */
 } adp_epilogue;
 
 typedef struct adp_direct_conv {   /* generic CUDA-core convolution (strided / tiny-channel / transposed layers) */
@@ -151,6 +155,21 @@ ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float
                const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth,
                float* pf1, float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused,
                int B, int S, int D, int P, int regress_pose, int x11_f16, void* stream);
+
+/* decode split for the tensor-core MLP path: adp_decode_gather = the gather-bound part (depth logits at the sampled pixels,
+ * softmax / soft-argmax, depth-guided fusion; network_v5.py:449-465) writing the MLP inputs as bf16 hi/lo
+ * (xfeat [B,P,32], xcat [B,P,96] columns 0..31); the per-point MLPs (network_v5.py:432-444,486-493) then run as 1x1
+ * convolutions through adp_conv_tc_*; adp_colsum = mean over points (sums), adp_pose_gbias = per-env bias of pose_mlp2's
+ * first layer, adp_rot_head = rotation MLP + Ortho6d2Mat (rotation_utils.py:18-27). */
+ADP_API int adp_decode_gather(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
+                      const int32_t* choose, const uint8_t* valid, const float* prob_w, float* depth, void* xfeat_hi,
+                      void* xfeat_lo, void* xcat_hi, void* xcat_lo, float* dbg_logits, float* dbg_fused, int B, int S, int D,
+                      int P, int x11_f16, void* stream);
+ADP_API int adp_colsum(const void* hi, const void* lo, const uint8_t* valid, float* out, int B, int P, int C, void* stream);
+ADP_API int adp_pose_gbias(const float* gsum, const float* q0_w, const float* q0_b, const uint8_t* valid, float* gb, int B,
+                           int P, void* stream);
+ADP_API int adp_rot_head(const float* psum, const uint8_t* valid, const adp_decode_weights* w, float* R, float* r6, int B,
+                         int P, void* stream);
 
 /* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
 /* scratch: B * P*(P-1)/2 floats (the pair ratios are evaluated once and parked there for the exact-median select). */

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libadapose_b200.so")
 
 ADP_ABI_VERSION = 1
 DT_U8, DT_F32, DT_F64 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_TANH = 0, 1, 2, 3
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -32,7 +32,8 @@ class TcGeom(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("scale", vp), ("bias", vp), ("prelu", C.c_float), ("act", i32), ("res_after_act", i32),
-                ("res_hi", vp), ("res_lo", vp), ("res_cstride", i32), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp), ("out_h16", vp)]
+                ("res_hi", vp), ("res_lo", vp), ("res_cstride", i32), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp), ("out_h16", vp),
+                ("out_cstride", i32), ("out_coff", i32), ("bias_per_batch", i32)]
 
 
 class DirectConv(C.Structure):
@@ -81,6 +82,10 @@ SIGNATURES = {
     "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_decode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DecodeWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp,
                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_decode_gather": (C.c_int, [vp] * 15 + [C.c_int] * 5 + [vp]),
+    "adp_colsum": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_pose_gbias": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
+    "adp_rot_head": (C.c_int, [vp, vp, C.POINTER(DecodeWeights), vp, vp, C.c_int, C.c_int, vp]),
     "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "adp_fit_umeyama": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }

@@ -48,6 +48,15 @@ int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const flo
                int planar, int num_sms);
 int conv0_run(Conv0Plan* pl, int batch, int* err_flag, cudaStream_t stream);
 
+int decode_gather_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
+                    const int* choose, const uint8_t* valid, const float* prob_w, float* depth, void* xfeat_hi, void* xfeat_lo,
+                    void* xcat_hi, void* xcat_lo, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P, int x11_f16,
+                    cudaStream_t stream);
+int colsum_run(const bf16* hi, const bf16* lo, const uint8_t* valid, float* out, int B, int P, int C, cudaStream_t stream);
+int pose_gbias_run(const float* gsum, const float* q0_w, const float* q0_b, const uint8_t* valid, float* gb, int B, int P,
+                   cudaStream_t stream);
+int rot_head_run(const float* psum, const uint8_t* valid, float* Rout, float* r6out, const adp_decode_weights* cw, int B, int P,
+                 cudaStream_t stream);
 struct TconvPlan;
 TconvPlan* tconv_alloc();
 void tconv_release(TconvPlan* p);
@@ -128,6 +137,7 @@ int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, 
     p.out_hi = reinterpret_cast<bf16*>(ep->out_hi); p.out_lo = reinterpret_cast<bf16*>(ep->out_lo);
     p.out_f32 = ep->out_f32;
     p.out_h16 = reinterpret_cast<__half*>(ep->out_h16);
+    p.out_cs = ep->out_cstride ? ep->out_cstride : cout; p.out_coff = ep->out_coff; p.bias_per_batch = ep->bias_per_batch;
     pl->num_sms = num_sms > 0 ? num_sms : 148;
     *plan = pl;
     return ADP_OK;
@@ -256,6 +266,34 @@ int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, co
     g_launches += regress_pose ? 3 : 1;
     return decode_run_c(feat_ref, feat_src, Mw, depths, x11, choose, valid, w, nocs, depth, pf1, gsum, psum, R, r6, dbg_logits,
                         dbg_fused, B, S, D, P, regress_pose, x11_f16, (cudaStream_t)stream);
+}
+
+int adp_decode_gather(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
+                      const int32_t* choose, const uint8_t* valid, const float* prob_w, float* depth, void* xfeat_hi, void* xfeat_lo,
+                      void* xcat_hi, void* xcat_lo, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P, int x11_f16,
+                      void* stream) {
+    ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && x11 && choose && prob_w && depth && xfeat_hi && xcat_hi, "null pointer");
+    g_launches += 1;
+    return decode_gather_c(feat_ref, feat_src, Mw, depths, x11, choose, valid, prob_w, depth, xfeat_hi, xfeat_lo, xcat_hi, xcat_lo,
+                           dbg_logits, dbg_fused, B, S, D, P, x11_f16, (cudaStream_t)stream);
+}
+
+int adp_colsum(const void* hi, const void* lo, const uint8_t* valid, float* out, int B, int P, int C, void* stream) {
+    ADP_CHECK_ARG(hi && out, "null pointer");
+    g_launches += 1;
+    return colsum_run(reinterpret_cast<const bf16*>(hi), reinterpret_cast<const bf16*>(lo), valid, out, B, P, C, (cudaStream_t)stream);
+}
+
+int adp_pose_gbias(const float* gsum, const float* q0_w, const float* q0_b, const uint8_t* valid, float* gb, int B, int P, void* stream) {
+    ADP_CHECK_ARG(gsum && q0_w && q0_b && gb, "null pointer");
+    g_launches += 1;
+    return pose_gbias_run(gsum, q0_w, q0_b, valid, gb, B, P, (cudaStream_t)stream);
+}
+
+int adp_rot_head(const float* psum, const uint8_t* valid, const adp_decode_weights* w, float* R, float* r6, int B, int P, void* stream) {
+    ADP_CHECK_ARG(psum && w && R, "null pointer");
+    g_launches += 1;
+    return rot_head_run(psum, valid, R, r6, w, B, P, (cudaStream_t)stream);
 }
 
 int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R, const double* E,

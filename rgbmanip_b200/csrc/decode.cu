@@ -86,6 +86,168 @@ struct DecodeArgs {
     int regress;             // 0: stop after NOCS + depth (no pose heads: direct_regression = False)
 };
 
+// ------------------------------------------------------------------------------------------------
+// decode, stage 1 (the gather-bound part): depth logits at the sampled pixels (the `prob` conv evaluated only there),
+// softmax over depth + soft-argmax, depth-guided fused feature, and the reference feature at the pixel.  The per-point
+// MLPs then run as 1x1 convolutions on the tcgen05 kernel (engine.py), so this kernel writes their inputs as bf16 hi/lo.
+//   xfeat [B,P,32]  (instance_color input)           xcat [B,P,96] columns 0..31 = fused feature (pose_mlp1 input)
+// ------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    DecodeArgs a;
+    bf16* xfeat_hi; bf16* xfeat_lo;
+    bf16* xcat_hi;  bf16* xcat_lo;
+};
+
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_gather_kernel(const GatherArgs ga, const float* __restrict__ prob_w) {
+    const DecodeArgs& a = ga.a;
+    extern __shared__ float smf[];
+    float* bufA = smf;                   // [PB][LDS] (only columns 0..31 used)
+    float* bufB = smf + PB * LDS;
+    float* s_logit = smf + 2 * PB * LDS;
+    float* s_probw = s_logit + PB * 24;
+    int* s_pix = reinterpret_cast<int*>(s_probw + 216);
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * PB;
+    if (a.valid && !a.valid[b]) return;
+    const int S = a.S, D = a.D;
+    for (int i = tid; i < 216; i += DEC_THREADS) s_probw[i] = prob_w[i];
+    if (tid < PB) s_pix[tid] = a.choose[(size_t)b * a.P + p0 + tid];
+    __syncthreads();
+
+    // ---- (a) depth logits at the sampled pixels: 3x3x3 conv over the 8-channel volume, zero padding
+    for (int e = tid; e < PB * D; e += DEC_THREADS) {
+        const int r = e / D, d = e - r * D;
+        const int pix = s_pix[r];
+        const int y = pix / S, x = pix - y * S;
+        float acc = 0.f;
+        for (int kz = 0; kz < 3; ++kz) {
+            const int dz = d + kz - 1;
+            if (dz < 0 || dz >= D) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = y + ky - 1;
+                if (yy < 0 || yy >= S) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = x + kx - 1;
+                    if (xx < 0 || xx >= S) continue;
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.x11 + ((((size_t)b * D + dz) * S + yy) * S + xx) * 8));
+                    const float* wt = s_probw + ((kz * 3 + ky) * 3 + kx) * 8;
+                    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float lo16, hi16;
+                        if (a.x11_f16) {
+                            lo16 = __half2float(__ushort_as_half((unsigned short)(u[q] & 0xffffu)));
+                            hi16 = __half2float(__ushort_as_half((unsigned short)(u[q] >> 16)));
+                        } else {
+                            lo16 = __uint_as_float(u[q] << 16);
+                            hi16 = __uint_as_float(u[q] & 0xffff0000u);
+                        }
+                        acc = fmaf(lo16, wt[2 * q], acc);
+                        acc = fmaf(hi16, wt[2 * q + 1], acc);
+                    }
+                }
+            }
+        }
+        s_logit[r * 24 + d] = acc;
+        if (a.dbg_logits) a.dbg_logits[((size_t)b * a.P + p0 + r) * D + d] = acc;
+    }
+    __syncthreads();
+
+    // ---- (b) softmax over depth + expectation: 8 lanes per pixel, shuffle reductions
+    {
+        const int r = tid >> 3, l = tid & 7;   // 32 pixels x 8 lanes
+        float v[3], m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { v[j] = s_logit[r * 24 + l + 8 * j]; m = fmaxf(m, v[j]); }
+        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { v[j] = expf(v[j] - m); s += v[j]; }
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        float dsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float pr = v[j] / s;
+            s_logit[r * 24 + l + 8 * j] = pr;
+            dsum = fmaf(pr, a.depths[l + 8 * j], dsum);
+        }
+        for (int o = 4; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        if (l == 0) a.depth[(size_t)b * a.P + p0 + r] = dsum;
+    }
+    __syncthreads();
+
+    // ---- (c) reference features at the pixel -> bufA[:, 0:32]; depth-guided fused features -> bufB[:, 0:32]
+    {
+        const int r = tid >> 3, cq = tid & 7;   // 4 channels per thread, 128-bit loads
+        const int pix = s_pix[r];
+        const int y = pix / S, x = pix - y * S;
+        const float4 fr = __ldg(reinterpret_cast<const float4*>(a.feat_ref + (((size_t)b * S + y) * S + x) * 32 + cq * 4));
+        *reinterpret_cast<float4*>(bufA + r * LDS + cq * 4) = fr;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* src = a.feat_src + (size_t)b * S * S * 32 + cq * 4;
+        for (int d = 0; d < D; ++d) {
+            const float pr = s_logit[r * 24 + d];
+            float ix, iy;
+            warp_coords(a.Mw + 12 * b, (float)x, (float)y, a.depths[d], S, S, &ix, &iy);
+            const Bilin bl = bilin_setup(ix, iy, S, S);
+            float4 v = fr;
+            if (bl.any) {
+                const float wts[4] = {bl.w00, bl.w01, bl.w10, bl.w11};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (wts[k] != 0.f) {
+                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(src + ((size_t)(bl.y0 + (k >> 1)) * S + bl.x0 + (k & 1)) * 32));
+                        v.x = fmaf(wts[k], s4.x, v.x); v.y = fmaf(wts[k], s4.y, v.y);
+                        v.z = fmaf(wts[k], s4.z, v.z); v.w = fmaf(wts[k], s4.w, v.w);
+                    }
+                }
+            }
+            acc.x = fmaf(pr, v.x, acc.x); acc.y = fmaf(pr, v.y, acc.y);
+            acc.z = fmaf(pr, v.z, acc.z); acc.w = fmaf(pr, v.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(bufB + r * LDS + cq * 4) = acc;
+        if (a.dbg_fused) *reinterpret_cast<float4*>(a.dbg_fused + ((size_t)b * a.P + p0 + r) * 32 + cq * 4) = acc;
+    }
+    __syncthreads();
+
+    // ---- write the MLP inputs as bf16 hi/lo
+    {
+        const int r = tid >> 3, c8 = (tid & 7) * 8;        // 32 pixels x 8 groups of 8 channels: groups 0-3 feat, 4-7 fused
+        const size_t pt = (size_t)b * a.P + p0 + r;
+        if (c8 < 32) st8_16(ga.xfeat_hi, ga.xfeat_lo, pt * 32 + c8, 0, bufA + r * LDS + c8);
+        else st8_16(ga.xcat_hi, ga.xcat_lo, pt * 96 + (c8 - 32), 0, bufB + r * LDS + (c8 - 32));
+    }
+}
+
+// column sums over the P points of an env: out[b, c] = sum_p x[b, p, c]   (hi + lo)
+__global__ void colsum_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, const uint8_t* __restrict__ valid,
+                              float* __restrict__ out, int P, int C, int rows_per_block) {
+    const int b = blockIdx.y;
+    if (valid && !valid[b]) return;
+    const int r0 = blockIdx.x * rows_per_block;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = r0; r < r0 + rows_per_block && r < P; ++r) s += ld_act(hi, lo, ((size_t)b * P + r) * C + c);
+        atomicAdd(out + (size_t)b * C + c, s);
+    }
+}
+
+// per-env bias of pose_mlp2's first layer: gb[b, n] = bias[n] + sum_k W[128 + k][n] * (gsum[b, k] / P)   (network_v5.py:491-493)
+__global__ void pose_gbias_kernel(const float* __restrict__ gsum, const float* __restrict__ q0_w, const float* __restrict__ q0_b,
+                                  const uint8_t* __restrict__ valid, float* __restrict__ gb, int P) {
+    __shared__ float gm[128];
+    const int b = blockIdx.x, n = threadIdx.x;     // 256 threads
+    if (valid && !valid[b]) return;
+    if (n < 128) gm[n] = gsum[(size_t)b * 128 + n] / (float)P;
+    __syncthreads();
+    float acc = q0_b[n];
+    for (int k = 0; k < 128; ++k) acc = fmaf(gm[k], __ldg(q0_w + (size_t)(128 + k) * 256 + n), acc);
+    gb[(size_t)b * 256 + n] = acc;
+}
+
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_points_kernel(const DecodeArgs a, const DecodeWeights w) {
     extern __shared__ float smf[];
@@ -342,6 +504,62 @@ int decode_run(const DecodeArgs& a, const DecodeWeights& w, float* psum, float* 
         ADP_CUDA(cudaGetLastError());
     }
     return ADP_OK;
+}
+
+int decode_gather_run(const DecodeArgs& a, const float* prob_w, bf16* xfeat_hi, bf16* xfeat_lo, bf16* xcat_hi, bf16* xcat_lo,
+                      cudaStream_t stream) {
+    ADP_CHECK_ARG(a.D == 24 && a.P % PB == 0, "24 depth hypotheses, P multiple of 32");
+    if (a.B == 0) return ADP_OK;
+    const size_t smem1 = (size_t)(2 * PB * LDS + PB * 24 + 216) * sizeof(float) + PB * sizeof(int);
+    static bool attr = false;
+    if (!attr) {
+        ADP_CUDA(cudaFuncSetAttribute(decode_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        attr = true;
+    }
+    GatherArgs ga;
+    ga.a = a; ga.xfeat_hi = xfeat_hi; ga.xfeat_lo = xfeat_lo; ga.xcat_hi = xcat_hi; ga.xcat_lo = xcat_lo;
+    decode_gather_kernel<<<dim3(a.P / PB, a.B), DEC_THREADS, smem1, stream>>>(ga, prob_w);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+int colsum_run(const bf16* hi, const bf16* lo, const uint8_t* valid, float* out, int B, int P, int C, cudaStream_t stream) {
+    if (B == 0) return ADP_OK;
+    ADP_CUDA(cudaMemsetAsync(out, 0, (size_t)B * C * sizeof(float), stream));
+    const int rpb = 64;
+    colsum_kernel<<<dim3((P + rpb - 1) / rpb, B), C < 256 ? C : 256, 0, stream>>>(hi, lo, valid, out, P, C, rpb);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+int pose_gbias_run(const float* gsum, const float* q0_w, const float* q0_b, const uint8_t* valid, float* gb, int B, int P,
+                   cudaStream_t stream) {
+    if (B == 0) return ADP_OK;
+    pose_gbias_kernel<<<B, 256, 0, stream>>>(gsum, q0_w, q0_b, valid, gb, P);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+int rot_head_run(const float* psum, const uint8_t* valid, float* Rout, float* r6out, const adp_decode_weights* cw, int B, int P,
+                 cudaStream_t stream) {
+    if (B == 0) return ADP_OK;
+    DecodeWeights w{};
+    w.r0_w = cw->r0_w; w.r0_b = cw->r0_b; w.r1_w = cw->r1_w; w.r1_b = cw->r1_b; w.r2_w = cw->r2_w; w.r2_b = cw->r2_b;
+    rot_head_kernel<<<B, 256, 0, stream>>>(psum, valid, Rout, r6out, w, P);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+int decode_gather_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
+                    const int* choose, const uint8_t* valid, const float* prob_w, float* depth, void* xfeat_hi, void* xfeat_lo,
+                    void* xcat_hi, void* xcat_lo, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P, int x11_f16,
+                    cudaStream_t stream) {
+    DecodeArgs a{};
+    a.feat_ref = feat_ref; a.feat_src = feat_src; a.Mw = Mw; a.depths = depths; a.x11 = reinterpret_cast<const bf16*>(x11);
+    a.choose = choose; a.valid = valid; a.nocs = nullptr; a.depth = depth; a.pf1 = nullptr; a.gsum = nullptr;
+    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16; a.regress = 0;
+    return decode_gather_run(a, prob_w, reinterpret_cast<bf16*>(xfeat_hi), reinterpret_cast<bf16*>(xfeat_lo),
+                             reinterpret_cast<bf16*>(xcat_hi), reinterpret_cast<bf16*>(xcat_lo), stream);
 }
 
 int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,

@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t make_idesc(int f16) {
 // ------------------------------------------------------------------------------------------------
 // Epilogue of one accumulator chunk: r[0..CH) fp32 accumulators of output pixel `pix`, channels [nbase, nbase + CH)
 template <int CH>
-__device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase) {
+__device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase, int b) {
                             const int nvalid = min(CH, p.Cout - nbase);
                             const size_t o = pix * p.Cout + nbase;
                             const size_t ro = pix * p.res_cs + nbase;
@@ -43,10 +43,12 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const u
                                 for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] *= __ldg(p.scale + nbase + j);
                             }
                             if (p.bias) {
+                                const float* bias = p.bias + (p.bias_per_batch ? (size_t)b * p.Cout : 0);
 #pragma unroll
-                                for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nbase + j);
+                                for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(bias + nbase + j);
                             }
-                            const bool vec_ok = ((p.Cout | p.res_cs) & 7) == 0;   // 128-bit accesses stay aligned
+                            const size_t oh = pix * p.out_cs + p.out_coff + nbase;   // out_hi / out_lo may be a column range of a wider tensor
+                            const bool vec_ok = ((p.Cout | p.res_cs | p.out_cs | p.out_coff) & 7) == 0;   // 128-bit accesses stay aligned
                             if (p.res_hi && !p.res_after_act) {
 #pragma unroll
                                 for (int j0 = 0; j0 < CH; j0 += 8) {
@@ -65,6 +67,9 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const u
                             } else if (p.act == 2) {
 #pragma unroll
                                 for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.prelu;
+                            } else if (p.act == 3) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) v[j] = tanhf(v[j]);
                             }
                             if (p.res_hi && p.res_after_act) {
 #pragma unroll
@@ -102,10 +107,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const u
 #pragma unroll
                                 for (int j0 = 0; j0 < CH; j0 += 8) {
                                     if (vec_ok && j0 + 8 <= nvalid) {
-                                        st8_16(p.out_hi, p.out_lo, o + j0, p.f16, v + j0);
+                                        st8_16(p.out_hi, p.out_lo, oh + j0, p.f16, v + j0);
                                     } else {
 #pragma unroll
-                                        for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) st_act16(p.out_hi, p.out_lo, o + j, v[j], p.f16);
+                                        for (int j = j0; j < j0 + 8; ++j) if (j < nvalid) st_act16(p.out_hi, p.out_lo, oh + j, v[j], p.f16);
                                     }
                                 }
                             }
@@ -299,7 +304,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (valid) {
                     const int nbase = n0 + c0;
                     if (nbase < p.Cout) {   // Cout may be padded up to BN (e.g. 8 -> 16)
-                        tc_epilogue_chunk<CH>(p, r, pix, nbase);
+                        tc_epilogue_chunk<CH>(p, r, pix, nbase, b);
                     }
                 }
             }

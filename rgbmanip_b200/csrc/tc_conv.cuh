@@ -39,7 +39,7 @@ struct TcConvParams {
     const float* bias;       // [Cout] or nullptr (BatchNorm shift is passed here too)
     const float* scale;      // [Cout] or nullptr (folded BatchNorm scale)
     float prelu;             // slope for act == 2
-    int act;                 // 0 none, 1 relu, 2 prelu
+    int act;                 // 0 none, 1 relu, 2 prelu, 3 tanh
     int res_after_act;       // 0: act(acc + res)   1: act(acc) + res   (3-D U-Net skips)
     const bf16* res_hi;
     const bf16* res_lo;
@@ -48,6 +48,8 @@ struct TcConvParams {
     bf16* out_lo;
     float* out_f32;
     __half* out_h16;         // optional extra fp16 copy
+    int out_cs, out_coff;    // channel pitch / first channel of out_hi, out_lo
+    int bias_per_batch;      // bias is [B, Cout]
     int* err;                // device error flag (pipeline watchdog)
 };
 

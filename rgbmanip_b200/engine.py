@@ -63,7 +63,7 @@ class Engine:
 
     def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="bf16x3", regress_pose=True, use_tc=True,
                  use_tc_3d=True, tc_strided=True, tc_transposed=True, conv0_ring=True, tconv_fused=True, volume_dtype="fp16", debug=False,
-                 img_size=IMG_SIZE, n_pts=N_PTS):
+                 img_size=IMG_SIZE, n_pts=N_PTS, decode_tc=True):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
         if precision not in ("bf16", "bf16x3"):
@@ -84,6 +84,7 @@ class Engine:
         self.tc_transposed = tc_transposed
         self.conv0_ring = conv0_ring and use_tc_3d
         self.tconv_fused = tconv_fused and use_tc_3d and tc_transposed
+        self.decode_tc = decode_tc and use_tc and int(n_pts) == 1024
         self._conv0_plans = []
         self._tconv_plans = []
         if volume_dtype not in ("fp16", "bf16"):
@@ -128,12 +129,12 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _epilogue(self, out: ActBuf | None, scale=None, bias=None, act=L.ACT_RELU, prelu=0.0, res: ActBuf | None = None,
-                  res_after_act=0, out_f32=None, out_h16=None):
+                  res_after_act=0, out_f32=None, out_h16=None, out_cstride=0, out_coff=0, bias_per_batch=0):
         return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act, res_after_act,
                           L.ptr(res.hi) if res else None, L.ptr(res.lo) if (res and res.lo is not None) else None,
                           res.Cn if res else 0,
                           L.ptr(out.hi) if out else None, L.ptr(out.lo) if (out and out.lo is not None) else None,
-                          L.ptr(out_f32), L.ptr(out_h16))
+                          L.ptr(out_f32), L.ptr(out_h16), out_cstride, out_coff, bias_per_batch)
 
     def _tc_plans(self, x: ActBuf, wt, cout, kd, ks, dil, npass, ep, geoms):
         """wt: fp32 [taps, CoutPad, Cin] packed weights -> callable(batch) launching one tcgen05 conv per geometry."""
@@ -421,6 +422,56 @@ class Engine:
         self.trans = torch.zeros((E, 3), dtype=torch.float64, device=dev)
         self.fit_scratch = torch.zeros((E, P * (P - 1) // 2), dtype=torch.float32, device=dev)
         self.rot64 = torch.zeros((E, 9), dtype=torch.float64, device=dev)
+        if self.decode_tc:
+            self._build_decode_tc()
+
+    def _build_decode_tc(self):
+        """Per-point MLPs (network_v5.py:432-444,486-493) as 1x1 convolutions on the tcgen05 kernel: the P = 1024 sampled
+        pixels of an env form a 32x32 "image", every layer is one split-precision (bf16x3) launch over all envs."""
+        sd, E, P = self.sd, self.E, self.P
+        assert P == 1024
+        pt = lambda Cn: self._act(E, 32, 32, Cn, split=True)
+        self.xfeat, self.xcat = pt(32), pt(96)
+        h_ic, h_n0, h_n1, self.nocs16 = pt(64), pt(128), pt(64), pt(16)
+
+        def fc(name, x, out, act=L.ACT_RELU, w=None, bias=None, **kw):
+            w = torch.as_tensor(sd[f"{name}.weight"]).float().reshape(sd[f"{name}.weight"].shape[0], -1) if w is None else w
+            cout, cin = w.shape
+            if cin < x.Cn:      # nocs_pts_mlp.0 reads the 3 NOCS coordinates out of a 16-channel buffer
+                w = torch.cat([w, torch.zeros(cout, x.Cn - cin)], 1)
+            cout_pad = (cout + 15) // 16 * 16
+            if cout_pad != cout:
+                w = torch.cat([w, torch.zeros(cout_pad - cout, w.shape[1])], 0)
+            bias = self._dev(sd[f"{name}.bias"]) if bias is None else bias
+            ep = self._epilogue(out, bias=bias, act=act, **kw)
+            return self._tc_plans(x, w[None].contiguous(), cout, 1, 1, 1, 3, ep, [None])
+
+        ops = [("ic", fc("instance_color.0", self.xfeat, h_ic)),
+               ("nh0", fc("nocs_head.0", h_ic, h_n0)),
+               ("nh1", fc("nocs_head.2", h_n0, h_n1)),
+               ("nh2", fc("nocs_head.4", h_n1, self.nocs16, act=L.ACT_TANH, out_f32=self.nocs, out_cstride=16))]
+        if self.regress_pose:
+            h_p0, h_m0, self.pf1b, h_q0, self.pf2b = pt(32), pt(128), pt(128), pt(256), pt(256)
+            self.gbias = torch.zeros((E, 256), dtype=torch.float32, device=self.device)
+            wq0 = torch.as_tensor(sd["pose_mlp2.0.weight"]).float().reshape(256, 256)
+            ops += [("np0", fc("nocs_pts_mlp.0", self.nocs16, h_p0)),
+                    ("np1", fc("nocs_pts_mlp.2", h_p0, self.xcat, out_cstride=96, out_coff=32)),
+                    ("pm0", fc("pose_mlp1.0", self.xcat, h_m0)),
+                    ("pm1", fc("pose_mlp1.2", h_m0, self.pf1b)),
+                    ("gmean", lambda n: (
+                        L.check(self.lib.adp_colsum(L.ptr(self.pf1b.hi), L.ptr(self.pf1b.lo), L.ptr(self.valid_env), L.ptr(self.gsum),
+                                                    n, P, 128, self.stream), "colsum"),
+                        L.check(self.lib.adp_pose_gbias(L.ptr(self.gsum), self.dw.q0_w, self.dw.q0_b, L.ptr(self.valid_env),
+                                                        L.ptr(self.gbias), n, P, self.stream), "pose_gbias"))),
+                    # pose_mlp2.0 on cat(pf, mean(pf)): the mean half of the product is the per-env bias computed above
+                    ("q0", fc("pose_mlp2.0", self.pf1b, h_q0, w=wq0[:, :128].contiguous(), bias=self.gbias, bias_per_batch=1)),
+                    ("q1", fc("pose_mlp2.2", h_q0, self.pf2b)),
+                    ("rot", lambda n: (
+                        L.check(self.lib.adp_colsum(L.ptr(self.pf2b.hi), L.ptr(self.pf2b.lo), L.ptr(self.valid_env), L.ptr(self.psum),
+                                                    n, P, 256, self.stream), "colsum"),
+                        L.check(self.lib.adp_rot_head(L.ptr(self.psum), L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.R),
+                                                      L.ptr(self.r6), n, P, self.stream), "rot_head")))]
+        self.dec_ops = ops
 
     # ------------------------------------------------------------------ stages
     @staticmethod
@@ -466,10 +517,19 @@ class Engine:
         for name, op in self.cr_ops:
             op(n)
             mark(name)
-        L.check(lib.adp_decode(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi), L.ptr(self.choose),
-                               L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.pf1),
-                               L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
-                               L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.vol_f16, st), "decode")
+        if self.decode_tc:
+            L.check(lib.adp_decode_gather(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi),
+                                          L.ptr(self.choose), L.ptr(self.valid_env), self.dw.prob_w, L.ptr(self.depth),
+                                          L.ptr(self.xfeat.hi), L.ptr(self.xfeat.lo), L.ptr(self.xcat.hi), L.ptr(self.xcat.lo),
+                                          L.ptr(self.dbg_logits), L.ptr(self.dbg_fused), n, S, D, P, self.vol_f16, st), "decode_gather")
+            mark("decode_gather")
+            for name, op in self.dec_ops:
+                op(n)
+        else:
+            L.check(lib.adp_decode(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi), L.ptr(self.choose),
+                                   L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.pf1),
+                                   L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
+                                   L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.vol_f16, st), "decode")
         mark("decode")
         if self.regress_pose:
             L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),

@@ -403,12 +403,14 @@ def _run_costreg_decode(G, sd, eng_kw):
     return eng
 
 
-def test_costreg_and_decode_match_oracle(G):
+@pytest.mark.parametrize("decode_tc", [True, False], ids=["mlp_tcgen05", "mlp_cuda_cores"])
+def test_costreg_and_decode_match_oracle(G, decode_tc):
     """Feed oracle feature maps into the device volume/cost-regularisation/decode stages."""
     from rgbmanip_b200.engine import Engine
     sd = weights.init_state_dict(0)
     batch, views = _stereo_inputs(2)
-    eng = Engine(sd, device=G.DEV, max_envs=2, debug=True)
+    eng = Engine(sd, device=G.DEV, max_envs=2, debug=True, decode_tc=decode_tc)
+    assert eng.decode_tc == decode_tc
     dev = G.DEV
     with torch.no_grad():
         img1 = torch.from_numpy(np.stack([v[0][0] for v in views])).float()
