@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--num-envs", type=int, default=1024)
     ap.add_argument("--chunk", type=int, default=64)
-    ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--precision", default="fp16x2")
     ap.add_argument("--unique", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")

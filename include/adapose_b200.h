@@ -123,19 +123,24 @@ ADP_API int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int 
 
 /* conv0 of the cost-regularisation U-Net (network_v5.py:263,283) as a depth-ring tcgen05 kernel: vol [B,D,H,W,32] ->
  * out [B,D,H,W,16] (8 channels + 8 zero), folded BatchNorm + ReLU.  w: 16-bit [9 (ky,kx)][4 chunks][32 (kz,co)][8].
- * vol_planar != 0: the volume is stored [B,D,H,4,W,8] (adp_build_volume planar) and a row arrives in one TMA box. */
+ * flags: bit 0 must be 0 (reserved: planar volume layout); bit 1 (ADP_LAYOUT_S2D) = write the 8 real channels
+ * space-to-depth(2): out [B,D/2,H/2,W/2,64], channel = ((d&1)*4 + (y&1)*2 + (x&1))*8 + co.  In that layout the stride-2
+ * conv1 and the skip connection of the transposed conv11 (network_v5.py:265,278,283) read it as a stride-1 tensor. */
+#define ADP_LAYOUT_F16 1
+#define ADP_LAYOUT_S2D 2
 typedef struct adp_conv0_plan adp_conv0_plan;
 ADP_API int adp_conv0_plan_create(adp_conv0_plan** plan, const adp_act* vol, const void* w_packed, const float* scale,
-                                  const float* shift, void* out, int vol_planar, int num_sms);
+                                  const float* shift, void* out, int flags, int num_sms);
 ADP_API int adp_conv0_run(adp_conv0_plan* plan, int batch, int32_t* err_flag, void* stream);
 ADP_API void adp_conv0_free(adp_conv0_plan* plan);
 
 /* ConvTranspose3d(k3, s2, p1, op1) + folded BN + ReLU + skip (network_v5.py:217-258,274-278,287-289) with all 8 output
  * parity classes in one tcgen05 kernel.  in [B,D,H,W,Cin] (Cin 16|32, single 16-bit plane), w 16-bit [27][pad16(Cout)][Cin],
- * res [B,2D,2H,2W,res_cstride] or NULL, out [B,2D,2H,2W,Cout]. */
+ * res [B,2D,2H,2W,res_cstride] or NULL, out [B,2D,2H,2W,Cout].  flags & ADP_LAYOUT_S2D: res and out are stored
+ * space-to-depth(2), [B,D,H,W,8*Cout] with channel = parity*Cout + c (res_cstride ignored). */
 typedef struct adp_tconv_plan adp_tconv_plan;
 ADP_API int adp_tconv_plan_create(adp_tconv_plan** plan, const adp_act* in, const void* w, int cout, const float* scale,
-                                  const float* bias, const void* res, int res_cstride, void* out, int num_sms);
+                                  const float* bias, const void* res, int res_cstride, void* out, int flags, int num_sms);
 ADP_API int adp_tconv_run(adp_tconv_plan* plan, int batch, int32_t* err_flag, void* stream);
 ADP_API void adp_tconv_free(adp_tconv_plan* plan);
 
@@ -151,10 +156,11 @@ ADP_API int adp_build_volume(const void* feat_ref, const void* feat_src, const f
                      int B, int D, int H, int W, int C, int f16, int feat_f16, int planar, void* stream);
 
 /* --- decode + heads: network_v5.py:432-465,486-499; rotation_utils.py:4-27 ----------------------------------- */
+/* x11_format: ADP_LAYOUT_F16 (IEEE half instead of bf16) | ADP_LAYOUT_S2D (x11 stored [B,D/2,S/2,S/2,64], see adp_conv0_plan_create) */
 ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth,
                float* pf1, float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused,
-               int B, int S, int D, int P, int regress_pose, int x11_f16, void* stream);
+               int B, int S, int D, int P, int regress_pose, int x11_format, void* stream);
 
 /* decode split for the tensor-core MLP path: adp_decode_gather = the gather-bound part (depth logits at the sampled pixels,
  * softmax / soft-argmax, depth-guided fusion; network_v5.py:449-465) writing the MLP inputs as bf16 hi/lo
@@ -164,7 +170,7 @@ ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float
 ADP_API int adp_decode_gather(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                       const int32_t* choose, const uint8_t* valid, const float* prob_w, float* depth, void* xfeat_hi,
                       void* xfeat_lo, void* xcat_hi, void* xcat_lo, float* dbg_logits, float* dbg_fused, int B, int S, int D,
-                      int P, int x11_f16, void* stream);
+                      int P, int x11_format, void* stream);
 ADP_API int adp_colsum(const void* hi, const void* lo, const uint8_t* valid, float* out, int B, int P, int C, void* stream);
 ADP_API int adp_pose_gbias(const float* gsum, const float* q0_w, const float* q0_b, const uint8_t* valid, float* gb, int B,
                            int P, void* stream);

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libadapose_b200.so")
 ADP_ABI_VERSION = 1
 DT_U8, DT_F32, DT_F64 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_TANH = 0, 1, 2, 3
+LAYOUT_F16, LAYOUT_S2D = 1, 2          # adp_decode x11_format / adp_conv0_plan_create flags
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -75,7 +76,7 @@ SIGNATURES = {
     "adp_conv0_plan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, vp, vp, C.c_int, C.c_int]),
     "adp_conv0_run": (C.c_int, [vp, C.c_int, vp, vp]),
     "adp_conv0_free": (None, [vp]),
-    "adp_tconv_plan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int]),
+    "adp_tconv_plan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int]),
     "adp_tconv_run": (C.c_int, [vp, C.c_int, vp, vp]),
     "adp_tconv_free": (None, [vp]),
     "adp_warp_matrices": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),

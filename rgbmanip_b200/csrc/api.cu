@@ -61,7 +61,7 @@ struct TconvPlan;
 TconvPlan* tconv_alloc();
 void tconv_release(TconvPlan* p);
 int tconv_plan(TconvPlan* pl, const Act& in, const bf16* w, int Cout, const float* scale, const float* bias, const bf16* res,
-               int res_cs, bf16* out, int num_sms);
+               int res_cs, bf16* out, int flags, int num_sms);
 int tconv_run(TconvPlan* pl, int batch, int* err_flag, cudaStream_t stream);
 
 struct DecodeWeights;
@@ -216,11 +216,11 @@ int adp_conv0_run(adp_conv0_plan* plan, int batch, int32_t* err_flag, void* stre
 void adp_conv0_free(adp_conv0_plan* plan) { conv0_release(reinterpret_cast<Conv0Plan*>(plan)); }
 
 int adp_tconv_plan_create(adp_tconv_plan** plan, const adp_act* in, const void* w, int cout, const float* scale, const float* bias,
-                          const void* res, int res_cstride, void* out, int num_sms) {
+                          const void* res, int res_cstride, void* out, int flags, int num_sms) {
     ADP_CHECK_ARG(plan && in && w && scale && bias && out, "null pointer");
     TconvPlan* pl = tconv_alloc();
     int r = tconv_plan(pl, to_act(in), reinterpret_cast<const bf16*>(w), cout, scale, bias, reinterpret_cast<const bf16*>(res),
-                       res_cstride, reinterpret_cast<bf16*>(out), num_sms);
+                       res_cstride, reinterpret_cast<bf16*>(out), flags, num_sms);
     if (r != ADP_OK) {
         tconv_release(pl);
         return r;

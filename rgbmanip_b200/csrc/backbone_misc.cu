@@ -5,10 +5,18 @@
 
 namespace adp {
 
-// 8 consecutive channels (16 B per plane) <-> fp32 registers
-__device__ __forceinline__ void ld8(const bf16* __restrict__ hi, const bf16* __restrict__ lo, size_t i, float* v) {
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + i));
+// 8 consecutive channels (16 B per plane) <-> fp32 registers; f16 = 1: a single IEEE-half plane
+__device__ __forceinline__ void ld8(const bf16* __restrict__ hi, const bf16* __restrict__ lo, size_t i, float* v, int f16) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + i));     // inputs are never written by these kernels
     const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+    if (f16) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[2 * u] = __half2float(__ushort_as_half((unsigned short)(hw[u] & 0xffffu)));
+            v[2 * u + 1] = __half2float(__ushort_as_half((unsigned short)(hw[u] >> 16)));
+        }
+        return;
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         v[2 * u] = __uint_as_float(hw[u] << 16);
@@ -24,24 +32,15 @@ __device__ __forceinline__ void ld8(const bf16* __restrict__ hi, const bf16* __r
         }
     }
 }
-__device__ __forceinline__ void st8(bf16* __restrict__ hi, bf16* __restrict__ lo, size_t i, const float* v) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const bf16 h0 = __float2bfloat16_rn(v[2 * u]), h1 = __float2bfloat16_rn(v[2 * u + 1]);
-        h[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        const bf16 l0 = __float2bfloat16_rn(v[2 * u] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * u + 1] - __bfloat162float(h1));
-        l[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    *reinterpret_cast<uint4*>(hi + i) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (lo) *reinterpret_cast<uint4*>(lo + i) = make_uint4(l[0], l[1], l[2], l[3]);
+__device__ __forceinline__ void st8(bf16* __restrict__ hi, bf16* __restrict__ lo, size_t i, const float* v, int f16) {
+    st8_16(hi, lo, i, f16, v);
 }
 
 // ---------------------------------------------------------------------------------------------
 // max-pool 3x3 stride 2 pad 1 (pspnet.py:39,69)
 // ---------------------------------------------------------------------------------------------
 __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
-                                    bf16* __restrict__ out_lo, int B, int Hi, int Wi, int Ho, int Wo, int C) {
+                                    bf16* __restrict__ out_lo, int B, int Hi, int Wi, int Ho, int Wo, int C, int f16) {
     const int C8 = C >> 3;
     const size_t total = (size_t)B * Ho * Wo * C8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -62,21 +61,21 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in_hi, const bf16* 
                 const int ix = ox * 2 - 1 + kx;
                 if (ix < 0 || ix >= Wi) continue;
                 float v[8];
-                ld8(in_hi, in_lo, (((size_t)b * Hi + iy) * Wi + ix) * C + c, v);
+                ld8(in_hi, in_lo, (((size_t)b * Hi + iy) * Wi + ix) * C + c, v, f16);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
             }
         }
-        st8(out_hi, out_lo, (((size_t)b * Ho + oy) * Wo + ox) * C + c, m);
+        st8(out_hi, out_lo, (((size_t)b * Ho + oy) * Wo + ox) * C + c, m, f16);
     }
 }
 
 int maxpool3x3s2(const Act& in, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(in.C == out.C && out.H == (in.H + 1) / 2 && out.W == (in.W + 1) / 2 && in.C % 8 == 0, "maxpool shapes");
+    ADP_CHECK_ARG(in.C == out.C && out.H == (in.H + 1) / 2 && out.W == (in.W + 1) / 2 && in.C % 8 == 0 && in.f16 == out.f16, "maxpool shapes");
     size_t total = (size_t)batch * out.H * out.W * (out.C / 8);
     int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (grid == 0) return ADP_OK;
-    maxpool3x3s2_kernel<<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, batch, in.H, in.W, out.H, out.W, in.C);
+    maxpool3x3s2_kernel<<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, batch, in.H, in.W, out.H, out.W, in.C, in.f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }
@@ -94,7 +93,7 @@ __device__ __forceinline__ void psp_cell(int cell, int* bins, int* cy, int* cx) 
 }
 
 __global__ void psp_pool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, float* __restrict__ pooled,
-                                int H, int W, int C) {
+                                int H, int W, int C, int f16) {
     const int b = blockIdx.y, cell = blockIdx.x;
     int bins, cy, cx;
     psp_cell(cell, &bins, &cy, &cx);
@@ -104,7 +103,7 @@ __global__ void psp_pool_kernel(const bf16* __restrict__ in_hi, const bf16* __re
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
         for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) s += ld_act(in_hi, in_lo, (((size_t)b * H + y) * W + x) * C + c);
+            for (int x = x0; x < x1; ++x) s += ld_act16(in_hi, in_lo, (((size_t)b * H + y) * W + x) * C + c, f16);
         pooled[((size_t)b * 50 + cell) * C + c] = s * inv;
     }
 }
@@ -127,7 +126,7 @@ __global__ void psp_conv_kernel(const float* __restrict__ pooled, const float* _
 int psp_priors(const Act& feat, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream) {
     ADP_CHECK_ARG(feat.C <= 1024, "psp channels");
     if (batch == 0) return ADP_OK;
-    psp_pool_kernel<<<dim3(50, batch), 256, 0, stream>>>(feat.hi, feat.lo, pooled, feat.H, feat.W, feat.C);
+    psp_pool_kernel<<<dim3(50, batch), 256, 0, stream>>>(feat.hi, feat.lo, pooled, feat.H, feat.W, feat.C, feat.f16);
     ADP_CUDA(cudaGetLastError());
     psp_conv_kernel<<<dim3(50, batch), 128, feat.C * sizeof(float), stream>>>(pooled, w, priors, feat.C);
     ADP_CUDA(cudaGetLastError());
@@ -164,7 +163,7 @@ __device__ __forceinline__ float prior_at(const float* __restrict__ pr, int bins
 // one block = one output row of one frame; the frame's 50 x 128 prior table sits in shared memory
 __global__ void __launch_bounds__(256)
 psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* __restrict__ f_lo, const float* __restrict__ priors,
-                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int H, int W, int C) {
+                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int H, int W, int C, int f16) {
     __shared__ __align__(16) float spr[50 * 128];
     const int Ho = 2 * H, Wo = 2 * W, Ct = C + 512, C8 = Ct >> 3;
     const int b = blockIdx.y, Y = blockIdx.x;
@@ -182,10 +181,10 @@ psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* __restrict__ f_l
         lin_coord(X, W, Wo, &x0, &x1, &wx);
         float v00[8], v01[8], v10[8], v11[8], o[8];
         if (c < C) {
-            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x0) * C + c, v00);
-            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x1) * C + c, v01);
-            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x0) * C + c, v10);
-            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x1) * C + c, v11);
+            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x0) * C + c, v00, f16);
+            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x1) * C + c, v01, f16);
+            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x0) * C + c, v10, f16);
+            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x1) * C + c, v11, f16);
         } else {
             const int s = (c - C) / 128, n0 = (c - C) % 128;
             const int bins = s == 0 ? 1 : s == 1 ? 2 : s == 2 ? 3 : 6;
@@ -225,14 +224,14 @@ psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* __restrict__ f_l
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             o[j] = (1.f - wy) * ((1.f - wx) * v00[j] + wx * v01[j]) + wy * ((1.f - wx) * v10[j] + wx * v11[j]);
-        st8(out_hi, out_lo, (((size_t)b * Ho + Y) * Wo + X) * Ct + c, o);
+        st8(out_hi, out_lo, (((size_t)b * Ho + Y) * Wo + X) * Ct + c, o, f16);
     }
 }
 
 int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(out.C == feat.C + 512 && out.H == 2 * feat.H && out.W == 2 * feat.W && feat.C % 8 == 0, "psp concat shapes");
+    ADP_CHECK_ARG(out.C == feat.C + 512 && out.H == 2 * feat.H && out.W == 2 * feat.W && feat.C % 8 == 0 && feat.f16 == out.f16, "psp concat shapes");
     if (batch == 0) return ADP_OK;
-    psp_concat_up_kernel<<<dim3(out.H, batch), 256, 0, stream>>>(feat.hi, feat.lo, priors, out.hi, out.lo, feat.H, feat.W, feat.C);
+    psp_concat_up_kernel<<<dim3(out.H, batch), 256, 0, stream>>>(feat.hi, feat.lo, priors, out.hi, out.lo, feat.H, feat.W, feat.C, feat.f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }
@@ -241,7 +240,7 @@ int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batc
 // x2 bilinear upsample, align_corners=True (pspnet.py:105)
 // ---------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
-                                  bf16* __restrict__ out_lo, int B, int H, int W, int C) {
+                                  bf16* __restrict__ out_lo, int B, int H, int W, int C, int f16) {
     const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;
     const size_t total = (size_t)B * Ho * Wo * C8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -256,23 +255,23 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __
         lin_coord(X, W, Wo, &x0, &x1, &wx);
         const size_t base = (size_t)b * H * W;
         float v00[8], v01[8], v10[8], v11[8], o[8];
-        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x0) * C + c, v00);
-        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x1) * C + c, v01);
-        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x0) * C + c, v10);
-        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x1) * C + c, v11);
+        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x0) * C + c, v00, f16);
+        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x1) * C + c, v01, f16);
+        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x0) * C + c, v10, f16);
+        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x1) * C + c, v11, f16);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             o[j] = (1.f - wy) * ((1.f - wx) * v00[j] + wx * v01[j]) + wy * ((1.f - wx) * v10[j] + wx * v11[j]);
-        st8(out_hi, out_lo, i * 8, o);
+        st8(out_hi, out_lo, i * 8, o, f16);
     }
 }
 
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(out.C == in.C && out.H == 2 * in.H && out.W == 2 * in.W && in.C % 8 == 0, "upsample shapes");
+    ADP_CHECK_ARG(out.C == in.C && out.H == 2 * in.H && out.W == 2 * in.W && in.C % 8 == 0 && in.f16 == out.f16, "upsample shapes");
     size_t total = (size_t)batch * out.H * out.W * (out.C / 8);
     if (total == 0) return ADP_OK;
     int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    upsample2x_kernel<<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, batch, in.H, in.W, in.C);
+    upsample2x_kernel<<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, batch, in.H, in.W, in.C, in.f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }
@@ -280,7 +279,7 @@ int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // fp32 crops [F,S,S,3] -> space-to-depth(2) [F,S/2,S/2,16]: channel (py*2+px)*3 + c, channels 12..15 zero
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_s2d_kernel(const float* __restrict__ crops, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int S) {
+__global__ void pack_s2d_kernel(const float* __restrict__ crops, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int S, int f16) {
     const int Hs = S / 2;
     const size_t total = (size_t)B * Hs * Hs * 2;     // two 8-channel halves per s2d pixel
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -301,7 +300,7 @@ __global__ void pack_s2d_kernel(const float* __restrict__ crops, bf16* __restric
             }
             v[j] = val;
         }
-        st8(out_hi, out_lo, i * 8, v);
+        st8(out_hi, out_lo, i * 8, v, f16);
     }
 }
 
@@ -310,7 +309,7 @@ int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t 
     size_t total = (size_t)batch * out.H * out.W * 2;
     if (total == 0) return ADP_OK;
     int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    pack_s2d_kernel<<<grid, 256, 0, stream>>>(crops, out.hi, out.lo, batch, S);
+    pack_s2d_kernel<<<grid, 256, 0, stream>>>(crops, out.hi, out.lo, batch, S, out.f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

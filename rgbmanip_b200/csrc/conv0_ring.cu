@@ -40,7 +40,8 @@ struct Conv0Params {
     const uint16_t* w;        // packed weights, C0_W_BYTES
     const float* scale;       // [8] folded BatchNorm
     const float* shift;       // [8]
-    uint16_t* out;            // [B, D, H, W, 16]
+    uint16_t* out;            // [B, D, H, W, 16], or space-to-depth(2) [B, D/2, H/2, W/2, 64] (channel = parity * 8 + co)
+    int out_s2d;
     int* err;
 };
 
@@ -221,9 +222,15 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                             o[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) |
                                    ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + ((((size_t)b * D + d) * p.H + y) * p.W + x) * 16);
-                    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                    dst[1] = make_uint4(0, 0, 0, 0);
+                    if (p.out_s2d) {
+                        // only the 8 real channels, in the layout conv1 (stride 2) and conv11's skip connection read as stride-1 tensors
+                        const size_t vox = (((size_t)b * (D >> 1) + (d >> 1)) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+                        *reinterpret_cast<uint4*>(p.out + vox * 64 + (((d & 1) * 4 + (y & 1) * 2 + (x & 1)) * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + ((((size_t)b * D + d) * p.H + y) * p.W + x) * 16);
+                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        dst[1] = make_uint4(0, 0, 0, 0);
+                    }
                   }
                 }
             }
@@ -251,7 +258,8 @@ Conv0Plan* conv0_alloc() { return new Conv0Plan(); }
 void conv0_release(Conv0Plan* p) { delete p; }
 
 int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const float* scale, const float* shift, uint16_t* out,
-               int planar, int num_sms) {
+               int flags, int num_sms) {
+    const int planar = flags & 1;
     ADP_TRY(tc_conv_init_driver());
     ADP_CHECK_ARG(in.C == 32 && in.W % C0_SEG == 0 && in.D % 4 == 0 && in.D >= 4 && in.H % C0_R == 0,
                   "conv0 ring kernel: C = 32, W % 112 == 0, D % 4 == 0, H % 4 == 0");
@@ -270,7 +278,7 @@ int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const flo
         return ADP_ERR_CUDA;
     }
     pl->p.B = in.B; pl->p.D = in.D; pl->p.H = in.H; pl->p.W = in.W; pl->p.f16 = in.f16;
-    pl->p.w = w_packed; pl->p.scale = scale; pl->p.shift = shift; pl->p.out = out; pl->p.err = nullptr;
+    pl->p.w = w_packed; pl->p.scale = scale; pl->p.shift = shift; pl->p.out = out; pl->p.err = nullptr; pl->p.out_s2d = (flags >> 1) & 1;
     pl->num_sms = num_sms > 0 ? num_sms : 148;
     return ADP_OK;
 }

@@ -83,6 +83,7 @@ struct DecodeArgs {
     float* dbg_fused;        // [B,P,32] or nullptr
     int B, S, D, P;
     int x11_f16;             // x11 holds IEEE half instead of bf16
+    int x11_s2d;             // x11 is stored space-to-depth(2): [B,D/2,S/2,S/2,64], channel = (pz*4+py*2+px)*8 + c
     int regress;             // 0: stop after NOCS + depth (no pose heads: direct_regression = False)
 };
 
@@ -92,6 +93,15 @@ struct DecodeArgs {
 // MLPs then run as 1x1 convolutions on the tcgen05 kernel (engine.py), so this kernel writes their inputs as bf16 hi/lo.
 //   xfeat [B,P,32]  (instance_color input)           xcat [B,P,96] columns 0..31 = fused feature (pose_mlp1 input)
 // ------------------------------------------------------------------------------------------------
+// element offset of the 8 channels of voxel (dz, yy, xx) of x11
+__device__ __forceinline__ size_t x11_offset(const DecodeArgs& a, int b, int dz, int yy, int xx) {
+    if (a.x11_s2d) {
+        const int S2 = a.S >> 1;
+        return ((((size_t)b * (a.D >> 1) + (dz >> 1)) * S2 + (yy >> 1)) * S2 + (xx >> 1)) * 64 + (((dz & 1) * 4 + (yy & 1) * 2 + (xx & 1)) * 8);
+    }
+    return ((((size_t)b * a.D + dz) * a.S + yy) * a.S + xx) * 8;
+}
+
 struct GatherArgs {
     DecodeArgs a;
     bf16* xfeat_hi; bf16* xfeat_lo;
@@ -132,7 +142,7 @@ decode_gather_kernel(const GatherArgs ga, const float* __restrict__ prob_w) {
                 for (int kx = 0; kx < 3; ++kx) {
                     const int xx = x + kx - 1;
                     if (xx < 0 || xx >= S) continue;
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.x11 + ((((size_t)b * D + dz) * S + yy) * S + xx) * 8));
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.x11 + x11_offset(a, b, dz, yy, xx)));
                     const float* wt = s_probw + ((kz * 3 + ky) * 3 + kx) * 8;
                     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -281,7 +291,7 @@ decode_points_kernel(const DecodeArgs a, const DecodeWeights w) {
                 for (int kx = 0; kx < 3; ++kx) {
                     const int xx = x + kx - 1;
                     if (xx < 0 || xx >= S) continue;
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.x11 + ((((size_t)b * D + dz) * S + yy) * S + xx) * 8));
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.x11 + x11_offset(a, b, dz, yy, xx)));
                     const float* wt = s_probw + ((kz * 3 + ky) * 3 + kx) * 8;
                     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -557,7 +567,7 @@ int decode_gather_c(const float* feat_ref, const float* feat_src, const float* M
     DecodeArgs a{};
     a.feat_ref = feat_ref; a.feat_src = feat_src; a.Mw = Mw; a.depths = depths; a.x11 = reinterpret_cast<const bf16*>(x11);
     a.choose = choose; a.valid = valid; a.nocs = nullptr; a.depth = depth; a.pf1 = nullptr; a.gsum = nullptr;
-    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16; a.regress = 0;
+    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16 & 1; a.x11_s2d = (x11_f16 >> 1) & 1; a.regress = 0;
     return decode_gather_run(a, prob_w, reinterpret_cast<bf16*>(xfeat_hi), reinterpret_cast<bf16*>(xfeat_lo),
                              reinterpret_cast<bf16*>(xcat_hi), reinterpret_cast<bf16*>(xcat_lo), stream);
 }
@@ -575,7 +585,7 @@ int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, 
     DecodeArgs a;
     a.feat_ref = feat_ref; a.feat_src = feat_src; a.Mw = Mw; a.depths = depths; a.x11 = reinterpret_cast<const bf16*>(x11);
     a.choose = choose; a.valid = valid; a.nocs = nocs; a.depth = depth; a.pf1 = pf1; a.gsum = gsum;
-    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16; a.regress = regress_pose;
+    a.dbg_logits = dbg_logits; a.dbg_fused = dbg_fused; a.B = B; a.S = S; a.D = D; a.P = P; a.x11_f16 = x11_f16 & 1; a.x11_s2d = (x11_f16 >> 1) & 1; a.regress = regress_pose;
     return decode_run(a, w, psum, R, r6, regress_pose, stream);
 }
 

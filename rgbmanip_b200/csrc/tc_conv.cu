@@ -118,14 +118,15 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const u
 
 constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
-// FUSED: split-precision layers whose tiles are L2-bound (small N) keep A_hi, A_lo, W_hi, W_lo of one (tap, K chunk) in
-// the same stage and issue the three MMA groups (hi*hi, lo*hi, hi*lo) from it: 2x the bytes of a single pass instead of 3x.
-template <int BN, int KC, bool FUSED = false>
+// FUSED = 1: split-precision bf16x3 layers keep A_hi, A_lo, W_hi, W_lo of one (tap, K chunk) in the same stage and issue the
+// three MMA groups (hi*hi, lo*hi, hi*lo) from it: 2x the bytes of a single pass instead of 3x.
+// FUSED = 2: "fp16x2" -- one fp16 activation plane against fp16 hi + lo weights: stage = [A | W_hi | W_lo], two MMA groups.
+template <int BN, int KC, int FUSED = 0>
 struct TcCfg {
     static constexpr int A_BYTES = 128 * KC * 2;
     static constexpr int B_BYTES = BN * KC * 2;
     static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
-    static constexpr int STAGE_BYTES = (FUSED ? 2 : 1) * (A_BYTES + B_PAD);
+    static constexpr int STAGE_BYTES = FUSED == 1 ? 2 * (A_BYTES + B_PAD) : FUSED == 2 ? (A_BYTES + 2 * B_PAD) : (A_BYTES + B_PAD);
     // small-N layers are latency bound per tile: fewer stages -> several CTAs per SM overlap their pipelines
     static constexpr int CTAS_PER_SM = FUSED ? (BN <= 64 ? 2 : 1) : (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
     static constexpr int SMEM_BUDGET = 196608 / CTAS_PER_SM;
@@ -135,7 +136,7 @@ struct TcCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int KC, bool FUSED>
+template <int BN, int KC, int FUSED>
 __global__ void __launch_bounds__(kTcThreads, TcCfg<BN, KC, FUSED>::CTAS_PER_SM)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -195,7 +196,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)((FUSED ? 2 : 1) * (rows_valid * KC * 2 + Cfg::B_BYTES));
+            const uint32_t tx_bytes = (uint32_t)(FUSED == 1 ? 2 * (rows_valid * KC * 2 + Cfg::B_BYTES)
+                                                 : FUSED == 2 ? (rows_valid * KC * 2 + 2 * Cfg::B_BYTES) : (rows_valid * KC * 2 + Cfg::B_BYTES));
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int t = tile;
                 const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -205,8 +207,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int b = t / p.D;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
                 for (int pass = 0; pass < npass_loop; ++pass) {
-                    const CUtensorMap* mapA = (pass == 1) ? &tmA_lo : &tmA_hi;
-                    const CUtensorMap* mapW = (pass == 2) ? &tmW_lo : &tmW_hi;
+                    // npass 3: (A_hi W_hi, A_lo W_hi, A_hi W_lo); npass 2: (A W_hi, A W_lo)
+                    const CUtensorMap* mapA = (p.npass == 3 && pass == 1) ? &tmA_lo : &tmA_hi;
+                    const CUtensorMap* mapW = (pass > 0 && pass == p.npass - 1) ? &tmW_lo : &tmW_hi;
                     for (int tap = 0; tap < taps; ++tap) {
                         const int cx = x0 * p.in_mul + p.tdx[tap], cy = y0 * p.in_mul + p.tdy[tap];
                         const int cz = d * p.in_mul + p.tdz[tap], wt = p.twt[tap];
@@ -214,7 +217,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
                             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                             ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-                            if (FUSED) {   // [A_hi | A_lo | W_hi | W_lo]
+                            if (FUSED == 2) {   // [A | W_hi | W_lo]
+                                ptx::tma_load_5d(&tmA_hi, full_bar(stage), sa, kc * KC, cx, cy, cz, b);
+                                ptx::tma_load_3d(&tmW_hi, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, n0, wt);
+                                ptx::tma_load_3d(&tmW_lo, full_bar(stage), sa + Cfg::A_BYTES + Cfg::B_PAD, kc * KC, n0, wt);
+                            } else if (FUSED == 1) {   // [A_hi | A_lo | W_hi | W_lo]
                                 ptx::tma_load_5d(&tmA_hi, full_bar(stage), sa, kc * KC, cx, cy, cz, b);
                                 ptx::tma_load_5d(&tmA_lo, full_bar(stage), sa + Cfg::A_BYTES, kc * KC, cx, cy, cz, b);
                                 ptx::tma_load_3d(&tmW_hi, full_bar(stage), sa + 2 * Cfg::A_BYTES, kc * KC, n0, wt);
@@ -245,7 +252,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 ptx::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    if (FUSED) {
+                    if (FUSED == 2) {
+                        const uint64_t ah = make_smem_desc<KC>(sa);
+                        const uint64_t wh = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+                        const uint64_t wl = make_smem_desc<KC>(sa + Cfg::A_BYTES + Cfg::B_PAD);
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k) {
+                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u);
+                        }
+                    } else if (FUSED == 1) {
                         const uint64_t ah = make_smem_desc<KC>(sa), al = make_smem_desc<KC>(sa + Cfg::A_BYTES);
                         const uint64_t wh = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES);
                         const uint64_t wl = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES + Cfg::B_PAD);
@@ -405,8 +421,9 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     ADP_TRY(tc_conv_init_driver());
     int KC = in.C % 64 == 0 ? 64 : in.C % 32 == 0 ? 32 : in.C % 16 == 0 ? 16 : 0;
     ADP_CHECK_ARG(KC != 0, "Cin must be a multiple of 16 for the tcgen05 path");
-    ADP_CHECK_ARG(npass == 1 || npass == 3, "npass");
-    ADP_CHECK_ARG(npass == 1 || (in.lo && w_lo), "split precision needs lo planes");
+    ADP_CHECK_ARG(npass >= 1 && npass <= 3, "npass");
+    ADP_CHECK_ARG(npass != 3 || (in.lo && w_lo && !f16), "bf16x3 needs bf16 lo planes of activations and weights");
+    ADP_CHECK_ARG(npass != 2 || (w_lo && f16), "fp16x2 needs fp16 activations and a lo plane of the weights");
     int coutPad = (Cout + 15) / 16 * 16;
     int BN = coutPad % 256 == 0 ? 256 : coutPad % 128 == 0 ? 128 : coutPad % 64 == 0 ? 64 : coutPad % 32 == 0 ? 32 : 16;
     if (KC < 64 && BN > 64) BN = 64;
@@ -450,7 +467,7 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
         const char* e = getenv("ADP_FUSE_MAXBN");
         g_fuse_max_bn = e ? atoi(e) : 256;
     }
-    L->fused = (npass == 3) && (BN <= g_fuse_max_bn) && KC >= 16;
+    L->fused = (npass >= 2) && (BN <= g_fuse_max_bn) && KC >= 16;
     ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, w_taps, KC, BN, f16));
@@ -459,7 +476,7 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     return ADP_OK;
 }
 
-template <int BN, int KC, bool FUSED = false>
+template <int BN, int KC, int FUSED = 0>
 static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
     using Cfg = TcCfg<BN, KC, FUSED>;
     static bool attr_set = false;
@@ -480,12 +497,19 @@ static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_
 int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
     ADP_CHECK_ARG(L->ready, "layer not planned");
     ADP_CHECK_ARG(batch <= L->p.B, "batch exceeds planned capacity");
-    if (L->p.npass == 3 && L->fused) {   // split precision, small N: one stage carries hi and lo operands
-        if (L->BN == 64 && L->KC == 64) return launch_impl<64, 64, true>(L, batch, num_sms, stream);
-        if (L->BN == 32 && L->KC == 64) return launch_impl<32, 64, true>(L, batch, num_sms, stream);
-        if (L->BN == 64 && L->KC == 16) return launch_impl<64, 16, true>(L, batch, num_sms, stream);
-        if (L->BN == 128 && L->KC == 64) return launch_impl<128, 64, true>(L, batch, num_sms, stream);
-        if (L->BN == 256 && L->KC == 64) return launch_impl<256, 64, true>(L, batch, num_sms, stream);
+    if (L->p.npass == 3 && L->fused) {   // bf16x3: one stage carries hi and lo operands
+        if (L->BN == 64 && L->KC == 64) return launch_impl<64, 64, 1>(L, batch, num_sms, stream);
+        if (L->BN == 32 && L->KC == 64) return launch_impl<32, 64, 1>(L, batch, num_sms, stream);
+        if (L->BN == 64 && L->KC == 16) return launch_impl<64, 16, 1>(L, batch, num_sms, stream);
+        if (L->BN == 128 && L->KC == 64) return launch_impl<128, 64, 1>(L, batch, num_sms, stream);
+        if (L->BN == 256 && L->KC == 64) return launch_impl<256, 64, 1>(L, batch, num_sms, stream);
+    }
+    if (L->p.npass == 2 && L->fused) {   // fp16x2: one stage carries A, W_hi, W_lo
+        if (L->BN == 64 && L->KC == 64) return launch_impl<64, 64, 2>(L, batch, num_sms, stream);
+        if (L->BN == 32 && L->KC == 64) return launch_impl<32, 64, 2>(L, batch, num_sms, stream);
+        if (L->BN == 64 && L->KC == 16) return launch_impl<64, 16, 2>(L, batch, num_sms, stream);
+        if (L->BN == 128 && L->KC == 64) return launch_impl<128, 64, 2>(L, batch, num_sms, stream);
+        if (L->BN == 256 && L->KC == 64) return launch_impl<256, 64, 2>(L, batch, num_sms, stream);
     }
 #define ADP_TC_CASE(bn, kc) if (L->BN == bn && L->KC == kc) return launch_impl<bn, kc>(L, batch, num_sms, stream)
     ADP_TC_CASE(256, 64); ADP_TC_CASE(128, 64); ADP_TC_CASE(64, 64); ADP_TC_CASE(32, 64); ADP_TC_CASE(16, 64);

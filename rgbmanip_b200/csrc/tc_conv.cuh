@@ -34,7 +34,7 @@ struct TcConvParams {
     int TW, TH;              // spatial tile; TW * TH <= 128
     int tiles_x, tiles_y, tiles_n;
     int kchunks;             // Cin / KC
-    int npass;               // 1 = bf16, 3 = bf16x3
+    int npass;               // 1 = single pass, 2 = fp16x2 (A W_hi + A W_lo), 3 = bf16x3
     // epilogue
     const float* bias;       // [Cout] or nullptr (BatchNorm shift is passed here too)
     const float* scale;      // [Cout] or nullptr (folded BatchNorm scale)

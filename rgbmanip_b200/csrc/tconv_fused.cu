@@ -21,6 +21,7 @@ struct TconvParams {
     int Cout;                // real output channels (<= BN)
     int res_cs;              // channel pitch of the skip tensor
     int f16;
+    int s2d;                 // out and res are space-to-depth(2): [B, D, H, W, 8 * Cout], channel = parity * Cout + c
     int TW, TH, tiles_x, tiles_y;
     const float* scale;
     const float* bias;
@@ -173,7 +174,8 @@ tconv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (valid) {
                     const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
                     const size_t pix = (((size_t)b * oD + (2 * d + pz)) * oH + (2 * y + py)) * oW + (2 * x + px);
-                    const size_t o = pix * p.Cout, ro = pix * p.res_cs;
+                    size_t o = pix * p.Cout, ro = pix * p.res_cs;
+                    if (p.s2d) o = ro = (((((size_t)b * p.D + d) * p.H + y) * p.W + x) * 8 + cls) * p.Cout;
 #pragma unroll
                     for (int j0 = 0; j0 < BN; j0 += 8) {
                         if (j0 < p.Cout) {
@@ -216,7 +218,7 @@ TconvPlan* tconv_alloc() { return new TconvPlan(); }
 void tconv_release(TconvPlan* p) { delete p; }
 
 int tconv_plan(TconvPlan* pl, const Act& in, const bf16* w, int Cout, const float* scale, const float* bias, const bf16* res,
-               int res_cs, bf16* out, int num_sms) {
+               int res_cs, bf16* out, int flags, int num_sms) {
     ADP_TRY(tc_conv_init_driver());
     ADP_CHECK_ARG((in.C == 16 || in.C == 32) && Cout % 8 == 0 && Cout <= 32, "fused transposed conv: Cin in {16,32}, Cout in {8,16,32}");
     ADP_CHECK_ARG(in.lo == nullptr, "single-plane activations only");
@@ -224,7 +226,7 @@ int tconv_plan(TconvPlan* pl, const Act& in, const bf16* w, int Cout, const floa
     const int BN = Cout <= 16 ? 16 : 32;
     TconvParams& p = pl->p;
     p = TconvParams{};
-    p.B = in.B; p.D = in.D; p.H = in.H; p.W = in.W; p.Cout = Cout; p.res_cs = res_cs ? res_cs : Cout; p.f16 = in.f16;
+    p.B = in.B; p.D = in.D; p.H = in.H; p.W = in.W; p.Cout = Cout; p.res_cs = res_cs ? res_cs : Cout; p.f16 = in.f16; p.s2d = (flags >> 1) & 1;
     tc_pick_tile(in.H, in.W, &p.TW, &p.TH);
     p.tiles_x = cdiv(in.W, p.TW); p.tiles_y = cdiv(in.H, p.TH);
     p.scale = scale; p.bias = bias; p.res = res; p.out = out; p.err = nullptr;

@@ -39,6 +39,7 @@ class ActBuf:
     W: int
     Cn: int
     f16: int = 0
+    s2d: bool = False        # level-0 U-Net tensor stored space-to-depth(2): logical [B, 2D, 2H, 2W, C/8]
 
     @property
     def c(self):
@@ -49,6 +50,8 @@ class ActBuf:
         v = self.hi.float()
         if self.lo is not None:
             v = v + self.lo.float()
+        if self.s2d:
+            v = G.from_s2d(v)
         return v if n is None else v[:n]
 
 
@@ -61,21 +64,26 @@ def _split_bf16(w: torch.Tensor):
 class Engine:
     """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
 
-    def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="bf16x3", regress_pose=True, use_tc=True,
+    def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="fp16x2", regress_pose=True, use_tc=True,
                  use_tc_3d=True, tc_strided=True, tc_transposed=True, conv0_ring=True, tconv_fused=True, volume_dtype="fp16", debug=False,
-                 img_size=IMG_SIZE, n_pts=N_PTS, decode_tc=True):
+                 img_size=IMG_SIZE, n_pts=N_PTS, decode_tc=True, level0_s2d=True):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
-        if precision not in ("bf16", "bf16x3"):
-            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        if precision not in ("bf16", "bf16x3", "fp16x2"):
+            raise ValueError("precision must be 'fp16x2', 'bf16x3' or 'bf16'")
         self.lib = L.load()
         self.device = torch.device(device)
         self.E = int(max_envs)
         self.F = 2 * self.E
         self.S = int(img_size)
         self.P = int(n_pts)
+        # backbone operand formats (DESIGN.md "precision policy"):
+        #   fp16x2  one fp16 activation plane x (fp16 hi + lo) weights, 2 MMA passes
+        #   bf16x3  (bf16 hi + lo) activations x (bf16 hi + lo) weights, 3 MMA passes
+        #   bf16    single pass (fast, outside the parity tolerance)
         self.split = precision == "bf16x3"
-        self.npass = 3 if self.split else 1
+        self.act_f16 = 1 if precision == "fp16x2" else 0
+        self.npass = {"bf16": 1, "fp16x2": 2, "bf16x3": 3}[precision]
         self.precision = precision
         self.regress_pose = bool(regress_pose)
         self.use_tc = use_tc
@@ -85,6 +93,7 @@ class Engine:
         self.conv0_ring = conv0_ring and use_tc_3d
         self.tconv_fused = tconv_fused and use_tc_3d and tc_transposed
         self.decode_tc = decode_tc and use_tc and int(n_pts) == 1024
+        self.level0_s2d = level0_s2d
         self._conv0_plans = []
         self._tconv_plans = []
         if volume_dtype not in ("fp16", "bf16"):
@@ -114,7 +123,10 @@ class Engine:
         self._keep.append(t)
         return t
 
-    def _act(self, B, H, Wd, Cn, D=1, split=None, f16=0):
+    def _act(self, B, H, Wd, Cn, D=1, split=None, f16=None):
+        if split is None and f16 is None:      # a backbone activation in the engine's precision
+            f16 = self.act_f16
+        f16 = int(f16 or 0)
         split = self.split if split is None else split
         shape = (B, D, H, Wd, Cn) if D > 1 else (B, H, Wd, Cn)
         dt = torch.float16 if f16 else torch.bfloat16
@@ -140,6 +152,8 @@ class Engine:
         """wt: fp32 [taps, CoutPad, Cin] packed weights -> callable(batch) launching one tcgen05 conv per geometry."""
         if x.f16:
             hi, lo = wt.to(torch.float16), None
+            if npass == 2:
+                lo = (wt - hi.float()).to(torch.float16).to(self.device).contiguous()
         else:
             hi, lo = _split_bf16(wt)
             lo = lo.to(self.device).contiguous()
@@ -149,7 +163,7 @@ class Engine:
         xa = x.c
         for g in geoms:
             plan = C.c_void_p()
-            L.check(self.lib.adp_conv_tc_plan(C.byref(plan), C.byref(xa), L.ptr(hi), L.ptr(lo) if npass == 3 else None,
+            L.check(self.lib.adp_conv_tc_plan(C.byref(plan), C.byref(xa), L.ptr(hi), L.ptr(lo) if npass >= 2 else None,
                                               cout, kd, ks, dil, npass, C.byref(ep), C.byref(g) if g is not None else None,
                                               self.num_sms), "conv_tc_plan")
             self._plans.append(plan)
@@ -180,7 +194,7 @@ class Engine:
         npass = self.npass if npass is None else npass
         if tc is None:
             tc = self.use_tc_3d if three_d else self.use_tc
-        can_tc = (tc and cin % 16 == 0 and ks in (1, 3) and (ks == w.shape[-2]) and (npass == 1 or x.lo is not None)
+        can_tc = (tc and cin % 16 == 0 and ks in (1, 3) and (ks == w.shape[-2]) and (npass == 1 or (npass == 2 and x.f16) or (npass == 3 and x.lo is not None))
                   and (stride == 1 or (stride == 2 and (self.tc_transposed if transposed else self.tc_strided))))
         ep = self._epilogue(out, **ep_kw)
         if three_d:
@@ -325,8 +339,16 @@ class Engine:
             return self._act(E, s, s, Cn, D=d, split=False, f16=self.vol_f16)
 
         pad0 = 16 if self.use_tc_3d else 8    # conv0's output carries 8 zero channels so that conv1 (Cin = 8) fits the K=16 MMA
-        c0 = act3(0, pad0); c1 = act3(1, 16); c2 = act3(1, 16); c3 = act3(2, 32); c4 = act3(2, 32)
-        c5 = act3(3, 64); c6 = act3(3, 64); x7 = act3(2, 32); x9 = act3(1, 16); x11 = act3(0, 8)
+        # With the depth-ring conv0 the two full-resolution tensors (conv0 output, conv11 output) live in space-to-depth(2)
+        # layout [E, D/2, S/2, S/2, 64]: conv1 (stride 2) and conv11 (transposed, + skip) become stride-1 2x2x2-tap convs.
+        self.l0_s2d = bool(self.conv0_ring and S % 224 == 0 and pad0 == 16 and self.level0_s2d)
+        if self.l0_s2d:
+            c0 = act3(1, 64); c0.s2d = True
+            x11 = act3(1, 64); x11.s2d = True
+        else:
+            c0 = act3(0, pad0); x11 = act3(0, 8)
+        c1 = act3(1, 16); c2 = act3(1, 16); c3 = act3(2, 32); c4 = act3(2, 32)
+        c5 = act3(3, 64); c6 = act3(3, 64); x7 = act3(2, 32); x9 = act3(1, 16)
         chain = [("conv0", self.vol, c0, 1), ("conv1", c0, c1, 2), ("conv2", c1, c2, 1), ("conv3", c2, c3, 2),
                  ("conv4", c3, c4, 1), ("conv5", c4, c5, 2), ("conv6", c5, c6, 1)]
         for nm, xin, out, stride in chain:
@@ -345,7 +367,7 @@ class Engine:
                 va = xin.c
                 self.vol_planar = 0
                 L.check(self.lib.adp_conv0_plan_create(C.byref(plan), C.byref(va), L.ptr(w16), L.ptr(sc), L.ptr(sh), L.ptr(out.hi),
-                                                       self.vol_planar, self.num_sms), "conv0_plan")
+                                                       L.LAYOUT_S2D if self.l0_s2d else 0, self.num_sms), "conv0_plan")
                 self._conv0_plans.append(plan)
 
                 def run0(batch, plan=plan):
@@ -353,9 +375,20 @@ class Engine:
                 run0.kind = "tc"
                 ops.append((f"cr.{nm}", run0))
                 continue
+            if nm == "conv1" and self.l0_s2d:
+                w_s2d = G.strided_s2d_weights(torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float())
+                ep = self._epilogue(out, scale=sc, bias=sh, act=L.ACT_RELU)
+                ops.append((f"cr.{nm}", self._tc_plans(xin, w_s2d, 16, 1, 1, 1, 1, ep, [G.strided_s2d(xin.D, xin.H, xin.W)])))
+                continue
             ops.append((f"cr.{nm}", self._conv(wgt.numpy(), xin, out, stride=stride, npass=1, scale=sc, bias=sh, act=L.ACT_RELU)))
         for nm, xin, skip, out in (("conv7", c6, c4, x7), ("conv9", x7, c2, x9), ("conv11", x9, c0, x11)):
             sc, sh = bn(nm)
+            if nm == "conv11" and self.l0_s2d and not self.tconv_fused:
+                w_s2d = G.transposed_s2d_weights(torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float())
+                sc8, sh8 = self._dev(sc.cpu().repeat(8)), self._dev(sh.cpu().repeat(8))
+                ep = self._epilogue(out, scale=sc8, bias=sh8, act=L.ACT_RELU, res=skip, res_after_act=1)
+                ops.append((f"cr.{nm}", self._tc_plans(xin, w_s2d, 64, 1, 1, 1, 1, ep, [G.transposed_s2d(xin.D, xin.H, xin.W)])))
+                continue
             if self.tconv_fused and xin.Cn in (16, 32) and xin.lo is None:
                 wgt = torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float()            # [Cin, Cout, 3,3,3]
                 cin, cout = wgt.shape[0], wgt.shape[1]
@@ -368,7 +401,8 @@ class Engine:
                 plan = C.c_void_p()
                 xa = xin.c
                 L.check(self.lib.adp_tconv_plan_create(C.byref(plan), C.byref(xa), L.ptr(w16), cout, L.ptr(sc), L.ptr(sh),
-                                                       L.ptr(skip.hi), skip.Cn, L.ptr(out.hi), self.num_sms), "tconv_plan")
+                                                       L.ptr(skip.hi), skip.Cn, L.ptr(out.hi),
+                                                       L.LAYOUT_S2D if out.s2d else 0, self.num_sms), "tconv_plan")
                 self._tconv_plans.append(plan)
 
                 def runt(batch, plan=plan):
@@ -382,6 +416,7 @@ class Engine:
         self.cr_taps = {"conv0": c0, "conv1": c1, "conv2": c2, "conv3": c3, "conv4": c4, "conv5": c5, "conv6": c6,
                         "conv7": x7, "conv9": x9, "conv11": x11}
         self.x11 = x11
+        self.x11_format = (L.LAYOUT_F16 if self.vol_f16 else 0) | (L.LAYOUT_S2D if self.l0_s2d else 0)
         # decode weights, transposed to [K][N]
         def tw(name):
             w = torch.as_tensor(sd[name]).float()
@@ -521,7 +556,7 @@ class Engine:
             L.check(lib.adp_decode_gather(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi),
                                           L.ptr(self.choose), L.ptr(self.valid_env), self.dw.prob_w, L.ptr(self.depth),
                                           L.ptr(self.xfeat.hi), L.ptr(self.xfeat.lo), L.ptr(self.xcat.hi), L.ptr(self.xcat.lo),
-                                          L.ptr(self.dbg_logits), L.ptr(self.dbg_fused), n, S, D, P, self.vol_f16, st), "decode_gather")
+                                          L.ptr(self.dbg_logits), L.ptr(self.dbg_fused), n, S, D, P, self.x11_format, st), "decode_gather")
             mark("decode_gather")
             for name, op in self.dec_ops:
                 op(n)
@@ -529,7 +564,7 @@ class Engine:
             L.check(lib.adp_decode(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi), L.ptr(self.choose),
                                    L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.pf1),
                                    L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
-                                   L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.vol_f16, st), "decode")
+                                   L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.x11_format, st), "decode")
         mark("decode")
         if self.regress_pose:
             L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),

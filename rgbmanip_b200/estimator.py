@@ -58,7 +58,7 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         device = device or cfg.get("device", "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0")
         self.device = torch.device(device)
         self.estimator = Engine(state_dict, device=self.device, max_envs=int(max_envs or cfg.get("max_envs_per_chunk", 16)),
-                                precision=precision or cfg.get("precision", "bf16x3"), regress_pose=regress,
+                                precision=precision or cfg.get("precision", "fp16x2"), regress_pose=regress,
                                 img_size=int(cfg.get("img_size", 224)), **engine_kw)
         self._seed = int(cfg.get("sample_seed", 0))
         self._calls = 0

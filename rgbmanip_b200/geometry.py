@@ -90,3 +90,79 @@ def conv0_ring_weights(w):
                 blk = w[:, :, kz, ky, kx]                       # [co, c]
                 out[ky * 3 + kx, :, kz * 8:(kz + 1) * 8, :] = blk.reshape(8, 4, 8).permute(1, 0, 2)
     return out.contiguous()
+
+
+# ---- level-0 tensors of the 3-D U-Net in space-to-depth(2) layout: [B, D/2, H/2, W/2, 64], channel = (pz*4+py*2+px)*8 + c
+def _s2d_grid(g, D2, H2, W2, ntaps):
+    g.in_mul = g.out_mul = 1
+    g.out_oz = g.out_oy = g.out_ox = 0
+    g.gD, g.gH, g.gW = D2, H2, W2
+    g.oD, g.oH, g.oW = D2, H2, W2
+    g.w_taps = ntaps
+    return g
+
+
+_S2D_OFFS = [(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+
+
+def strided_s2d(D2, H2, W2):
+    """3x3x3 stride-2 pad-1 conv (network_v5.py:265 conv1) over an s2d(2) input: output o reads inputs 2o + k - 1, i.e.
+    k = 0 -> cell o-1 parity 1, k = 1 -> cell o parity 0, k = 2 -> cell o parity 1: a 2x2x2 stride-1 window (cell offsets
+    -1, 0 per axis) over 64 channels.  The M tiles walk the output grid = the s2d grid [D2,H2,W2]."""
+    taps = [(a - 1, b - 1, c - 1, i) for i, (a, b, c) in enumerate(_S2D_OFFS)]
+    return _s2d_grid(_fill(L.TcGeom(), taps), D2, H2, W2, 8)
+
+
+def strided_s2d_weights(w, cin_real=8):
+    """[Cout, Cin, 3,3,3] torch weights -> [8 taps (cell offset -1/0 per axis), Cout, 64] (zero where the window ends)."""
+    import torch
+    kmap = {(0, 1): 0, (1, 0): 1, (1, 1): 2}            # (tap index 0 = offset -1 / 1 = offset 0, parity) -> k
+    cout = w.shape[0]
+    out = torch.zeros(8, cout, 64)
+    for t, offs in enumerate(_S2D_OFFS):
+        for par in _S2D_OFFS:
+            ks = [kmap.get((o, p)) for o, p in zip(offs, par)]
+            if None in ks:
+                continue
+            pi = par[0] * 4 + par[1] * 2 + par[2]
+            out[t, :, pi * 8:pi * 8 + cin_real] = w[:, :cin_real, ks[0], ks[1], ks[2]]
+    return out.contiguous()
+
+
+def transposed_s2d(D2, H2, W2):
+    """ConvTranspose3d(k=3, s=2, p=1, output_padding=1) (network_v5.py:278 conv11) writing its output in s2d(2) layout:
+    output 2v + p = 2i - 1 + k  ->  p = 0: (i = v, k = 1);  p = 1: (i = v, k = 2), (i = v + 1, k = 0).  A 2x2x2 stride-1
+    window (cell offsets 0, +1) over the input grid [D2,H2,W2] producing 8 parities x Cout channels per cell."""
+    taps = [(a, b, c, i) for i, (a, b, c) in enumerate(_S2D_OFFS)]
+    return _s2d_grid(_fill(L.TcGeom(), taps), D2, H2, W2, 8)
+
+
+def transposed_s2d_weights(w):
+    """[Cin, Cout, 3,3,3] torch weights -> [8 taps (input offset 0/+1 per axis), 8 * Cout (parity-major), Cin]."""
+    import torch
+    kmap = {(0, 0): 1, (0, 1): 2, (1, 1): 0}            # (input offset, output parity) -> k
+    cin, cout = w.shape[0], w.shape[1]
+    out = torch.zeros(8, 8 * cout, cin)
+    for t, offs in enumerate(_S2D_OFFS):
+        for par in _S2D_OFFS:
+            ks = [kmap.get((o, p)) for o, p in zip(offs, par)]
+            if None in ks:
+                continue
+            pi = par[0] * 4 + par[1] * 2 + par[2]
+            out[t, pi * cout:(pi + 1) * cout, :] = w[:, :, ks[0], ks[1], ks[2]].t()
+    return out.contiguous()
+
+
+def to_s2d(x):
+    """[B, D, H, W, C] -> [B, D/2, H/2, W/2, 8*C] (channel = (pz*4+py*2+px)*C + c)."""
+    B, D, H, W, Cn = x.shape
+    return (x.reshape(B, D // 2, 2, H // 2, 2, W // 2, 2, Cn).permute(0, 1, 3, 5, 2, 4, 6, 7)
+            .reshape(B, D // 2, H // 2, W // 2, 8 * Cn).contiguous())
+
+
+def from_s2d(x):
+    """inverse of :func:`to_s2d`."""
+    B, D2, H2, W2, C8 = x.shape
+    Cn = C8 // 8
+    return (x.reshape(B, D2, H2, W2, 2, 2, 2, Cn).permute(0, 1, 4, 2, 5, 3, 6, 7)
+            .reshape(B, 2 * D2, 2 * H2, 2 * W2, Cn).contiguous())

@@ -85,7 +85,10 @@ def tc_conv(x_cl, w, *, dil=1, npass=3, bias=None, scale=None, act_code=L.ACT_NO
         wt = torch.cat([wt, torch.zeros(wt.shape[0], cpad - Cout, Cin)], 1).contiguous()
     if f16:
         xh, xl = x_cl.to(torch.float16).to(DEV).contiguous(), None
-        wh, wl = wt.to(torch.float16).to(DEV).contiguous(), None
+        wh16 = wt.to(torch.float16)
+        wh, wl = wh16.to(DEV).contiguous(), None
+        if npass == 2:      # fp16x2: the rounding residual of the weights rides in a second fp16 plane
+            wl = (wt - wh16.float()).to(torch.float16).to(DEV).contiguous()
         dt16 = torch.float16
     else:
         xh, xl = split(x_cl, npass == 3)

@@ -68,6 +68,23 @@ def test_tc_conv2d_matches_oracle(G, case, npass):
     assert G.rel_err(G.from_cl(out16), ref) < (2e-4 if npass == 3 else 2e-2)
 
 
+@pytest.mark.parametrize("case", TC2D_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_tc_conv2d_fp16x2_matches_oracle(G, case):
+    """fp16x2: one fp16 activation plane against fp16 hi + lo weights (two MMA passes).  The inputs are made exactly
+    representable in fp16, so what is left is the weight split (~2^-22) and fp32 accumulation order."""
+    B, H, W, Cin, Cout, k, dil = case
+    rng = _rng(hash(case) % 2**31 + 1)
+    x = _t(rng, B, Cin, H, W).half().float()
+    w = _t(rng, Cout, Cin, k, k, scale=math.sqrt(2.0 / (k * k * Cin)))
+    bias = _t(rng, Cout)
+    res = _t(rng, B, Cout, H, W).half().float()
+    ref = F.relu(F.conv2d(x.double(), w.double(), bias.double(), padding=dil * (k // 2), dilation=dil) + res.double()).float()
+    out32, out16 = G.tc_conv(G.to_cl(x), w, dil=dil, npass=2, bias=bias, act_code=L.ACT_RELU, res_cl=G.to_cl(res), f16=1)
+    assert torch.isfinite(out32).all()
+    assert G.rel_err(G.from_cl(out32), ref) < 2e-5
+    assert G.rel_err(G.from_cl(out16), ref) < 6e-4          # fp16 storage: 2^-11
+
+
 TC3D_CASES = [
     # (B, D, H, W, Cin, Cout)
     (1, 6, 28, 28, 32, 8),
@@ -169,6 +186,15 @@ def test_conv0_depth_ring_kernel(G, f16, planar=0):
     assert torch.isfinite(got).all()
     assert float(got[..., 8:].abs().max()) == 0.0
     assert G.rel_err(G.from_cl(got[..., :8].contiguous()), ref) < (2e-3 if f16 else 1.2e-2)   # 16-bit output rounding
+    if planar:
+        return
+    # same launch writing the 8 real channels space-to-depth(2): bit-identical values, [B,D/2,H/2,W/2,64] layout
+    out2 = torch.full((B, D // 2, H // 2, W // 2, 64), float("nan"), dtype=dt, device=G.DEV)
+    L.check(lib.adp_conv0_plan_create(C.byref(plan), C.byref(a), L.ptr(wd), L.ptr(sc), L.ptr(sh), L.ptr(out2), L.LAYOUT_S2D, 148), "plan")
+    L.check(lib.adp_conv0_run(plan, B, L.ptr(err), G.stream()), "run")
+    torch.cuda.synchronize()
+    lib.adp_conv0_free(plan)
+    assert torch.equal(geometry.from_s2d(out2.float().cpu()), got[..., :8])
 
 
 @pytest.mark.parametrize("case", [(2, 4, 28, 28, 16, 8, 1), (1, 3, 56, 56, 32, 16, 1), (1, 4, 28, 28, 16, 8, 0), (1, 5, 20, 12, 32, 16, 1)],
@@ -199,7 +225,7 @@ def test_tconv_fused_kernel(G, case):
     a = G.act(xd, None, B, D, H, W, Cin, f16)
     sc, sh = scale.to(G.DEV), shift.to(G.DEV)
     L.check(lib.adp_tconv_plan_create(C.byref(plan), C.byref(a), L.ptr(wd), Cout, L.ptr(sc), L.ptr(sh), L.ptr(rd), res_c, L.ptr(out),
-                                      148), "plan")
+                                      0, 148), "plan")
     L.check(lib.adp_tconv_run(plan, B, L.ptr(err), G.stream()), "run")
     torch.cuda.synchronize()
     lib.adp_tconv_free(plan)
@@ -207,6 +233,60 @@ def test_tconv_fused_kernel(G, case):
     got = out.float().cpu()
     assert torch.isfinite(got).all()
     assert G.rel_err(G.from_cl(got), ref) < (2e-3 if f16 else 1.2e-2)       # 16-bit output rounding
+    if Cout != 8:
+        return
+    # space-to-depth(2) skip / output tensors (the level-0 layout of the engine): same values, [B,D,H,W,64]
+    from rgbmanip_b200 import geometry
+    rd2 = geometry.to_s2d(G.to_cl(res)[..., :Cout].contiguous()).to(dt).to(G.DEV).contiguous()
+    out2 = torch.full((B, D, H, W, 8 * Cout), float("nan"), dtype=dt, device=G.DEV)
+    L.check(lib.adp_tconv_plan_create(C.byref(plan), C.byref(a), L.ptr(wd), Cout, L.ptr(sc), L.ptr(sh), L.ptr(rd2), 0, L.ptr(out2),
+                                      L.LAYOUT_S2D, 148), "plan")
+    L.check(lib.adp_tconv_run(plan, B, L.ptr(err), G.stream()), "run")
+    torch.cuda.synchronize()
+    lib.adp_tconv_free(plan)
+    assert int(err.item()) == 0
+    assert torch.equal(geometry.from_s2d(out2.float().cpu()), got)
+
+
+def test_level0_s2d_convs_on_generic_kernel(G):
+    """conv1 (stride 2) reading and conv11 (transposed + skip) writing space-to-depth(2) tensors as stride-1 2x2x2-tap
+    convolutions on the generic tcgen05 kernel (geometry.strided_s2d / transposed_s2d)."""
+    from rgbmanip_b200 import geometry
+    lib = L.load()
+    rng = _rng(77)
+    B, D2, H2, W2 = 1, 3, 16, 32
+    dt = torch.float16
+
+    def run(x_cl, wt, cout, geom, **ep_kw):
+        xd = x_cl.to(dt).to(G.DEV).contiguous()
+        wd = wt.to(dt).to(G.DEV).contiguous()
+        out32 = torch.full((B, D2, H2, W2, cout), float("nan"), dtype=torch.float32, device=G.DEV)
+        ep = G.epilogue(None, None, out32, **ep_kw)
+        a = G.act(xd, None, B, D2, H2, W2, x_cl.shape[-1], 1)
+        err = torch.zeros(1, dtype=torch.int32, device=G.DEV)
+        plan = C.c_void_p()
+        L.check(lib.adp_conv_tc_plan(C.byref(plan), C.byref(a), L.ptr(wd), None, cout, 1, 1, 1, 1, C.byref(ep), C.byref(geom), 148), "plan")
+        L.check(lib.adp_conv_tc_run(plan, B, L.ptr(err), G.stream()), "run")
+        torch.cuda.synchronize()
+        lib.adp_conv_tc_free(plan)
+        assert int(err.item()) == 0
+        return out32.cpu()
+
+    # conv1: Conv3d(8 -> 16, k3, s2, p1) on the s2d tensor
+    x = _t(rng, B, 8, 2 * D2, 2 * H2, 2 * W2).half().float()
+    w = _t(rng, 16, 8, 3, 3, 3, scale=0.1).half().float()
+    ref = F.conv3d(x, w, stride=2, padding=1)
+    got = run(geometry.to_s2d(G.to_cl(x)), geometry.strided_s2d_weights(w), 16, geometry.strided_s2d(D2, H2, W2))
+    assert G.rel_err(G.from_cl(got), ref) < 1e-5
+    # conv11: ConvTranspose3d(16 -> 8, k3, s2, p1, op1) + skip, output in s2d layout
+    x = _t(rng, B, 16, D2, H2, W2).half().float()
+    w = _t(rng, 16, 8, 3, 3, 3, scale=0.1).half().float()
+    res = _t(rng, B, 8, 2 * D2, 2 * H2, 2 * W2).half().float()
+    ref = F.relu(F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1)) + res
+    rd = geometry.to_s2d(G.to_cl(res)).to(dt).to(G.DEV).contiguous()
+    got = run(G.to_cl(x), geometry.transposed_s2d_weights(w), 64, geometry.transposed_s2d(D2, H2, W2),
+              act_code=L.ACT_RELU, res_hi=rd, res_after_act=1)
+    assert G.rel_err(G.from_cl(geometry.from_s2d(got)), ref) < 1e-5
 
 
 DIRECT_CASES = [
@@ -281,6 +361,40 @@ def test_maxpool_psp_upsample(G):
     L.check(lib.adp_upsample2x(C.byref(G.act(yh, yl, 1, 1, 12, 20, 64)), C.byref(G.act(zh, zl, 1, 1, 24, 40, 64)), 1, st), "up")
     ref = F.interpolate(G.from_cl(G.val(yh, yl).cpu()), scale_factor=2, mode="bilinear", align_corners=True)
     assert G.rel_err(G.from_cl(G.val(zh, zl).cpu()), ref) < 5e-5
+
+
+def test_maxpool_psp_upsample_fp16_planes(G):
+    """Same helpers on a single fp16 activation plane (the fp16x2 backbone)."""
+    lib = L.load()
+    rng = _rng(5)
+    st = G.stream()
+    h = lambda t: G.to_cl(t).to(torch.float16).to(G.DEV).contiguous()
+    A = lambda t, *dims: G.act(t, None, *dims, 1)
+    x = _t(rng, 2, 64, 30, 26)
+    xh = h(x)
+    oh = torch.zeros((2, 15, 13, 64), dtype=torch.float16, device=G.DEV)
+    L.check(lib.adp_maxpool3x3s2(C.byref(A(xh, 2, 1, 30, 26, 64)), C.byref(A(oh, 2, 1, 15, 13, 64)), 2, st), "mp")
+    ref = F.max_pool2d(G.from_cl(xh.float().cpu()), 3, 2, 1)
+    assert G.rel_err(G.from_cl(oh.float().cpu()), ref) == 0.0
+    sd = weights.init_state_dict(2)
+    f = _t(rng, 2, 512, 28, 28).abs()
+    fh = h(f)
+    wpsp = torch.stack([torch.from_numpy(sd[f"img_extractor.psp.stages.{s}.1.weight"]).reshape(128, 512).t().contiguous()
+                        for s in range(4)]).contiguous().to(G.DEV)
+    pooled = torch.zeros((2, 50, 512), device=G.DEV)
+    priors = torch.zeros((2, 50, 128), device=G.DEV)
+    fa = A(fh, 2, 1, 28, 28, 512)
+    L.check(lib.adp_psp_priors(C.byref(fa), L.ptr(wpsp), L.ptr(pooled), L.ptr(priors), 2, st), "psp")
+    uh = torch.zeros((2, 56, 56, 1024), dtype=torch.float16, device=G.DEV)
+    L.check(lib.adp_psp_concat_up(C.byref(fa), L.ptr(priors), C.byref(A(uh, 2, 1, 56, 56, 1024)), 2, st), "cat")
+    ref = F.interpolate(O.psp_module(sd, G.from_cl(fh.float().cpu())), scale_factor=2, mode="bilinear", align_corners=True)
+    assert G.rel_err(G.from_cl(uh.float().cpu()), ref) < 6e-4
+    y = _t(rng, 1, 64, 12, 20)
+    yh = h(y)
+    zh = torch.zeros((1, 24, 40, 64), dtype=torch.float16, device=G.DEV)
+    L.check(lib.adp_upsample2x(C.byref(A(yh, 1, 1, 12, 20, 64)), C.byref(A(zh, 1, 1, 24, 40, 64)), 1, st), "up")
+    ref = F.interpolate(G.from_cl(yh.float().cpu()), scale_factor=2, mode="bilinear", align_corners=True)
+    assert G.rel_err(G.from_cl(zh.float().cpu()), ref) < 6e-4
 
 
 # ------------------------------------------------------------------------------------------------ preprocess
@@ -497,7 +611,7 @@ def test_fit_median_is_exact_and_sentinel(G):
 
 
 # ------------------------------------------------------------------------------------------------ backbone end to end
-@pytest.mark.parametrize("precision,tol", [("bf16x3", 2e-3), ("bf16", 6e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp16x2", 3e-3), ("bf16x3", 2e-3), ("bf16", 6e-2)])
 def test_backbone_matches_oracle(G, precision, tol):
     from rgbmanip_b200.engine import Engine
     sd = weights.init_state_dict(0)

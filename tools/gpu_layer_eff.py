@@ -6,7 +6,7 @@ from rgbmanip_b200 import weights
 from rgbmanip_b200.engine import Engine
 
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
+prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x2"
 sd = weights.init_state_dict(0)
 eng = Engine(sd, max_envs=E, precision=prec)
 F = 2 * E

@@ -24,6 +24,8 @@ def run(op2d=None, op3d=None, store2d=None, store3d=None, store_feat=None, resid
             xh = x.bfloat16().float(); xl = (x - xh).bfloat16().float()
             wh = w.bfloat16().float(); wl = (w - wh).bfloat16().float()
             return c2(xh, wh, b, *a2, **k) + c2(xl, wh, None, *a2, **k) + c2(xh, wl, None, *a2, **k)
+        if op2d == "fp16a":      # activations single fp16, weights split hi+lo (2 MMA passes)
+            return c2(x.half().float(), w, *a, **k)
         return c2(rnd(x, op2d), rnd(w, op2d), *a, **k)
     def conv3d(x, w, *a, **k): return c3(rnd(x, op3d), rnd(w, op3d), *a, **k)
     def convt3d(x, w, *a, **k): return ct3(rnd(x, op3d), rnd(w, op3d), *a, **k)
@@ -62,6 +64,8 @@ variants = {
   "bf16 2d operands + bf16 storage, fp32 residual stream, fp32 feat": dict(op2d=bf, store2d=bf),
   "bf16 2d all (bf16 residual, bf16 feat)": dict(op2d=bf, store2d=bf, store_feat=bf, resid_fp32=False),
   "bf16 2d, fp32 resid, bf16 feat": dict(op2d=bf, store2d=bf, store_feat=bf),
+  "fp16a 2d (fp16 act operands+storage, split weights) + fp16 3d": dict(op2d="fp16a", store2d=hf, store_feat=hf, resid_fp32=False, op3d=hf, store3d=hf),
+  "fp16a 2d fp32resid + fp16 3d": dict(op2d="fp16a", store2d=hf, store_feat=hf, resid_fp32=True, op3d=hf, store3d=hf),
   "fp16 2d all": dict(op2d=hf, store2d=hf, store_feat=hf, resid_fp32=False),
   "bf16 3d only (operands+storage)": dict(op3d=bf, store3d=bf),
   "fp16 3d only": dict(op3d=hf, store3d=hf),
