@@ -178,7 +178,8 @@ ADP_API int adp_rot_head(const float* psum, const uint8_t* valid, const adp_deco
                          int P, void* stream);
 
 /* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
-/* scratch: B * P*(P-1)/2 floats (the pair ratios are evaluated once and parked there for the exact-median select). */
+/* One 4-CTA thread-block cluster per environment; the exact-median radix select recomputes the pair ratios in every pass.
+ * scratch: unused (kept for ABI stability), may be NULL. */
 ADP_API int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R,
             const double* E, const uint8_t* valid, double* bbox, double* scale, double* trans, float* scratch, int B, int P,
             int S, void* stream);

@@ -298,7 +298,7 @@ int adp_rot_head(const float* psum, const uint8_t* valid, const adp_decode_weigh
 
 int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R, const double* E,
             const uint8_t* valid, double* bbox, double* scale, double* trans, float* scratch, int B, int P, int S, void* stream) {
-    ADP_CHECK_ARG(nocs && depth && choose && Kp && R && E && bbox && scratch, "null pointer");
+    ADP_CHECK_ARG(nocs && depth && choose && Kp && R && E && bbox, "null pointer");
     g_launches += 1;
     return fit_run(nocs, depth, choose, Kp, R, E, valid, bbox, scale, trans, scratch, B, P, S, (cudaStream_t)stream);
 }

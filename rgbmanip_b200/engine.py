@@ -455,7 +455,6 @@ class Engine:
         self.bbox = torch.zeros((E, 8, 3), dtype=torch.float64, device=dev)
         self.scale = torch.zeros(E, dtype=torch.float64, device=dev)
         self.trans = torch.zeros((E, 3), dtype=torch.float64, device=dev)
-        self.fit_scratch = torch.zeros((E, P * (P - 1) // 2), dtype=torch.float32, device=dev)
         self.rot64 = torch.zeros((E, 9), dtype=torch.float64, device=dev)
         if self.decode_tc:
             self._build_decode_tc()
@@ -569,7 +568,7 @@ class Engine:
         if self.regress_pose:
             L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
                                 L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans),
-                                L.ptr(self.fit_scratch), n, P, S, st), "fit")
+                                None, n, P, S, st), "fit")
         else:   # direct_regression = False, use_depth = True: RANSAC + Umeyama (interface_v5.py:322-338)
             L.check(lib.adp_fit_umeyama(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(E1),
                                         L.ptr(self.valid_env), L.ptr(ransac_idx), seed & 0xFFFFFFFF, L.ptr(self.bbox),
