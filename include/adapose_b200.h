@@ -114,7 +114,10 @@ ADP_API int adp_conv_tc_run(adp_conv_plan* plan, int batch, int32_t* err_flag, v
 ADP_API void adp_conv_tc_free(adp_conv_plan* plan);
 ADP_API int adp_conv_direct(const adp_direct_conv* desc, int batch, void* stream);
 ADP_API int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, void* stream);                 /* pspnet.py:39 */
-ADP_API int adp_psp_priors(const adp_act* feat, const float* w, float* pooled, float* priors, int batch, void* stream); /* :84-90 */
+/* feat_cstride: channel pitch of feat (0 = dense); the engine lets layer4's last conv write straight into the first 512
+ * channels of the 1024-channel concat tensor, adp_psp_fill_priors writes the resized priors behind them (:92-94). */
+ADP_API int adp_psp_priors(const adp_act* feat, int feat_cstride, const float* w, float* pooled, float* priors, int batch, void* stream); /* :84-90 */
+ADP_API int adp_psp_fill_priors(const float* priors, const adp_act* out, int coff, int batch, void* stream);
 ADP_API int adp_psp_concat_up(const adp_act* feat, const float* priors, const adp_act* out, int batch, void* stream);   /* :92-94,105 */
 ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream);                   /* pspnet.py:105 */
 /* fp32 crops [F,S,S,3] -> space-to-depth(2) activation [F,S/2,S/2,16] (channel = (py*2+px)*3 + c, 12 used): the 7x7/2

@@ -69,7 +69,8 @@ SIGNATURES = {
     "adp_conv_tc_free": (None, [vp]),
     "adp_conv_direct": (C.c_int, [C.POINTER(DirectConv), C.c_int, vp]),
     "adp_maxpool3x3s2": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
-    "adp_psp_priors": (C.c_int, [C.POINTER(Act), vp, vp, vp, C.c_int, vp]),
+    "adp_psp_priors": (C.c_int, [C.POINTER(Act), C.c_int, vp, vp, vp, C.c_int, vp]),
+    "adp_psp_fill_priors": (C.c_int, [vp, C.POINTER(Act), C.c_int, C.c_int, vp]),
     "adp_psp_concat_up": (C.c_int, [C.POINTER(Act), vp, C.POINTER(Act), C.c_int, vp]),
     "adp_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
     "adp_pack_s2d": (C.c_int, [vp, C.POINTER(Act), C.c_int, C.c_int, vp]),

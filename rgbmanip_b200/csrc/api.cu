@@ -23,7 +23,8 @@ void set_last_error(const char* fmt, ...) {
 
 // implemented in the stage translation units
 int maxpool3x3s2(const Act& in, const Act& out, int batch, cudaStream_t stream);
-int psp_priors(const Act& feat, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream);
+int psp_priors(const Act& feat, int feat_cs, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream);
+int psp_fill_priors(const float* priors, const Act& out, int coff, int batch, cudaStream_t stream);
 int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream);
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream);
 int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t stream);
@@ -175,16 +176,22 @@ int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, void* str
     return maxpool3x3s2(to_act(in), to_act(out), batch, (cudaStream_t)stream);
 }
 
-int adp_psp_priors(const adp_act* feat, const float* w, float* pooled, float* priors, int batch, void* stream) {
+int adp_psp_priors(const adp_act* feat, int feat_cstride, const float* w, float* pooled, float* priors, int batch, void* stream) {
     ADP_CHECK_ARG(feat && w && pooled && priors, "null pointer");
     g_launches += 2;
-    return psp_priors(to_act(feat), w, pooled, priors, batch, (cudaStream_t)stream);
+    return psp_priors(to_act(feat), feat_cstride, w, pooled, priors, batch, (cudaStream_t)stream);
 }
 
 int adp_psp_concat_up(const adp_act* feat, const float* priors, const adp_act* out, int batch, void* stream) {
     ADP_CHECK_ARG(feat && priors && out, "null pointer");
     g_launches += 1;
     return psp_concat_up(to_act(feat), priors, to_act(out), batch, (cudaStream_t)stream);
+}
+
+int adp_psp_fill_priors(const float* priors, const adp_act* out, int coff, int batch, void* stream) {
+    ADP_CHECK_ARG(priors && out, "null pointer");
+    g_launches += 1;
+    return psp_fill_priors(priors, to_act(out), coff, batch, (cudaStream_t)stream);
 }
 
 int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream) {

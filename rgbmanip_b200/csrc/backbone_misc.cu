@@ -92,19 +92,39 @@ __device__ __forceinline__ void psp_cell(int cell, int* bins, int* cy, int* cx) 
     else { *bins = 6; *cy = (cell - 14) / 6; *cx = (cell - 14) % 6; }
 }
 
-__global__ void psp_pool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, float* __restrict__ pooled,
-                                int H, int W, int C, int f16) {
+// one block per (cell, frame): 128-bit loads of 8 channels, the window rows split over blockDim.x / (C / 8) thread groups
+__global__ void __launch_bounds__(256)
+psp_pool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, float* __restrict__ pooled,
+                int H, int W, int C, int cs, int f16) {
+    __shared__ float part[4][1024];
     const int b = blockIdx.y, cell = blockIdx.x;
     int bins, cy, cx;
     psp_cell(cell, &bins, &cy, &cx);
     const int y0 = (cy * H) / bins, y1 = ((cy + 1) * H + bins - 1) / bins;
     const int x0 = (cx * W) / bins, x1 = ((cx + 1) * W + bins - 1) / bins;
     const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+    const int groups = C >> 3;                       // 8-channel groups (<= 128)
+    const int parts = blockDim.x / groups;           // row partitions (>= 1, <= 4 used)
+    const int g = threadIdx.x % groups, pr = threadIdx.x / groups;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (pr < parts && pr < 4) {
+        const int np = parts < 4 ? parts : 4;
+        for (int y = y0 + pr; y < y1; y += np)
+            for (int x = x0; x < x1; ++x) {
+                float v[8];
+                ld8(in_hi, in_lo, (((size_t)b * H + y) * W + x) * cs + g * 8, v, f16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += v[j];
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[pr][g * 8 + j] = s[j];
+    }
+    __syncthreads();
+    const int np = (parts < 4 ? parts : 4);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) s += ld_act16(in_hi, in_lo, (((size_t)b * H + y) * W + x) * C + c, f16);
-        pooled[((size_t)b * 50 + cell) * C + c] = s * inv;
+        float t = 0.f;
+        for (int q = 0; q < np; ++q) t += part[q][c];
+        pooled[((size_t)b * 50 + cell) * C + c] = t * inv;
     }
 }
 
@@ -123,10 +143,10 @@ __global__ void psp_conv_kernel(const float* __restrict__ pooled, const float* _
     priors[((size_t)b * 50 + cell) * 128 + n] = fmaxf(acc, 0.f);
 }
 
-int psp_priors(const Act& feat, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(feat.C <= 1024, "psp channels");
+int psp_priors(const Act& feat, int feat_cs, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream) {
+    ADP_CHECK_ARG(feat.C <= 1024 && feat.C % 8 == 0 && 256 % (feat.C / 8) == 0, "psp channels");
     if (batch == 0) return ADP_OK;
-    psp_pool_kernel<<<dim3(50, batch), 256, 0, stream>>>(feat.hi, feat.lo, pooled, feat.H, feat.W, feat.C, feat.f16);
+    psp_pool_kernel<<<dim3(50, batch), 256, 0, stream>>>(feat.hi, feat.lo, pooled, feat.H, feat.W, feat.C, feat_cs > 0 ? feat_cs : feat.C, feat.f16);
     ADP_CUDA(cudaGetLastError());
     psp_conv_kernel<<<dim3(50, batch), 128, feat.C * sizeof(float), stream>>>(pooled, w, priors, feat.C);
     ADP_CUDA(cudaGetLastError());
@@ -237,41 +257,136 @@ int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batc
 }
 
 // ---------------------------------------------------------------------------------------------
-// x2 bilinear upsample, align_corners=True (pspnet.py:105)
+// pyramid priors resized to the feature grid (pspnet.py:92-93, align_corners=True) and written into channels
+// [coff, coff + 512) of the concat tensor out[b, y, x, :]; the 512 feature channels in front of them are written by the
+// producing convolution itself (epilogue channel pitch), so the concat never exists as a separate pass.
 // ---------------------------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
-                                  bf16* __restrict__ out_lo, int B, int H, int W, int C, int f16) {
-    const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;
-    const size_t total = (size_t)B * Ho * Wo * C8;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C8) * 8;
-        size_t t = i / C8;
-        const int X = (int)(t % Wo); t /= Wo;
-        const int Y = (int)(t % Ho);
-        const int b = (int)(t / Ho);
-        int y0, y1, x0, x1;
-        float wy, wx;
+__global__ void __launch_bounds__(256)
+psp_fill_priors_kernel(const float* __restrict__ priors, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int H, int W, int Ct,
+                       int coff, int f16) {
+    __shared__ __align__(16) float spr[50 * 128];
+    const int b = blockIdx.y, y = blockIdx.x;
+    for (int i = threadIdx.x; i < 50 * 128 / 4; i += blockDim.x)
+        reinterpret_cast<float4*>(spr)[i] = __ldg(reinterpret_cast<const float4*>(priors + (size_t)b * 50 * 128) + i);
+    __syncthreads();
+    for (int it = threadIdx.x; it < W * 64; it += blockDim.x) {
+        const int x = it >> 6, c = (it & 63) * 8;                  // 512 prior channels = 64 groups of 8
+        const int s = c >> 7, n0 = c & 127;
+        const int bins = s == 0 ? 1 : s == 1 ? 2 : s == 2 ? 3 : 6;
+        const int off = s == 0 ? 0 : s == 1 ? 1 : s == 2 ? 5 : 14;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = prior_at(spr + off * 128, bins, y, x, H, W, n0 + j);
+        st8(out_hi, out_lo, (((size_t)b * H + y) * W + x) * Ct + coff + c, o, f16);
+    }
+}
+
+int psp_fill_priors(const float* priors, const Act& out, int coff, int batch, cudaStream_t stream) {
+    ADP_CHECK_ARG(coff % 8 == 0 && coff + 512 <= out.C, "psp prior channel range");
+    if (batch == 0) return ADP_OK;
+    psp_fill_priors_kernel<<<dim3(out.H, batch), 256, 0, stream>>>(priors, out.hi, out.lo, out.H, out.W, out.C, coff, out.f16);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// x2 bilinear upsample, align_corners=True (pspnet.py:105).  One block = a 16 x 16 output tile of a 64-channel slab: the
+// <= 10 x 10 input pixels it reads are staged in shared memory once (0.39 bytes read per byte written instead of up to 4
+// through L1/L2), each thread then produces 8 channels of 8 output pixels with 128-bit stores.
+// ---------------------------------------------------------------------------------------------
+constexpr int UP_T = 16;        // output tile edge
+constexpr int UP_IN = 10;       // input rows / columns a tile can touch
+constexpr int UP_CS = 64;       // channels per slab (128 B per pixel)
+
+__device__ __forceinline__ void up_unpack8(const uint4& u, float* v, bool f16) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (f16) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+            v[2 * q] = f.x; v[2 * q + 1] = f.y;
+        } else {
+            v[2 * q] = __uint_as_float(w[q] << 16); v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+        }
+    }
+}
+
+// SPLIT: activations are bf16 hi + lo planes (two raw tiles); otherwise one 16-bit plane (fp16 or bf16)
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
+                  bf16* __restrict__ out_lo, int H, int W, int C, int tiles_x, int f16) {
+    __shared__ uint4 tile[(SPLIT ? 2 : 1) * UP_IN * UP_IN * (UP_CS / 8)];      // raw 16-bit values, 16 B per (pixel, 8 channels)
+    constexpr int PLANE = UP_IN * UP_IN * (UP_CS / 8);
+    const int Ho = 2 * H, Wo = 2 * W;
+    const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
+    const int c0 = blockIdx.y * UP_CS, b = blockIdx.z;
+    const int Y0 = tyi * UP_T, X0 = txi * UP_T;
+    int iy0, ix0, dummy;
+    float wdummy;
+    lin_coord(Y0, H, Ho, &iy0, &dummy, &wdummy);
+    lin_coord(X0, W, Wo, &ix0, &dummy, &wdummy);
+    const size_t base = (size_t)b * H * W;
+    for (int i = threadIdx.x; i < PLANE; i += 256) {
+        const int g = i & 7, px = i >> 3;
+        const int ly = px / UP_IN, lx = px - ly * UP_IN;
+        const int y = min(iy0 + ly, H - 1), x = min(ix0 + lx, W - 1);
+        const size_t off = (base + (size_t)y * W + x) * C + c0 + g * 8;
+        tile[i] = __ldg(reinterpret_cast<const uint4*>(in_hi + off));
+        if (SPLIT) tile[PLANE + i] = __ldg(reinterpret_cast<const uint4*>(in_lo + off));
+    }
+    __syncthreads();
+    // thread -> (8-channel group g, output column X, output rows Y0 + r0, r0 + 2, ...): the x interpolation is hoisted
+    const int g = threadIdx.x & 7;
+    const int X = X0 + ((threadIdx.x >> 3) & (UP_T - 1));
+    const int r0 = threadIdx.x >> 7;
+    if (X >= Wo) return;
+    int x0, x1;
+    float wx;
+    lin_coord(X, W, Wo, &x0, &x1, &wx);
+    const int cx0 = (x0 - ix0) * 8 + g, cx1 = (x1 - ix0) * 8 + g;
+#pragma unroll 2
+    for (int r = r0; r < UP_T; r += 2) {
+        const int Y = Y0 + r;
+        if (Y >= Ho) break;
+        int y0, y1;
+        float wy;
         lin_coord(Y, H, Ho, &y0, &y1, &wy);
-        lin_coord(X, W, Wo, &x0, &x1, &wx);
-        const size_t base = (size_t)b * H * W;
-        float v00[8], v01[8], v10[8], v11[8], o[8];
-        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x0) * C + c, v00, f16);
-        ld8(in_hi, in_lo, (base + (size_t)y0 * W + x1) * C + c, v01, f16);
-        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x0) * C + c, v10, f16);
-        ld8(in_hi, in_lo, (base + (size_t)y1 * W + x1) * C + c, v11, f16);
+        const int ry0 = (y0 - iy0) * UP_IN * 8, ry1 = (y1 - iy0) * UP_IN * 8;
+        float a[8], bq[8], c[8], d[8], o[8];
+        up_unpack8(tile[ry0 + cx0], a, !SPLIT && f16);
+        up_unpack8(tile[ry0 + cx1], bq, !SPLIT && f16);
+        up_unpack8(tile[ry1 + cx0], c, !SPLIT && f16);
+        up_unpack8(tile[ry1 + cx1], d, !SPLIT && f16);
+        if (SPLIT) {
+            float t[8];
+            up_unpack8(tile[PLANE + ry0 + cx0], t, false);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += t[j];
+            up_unpack8(tile[PLANE + ry0 + cx1], t, false);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] += t[j];
+            up_unpack8(tile[PLANE + ry1 + cx0], t, false);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] += t[j];
+            up_unpack8(tile[PLANE + ry1 + cx1], t, false);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] += t[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            o[j] = (1.f - wy) * ((1.f - wx) * v00[j] + wx * v01[j]) + wy * ((1.f - wx) * v10[j] + wx * v11[j]);
-        st8(out_hi, out_lo, i * 8, o, f16);
+            o[j] = (1.f - wy) * ((1.f - wx) * a[j] + wx * bq[j]) + wy * ((1.f - wx) * c[j] + wx * d[j]);
+        st8(out_hi, out_lo, (((size_t)b * Ho + Y) * Wo + X) * C + c0 + g * 8, o, f16);
     }
 }
 
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(out.C == in.C && out.H == 2 * in.H && out.W == 2 * in.W && in.C % 8 == 0 && in.f16 == out.f16, "upsample shapes");
-    size_t total = (size_t)batch * out.H * out.W * (out.C / 8);
-    if (total == 0) return ADP_OK;
-    int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    upsample2x_kernel<<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, batch, in.H, in.W, in.C, in.f16);
+    ADP_CHECK_ARG(out.C == in.C && out.H == 2 * in.H && out.W == 2 * in.W && in.C % UP_CS == 0 && in.f16 == out.f16, "upsample shapes");
+    if (batch == 0) return ADP_OK;
+    const int tiles_x = (out.W + UP_T - 1) / UP_T, tiles_y = (out.H + UP_T - 1) / UP_T;
+    const dim3 grid(tiles_x * tiles_y, in.C / UP_CS, batch);
+    if (in.lo && !in.f16) upsample2x_kernel<true><<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, in.H, in.W, in.C, tiles_x, 0);
+    else upsample2x_kernel<false><<<grid, 256, 0, stream>>>(in.hi, nullptr, out.hi, out.lo, in.H, in.W, in.C, tiles_x, in.f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

@@ -260,6 +260,8 @@ class Engine:
             self.lib.adp_maxpool3x3s2(C.byref(a.c), C.byref(o.c), b, self.stream), "maxpool")))
         x = mp
         self.taps = {"conv1": c1, "maxpool": mp}
+        # layer4's last conv writes straight into channels [0, 512) of the pyramid concat tensor (epilogue channel pitch 1024)
+        cat = self._act(F, S // 8, S // 8, 1024)
         for li, (planes, blocks, stride, dil) in enumerate(((64, 3, 1, 1), (128, 4, 2, 1), (256, 6, 1, 2), (512, 3, 1, 4)), 1):
             Hn = x.H // stride
             for bi in range(blocks):
@@ -273,9 +275,15 @@ class Engine:
                     res = self._act(F, Hn, Hn, planes)
                     ops.append((f"{pre}.down", self._conv(sd[f"{pre}.downsample.0.weight"], x, res, stride=s_b, dil=1,
                                                           act=L.ACT_NONE)))
-                o = self._act(F, Hn, Hn, planes)
-                ops.append((f"{pre}.conv2", self._conv(sd[f"{pre}.conv2.weight"], t, o, stride=1, dil=d_b, act=L.ACT_RELU,
-                                                       res=res)))
+                last = (li == 4 and bi == blocks - 1) and self.use_tc
+                if last:
+                    o = ActBuf(cat.hi[..., :planes], cat.lo[..., :planes] if cat.lo is not None else None, F, 1, Hn, Hn, planes, cat.f16)
+                    ops.append((f"{pre}.conv2", self._conv(sd[f"{pre}.conv2.weight"], t, o, stride=1, dil=d_b, act=L.ACT_RELU,
+                                                           res=res, out_cstride=1024)))
+                else:
+                    o = self._act(F, Hn, Hn, planes)
+                    ops.append((f"{pre}.conv2", self._conv(sd[f"{pre}.conv2.weight"], t, o, stride=1, dil=d_b, act=L.ACT_RELU,
+                                                           res=res)))
                 self.taps[pre] = o
                 x = o
         # pyramid pooling + concat + first upsample
@@ -285,11 +293,19 @@ class Engine:
         self.pooled = torch.zeros((F, 50, 512), dtype=torch.float32, device=self.device)
         self.priors = torch.zeros((F, 50, 128), dtype=torch.float32, device=self.device)
         l4 = x
-        ops.append(("psp_priors", lambda b, a=l4: L.check(
-            self.lib.adp_psp_priors(C.byref(a.c), L.ptr(wpsp), L.ptr(self.pooled), L.ptr(self.priors), b, self.stream), "psp")))
         u1 = self._act(F, 2 * l4.H, 2 * l4.W, 1024)
-        ops.append(("psp_concat_up", lambda b, a=l4, o=u1: L.check(
-            self.lib.adp_psp_concat_up(C.byref(a.c), L.ptr(self.priors), C.byref(o.c), b, self.stream), "psp_concat_up")))
+        if self.use_tc:
+            ops.append(("psp_priors", lambda b, a=l4: L.check(
+                self.lib.adp_psp_priors(C.byref(a.c), 1024, L.ptr(wpsp), L.ptr(self.pooled), L.ptr(self.priors), b, self.stream), "psp")))
+            ops.append(("psp_fill_priors", lambda b, o=cat: L.check(
+                self.lib.adp_psp_fill_priors(L.ptr(self.priors), C.byref(o.c), 512, b, self.stream), "psp_fill")))
+            ops.append(("psp_upsample", lambda b, a=cat, o=u1: L.check(
+                self.lib.adp_upsample2x(C.byref(a.c), C.byref(o.c), b, self.stream), "psp_upsample")))
+        else:
+            ops.append(("psp_priors", lambda b, a=l4: L.check(
+                self.lib.adp_psp_priors(C.byref(a.c), 0, L.ptr(wpsp), L.ptr(self.pooled), L.ptr(self.priors), b, self.stream), "psp")))
+            ops.append(("psp_concat_up", lambda b, a=l4, o=u1: L.check(
+                self.lib.adp_psp_concat_up(C.byref(a.c), L.ptr(self.priors), C.byref(o.c), b, self.stream), "psp_concat_up")))
         x = u1
         for nm, cout in (("up_1", 256), ("up_2", 64), ("up_3", 64)):
             o = self._act(F, x.H, x.W, cout)

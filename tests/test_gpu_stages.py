@@ -346,7 +346,7 @@ def test_maxpool_psp_upsample(G):
     pooled = torch.zeros((2, 50, 512), device=G.DEV)
     priors = torch.zeros((2, 50, 128), device=G.DEV)
     fa = G.act(fh, fl, 2, 1, 28, 28, 512)
-    L.check(lib.adp_psp_priors(C.byref(fa), L.ptr(wpsp), L.ptr(pooled), L.ptr(priors), 2, st), "psp")
+    L.check(lib.adp_psp_priors(C.byref(fa), 0, L.ptr(wpsp), L.ptr(pooled), L.ptr(priors), 2, st), "psp")
     uh = torch.zeros((2, 56, 56, 1024), dtype=torch.bfloat16, device=G.DEV)
     ul = torch.zeros_like(uh)
     L.check(lib.adp_psp_concat_up(C.byref(fa), L.ptr(priors), C.byref(G.act(uh, ul, 2, 1, 56, 56, 1024)), 2, st), "cat")
@@ -384,7 +384,7 @@ def test_maxpool_psp_upsample_fp16_planes(G):
     pooled = torch.zeros((2, 50, 512), device=G.DEV)
     priors = torch.zeros((2, 50, 128), device=G.DEV)
     fa = A(fh, 2, 1, 28, 28, 512)
-    L.check(lib.adp_psp_priors(C.byref(fa), L.ptr(wpsp), L.ptr(pooled), L.ptr(priors), 2, st), "psp")
+    L.check(lib.adp_psp_priors(C.byref(fa), 0, L.ptr(wpsp), L.ptr(pooled), L.ptr(priors), 2, st), "psp")
     uh = torch.zeros((2, 56, 56, 1024), dtype=torch.float16, device=G.DEV)
     L.check(lib.adp_psp_concat_up(C.byref(fa), L.ptr(priors), C.byref(A(uh, 2, 1, 56, 56, 1024)), 2, st), "cat")
     ref = F.interpolate(O.psp_module(sd, G.from_cl(fh.float().cpu())), scale_factor=2, mode="bilinear", align_corners=True)
