@@ -511,6 +511,36 @@ def test_warp_matrices_and_volume(G):
     assert float((diff > 0.05).float().mean()) < 2e-4
 
 
+@pytest.mark.parametrize("case", ["shift", "rot40_scale1.3", "shrink0.6"])
+def test_volume_tiled_fp16_features(G, case):
+    """adp_build_volume on fp16 feature maps (the engine's path: shared-memory staged footprints, direct-gather fallback
+    when the footprint of a tile exceeds the staging buffer) against grid_sample with the reference's coordinate convention
+    (network_v5.py:389-413).  The warp is an affine map of the pixel grid, the same for every depth plane."""
+    lib = L.load()
+    rng = _rng(41)
+    B, D, S = 2, 8, 224
+    th, sc, tx, ty = {"shift": (0.0, 1.0, 3.3, -2.6), "rot40_scale1.3": (math.radians(40), 1.3, 60.0, -80.0),
+                      "shrink0.6": (math.radians(-8), 0.6, 40.0, 50.0)}[case]
+    A = np.array([[sc * math.cos(th), -sc * math.sin(th), tx], [sc * math.sin(th), sc * math.cos(th), ty], [0, 0, 1]], np.float32)
+    Mw = torch.from_numpy(np.tile(np.concatenate([A.reshape(9), np.zeros(3, np.float32)]), (B, 1))).to(G.DEV)
+    f1 = _t(rng, B, 32, S, S).half()
+    f2 = _t(rng, B, 32, S, S).half()
+    depths = torch.from_numpy(O.depth_hypotheses()[:D].copy()).to(G.DEV)
+    vol = torch.zeros((B, D, S, S, 32), dtype=torch.float16, device=G.DEV)
+    f1d, f2d = G.to_cl(f1).to(G.DEV).contiguous(), G.to_cl(f2).to(G.DEV).contiguous()
+    L.check(lib.adp_build_volume(L.ptr(f1d), L.ptr(f2d), L.ptr(Mw), L.ptr(depths), L.ptr(vol), B, D, S, S, 32, 1, 1, 0, G.stream()), "vol")
+    torch.cuda.synchronize()
+    ys, xs = torch.meshgrid(torch.arange(S, dtype=torch.float32), torch.arange(S, dtype=torch.float32), indexing="ij")
+    px = A[0, 0] * xs + A[0, 1] * ys + A[0, 2]
+    py = A[1, 0] * xs + A[1, 1] * ys + A[1, 2]
+    grid = torch.stack([px / ((S - 1) / 2) - 1, py / ((S - 1) / 2) - 1], -1)[None].repeat(B, 1, 1, 1)
+    ref = f1.float() + F.grid_sample(f2.float(), grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    got = vol.float().cpu().permute(0, 4, 1, 2, 3)
+    for d in range(D):      # every depth plane sees the same warp
+        diff = (got[:, :, d] - ref).abs()
+        assert float(diff.max()) < 0.02 and float(diff.mean()) < 1e-3, (d, float(diff.max()), float(diff.mean()))   # fp16 storage of O(1..5) values
+
+
 def _run_costreg_decode(G, sd, eng_kw):
     from rgbmanip_b200.engine import Engine
     eng = Engine(sd, device=G.DEV, max_envs=2, debug=True, **eng_kw)
