@@ -8,10 +8,10 @@
 //   out[d][pixel, co]      = P[d-1][kz=0] + P[d][kz=1] + P[d+1][kz=2]
 //
 // One work unit = one image row segment of 112 pixels (M = 128 rows of the UMMA tile) for all 24 depths.  For each
-// input plane d' the three rows y-1, y, y+1 (with a one-pixel halo in x) are brought in by TMA in the canonical
-// NO-SWIZZLE K-major layout ([16-byte channel chunk][pixel][8 channels]), in which the x taps are plain +16-byte
-// shifts of the shared-memory descriptor start address, so every volume row is read 3 times (once per ky) instead
-// of 27.  P[d'] accumulates in one of four 32-column TMEM slots (a ring over depth); the epilogue warps add the three
+// input plane d' the rows y-1 .. y+R (with a one-pixel halo in x) are brought in by ONE TMA box in pixel-major
+// 64-byte-swizzled K-major layout ([row][pixel][32 channels]); the swizzle is a function of the absolute shared-memory
+// address, so the (ky, kx) taps are plain row/pixel shifts of the descriptor start address (+64 B per pixel) and every
+// volume row is read (R+2)/R times instead of 27.  P[d'] accumulates in one of four 32-column TMEM slots (a ring over depth); the epilogue warps add the three
 // lane-aligned column groups of three consecutive slots, apply the folded BatchNorm + ReLU and store 16 channels
 // (8 real + 8 zero: conv1 needs Cin = 16 for the K = 16 MMA).
 #include "common.cuh"
@@ -26,9 +26,9 @@ constexpr int C0_THREADS = 192;
 constexpr int C0_SEG = 112;                 // pixels per unit (224 = 2 x 112)
 constexpr int C0_R = 4;                                   // output rows per unit: rows y0-1 .. y0+R are loaded once for R outputs
 constexpr int C0_PIXPITCH = 120;                          // pixels per slab row in smem (112 + halo, padded so that a row is a 128-byte multiple)
-constexpr int C0_ROWPITCH = C0_PIXPITCH * 16;             // 1920 bytes
-constexpr int C0_CHUNK_BYTES = (C0_R + 2) * C0_ROWPITCH;  // one 8-channel chunk plane [row][pixel][16 B] = ONE TMA box; LBO of the A descriptor
-constexpr int C0_STAGE_BYTES = 4 * C0_CHUNK_BYTES + 512;  // one depth plane of the unit (+ slack: the M = 128 tile overhangs the last slab row)
+constexpr int C0_ROWPITCH = C0_PIXPITCH * 64;             // 7680 bytes: one slab row, 32 channels per pixel (a multiple of the 512-byte swizzle atom)
+constexpr int C0_BOX_BYTES = (C0_R + 2) * C0_ROWPITCH;    // one depth plane of the unit = ONE TMA box
+constexpr int C0_STAGE_BYTES = C0_BOX_BYTES + 1024;       // + slack: the M = 128 tile overhangs the last slab row by 10 pixels
 constexpr int C0_STAGES = 4;
 constexpr int C0_W_BYTES = 9 * 4 * 32 * 16;               // [tap][chunk][n = 32][8 ch] 16-bit
 constexpr int C0_SLOTS = 4;                               // depth ring; TMEM column = (row * 4 + slot) * 32
@@ -45,8 +45,12 @@ struct Conv0Params {
     int* err;
 };
 
-// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = byte distance between the two 16-byte K chunks of one MMA,
-// SBO = byte distance between consecutive 8-row groups.
+// A operand: K-major, 64-byte swizzle (rows of 64 B = 32 channels; one MMA consumes 32 B of each row), SBO = 8 rows.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// B operand (weights): K-major, no swizzle: 8-row x 16-byte core matrices; LBO = byte distance between the two 16-byte K
+// chunks of one MMA, SBO = byte distance between consecutive 8-row groups.
 __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
@@ -102,7 +106,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     const int D = p.D;
 
     if (warp == 0) {
-        // ===================== TMA producer: one box per 8-channel chunk = (R + 2) rows x 120 pixels x 16 bytes =====================
+        // ===================== TMA producer: one box per plane = (R + 2) rows x 120 pixels x 64 bytes =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -112,19 +116,20 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                 for (int d = 0; d < D; ++d) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 11);
                     const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), 4u * C0_CHUNK_BYTES);
-#pragma unroll
-                    for (int kc = 0; kc < 4; ++kc)
-                        ptx::tma_load_5d(&tmIn, full_bar(stage), sa + kc * C0_CHUNK_BYTES, kc * 8, x0, y - 1, d, b);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)C0_BOX_BYTES);
+                    ptx::tma_load_5d(&tmIn, full_bar(stage), sa, 0, x0, y - 1, d, b);
                     if (++stage == C0_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: 9 (ky,kx) taps x 2 K steps per plane into TMEM slot g % 4 =====================
+        // warp-convergent: all lanes carry the same descriptors, the elected lane issues (see ptx::umma_bf16_elected)
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t idesc = make_idesc_n(32, p.f16);
+        const uint32_t elected = ptx::elect_one();
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
         unsigned g = 0;   // running plane counter (D % 4 == 0 keeps slot == depth % 4)
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             for (int d = 0; d < D; ++d, ++g) {
@@ -132,106 +137,103 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                 ptx::mbar_wait(tempty_bar(slot), ((g >> 2) & 1) ^ 1, p.err, 12);
                 ptx::mbar_wait(full_bar(stage), phase, p.err, 13);
                 ptx::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
+                const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
+                const uint64_t a0 = make_desc_sw64(sa);
+                const uint64_t b0 = make_desc_noswz(w_base, 512, 128);
 #pragma unroll
-                    for (int r = 0; r < C0_R; ++r) {
-                        const uint32_t tmem_d = tmem_base + (uint32_t)((r * C0_SLOTS + slot) * 32);
-                        int first = 1;
+                for (int r = 0; r < C0_R; ++r) {
+                    const uint32_t tmem_d = tbase + (uint32_t)((r * C0_SLOTS + slot) * 32);
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
+                    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx)
+                        for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                                for (int ks = 0; ks < 2; ++ks) {
-                                    const uint64_t adesc = make_desc_noswz(sa + (2 * ks) * C0_CHUNK_BYTES + (r + ky) * C0_ROWPITCH + kx * 16,
-                                                                           C0_CHUNK_BYTES, 128);
-                                    const uint64_t bdesc = make_desc_noswz(w_base + ((ky * 3 + kx) * 4 + 2 * ks) * 512, 512, 128);
-                                    ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-                                    first = 0;
-                                }
-                    }
-                    ptx::umma_commit(empty_bar(stage));
-                    ptx::umma_commit(tfull_bar(slot));
+                            for (int ks = 0; ks < 2; ++ks) {
+                                // start-address field is (addr >> 4): constant offsets are plain adds (no carry out of the 14-bit field below 256 KB)
+                                const uint64_t adesc = a0 + (uint64_t)(((r + ky) * C0_ROWPITCH + kx * 64 + ks * 32) >> 4);
+                                const uint64_t bdesc = b0 + (uint64_t)((((ky * 3 + kx) * 4 + 2 * ks) * 512) >> 4);
+                                ptx::umma_bf16_elected(tmem_d, adesc, bdesc, idesc, (ky | kx | ks) ? 1u : 0u, elected);
+                            }
                 }
+                ptx::umma_commit_elected(empty_bar(stage), elected);
+                ptx::umma_commit_elected(tfull_bar(slot), elected);
                 __syncwarp();
                 if (++stage == C0_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
         // ===================== epilogue: out[d] = P[d-1][kz=0] + P[d][kz=1] + P[d+1][kz=2] =====================
+        // Each plane's partial sums are pulled out of TMEM exactly once, as soon as the plane completes, and its slot is
+        // released immediately: the three-plane sum lives in registers (two carried accumulators per output row), so the MMA
+        // warp can run the whole ring (3 planes) ahead instead of waiting for the epilogue of the plane before last.
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         float sc[8], sh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = p.scale[j]; sh[j] = p.shift[j]; }
-        unsigned g0 = 0;   // plane counter at the start of the unit
-        for (int u = blockIdx.x; u < units; u += gridDim.x, g0 += (unsigned)D) {
+        auto store_row = [&](const float* acc, int b, int d, int y, int x) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v0 = fmaxf(fmaf(acc[2 * j], sc[2 * j], sh[2 * j]), 0.f);
+                const float v1 = fmaxf(fmaf(acc[2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]), 0.f);
+                if (p.f16)
+                    o[j] = (uint32_t)__half_as_ushort(__float2half_rn(v0)) | ((uint32_t)__half_as_ushort(__float2half_rn(v1)) << 16);
+                else
+                    o[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) |
+                           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
+            }
+            if (p.out_s2d) {
+                // only the 8 real channels, in the layout conv1 (stride 2) and conv11's skip connection read as stride-1 tensors
+                const size_t vox = (((size_t)b * (D >> 1) + (d >> 1)) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+                *reinterpret_cast<uint4*>(p.out + vox * 64 + (((d & 1) * 4 + (y & 1) * 2 + (x & 1)) * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + ((((size_t)b * D + d) * p.H + y) * p.W + x) * 16);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(0, 0, 0, 0);
+            }
+        };
+        unsigned g = 0;   // running plane counter (matches the MMA warp's)
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int seg = u % segs, y0 = ((u / segs) % ygroups) * C0_R, b = u / (segs * ygroups);
             const int x = seg * C0_SEG + m;
             const bool valid = m < C0_SEG;
-            for (int d = 0; d < D; ++d) {
-                // planes complete in order: waiting for plane d+1 (or d at the last depth) covers d-1 and d
-                const unsigned gl = g0 + (unsigned)(d + 1 < D ? d + 1 : d);
-                ptx::mbar_wait(tfull_bar(gl & 3), (gl >> 2) & 1, p.err, 14);
+            float acc_cur[C0_R][8];     // out[d']   so far: P[d'-1][kz=0] (+ P[d'][kz=1] once plane d' is in)
+            float acc_nxt[C0_R][8];     // out[d'+1] so far: P[d'][kz=0]
+#pragma unroll
+            for (int r = 0; r < C0_R; ++r)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc_cur[r][j] = 0.f; acc_nxt[r][j] = 0.f; }
+            for (int d = 0; d < D; ++d, ++g) {
+                const int slot = g & 3;
+                ptx::mbar_wait(tfull_bar(slot), (g >> 2) & 1, p.err, 14);
                 ptx::tc_fence_after();
-                // issue every TMEM load of this depth first, wait once: the loads overlap instead of paying 12 round trips
                 uint32_t rr[C0_R][3][8];
 #pragma unroll
                 for (int r = 0; r < C0_R; ++r)
 #pragma unroll
-                    for (int kz = 0; kz < 3; ++kz) {
-                        const int dp = d + kz - 1;
-                        const int dpc = dp < 0 ? 0 : (dp >= D ? D - 1 : dp);     // clamped (masked below): keeps the loads uniform
-                        tmem_ld8(lane_addr + (uint32_t)((r * C0_SLOTS + ((g0 + dpc) & 3)) * 32 + kz * 8), rr[r][kz]);
-                    }
+                    for (int kz = 0; kz < 3; ++kz)
+                        tmem_ld8(lane_addr + (uint32_t)((r * C0_SLOTS + slot) * 32 + kz * 8), rr[r][kz]);
                 ptx::tmem_ld_wait();
-                float acc[C0_R][8];
-#pragma unroll
-                for (int r = 0; r < C0_R; ++r) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
-#pragma unroll
-                    for (int kz = 0; kz < 3; ++kz) {
-                        const int dp = d + kz - 1;
-                        if (dp < 0 || dp >= D) continue;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[r][j] += __uint_as_float(rr[r][kz][j]);
-                    }
-                }
                 ptx::tc_fence_before();
                 __syncwarp();
-                // plane d-1 is no longer needed once out[d] has been formed; the last step also frees plane D-1
-                if (lane == 0) {
-                    if (d >= 1) ptx::mbar_arrive(tempty_bar((g0 + d - 1) & 3));
-                    if (d == D - 1) ptx::mbar_arrive(tempty_bar((g0 + d) & 3));
-                }
-                if (valid) {
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(slot));       // the slot is free as soon as it has been read
 #pragma unroll
-                  for (int r = 0; r < C0_R; ++r) {
-                    const int y = y0 + r;
-                    uint32_t o[4];
+                for (int r = 0; r < C0_R; ++r) {
+                    // plane d contributes kz=2 to out[d-1] (now complete), kz=1 to out[d], kz=0 to out[d+1]
+                    if (d >= 1) {
+                        float prev[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float v0 = fmaxf(fmaf(acc[r][2 * j], sc[2 * j], sh[2 * j]), 0.f);
-                        const float v1 = fmaxf(fmaf(acc[r][2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]), 0.f);
-                        if (p.f16)
-                            o[j] = (uint32_t)__half_as_ushort(__float2half_rn(v0)) | ((uint32_t)__half_as_ushort(__float2half_rn(v1)) << 16);
-                        else
-                            o[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) |
-                                   ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
+                        for (int j = 0; j < 8; ++j) prev[j] = acc_cur[r][j] + __uint_as_float(rr[r][2][j]);
+                        if (valid) store_row(prev, b, d - 1, y0 + r, x);
                     }
-                    if (p.out_s2d) {
-                        // only the 8 real channels, in the layout conv1 (stride 2) and conv11's skip connection read as stride-1 tensors
-                        const size_t vox = (((size_t)b * (D >> 1) + (d >> 1)) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
-                        *reinterpret_cast<uint4*>(p.out + vox * 64 + (((d & 1) * 4 + (y & 1) * 2 + (x & 1)) * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    } else {
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + ((((size_t)b * D + d) * p.H + y) * p.W + x) * 16);
-                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc_cur[r][j] = acc_nxt[r][j] + __uint_as_float(rr[r][1][j]);
+                        acc_nxt[r][j] = __uint_as_float(rr[r][0][j]);
                     }
-                  }
+                    if (d == D - 1 && valid) store_row(acc_cur[r], b, d, y0 + r, x);
                 }
             }
         }
@@ -266,12 +268,12 @@ int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const flo
     cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.D, (cuuint64_t)in.B};
     cuuint64_t strides[4] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2,
                              (cuuint64_t)in.D * in.H * in.W * in.C * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)C0_PIXPITCH, (cuuint32_t)(C0_R + 2), 1, 1};
+    cuuint32_t box[5] = {32, (cuuint32_t)C0_PIXPITCH, (cuuint32_t)(C0_R + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     ADP_CHECK_ARG(!planar, "the depth-ring kernel reads the channels-last volume");
     const int rank = 5;
     CUresult r = g_encode_shared(&pl->tmIn, in.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, in.hi, dims,
-                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(conv0 volume) failed: %d", (int)r);

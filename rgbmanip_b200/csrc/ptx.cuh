@@ -95,6 +95,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// Warp-convergent issue: every lane executes the surrounding code with identical (warp-uniform) operands and only the
+// elected lane's instruction takes effect.  Inside an `if (lane == 0)` branch ptxas must assume divergent, per-lane operands
+// and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~10 issue slots + a branch per MMA), which
+// bounds small-N MMAs (16-32 cycles of tensor work each) by the issuing thread instead of the tensor pipe.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void umma_bf16_elected(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                                  uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elected(uint32_t bar, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(elected) : "memory");
+}
 // mbarrier arrives once all tcgen05 ops previously issued by this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -238,52 +238,52 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // warp-convergent: all lanes carry the same (uniform) descriptors and only the elected lane's tcgen05 instructions take
+        // effect -- see ptx::umma_bf16_elected for why this is not written as `if (lane == 0)`
         int stage = 0;
         uint32_t phase = 0;
         int as = 0;
         uint32_t aphase = 0;
         const uint32_t idesc = make_idesc<BN>(p.f16);
+        const uint32_t elected = ptx::elect_one();
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             ptx::mbar_wait(tempty_bar(as), aphase ^ 1, p.err, 2);
             ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE);
+            const uint32_t tmem_d = tbase + (uint32_t)(as * Cfg::ACC_STRIDE);
             for (int it = 0; it < k_iters; ++it) {
                 ptx::mbar_wait(full_bar(stage), phase, p.err, 3);
                 ptx::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    if (FUSED == 2) {
-                        const uint64_t ah = make_smem_desc<KC>(sa);
-                        const uint64_t wh = make_smem_desc<KC>(sa + Cfg::A_BYTES);
-                        const uint64_t wl = make_smem_desc<KC>(sa + Cfg::A_BYTES + Cfg::B_PAD);
+                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                if (FUSED == 2) {
+                    const uint64_t ah = make_smem_desc<KC>(sa);
+                    const uint64_t wh = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+                    const uint64_t wl = make_smem_desc<KC>(sa + Cfg::A_BYTES + Cfg::B_PAD);
 #pragma unroll
-                        for (int k = 0; k < KC / 16; ++k) {
-                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
-                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u);
-                        }
-                    } else if (FUSED == 1) {
-                        const uint64_t ah = make_smem_desc<KC>(sa), al = make_smem_desc<KC>(sa + Cfg::A_BYTES);
-                        const uint64_t wh = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES);
-                        const uint64_t wl = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES + Cfg::B_PAD);
-#pragma unroll
-                        for (int k = 0; k < KC / 16; ++k) {
-                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
-                            ptx::umma_bf16(tmem_d, al + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, 1u);
-                            ptx::umma_bf16(tmem_d, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u);
-                        }
-                    } else {
-                        const uint64_t adesc = make_smem_desc<KC>(sa);
-                        const uint64_t bdesc = make_smem_desc<KC>(sa + Cfg::A_BYTES);
-#pragma unroll
-                        for (int k = 0; k < KC / 16; ++k) {
-                            // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the >>4 address field
-                            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                           (it > 0 || k > 0) ? 1u : 0u);
-                        }
+                    for (int k = 0; k < KC / 16; ++k) {
+                        // advance 16 elements = 32 bytes along K inside the swizzled row: +2 in the >>4 address field
+                        ptx::umma_bf16_elected(tmem_d, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u, elected);
+                        ptx::umma_bf16_elected(tmem_d, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u, elected);
                     }
-                    ptx::umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
-                    if (it == k_iters - 1) ptx::umma_commit(tfull_bar(as));   // accumulator complete
+                } else if (FUSED == 1) {
+                    const uint64_t ah = make_smem_desc<KC>(sa), al = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+                    const uint64_t wh = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES);
+                    const uint64_t wl = make_smem_desc<KC>(sa + 2 * Cfg::A_BYTES + Cfg::B_PAD);
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k) {
+                        ptx::umma_bf16_elected(tmem_d, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u, elected);
+                        ptx::umma_bf16_elected(tmem_d, al + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, 1u, elected);
+                        ptx::umma_bf16_elected(tmem_d, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u, elected);
+                    }
+                } else {
+                    const uint64_t adesc = make_smem_desc<KC>(sa);
+                    const uint64_t bdesc = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k)
+                        ptx::umma_bf16_elected(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u, elected);
                 }
+                ptx::umma_commit_elected(empty_bar(stage), elected);          // frees the smem slot when these MMAs retire
+                if (it == k_iters - 1) ptx::umma_commit_elected(tfull_bar(as), elected);   // accumulator complete
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }

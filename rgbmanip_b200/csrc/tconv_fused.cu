@@ -114,15 +114,17 @@ tconv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
         const uint32_t idesc = make_idesc_n(BN, p.f16);
+        const uint32_t elected = ptx::elect_one();       // warp-convergent issue, see ptx::umma_bf16_elected
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
         ptx::mbar_wait(w_bar, 0, p.err, 22);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             ptx::mbar_wait(tempty_bar(as), aphase ^ 1, p.err, 23);
             ptx::tc_fence_after();
-            const uint32_t tmem_set = tmem_base + (uint32_t)(as * 8 * Cfg::REGION);
+            const uint32_t tmem_set = tbase + (uint32_t)(as * 8 * Cfg::REGION);
             for (int o = 0; o < 8; ++o) {
                 ptx::mbar_wait(full_bar(stage), phase, p.err, 24);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                {
                     const uint64_t adesc = tf_smem_desc<KC>(smem_base + stage * Cfg::A_BYTES);
                     const int oz = o >> 2, oy = (o >> 1) & 1, ox = o & 1;
                     // per axis: offset 0 serves (parity 0, k = 1) and (parity 1, k = 2); offset 1 serves (parity 1, k = 0)
@@ -136,11 +138,11 @@ tconv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 const uint32_t tmem_d = tmem_set + (uint32_t)(cls * Cfg::REGION);
 #pragma unroll
                                 for (int k = 0; k < KC / 16; ++k)
-                                    ptx::umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                                   (o > 0 || k > 0) ? 1u : 0u);
+                                    ptx::umma_bf16_elected(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                                           (o > 0 || k > 0) ? 1u : 0u, elected);
                             }
-                    ptx::umma_commit(empty_bar(stage));
-                    if (o == 7) ptx::umma_commit(tfull_bar(as));
+                    ptx::umma_commit_elected(empty_bar(stage), elected);
+                    if (o == 7) ptx::umma_commit_elected(tfull_bar(as), elected);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
