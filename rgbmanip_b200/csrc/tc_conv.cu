@@ -31,11 +31,9 @@ __device__ __forceinline__ uint32_t make_idesc(int f16) {
 // ------------------------------------------------------------------------------------------------
 // Epilogue of one accumulator chunk: r[0..CH) fp32 accumulators of output pixel `pix`, channels [nbase, nbase + CH)
 template <int CH>
-__device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase, int b) {
+__device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase, int b, float* v) {
                             const int nvalid = min(CH, p.Cout - nbase);
-                            const size_t o = pix * p.Cout + nbase;
                             const size_t ro = pix * p.res_cs + nbase;
-                            float v[32];
 #pragma unroll
                             for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
                             if (p.scale) {
@@ -47,7 +45,6 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const u
 #pragma unroll
                                 for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(bias + nbase + j);
                             }
-                            const size_t oh = pix * p.out_cs + p.out_coff + nbase;   // out_hi / out_lo may be a column range of a wider tensor
                             const bool vec_ok = ((p.Cout | p.res_cs | p.out_cs | p.out_coff) & 7) == 0;   // 128-bit accesses stay aligned
                             if (p.res_hi && !p.res_after_act) {
 #pragma unroll
@@ -83,6 +80,15 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const u
                                     }
                                 }
                             }
+}
+
+// per-lane stores of one chunk (every lane writes its own pixel row): partial chunks, split hi + lo planes
+template <int CH>
+__device__ __forceinline__ void tc_epilogue_store_lane(const TcConvParams& p, const float* v, size_t pix, int nbase) {
+                            const int nvalid = min(CH, p.Cout - nbase);
+                            const size_t o = pix * p.Cout + nbase;
+                            const size_t oh = pix * p.out_cs + p.out_coff + nbase;   // out_hi / out_lo may be a column range of a wider tensor
+                            const bool vec_ok = ((p.Cout | p.res_cs | p.out_cs | p.out_coff) & 7) == 0;   // 128-bit accesses stay aligned
                             if (p.out_f32) {
                                 if (nvalid == CH && (p.Cout & 3) == 0) {
 #pragma unroll
@@ -116,6 +122,74 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcConvParams& p, const u
                             }
 }
 
+// Warp-cooperative stores of one chunk.  A lane owns one pixel row, so per-lane 128-bit stores make every instruction touch
+// 32 separate lines (2.2-3.7 TB/s measured, tools/micro/store_pattern.cu); here the rows go through a 2 KB per-warp transpose
+// buffer (XOR-swizzled: conflict free both ways) and every store instruction writes whole 64-byte row pieces of 8 (16) rows.
+// NP = 16-byte pieces per row in this call (4: 32 x 16-bit or 16 x fp32; 2: 16 x 16-bit).
+template <int NP>
+__device__ __forceinline__ void tc_store_rows(uint4* wbuf, int lane, const uint4* pieces, size_t pix, unsigned int validmask,
+                                              uint8_t* base, size_t row_pitch_bytes, size_t col_off_bytes) {
+    constexpr int SH = NP == 4 ? 1 : 2;            // swizzle source bits: lane >> SH
+#pragma unroll
+    for (int j = 0; j < NP; ++j) wbuf[lane * NP + (j ^ ((lane >> SH) & (NP - 1)))] = pieces[j];
+    __syncwarp();
+    constexpr int RPI = 32 / NP;                   // rows per store instruction
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const int row = RPI * k + lane / NP, piece = lane % NP;
+        const uint4 val = wbuf[row * NP + (piece ^ ((row >> SH) & (NP - 1)))];
+        const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)pix, row);
+        if ((validmask >> row) & 1u) *reinterpret_cast<uint4*>(base + (size_t)rp * row_pitch_bytes + col_off_bytes + piece * 16) = val;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint4 tc_pack8(const float* v, int f16) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (f16) {
+            const __half2 h = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+            w[q] = *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            w[q] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int CH>
+__device__ __forceinline__ void tc_epilogue_store_warp(const TcConvParams& p, const float* v, size_t pix, int nbase, unsigned int validmask,
+                                                       uint4* wbuf, int lane) {
+    constexpr int NP16 = CH / 8;
+    if (p.out_f32) {
+#pragma unroll
+        for (int h = 0; h < CH / 16; ++h) {
+            uint4 pc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                pc[j] = make_uint4(__float_as_uint(v[16 * h + 4 * j]), __float_as_uint(v[16 * h + 4 * j + 1]),
+                                   __float_as_uint(v[16 * h + 4 * j + 2]), __float_as_uint(v[16 * h + 4 * j + 3]));
+            tc_store_rows<4>(wbuf, lane, pc, pix, validmask, reinterpret_cast<uint8_t*>(p.out_f32), (size_t)p.Cout * 4,
+                             (size_t)(nbase + 16 * h) * 4);
+        }
+    }
+    if (p.out_h16) {
+        uint4 pc[NP16];
+#pragma unroll
+        for (int j = 0; j < NP16; ++j) pc[j] = tc_pack8(v + 8 * j, 1);
+        tc_store_rows<NP16>(wbuf, lane, pc, pix, validmask, reinterpret_cast<uint8_t*>(p.out_h16), (size_t)p.Cout * 2, (size_t)nbase * 2);
+    }
+    if (p.out_hi) {
+        uint4 pc[NP16];
+#pragma unroll
+        for (int j = 0; j < NP16; ++j) pc[j] = tc_pack8(v + 8 * j, p.f16);
+        tc_store_rows<NP16>(wbuf, lane, pc, pix, validmask, reinterpret_cast<uint8_t*>(p.out_hi), (size_t)p.out_cs * 2,
+                            (size_t)(p.out_coff + nbase) * 2);
+    }
+}
+
 constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 // FUSED = 1: split-precision bf16x3 layers keep A_hi, A_lo, W_hi, W_lo of one (tap, K chunk) in the same stage and issue the
@@ -129,11 +203,12 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = FUSED == 1 ? 2 * (A_BYTES + B_PAD) : FUSED == 2 ? (A_BYTES + 2 * B_PAD) : (A_BYTES + B_PAD);
     // small-N layers are latency bound per tile: fewer stages -> several CTAs per SM overlap their pipelines
     static constexpr int CTAS_PER_SM = FUSED ? (BN <= 64 ? 2 : 1) : (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
-    static constexpr int SMEM_BUDGET = 196608 / CTAS_PER_SM;
+    static constexpr int EPI_BYTES = 4 * 2048;                  // per-epilogue-warp transpose buffers (coalesced stores)
+    static constexpr int SMEM_BUDGET = (220 * 1024 - CTAS_PER_SM * (EPI_BYTES + 2048)) / CTAS_PER_SM;
     static constexpr int STAGES = (STAGE_BYTES * 6 <= SMEM_BUDGET) ? 6 : (SMEM_BUDGET / STAGE_BYTES);
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns per accumulator stage
     static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : (2 * ACC_STRIDE <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, int KC, int FUSED>
@@ -145,7 +220,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint4* epi_buf = reinterpret_cast<uint4*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
@@ -297,6 +373,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int as = 0;
         uint32_t aphase = 0;
         constexpr int CH = (BN < 32) ? BN : 32;
+        uint4* wbuf = epi_buf + q * 128;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int t = tile;
             const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -317,10 +394,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 ptx::tmem_ld16(taddr, r);
                 if (CH == 32) ptx::tmem_ld16(taddr + 16, r + 16);
                 ptx::tmem_ld_wait();
-                if (valid) {
-                    const int nbase = n0 + c0;
-                    if (nbase < p.Cout) {   // Cout may be padded up to BN (e.g. 8 -> 16)
-                        tc_epilogue_chunk<CH>(p, r, pix, nbase, b);
+                const int nbase = n0 + c0;
+                if (nbase < p.Cout) {       // Cout may be padded up to BN (e.g. 8 -> 16); uniform over the warp
+                    float v[32];
+                    if (valid) tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
+                    if (p.coalesce) {
+                        const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
+                        tc_epilogue_store_warp<CH>(p, v, pix, nbase, vmask, wbuf, lane);
+                    } else if (valid) {
+                        tc_epilogue_store_lane<CH>(p, v, pix, nbase);
                     }
                 }
             }

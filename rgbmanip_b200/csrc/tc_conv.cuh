@@ -50,6 +50,7 @@ struct TcConvParams {
     __half* out_h16;         // optional extra fp16 copy
     int out_cs, out_coff;    // channel pitch / first channel of out_hi, out_lo
     int bias_per_batch;      // bias is [B, Cout]
+    int coalesce;            // epilogue stores go through the per-warp transpose buffers (full chunks, single 16-bit plane)
     int* err;                // device error flag (pipeline watchdog)
 };
 
