@@ -31,7 +31,8 @@ __device__ __forceinline__ uint32_t make_idesc(int f16) {
 // ------------------------------------------------------------------------------------------------
 // Epilogue of one accumulator chunk: r[0..CH) fp32 accumulators of output pixel `pix`, channels [nbase, nbase + CH)
 template <int CH>
-__device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase, int b, float* v) {
+__device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase, int b, float* v,
+                                                 const float* res_pre = nullptr) {
                             const int nvalid = min(CH, p.Cout - nbase);
                             const size_t ro = pix * p.res_cs + nbase;
 #pragma unroll
@@ -46,7 +47,10 @@ __device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const ui
                                 for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(bias + nbase + j);
                             }
                             const bool vec_ok = ((p.Cout | p.res_cs | p.out_cs | p.out_coff) & 7) == 0;   // 128-bit accesses stay aligned
-                            if (p.res_hi && !p.res_after_act) {
+                            if (res_pre && !p.res_after_act) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) v[j] += res_pre[j];
+                            } else if (p.res_hi && !p.res_after_act) {
 #pragma unroll
                                 for (int j0 = 0; j0 < CH; j0 += 8) {
                                     if (vec_ok && j0 + 8 <= nvalid) {
@@ -68,7 +72,10 @@ __device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const ui
 #pragma unroll
                                 for (int j = 0; j < CH; ++j) v[j] = tanhf(v[j]);
                             }
-                            if (p.res_hi && p.res_after_act) {
+                            if (res_pre && p.res_after_act) {
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) v[j] += res_pre[j];
+                            } else if (p.res_hi && p.res_after_act) {
 #pragma unroll
                                 for (int j0 = 0; j0 < CH; j0 += 8) {
                                     if (vec_ok && j0 + 8 <= nvalid) {
@@ -142,6 +149,63 @@ __device__ __forceinline__ void tc_store_rows(uint4* wbuf, int lane, const uint4
         if ((validmask >> row) & 1u) *reinterpret_cast<uint4*>(base + (size_t)rp * row_pitch_bytes + col_off_bytes + piece * 16) = val;
     }
     __syncwarp();
+}
+
+// reverse direction: every load instruction reads whole row pieces of 8 (16) rows, each lane ends up with its own row.
+// Two phases, so that the global loads can be issued early (before the accumulator is ready) and their latency overlaps
+// the wait: issue = coalesced loads into registers, finish = transpose through the warp buffer.
+template <int NP>
+__device__ __forceinline__ void tc_load_rows_issue(int lane, uint4* regs, size_t pix, unsigned int validmask, const uint8_t* base,
+                                                   size_t row_pitch_bytes, size_t col_off_bytes) {
+    constexpr int RPI = 32 / NP;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const int row = RPI * k + lane / NP, piece = lane % NP;
+        const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)pix, row);
+        regs[k] = make_uint4(0, 0, 0, 0);
+        if ((validmask >> row) & 1u) regs[k] = *reinterpret_cast<const uint4*>(base + (size_t)rp * row_pitch_bytes + col_off_bytes + piece * 16);
+    }
+}
+template <int NP>
+__device__ __forceinline__ void tc_load_rows_finish(uint4* wbuf, int lane, const uint4* regs, uint4* pieces) {
+    constexpr int SH = NP == 4 ? 1 : 2;
+    constexpr int RPI = 32 / NP;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const int row = RPI * k + lane / NP, piece = lane % NP;
+        wbuf[row * NP + (piece ^ ((row >> SH) & (NP - 1)))] = regs[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NP; ++j) pieces[j] = wbuf[lane * NP + (j ^ ((lane >> SH) & (NP - 1)))];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void tc_unpack8(const uint4& u, int f16, float* v) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (f16) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+            v[2 * q] = f.x; v[2 * q + 1] = f.y;
+        } else {
+            v[2 * q] = __uint_as_float(w[q] << 16); v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+        }
+    }
+}
+
+// residual of one chunk for every lane's own row, fetched with coalesced row-piece loads
+template <int CH>
+__device__ __forceinline__ void tc_epilogue_res_issue(const TcConvParams& p, uint4* regs, size_t pix, int nbase, unsigned int validmask, int lane) {
+    tc_load_rows_issue<CH / 8>(lane, regs, pix, validmask, reinterpret_cast<const uint8_t*>(p.res_hi), (size_t)p.res_cs * 2, (size_t)nbase * 2);
+}
+template <int CH>
+__device__ __forceinline__ void tc_epilogue_res_finish(const TcConvParams& p, const uint4* regs, float* res, uint4* wbuf, int lane) {
+    constexpr int NP16 = CH / 8;
+    uint4 pc[NP16];
+    tc_load_rows_finish<NP16>(wbuf, lane, regs, pc);
+#pragma unroll
+    for (int j = 0; j < NP16; ++j) tc_unpack8(pc[j], p.f16, res + 8 * j);
 }
 
 __device__ __forceinline__ uint4 tc_pack8(const float* v, int f16) {
@@ -373,6 +437,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int as = 0;
         uint32_t aphase = 0;
         constexpr int CH = (BN < 32) ? BN : 32;
+        constexpr bool RES_PREFETCH = BN <= 64;          // residual of the whole tile fits in registers (<= 8 x 16 B per lane)
+        const bool res_co = p.coalesce && p.res_hi && !p.res_lo && (p.res_cs & 7) == 0;
         uint4* wbuf = epi_buf + q * 128;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int t = tile;
@@ -385,9 +451,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const bool valid = (m < rows_valid) && (x < p.W) && (y < p.H);
             const size_t pix = (((size_t)b * p.oD + (d * p.out_mul + p.out_oz)) * p.oH + (y * p.out_mul + p.out_oy)) * p.oW +
                                (x * p.out_mul + p.out_ox);
+            const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
+            uint4 res_regs[RES_PREFETCH ? BN / CH : 1][CH / 8];
+            if (RES_PREFETCH && res_co) {      // residual loads in flight while the accumulator is still being produced
+#pragma unroll
+                for (int c = 0; c < BN / CH; ++c)
+                    if (n0 + c * CH < p.Cout) tc_epilogue_res_issue<CH>(p, res_regs[c], pix, n0 + c * CH, vmask, lane);
+            }
             ptx::mbar_wait(tfull_bar(as), aphase, p.err, 4);
             ptx::tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < BN; c0 += CH) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::ACC_STRIDE + c0);
@@ -397,11 +470,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int nbase = n0 + c0;
                 if (nbase < p.Cout) {       // Cout may be padded up to BN (e.g. 8 -> 16); uniform over the warp
                     float v[32];
-                    if (valid) tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
                     if (p.coalesce) {
-                        const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
+                        if (res_co) {
+                            float res[CH];
+                            if (!RES_PREFETCH) tc_epilogue_res_issue<CH>(p, res_regs[0], pix, nbase, vmask, lane);
+                            tc_epilogue_res_finish<CH>(p, res_regs[RES_PREFETCH ? c0 / CH : 0], res, wbuf, lane);
+                            if (valid) tc_epilogue_math<CH>(p, r, pix, nbase, b, v, res);
+                        } else if (valid) {
+                            tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
+                        }
                         tc_epilogue_store_warp<CH>(p, v, pix, nbase, vmask, wbuf, lane);
                     } else if (valid) {
+                        tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
                         tc_epilogue_store_lane<CH>(p, v, pix, nbase);
                     }
                 }
@@ -413,6 +493,203 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     }
 
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Slab variant for small-channel 3-D convolutions (Cin = KC <= 64, Cout <= 64, one pass).
+//
+// The generic kernel above re-loads the shifted 128-pixel activation tile once per tap; with 16 or 32 channels a tile row
+// is only 32-64 bytes and the TMA unit is bound by the NUMBER of rows it moves (27 taps x 128 rows per tile), not by bytes.
+// Here a tile is 8 (x) x 16 (y) x 1 (z) output pixels and ONE box load brings the whole halo slab
+// [SZ][SY][SX] pixels x KC channels (e.g. 3 x 18 x 10 = 540 rows for a 3x3x3 window) into swizzled K-major shared memory.
+// The swizzle is a function of the absolute shared-memory address, so the A operand of tap (dz, dy, dx) is just the same
+// slab read through a descriptor whose start address is shifted by ((dz SY + dy) SX + dx) rows and whose 8-row-group stride
+// (SBO) is the slab's x pitch: 8 consecutive x pixels form one core-matrix group, consecutive y rows are SX rows apart.
+// All tap weight tiles stay resident in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int KC>
+__device__ __forceinline__ uint64_t make_slab_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
+    constexpr uint64_t layout = (KC == 64) ? 2ull : (KC == 32) ? 4ull : 6ull;   // SWIZZLE_128B / 64B / 32B
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int BN, int KC>
+struct SlabCfg {
+    static constexpr int W_SLOT = (BN * KC * 2 + 1023) / 1024 * 1024;
+    static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : 256;
+    static constexpr int EPI_BYTES = 4 * 2048;
+    static constexpr int MAX_STAGES = 6;
+};
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(kTcThreads, 2)
+slab_conv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant__ CUtensorMap tmW, const TcConvParams p, int batch) {
+    using Cfg = SlabCfg<BN, KC>;
+    const int STAGES = p.slab_stages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
+    uint8_t* wsm = smem + STAGES * stage_bytes;
+    uint4* epi_buf = reinterpret_cast<uint4*>(wsm + p.ntaps * Cfg::W_SLOT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_buf) + Cfg::EPI_BYTES);
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4] weights, then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::MAX_STAGES + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t w_base = ptx::smem_u32(wsm);
+    const uint32_t bar_base = ptx::smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::MAX_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + 2 + s); };
+    const uint32_t w_bar = bar_base + 8u * (2 * Cfg::MAX_STAGES + 4);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmSlab);
+        ptx::prefetch_tmap(&tmW);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 4);
+        }
+        ptx::mbar_init(w_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.D * p.tiles_y * p.tiles_x;
+    const int total_tiles = batch * tiles_per_img;
+
+    if (warp == 0) {
+        // ===================== TMA producer: resident weights once, then one halo slab per tile =====================
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(p.ntaps * BN * KC * 2));
+            for (int t = 0; t < p.ntaps; ++t) ptx::tma_load_3d(&tmW, w_bar, w_base + t * Cfg::W_SLOT, 0, 0, p.twt[t]);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int tx = t % p.tiles_x; t /= p.tiles_x;
+                const int ty = t % p.tiles_y; t /= p.tiles_y;
+                const int d = t % p.D;
+                const int b = t / p.D;
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 31);
+                ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.slab_bytes);
+                ptx::tma_load_5d(&tmSlab, full_bar(stage), smem_base + stage * stage_bytes, 0, tx * p.TW + p.slox, ty * p.TH + p.sloy,
+                                 d + p.sloz, b);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-convergent, elected lane) =====================
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        const uint32_t idesc = make_idesc<BN>(p.f16);
+        const uint32_t elected = ptx::elect_one();
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t sbo = (uint32_t)(p.sSX * KC * 2);
+        ptx::mbar_wait(w_bar, 0, p.err, 32);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(tempty_bar(as), aphase ^ 1, p.err, 33);
+            ptx::mbar_wait(full_bar(stage), phase, p.err, 34);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tbase + (uint32_t)(as * Cfg::ACC_STRIDE);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            for (int t = 0; t < p.ntaps; ++t) {
+                const int row = ((p.tdz[t] - p.sloz) * p.sSY + (p.tdy[t] - p.sloy)) * p.sSX + (p.tdx[t] - p.slox);
+                const uint64_t adesc = make_slab_desc<KC>(sa + (uint32_t)(row * KC * 2), sbo);
+                const uint64_t bdesc = make_smem_desc<KC>(w_base + t * Cfg::W_SLOT);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                    ptx::umma_bf16_elected(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (t > 0 || k > 0) ? 1u : 0u, elected);
+            }
+            ptx::umma_commit_elected(empty_bar(stage), elected);
+            ptx::umma_commit_elected(tfull_bar(as), elected);
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (same as the generic kernel; tile = TW 8 x TH 16) =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int ty_l = m / p.TW, tx_l = m - ty_l * p.TW;
+        int as = 0;
+        uint32_t aphase = 0;
+        constexpr int CH = (BN < 32) ? BN : 32;
+        constexpr bool RES_PREFETCH = BN <= 64;          // residual of the whole tile fits in registers (<= 8 x 16 B per lane)
+        const bool res_co = p.coalesce && p.res_hi && !p.res_lo && (p.res_cs & 7) == 0;
+        uint4* wbuf = epi_buf + q * 128;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int tx = t % p.tiles_x; t /= p.tiles_x;
+            const int ty = t % p.tiles_y; t /= p.tiles_y;
+            const int d = t % p.D;
+            const int b = t / p.D;
+            const int x = tx * p.TW + tx_l, y = ty * p.TH + ty_l;
+            const bool valid = (x < p.W) && (y < p.H);
+            const size_t pix = (((size_t)b * p.oD + d) * p.oH + y) * p.oW + x;
+            const int n0 = 0;
+            const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
+            uint4 res_regs[RES_PREFETCH ? BN / CH : 1][CH / 8];
+            if (RES_PREFETCH && res_co) {      // residual loads in flight while the accumulator is still being produced
+#pragma unroll
+                for (int c = 0; c < BN / CH; ++c)
+                    if (n0 + c * CH < p.Cout) tc_epilogue_res_issue<CH>(p, res_regs[c], pix, n0 + c * CH, vmask, lane);
+            }
+            ptx::mbar_wait(tfull_bar(as), aphase, p.err, 35);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::ACC_STRIDE + c0);
+                ptx::tmem_ld16(taddr, r);
+                if (CH == 32) ptx::tmem_ld16(taddr + 16, r + 16);
+                ptx::tmem_ld_wait();
+                const int nbase = c0;
+                if (nbase < p.Cout) {
+                    float v[32];
+                    if (p.coalesce) {
+                        if (res_co) {
+                            float res[CH];
+                            if (!RES_PREFETCH) tc_epilogue_res_issue<CH>(p, res_regs[0], pix, nbase, vmask, lane);
+                            tc_epilogue_res_finish<CH>(p, res_regs[RES_PREFETCH ? c0 / CH : 0], res, wbuf, lane);
+                            if (valid) tc_epilogue_math<CH>(p, r, pix, nbase, b, v, res);
+                        } else if (valid) {
+                            tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
+                        }
+                        tc_epilogue_store_warp<CH>(p, v, pix, nbase, vmask, wbuf, lane);
+                    } else if (valid) {
+                        tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
+                        tc_epilogue_store_lane<CH>(p, v, pix, nbase);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -550,6 +827,50 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
         g_fuse_max_bn = e ? atoi(e) : 256;
     }
     L->fused = (npass >= 2) && (BN <= g_fuse_max_bn) && KC >= 16;
+    // slab mode: single K chunk, single pass, small N, unit strides, a tap window of at most 3 per axis, 8 | W
+    L->slab = false;
+    {
+        static const bool off = getenv("ADP_NO_SLAB") != nullptr;
+        int lo[3] = {127, 127, 127}, hi[3] = {-127, -127, -127};
+        for (int t = 0; t < p.ntaps; ++t) {
+            const int o[3] = {p.tdz[t], p.tdy[t], p.tdx[t]};
+            for (int a = 0; a < 3; ++a) { lo[a] = o[a] < lo[a] ? o[a] : lo[a]; hi[a] = o[a] > hi[a] ? o[a] : hi[a]; }
+        }
+        const bool shape_ok = (BN == 16 && (KC == 16 || KC == 64)) || (BN == 64 && KC == 16) || (BN == 32 && KC == 32);
+        if (!off && in.D > 1 && p.kchunks == 1 && npass == 1 && coutPad == BN && shape_ok && p.in_mul == 1 && p.out_mul == 1 &&
+            p.out_oz == 0 && p.out_oy == 0 && p.out_ox == 0 && p.W % 8 == 0 && p.ntaps >= 4 &&
+            hi[0] - lo[0] <= 2 && hi[1] - lo[1] <= 2 && hi[2] - lo[2] <= 2) {
+            p.TW = 8; p.TH = 16;
+            p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
+            p.sSX = 8 + hi[2] - lo[2]; p.sSY = 16 + hi[1] - lo[1]; p.sSZ = 1 + hi[0] - lo[0];
+            p.sloz = lo[0]; p.sloy = lo[1]; p.slox = lo[2];
+            p.slab_bytes = p.sSX * p.sSY * p.sSZ * KC * 2;
+            const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
+            const int w_slot = (BN * KC * 2 + 1023) / 1024 * 1024;
+            const int fixed = p.ntaps * w_slot + 8192 + 1024 + 512;
+            int stages = (110 * 1024 - fixed) / stage_bytes;       // two CTAs per SM
+            stages = stages > 6 ? 6 : stages;
+            if (stages >= 2) {
+                p.slab_stages = stages;
+                cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.D, (cuuint64_t)in.B};
+                cuuint64_t strides[4] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2,
+                                         (cuuint64_t)in.D * in.H * in.W * in.C * 2};
+                cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)p.sSX, (cuuint32_t)p.sSY, (cuuint32_t)p.sSZ, 1};
+                cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                CUresult r = g_encode(&L->tmSlab, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, in.hi, dims,
+                                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    set_last_error("cuTensorMapEncodeTiled(slab %dx%dx%d x %d) failed: %d", p.sSX, p.sSY, p.sSZ, KC, (int)r);
+                    return ADP_ERR_CUDA;
+                }
+                L->slab = true;
+            } else {
+                tc_pick_tile(p.H, p.W, &p.TW, &p.TH);
+                p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
+            }
+        }
+    }
     ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, w_taps, KC, BN, f16));
@@ -576,9 +897,37 @@ static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_
     return ADP_OK;
 }
 
+template <int BN, int KC>
+static int launch_slab(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
+    using Cfg = SlabCfg<BN, KC>;
+    const TcConvParams& p = L->p;
+    const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
+    const int smem = p.slab_stages * stage_bytes + p.ntaps * Cfg::W_SLOT + Cfg::EPI_BYTES + 1024 + 512;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        ADP_CUDA(cudaFuncSetAttribute(slab_conv_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    const long long total = (long long)batch * p.D * p.tiles_y * p.tiles_x;
+    const long long slots = (long long)num_sms * 2;
+    const int grid = (int)(total < slots ? total : slots);
+    if (grid <= 0) return ADP_OK;
+    slab_conv_kernel<BN, KC><<<grid, kTcThreads, smem, stream>>>(L->tmSlab, L->tmW_hi, p, batch);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
 int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
     ADP_CHECK_ARG(L->ready, "layer not planned");
     ADP_CHECK_ARG(batch <= L->p.B, "batch exceeds planned capacity");
+    if (L->slab) {
+        if (L->BN == 16 && L->KC == 16) return launch_slab<16, 16>(L, batch, num_sms, stream);
+        if (L->BN == 16 && L->KC == 64) return launch_slab<16, 64>(L, batch, num_sms, stream);
+        if (L->BN == 64 && L->KC == 16) return launch_slab<64, 16>(L, batch, num_sms, stream);
+        if (L->BN == 32 && L->KC == 32) return launch_slab<32, 32>(L, batch, num_sms, stream);
+        set_last_error("no slab conv instantiation for BN=%d KC=%d", L->BN, L->KC);
+        return ADP_ERR_ARG;
+    }
     if (L->p.npass == 3 && L->fused) {   // bf16x3: one stage carries hi and lo operands
         if (L->BN == 64 && L->KC == 64) return launch_impl<64, 64, 1>(L, batch, num_sms, stream);
         if (L->BN == 32 && L->KC == 64) return launch_impl<32, 64, 1>(L, batch, num_sms, stream);

@@ -50,6 +50,8 @@ struct TcConvParams {
     __half* out_h16;         // optional extra fp16 copy
     int out_cs, out_coff;    // channel pitch / first channel of out_hi, out_lo
     int bias_per_batch;      // bias is [B, Cout]
+    // slab mode (small-channel 3-D convs, see slab_conv_kernel): halo slab extents / origin offset, bytes per stage
+    int sSX, sSY, sSZ, slox, sloy, sloz, slab_bytes, slab_stages;
     int coalesce;            // epilogue stores go through the per-warp transpose buffers (full chunks, single 16-bit plane)
     int* err;                // device error flag (pipeline watchdog)
 };
@@ -61,6 +63,8 @@ struct TcConvLayer {
     int BN;
     int KC;                  // channels per K step (64 -> SWIZZLE_128B, 32 -> 64B, 16 -> 32B)
     bool fused = false;      // split precision with hi and lo operands sharing a pipeline stage
+    bool slab = false;       // one halo slab per tile, taps by descriptor offsets, weights resident (slab_conv_kernel)
+    CUtensorMap tmSlab;
     bool ready = false;
 };
 

@@ -399,7 +399,7 @@ class Engine:
             ops.append((f"cr.{nm}", self._conv(wgt.numpy(), xin, out, stride=stride, npass=1, scale=sc, bias=sh, act=L.ACT_RELU)))
         for nm, xin, skip, out in (("conv7", c6, c4, x7), ("conv9", x7, c2, x9), ("conv11", x9, c0, x11)):
             sc, sh = bn(nm)
-            if nm == "conv11" and self.l0_s2d and not self.tconv_fused:
+            if nm == "conv11" and self.l0_s2d:    # stride-1 2x2x2-tap conv writing s2d layout: the slab tcgen05 kernel
                 w_s2d = G.transposed_s2d_weights(torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float())
                 sc8, sh8 = self._dev(sc.cpu().repeat(8)), self._dev(sh.cpu().repeat(8))
                 ep = self._epilogue(out, scale=sc8, bias=sh8, act=L.ACT_RELU, res=skip, res_after_act=1)
