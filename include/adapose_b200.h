@@ -97,6 +97,8 @@ ADP_API int adp_abi_version(void);
 ADP_API const char* adp_last_error(void);
 /* number of kernels launched by this library since load (bench.py reports it as gpu_launches) */
 ADP_API uint64_t adp_launch_count(void);
+/* a captured CUDA graph replays kernels without passing through the entry points: the host adds the replayed launches */
+ADP_API void adp_launch_count_add(uint64_t n);
 ADP_API int adp_device_info(int device, int* num_sms, int* cc_major, int* cc_minor);
 
 /* --- preprocessing: interface_v5.py:58-170 (prepare_model_input), utils.py:10-38 (get_bbox) ------------------

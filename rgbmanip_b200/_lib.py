@@ -60,6 +60,7 @@ SIGNATURES = {
     "adp_abi_version": (C.c_int, []),
     "adp_last_error": (C.c_char_p, []),
     "adp_launch_count": (C.c_uint64, []),
+    "adp_launch_count_add": (None, [C.c_uint64]),
     "adp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "adp_preprocess": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_uint32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),

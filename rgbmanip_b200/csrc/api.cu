@@ -95,6 +95,7 @@ extern "C" {
 int adp_abi_version(void) { return ADP_ABI_VERSION; }
 const char* adp_last_error(void) { return g_err; }
 uint64_t adp_launch_count(void) { return g_launches.load(); }
+void adp_launch_count_add(uint64_t n) { g_launches += n; }
 
 int adp_device_info(int device, int* num_sms, int* cc_major, int* cc_minor) {
     cudaDeviceProp prop;

@@ -66,7 +66,7 @@ class Engine:
 
     def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="fp16x2", regress_pose=True, use_tc=True,
                  use_tc_3d=True, tc_strided=True, tc_transposed=True, conv0_ring=True, tconv_fused=True, volume_dtype="fp16", debug=False,
-                 img_size=IMG_SIZE, n_pts=N_PTS, decode_tc=True, level0_s2d=True):
+                 img_size=IMG_SIZE, n_pts=N_PTS, decode_tc=True, level0_s2d=True, use_graph=True):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
         if precision not in ("bf16", "bf16x3", "fp16x2"):
@@ -94,6 +94,10 @@ class Engine:
         self.tconv_fused = tconv_fused and use_tc_3d and tc_transposed
         self.decode_tc = decode_tc and use_tc and int(n_pts) == 1024
         self.level0_s2d = level0_s2d
+        self.use_graph = bool(use_graph) and not debug
+        self._graph = None
+        self._graph_launches = 0
+        self._full_chunks = 0
         self._conv0_plans = []
         self._tconv_plans = []
         if volume_dtype not in ("fp16", "bf16"):
@@ -339,6 +343,8 @@ class Engine:
         self.depths = self._dev(np.arange(0.1, 0.1 * (D - 0.5) + 0.1, 0.1, dtype=np.float32))
         self.Mw = torch.zeros((E, 12), dtype=torch.float32, device=dev)
         self.valid_env = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self.E1buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
+        self.E2buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
         self.vol = self._act(E, S, S, 32, D=D, split=False, f16=self.vol_f16)
         self.vol_planar = 0     # set when conv0 runs as the depth-ring kernel, which reads the chunk-planar layout
         cr = "cost_regularization"
@@ -597,12 +603,47 @@ class Engine:
         assert n <= self.E
         self.preprocess(0, rgb1, mask1, K, n, seed, choose1)
         self.preprocess(1, rgb2, mask2, K, n, seed, choose2)
+        if n == self.E and self.use_graph and self.regress_pose:
+            # a full chunk is ~95 launches from fixed buffers: replayed as one CUDA graph (captured on the second full chunk,
+            # after every kernel has run once and set its attributes)
+            self.E1buf.copy_(E1.reshape(n, 16))
+            self.E2buf.copy_(E2.reshape(n, 16))
+            if self._graph is not None:
+                self._graph.replay()
+                self.lib.adp_launch_count_add(self._graph_launches)
+                return self.bbox[:n]
+            self._full_chunks += 1
+            if self._full_chunks == 2:
+                self._capture_graph()
+                if self._graph is not None:
+                    self._graph.replay()
+                    self.lib.adp_launch_count_add(self._graph_launches)
+                    return self.bbox[:n]
+            self.run_backbone(self.F)
+            self.stereo(n, self.E1buf, self.E2buf)
+            return self.bbox[:n]
         if n == self.E:
             self.run_backbone(self.F)
         else:   # the two views are not adjacent in the frame buffers: run them one after the other
             self._backbone_partial(n)
         self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed)
         return self.bbox[:n]
+
+    def _capture_graph(self):
+        import warnings
+        l0 = self.lib.adp_launch_count()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run_backbone(self.F)
+                self.stereo(self.E, self.E1buf, self.E2buf)
+            self._graph = g
+            self._graph_launches = int(self.lib.adp_launch_count() - l0)
+            self.lib.adp_launch_count_add(C.c_uint64(-self._graph_launches & 0xFFFFFFFFFFFFFFFF))   # capture itself launched nothing
+        except Exception as e:      # stay on the eager launch path (same kernels), say so once
+            warnings.warn(f"CUDA graph capture of a chunk failed ({e}); launching eagerly")
+            self._graph = None
+            self.use_graph = False
 
     def _backbone_partial(self, n):
         # view-2 frames start at frame E; with n < E process frames [0, E + n) (the gap computes on stale crops, harmless)
@@ -614,6 +655,7 @@ class Engine:
             raise L.AdpError(f"device pipeline watchdog tripped (code {v})")
 
     def close(self):
+        self._graph = None           # the captured graph references the plans' parameter blocks
         for p in self._plans:
             self.lib.adp_conv_tc_free(p)
         self._plans = []
