@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--ring", action="store_true", help="also time the device view ring (one new view per controller step, "
+                                                        "cached features for the other; SURVEY 8(f)-1) and add it as `view_ring`")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
@@ -270,6 +272,28 @@ def main():
         e2e = {"value": N * max(1, args.steps) / wall_h, "unit": "estimates/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(n_loc * 24 * 8), "timed": "host wall clock around estimate(); pinned host inputs"}
 
+    ring_info = None
+    if args.ring:
+        from rgbmanip_b200.view_ring import ViewRing
+        ring = ViewRing(est, n_loc, 5)
+        views = [{"camera0": {"Color": devt["rgb1"], "Mask": devt["mask1"], "Intrinsic": devt["K"], "Extrinsic": devt["E1"]}},
+                 {"camera0": {"Color": devt["rgb2"], "Mask": devt["mask2"], "Intrinsic": devt["K"], "Extrinsic": devt["E2"]}}]
+        pose = torch.zeros((n_loc, 7), dtype=torch.float64, device=dev)
+        state = {"t": 0}
+
+        def step_ring():
+            ring.add_view(views[state["t"] % 2], pose)
+            ring.accumulate_steps += 1
+            state["t"] += 1
+            return ring.get_estimation(return_tensor=True)
+
+        ms_r, _, _ = timed(step_ring, max(2, args.steps), 3)
+        ring_info = {"value": N * max(2, args.steps) / (ms_r / 1e3), "unit": "estimates/s", "ms_per_step": ms_r / max(2, args.steps),
+                     "what": "controller step = add_view (1 new frame per env: preprocess + backbone) + get_estimation (stereo head on "
+                             "cached features), frames resident in HBM", "cache_gb": ring.feat.numel() * 6 / 1e9}
+        del ring
+        torch.cuda.empty_cache()
+
     # per-kernel-class timing of one chunk, live, on the launching stream
     n_chunk = min(eng.E, n_loc)
     E1c = devt["E1"][:n_chunk].contiguous(); E2c = devt["E2"][:n_chunk].contiguous()
@@ -314,6 +338,8 @@ def main():
                                                    "sample": f"{args.cpu_sample} envs of the workload through the oracle's per-env loop ({cpu_dt:.1f} s)"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels,
                 "wall_s_timed_region": wall}
+        if ring_info is not None:
+            line["view_ring"] = ring_info
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

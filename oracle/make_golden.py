@@ -6,7 +6,7 @@ imported as-is with MagicMock stand-ins for the simulator packages it imports tr
 Weights are ``rgbmanip_b200.weights.init_state_dict(seed)`` loaded with ``strict=True`` so every consumer
 can regenerate them; inputs come from ``rgbmanip_b200.synth``.
 
-    python oracle/make_golden.py            # writes tests/golden/{e2e,preprocess,units}.npz
+    python oracle/make_golden.py            # writes tests/golden/{e2e,preprocess,units,branch_b,view_ring}.npz
 """
 from __future__ import annotations
 
@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 
 from rgbmanip_b200 import synth, weights  # noqa: E402
+from oracle.view_ring_oracle import view_ring_script  # noqa: E402
 
 
 def import_reference():
@@ -113,6 +114,43 @@ def golden_branch_b(interface_v5, out_dir):
     boxes = est.estimate(*batch.args())
     np.savez_compressed(os.path.join(out_dir, "branch_b.npz"), boxes=boxes)
     print("branch B boxes", boxes.shape, np.isfinite(boxes).all())
+
+
+def golden_view_ring(out_dir):
+    """Caller-side queues of the RL controller (models/controller/rl_pose.py:85-97,118-150,189-223), executed unmodified."""
+    for m in ["tensorboard", "torch.utils.tensorboard", "ipdb", "open3d", "sapien.utils.viewer"]:
+        sys.modules.setdefault(m, MagicMock())
+    from models.controller import rl_pose
+    calls = []
+
+    class Stub:
+        cfg = {"task_name": "one_drawer_cabinet"}
+
+        def estimate(self, K, rgb1, m1, E1, rgb2, m2, E2):
+            calls.append(dict(K=K[:, 0, 0].copy(), rgb1=rgb1[:, 0, 0, 0].copy(), rgb2=rgb2[:, 0, 0, 0].copy(), m1=m1.sum((1, 2)),
+                              m2=m2.sum((1, 2)), E1=E1[:, 0, 0].copy(), E2=E2[:, 0, 0].copy()))
+            return np.arange(K.shape[0] * 24, dtype=np.float64).reshape(-1, 8, 3)
+
+    ci = object.__new__(rl_pose.ControlInterface)
+    ci.num_envs, ci.max_steps, ci.estimator = 3, 5, Stub()
+    ci.accumulate_steps = 0
+    ci.reset_queue()
+    rec = {}
+    for t, (color, mask, K, E, pose) in enumerate(view_ring_script()):
+        image = {"camera0": {"Color": color, "Mask": mask, "Intrinsic": K, "Extrinsic": E}}
+        ci.add_view(image, pose)
+        ci.accumulate_steps += 1                      # as reset_robot / step do (rl_pose.py:116,...)
+        box = ci.get_estimation()
+        c = calls[-1]
+        rec[f"s{t}_available"] = ci.available.copy(); rec[f"s{t}_available_num"] = ci.available_num.copy()
+        rec[f"s{t}_bbox_queue"] = ci.bbox_queue.copy(); rec[f"s{t}_pose_queue"] = ci.pose_queue.copy()
+        for k, v in c.items():
+            rec[f"s{t}_{k}"] = v
+        rec[f"s{t}_box"] = box
+    ci.estimator.cfg = {"task_name": "mugs"}
+    rec["mug_box"] = ci.get_estimation()
+    np.savez_compressed(os.path.join(out_dir, "view_ring.npz"), **rec)
+    print("view ring golden:", len(rec), "arrays")
 
 
 def golden_preprocess(interface_v5, utils, out_dir):
@@ -216,7 +254,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     interface_v5, network_v5, rotation_utils, utils, align = import_reference()
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b"]
+    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring"]
     if "units" in what:
         golden_units(network_v5, rotation_utils, utils, align, out_dir)
     if "preprocess" in what:
@@ -225,6 +263,8 @@ def main():
         golden_e2e(interface_v5, out_dir)
     if "branch_b" in what:
         golden_branch_b(interface_v5, out_dir)
+    if "view_ring" in what:
+        golden_view_ring(out_dir)
 
 
 if __name__ == "__main__":
