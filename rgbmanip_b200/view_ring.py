@@ -91,8 +91,8 @@ class ViewRing:
         self._adds += 1
         with torch.cuda.device(self.device):
             any_pixel = torch.zeros((), dtype=torch.bool, device=self.device)
-            for lo in range(0, N, eng.E):
-                hi = min(N, lo + eng.E)
+            for lo in range(0, N, eng.F):                 # the frame buffers hold 2 x max_envs frames: full-size backbone launches
+                hi = min(N, lo + eng.F)
                 n = hi - lo
                 rgb_d = self._dev(color[lo:hi])
                 if rgb_d.dtype not in (torch.float32, torch.float64):
