@@ -119,6 +119,24 @@ def test_predict_and_dtypes(golden):
     est.estimator.close()
 
 
+def test_checkpoint_path_loading_equals_state_dict(tmp_path):
+    """cfg['load'] = True + cfg['checkpoint_path'] (interface_v5.py:55-56): a DataParallel-prefixed .pth gives the same boxes."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200.estimator import AdaPoseEstimator_v5
+    sd = weights.init_state_dict(0)
+    path = str(tmp_path / "adapose_drawer.pth")
+    torch.save({"module." + k: torch.from_numpy(np.asarray(v).copy()) for k, v in sd.items()}, path)
+    batch = synth.make_batch(2, seed=6, special=False)
+    a = _make(max_envs=2)
+    cfg = dict(a.cfg, load=True, checkpoint_path=path)
+    b = AdaPoseEstimator_v5(None, cfg, None, max_envs=2)
+    np.testing.assert_allclose(a.estimate(*batch.args()), b.estimate(*batch.args()), rtol=0, atol=1e-5)
+    a.estimator.close(); b.estimator.close()
+    with pytest.raises(FileNotFoundError):
+        AdaPoseEstimator_v5(None, dict(cfg, checkpoint_path=str(tmp_path / "missing.pth")), None, max_envs=2)
+
+
 def test_four_task_configs_share_the_path():
     """cabinet / drawer / mug / pot yamls differ only in task_name and checkpoint path (cfg/pose_estimator/adapose_*.yaml)."""
     if not torch.cuda.is_available():
