@@ -182,6 +182,14 @@ ADP_API int adp_pose_gbias(const float* gsum, const float* q0_w, const float* q0
 ADP_API int adp_rot_head(const float* psum, const uint8_t* valid, const adp_decode_weights* w, float* R, float* r6, int B,
                          int P, void* stream);
 
+/* --- controller observation + actor forward: rl_pose.py:173-187 (get_observation: [N, T*11] pose/bbox
+ * history ++ one_hot(step, T), from the device-resident queues of the view ring) and algo/ppo/ppo/module.py:24-34,89-91
+ * (act_inference: Linear/ELU stack, torch weight layout [out][in]).  dims[0] = T*12, dims[nlayers] = action width;
+ * weights / biases: host arrays of nlayers device pointers.  obs_out [N, T*12] may be NULL. */
+ADP_API int adp_actor_forward(const double* pose_queue, const double* bbox_queue, int T, int N, int step, int nlayers,
+                              const int32_t* dims, const float* const* weights, const float* const* biases, float* obs_out,
+                              float* act_out, void* stream);
+
 /* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
 /* One 4-CTA thread-block cluster per environment; the exact-median radix select recomputes the pair ratios in every pass.
  * scratch: unused (kept for ABI stability), may be NULL. */

@@ -153,6 +153,38 @@ def golden_view_ring(out_dir):
     print("view ring golden:", len(rec), "arrays")
 
 
+def golden_actor(out_dir):
+    """Observation of the controller (rl_pose.py:173-187) and the actor forward (module.py:24-34,89-91), reference code
+    executed unmodified: ControlInterface.get_observation on scripted queues, ActorCritic.act_inference on it."""
+    for m in ["tensorboard", "torch.utils.tensorboard", "ipdb", "open3d", "sapien.utils.viewer"]:
+        sys.modules.setdefault(m, MagicMock())
+    from algo.ppo.ppo.module import ActorCritic
+    from models.controller import rl_pose
+    pol = yaml.safe_load(open(f"{REF}/cfg/controller/rl.yaml"))["policy"]
+    torch.manual_seed(3)
+    ac = ActorCritic((60,), (75,), (12,), 0.6, pol, asymmetric=False)
+    with torch.no_grad():                      # move the last layer off its 0.01-gain init so that the output is informative
+        ac.actor[-1].weight.mul_(30.0)
+        for m in ac.actor:
+            if isinstance(m, nn.Linear):
+                m.bias.normal_(0, 0.1)
+    ci = object.__new__(rl_pose.ControlInterface)
+    ci.num_envs, ci.max_steps = 3, 5
+    ci.accumulate_steps = 0
+    ci.reset_queue()
+    rec = {k: v.detach().numpy() for k, v in ac.state_dict().items() if k.startswith("actor.")}
+    for t, (color, mask, K, E, pose) in enumerate(view_ring_script()):
+        ci.add_view({"camera0": {"Color": color, "Mask": mask, "Intrinsic": K, "Extrinsic": E}}, pose * 0.1)
+        ci.accumulate_steps += 1
+        if t >= 5:            # the controller resets its queues before the step counter wraps; stay inside one episode
+            break
+        obs = ci.get_observation()
+        rec[f"s{t}_obs"] = obs.numpy()
+        rec[f"s{t}_act"] = ac.act_inference(obs).numpy()
+    np.savez_compressed(os.path.join(out_dir, "actor.npz"), **rec)
+    print("actor golden:", len(rec), "arrays; obs", obs.shape)
+
+
 def golden_preprocess(interface_v5, utils, out_dir):
     est, cfg, _ = build_reference_estimator(interface_v5)
     rng = np.random.default_rng(7)
@@ -254,7 +286,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     interface_v5, network_v5, rotation_utils, utils, align = import_reference()
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring"]
+    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring", "actor"]
     if "units" in what:
         golden_units(network_v5, rotation_utils, utils, align, out_dir)
     if "preprocess" in what:
@@ -265,6 +297,8 @@ def main():
         golden_branch_b(interface_v5, out_dir)
     if "view_ring" in what:
         golden_view_ring(out_dir)
+    if "actor" in what:
+        golden_actor(out_dir)
 
 
 if __name__ == "__main__":

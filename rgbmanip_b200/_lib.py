@@ -89,6 +89,7 @@ SIGNATURES = {
     "adp_colsum": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "adp_pose_gbias": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "adp_rot_head": (C.c_int, [vp, vp, C.POINTER(DecodeWeights), vp, vp, C.c_int, C.c_int, vp]),
+    "adp_actor_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "adp_fit_umeyama": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }

@@ -59,6 +59,12 @@ int pose_gbias_run(const float* gsum, const float* q0_w, const float* q0_b, cons
                    cudaStream_t stream);
 int rot_head_run(const float* psum, const uint8_t* valid, float* Rout, float* r6out, const adp_decode_weights* cw, int B, int P,
                  cudaStream_t stream);
+constexpr int ACT_MAXL_API = 8;
+struct ActorArgs {
+    const double* pose; const double* bbox; int T, N, step; int nlayers; int dims[ACT_MAXL_API + 1];
+    const float* W[ACT_MAXL_API]; const float* b[ACT_MAXL_API]; float* obs_out; float* act_out;
+};
+int actor_forward(const ActorArgs& a, cudaStream_t stream);
 struct TconvPlan;
 TconvPlan* tconv_alloc();
 void tconv_release(TconvPlan* p);
@@ -309,6 +315,19 @@ int adp_rot_head(const float* psum, const uint8_t* valid, const adp_decode_weigh
     ADP_CHECK_ARG(psum && w && R, "null pointer");
     g_launches += 1;
     return rot_head_run(psum, valid, R, r6, w, B, P, (cudaStream_t)stream);
+}
+
+int adp_actor_forward(const double* pose_queue, const double* bbox_queue, int T, int N, int step, int nlayers, const int32_t* dims,
+                      const float* const* weights, const float* const* biases, float* obs_out, float* act_out, void* stream) {
+    ADP_CHECK_ARG(pose_queue && bbox_queue && dims && weights && biases && act_out, "null pointer");
+    ADP_CHECK_ARG(nlayers >= 1 && nlayers <= ACT_MAXL_API, "1..8 layers");
+    ActorArgs a{};
+    a.pose = pose_queue; a.bbox = bbox_queue; a.T = T; a.N = N; a.step = step; a.nlayers = nlayers;
+    for (int l = 0; l <= nlayers; ++l) a.dims[l] = dims[l];
+    for (int l = 0; l < nlayers; ++l) { a.W[l] = weights[l]; a.b[l] = biases[l]; }
+    a.obs_out = obs_out; a.act_out = act_out;
+    g_launches += 1;
+    return actor_forward(a, (cudaStream_t)stream);
 }
 
 int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R, const double* E,

@@ -101,3 +101,28 @@ def test_mug_corner_order():
         outs.append(ring.get_estimation())
         est.estimator.close()
     np.testing.assert_allclose(outs[1], outs[0][:, MUG_CORNER_ORDER], rtol=0, atol=2e-5)
+
+
+def test_device_actor_matches_reference(golden_dir):
+    """adp_actor_forward on the ring's device queues against the reference's get_observation + act_inference (golden)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200.actor import DeviceActor
+    from rgbmanip_b200.view_ring import ViewRing
+    g = np.load(os.path.join(golden_dir, "actor.npz"))
+    sd = {k: g[k] for k in g.files if k.startswith("actor.")}
+    est = _estimator(2)
+    ring = ViewRing(est, 3, 5)
+    actor = DeviceActor(sd, ring)
+    assert actor.dims == [60, 96, 96, 32, 12]
+    for t, (color, mask, K, E, pose) in enumerate(V.view_ring_script()):
+        if t >= 5:
+            break
+        ring.add_view({"camera0": {"Color": color, "Mask": mask, "Intrinsic": K, "Extrinsic": E}}, pose * 0.1)
+        ring.accumulate_steps += 1
+        act, obs = actor.act_inference()
+        np.testing.assert_array_equal(obs.cpu().numpy(), g[f"s{t}_obs"])
+        np.testing.assert_allclose(act.cpu().numpy(), g[f"s{t}_act"], rtol=0, atol=2e-5)
+    with pytest.raises(IndexError):
+        actor.act_inference(accumulate_steps=6)
+    est.estimator.close()
