@@ -176,7 +176,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--num-envs", type=int, default=1024)
-    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--chunk", type=int, default=74,
+                    help="envs per chunk; 74 = num_SMs / 2: 148 frames per backbone launch = whole waves of 128-row tiles on 148 SMs")
     ap.add_argument("--precision", default="fp16x2")
     ap.add_argument("--unique", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=8)

@@ -537,10 +537,11 @@ class Engine:
             raise TypeError(f"unsupported dtype {t.dtype}")
         return code
 
-    def preprocess(self, view, rgb, mask, K, n, seed=0, choose=None):
-        """view 0/1; rgb [n,H,W,3] f32|f64, mask [n,H,W] u8|bool|f32|f64, K [n,3,3] f64 -- device tensors."""
+    def preprocess(self, view, rgb, mask, K, n, seed=0, choose=None, offset=None):
+        """view 0/1; rgb [n,H,W,3] f32|f64, mask [n,H,W] u8|bool|f32|f64, K [n,3,3] f64 -- device tensors.
+        The frames land at [offset, offset + n) of the frame buffers (default: view * max_envs)."""
         E = self.E
-        o = view * E
+        o = view * E if offset is None else offset
         assert rgb.is_cuda and mask.is_cuda and K.is_cuda and K.dtype == torch.float64
         assert rgb.is_contiguous() and mask.is_contiguous() and K.is_contiguous()
         H, Wd = rgb.shape[1], rgb.shape[2]
@@ -554,10 +555,12 @@ class Engine:
             L.ptr(self.bbox_ws[o:]), L.ptr(self.win[o:]), L.ptr(self.Kp[o:]), L.ptr(self.valid[o:]), L.ptr(self.crops[o:]),
             L.ptr(self.choose[o:]), L.ptr(self.counts[o:]), self.stream), "preprocess")
 
-    def stereo(self, n, E1, E2, mark=None, ransac_idx=None, seed=0):
+    def stereo(self, n, E1, E2, mark=None, ransac_idx=None, seed=0, o2=None):
         """Frames [0,n) are view 1 and [E,E+n) view 2 of envs [0,n).  E1/E2 [n,4,4] f64 device tensors.
         ``mark(name)`` (optional) is called after each stage, e.g. to record CUDA events."""
         E, S, D, P = self.E, self.S, N_DEPTH, self.P
+        if o2 is not None:
+            E = o2          # view-2 frames start at frame o2 (partial chunks pack them right behind view 1)
         lib, st = self.lib, self.stream
         mark = mark or (lambda name: None)
         L.check(lib.adp_warp_matrices(L.ptr(self.Kp), L.ptr(E1), L.ptr(self.Kp[E:]), L.ptr(E2), L.ptr(self.Mw),
@@ -601,8 +604,9 @@ class Engine:
         """Device tensors for n <= max_envs environments -> self.bbox[:n] ([n,8,3] f64, world frame)."""
         n = K.shape[0]
         assert n <= self.E
+        # view 2 sits right behind view 1 (frame n): a partial chunk runs the backbone on exactly 2 n frames
         self.preprocess(0, rgb1, mask1, K, n, seed, choose1)
-        self.preprocess(1, rgb2, mask2, K, n, seed, choose2)
+        self.preprocess(1, rgb2, mask2, K, n, seed, choose2, offset=n)
         if n == self.E and self.use_graph and self.regress_pose:
             # a full chunk is ~95 launches from fixed buffers: replayed as one CUDA graph (captured on the second full chunk,
             # after every kernel has run once and set its attributes)
@@ -622,11 +626,8 @@ class Engine:
             self.run_backbone(self.F)
             self.stereo(n, self.E1buf, self.E2buf)
             return self.bbox[:n]
-        if n == self.E:
-            self.run_backbone(self.F)
-        else:   # the two views are not adjacent in the frame buffers: run them one after the other
-            self._backbone_partial(n)
-        self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed)
+        self.run_backbone(2 * n)
+        self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed, o2=n)
         return self.bbox[:n]
 
     def _capture_graph(self):
@@ -645,9 +646,6 @@ class Engine:
             self._graph = None
             self.use_graph = False
 
-    def _backbone_partial(self, n):
-        # view-2 frames start at frame E; with n < E process frames [0, E + n) (the gap computes on stale crops, harmless)
-        self.run_backbone(self.E + n)
 
     def check_error_flag(self):
         v = int(self.err_flag.item())
