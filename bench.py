@@ -180,7 +180,7 @@ def main():
                     help="envs per chunk; 74 = num_SMs / 2: 148 frames per backbone launch = whole waves of 128-row tiles on 148 SMs")
     ap.add_argument("--precision", default="fp16x2")
     ap.add_argument("--unique", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--ring", action="store_true", help="also time the device view ring (one new view per controller step, "
