@@ -166,6 +166,7 @@ build_volume_tile_kernel(const __half* __restrict__ f_ref, const __half* __restr
     __shared__ uint4 stage[4][VT_MAXPX];        // [16-byte channel chunk][pixel]: consecutive lanes -> consecutive words
     __shared__ uint4 obuf[8][32 * 4];           // per-warp output transpose: 32 voxels x 64 B
     __shared__ int s_box[4];
+    __shared__ unsigned char s_empty[VT_DG];
     const int tid = threadIdx.x;
     const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
     const int b = blockIdx.z, d0 = blockIdx.y * VT_DG;
@@ -179,7 +180,46 @@ build_volume_tile_kernel(const __half* __restrict__ f_ref, const __half* __restr
 #pragma unroll
         for (int q = 0; q < 4; ++q) ref[q] = __ldg(rp + q);
     }
+    // Cheap emptiness test per depth plane: with positive projective depth at the four tile corners the tile maps to the convex
+    // hull of its corner images, so if all four fall outside the source map on the same side no voxel of the tile samples
+    // anything and the plane is the reference features bit for bit (one warp: 8 planes x 4 corners; 0.01 px safety margin).
+    if (tid < 32) {
+        const int dd = tid >> 2, c = tid & 3;
+        const int cx = min(txi * VT_T + ((c & 1) ? VT_T - 1 : 0), W - 1), cy = min(tyi * VT_T + ((c & 2) ? VT_T - 1 : 0), H - 1);
+        bool bad = true, left = false, right = false, top = false, bottom = false;
+        if (d0 + dd < D) {
+            const float dep = depths[d0 + dd];
+            const float Z = (M[6] * (float)cx + M[7] * (float)cy + M[8]) * dep + M[11];
+            float ix, iy;
+            warp_coords(M, (float)cx, (float)cy, dep, W, H, &ix, &iy);
+            bad = !(Z > 1e-6f) || !isfinite(ix) || !isfinite(iy);
+            left = ix < -1.01f; right = ix > (float)W + 0.01f; top = iy < -1.01f; bottom = iy > (float)H + 0.01f;
+        }
+        unsigned int bits = (bad ? 1u : 0u) | (left ? 0u : 2u) | (right ? 0u : 4u) | (top ? 0u : 8u) | (bottom ? 0u : 16u);   // OR-reducible
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        // bit 0 clear: every corner is in front of the camera; bit k clear (k = 1..4): every corner is outside on side k
+        if (c == 0) s_empty[dd] = (!(bits & 1u) && ((bits & 30u) != 30u)) ? 1 : 0;
+    }
+    __syncthreads();
     for (int d = d0; d < d0 + VT_DG && d < D; ++d) {
+        if (s_empty[d - d0] && f16) {       // uniform over the block
+            const int ln = tid & 31;
+            uint4* obw = obuf[tid >> 5];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) obw[ln * 4 + (q ^ ((ln >> 1) & 3))] = ref[q];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int vx = 8 * k + (ln >> 2), c = ln & 3;
+                const uint4 o = obw[vx * 4 + (c ^ ((vx >> 1) & 3))];
+                const int oy = tyi * VT_T + (tid >> 5) * 2 + (vx >> 4), ox = txi * VT_T + (vx & 15);
+                if (oy < H && ox < W)
+                    *(reinterpret_cast<uint4*>(vol + ((((size_t)b * D + d) * H + oy) * W + ox) * C) + c) = o;
+            }
+            __syncwarp();
+            continue;
+        }
         if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; }
         __syncthreads();                         // also: the previous depth's readers of `stage` are done
         Bilin bl;
