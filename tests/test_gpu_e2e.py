@@ -137,6 +137,31 @@ def test_checkpoint_path_loading_equals_state_dict(tmp_path):
         AdaPoseEstimator_v5(None, dict(cfg, checkpoint_path=str(tmp_path / "missing.pth")), None, max_envs=2)
 
 
+def test_empty_batch_and_all_blind_environments():
+    """num_envs = 0 returns an empty [0,8,3]; environments whose masks are empty in either view get the sentinel box
+    (interface_v5.py:232-241,256-257) bit for bit, whatever the other environments hold."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    est = _make(max_envs=4)
+    z = lambda *s, dt=np.float32: np.zeros(s, dt)
+    out = est.estimate(z(0, 3, 3, dt=np.float64), z(0, 480, 640, 3), z(0, 480, 640, dt=bool), z(0, 4, 4, dt=np.float64),
+                       z(0, 480, 640, 3), z(0, 480, 640, dt=bool), z(0, 4, 4, dt=np.float64))
+    assert out.shape == (0, 8, 3) and out.dtype == np.float64
+    b = synth.make_batch(5, seed=9, special=False)
+    m1, m2 = b.mask1.copy(), b.mask2.copy()
+    m1[0] = 0                  # blind in view 1
+    m2[3] = 0                  # blind in view 2
+    m1[4] = 0; m2[4] = 0       # blind in both (and the partial second chunk)
+    out = est.estimate(b.K, b.rgb1, m1, b.E1, b.rgb2, m2, b.E2)
+    for e in (0, 3, 4):
+        np.testing.assert_array_equal(out[e], O.DEFAULT_BBOX)
+    for e in (1, 2):
+        assert np.isfinite(out[e]).all() and not np.array_equal(out[e], O.DEFAULT_BBOX)
+    blind = est.estimate(b.K, b.rgb1, np.zeros_like(m1), b.E1, b.rgb2, np.zeros_like(m2), b.E2)
+    np.testing.assert_array_equal(blind, np.broadcast_to(O.DEFAULT_BBOX, (5, 8, 3)))
+    est.estimator.close()
+
+
 def test_four_task_configs_share_the_path():
     """cabinet / drawer / mug / pot yamls differ only in task_name and checkpoint path (cfg/pose_estimator/adapose_*.yaml)."""
     if not torch.cuda.is_available():
