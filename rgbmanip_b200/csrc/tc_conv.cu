@@ -30,13 +30,34 @@ __device__ __forceinline__ uint32_t make_idesc(int f16) {
 // kernel
 // ------------------------------------------------------------------------------------------------
 // Epilogue of one accumulator chunk: r[0..CH) fp32 accumulators of output pixel `pix`, channels [nbase, nbase + CH)
-template <int CH>
+// FULL: the chunk is known to hold CH valid channels with 16-byte aligned per-channel vectors (the coalesced-store mode):
+// scale / bias arrive as 128-bit broadcast loads and the per-element `j < nvalid` predicates disappear.  The epilogue of the
+// small-K layers is instruction bound (ncu: the MMA warp waits on tmem_empty), so the issue slots matter.
+template <int CH, bool FULL = false>
 __device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const uint32_t* r, size_t pix, int nbase, int b, float* v,
                                                  const float* res_pre = nullptr) {
-                            const int nvalid = min(CH, p.Cout - nbase);
+                            const int nvalid = FULL ? CH : min(CH, p.Cout - nbase);
                             const size_t ro = pix * p.res_cs + nbase;
 #pragma unroll
                             for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+                            if (FULL) {
+                                if (p.scale) {
+                                    const float4* s4 = reinterpret_cast<const float4*>(p.scale + nbase);
+#pragma unroll
+                                    for (int j = 0; j < CH; j += 4) {
+                                        const float4 q = __ldg(s4 + (j >> 2));
+                                        v[j] *= q.x; v[j + 1] *= q.y; v[j + 2] *= q.z; v[j + 3] *= q.w;
+                                    }
+                                }
+                                if (p.bias) {
+                                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.bias_per_batch ? (size_t)b * p.Cout : 0) + nbase);
+#pragma unroll
+                                    for (int j = 0; j < CH; j += 4) {
+                                        const float4 q = __ldg(b4 + (j >> 2));
+                                        v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                                    }
+                                }
+                            } else {
                             if (p.scale) {
 #pragma unroll
                                 for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] *= __ldg(p.scale + nbase + j);
@@ -45,6 +66,7 @@ __device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const ui
                                 const float* bias = p.bias + (p.bias_per_batch ? (size_t)b * p.Cout : 0);
 #pragma unroll
                                 for (int j = 0; j < CH; ++j) if (j < nvalid) v[j] += __ldg(bias + nbase + j);
+                            }
                             }
                             const bool vec_ok = ((p.Cout | p.res_cs | p.out_cs | p.out_coff) & 7) == 0;   // 128-bit accesses stay aligned
                             if (res_pre && !p.res_after_act) {
@@ -475,9 +497,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             float res[CH];
                             if (!RES_PREFETCH) tc_epilogue_res_issue<CH>(p, res_regs[0], pix, nbase, vmask, lane);
                             tc_epilogue_res_finish<CH>(p, res_regs[RES_PREFETCH ? c0 / CH : 0], res, wbuf, lane);
-                            if (valid) tc_epilogue_math<CH>(p, r, pix, nbase, b, v, res);
+                            if (valid) tc_epilogue_math<CH, true>(p, r, pix, nbase, b, v, res);
                         } else if (valid) {
-                            tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
+                            tc_epilogue_math<CH, true>(p, r, pix, nbase, b, v);
                         }
                         tc_epilogue_store_warp<CH>(p, v, pix, nbase, vmask, wbuf, lane);
                     } else if (valid) {
@@ -673,9 +695,9 @@ slab_conv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_consta
                             float res[CH];
                             if (!RES_PREFETCH) tc_epilogue_res_issue<CH>(p, res_regs[0], pix, nbase, vmask, lane);
                             tc_epilogue_res_finish<CH>(p, res_regs[RES_PREFETCH ? c0 / CH : 0], res, wbuf, lane);
-                            if (valid) tc_epilogue_math<CH>(p, r, pix, nbase, b, v, res);
+                            if (valid) tc_epilogue_math<CH, true>(p, r, pix, nbase, b, v, res);
                         } else if (valid) {
-                            tc_epilogue_math<CH>(p, r, pix, nbase, b, v);
+                            tc_epilogue_math<CH, true>(p, r, pix, nbase, b, v);
                         }
                         tc_epilogue_store_warp<CH>(p, v, pix, nbase, vmask, wbuf, lane);
                     } else if (valid) {
