@@ -41,16 +41,22 @@ __device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const ui
 #pragma unroll
                             for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
                             if (FULL) {
-                                if (p.scale) {
-                                    const float4* s4 = reinterpret_cast<const float4*>(p.scale + nbase);
+                                const float4* s4 = reinterpret_cast<const float4*>(p.scale + nbase);
+                                const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.bias_per_batch ? (size_t)b * p.Cout : 0) + nbase);
+                                if (p.scale && p.bias) {          // folded BatchNorm: one FFMA per channel
+#pragma unroll
+                                    for (int j = 0; j < CH; j += 4) {
+                                        const float4 q = __ldg(s4 + (j >> 2)), t = __ldg(b4 + (j >> 2));
+                                        v[j] = fmaf(v[j], q.x, t.x); v[j + 1] = fmaf(v[j + 1], q.y, t.y);
+                                        v[j + 2] = fmaf(v[j + 2], q.z, t.z); v[j + 3] = fmaf(v[j + 3], q.w, t.w);
+                                    }
+                                } else if (p.scale) {
 #pragma unroll
                                     for (int j = 0; j < CH; j += 4) {
                                         const float4 q = __ldg(s4 + (j >> 2));
                                         v[j] *= q.x; v[j + 1] *= q.y; v[j + 2] *= q.z; v[j + 3] *= q.w;
                                     }
-                                }
-                                if (p.bias) {
-                                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.bias_per_batch ? (size_t)b * p.Cout : 0) + nbase);
+                                } else if (p.bias) {
 #pragma unroll
                                     for (int j = 0; j < CH; j += 4) {
                                         const float4 q = __ldg(b4 + (j >> 2));
