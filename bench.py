@@ -35,10 +35,10 @@ GF_BACKBONE_PER_FRAME = 57.0177e9       # SURVEY.md A.3 (2 * MACs of every conv 
 GF_BACKBONE_TC_PER_FRAME = 57.0177e9 - 0.2360e9 - 0.1156e9 - 0.0128e9 - 0.0066e9   # minus conv1, layer2.0 strided convs, psp
 GF_COSTREG_PER_VIEW = 24.4506e9
 DECODE_BYTES_PER_VIEW = 1708092
-# ncu capture of the 40 backbone tc_conv_kernel launches of one chunk (128 frames): dram__bytes_read + write summed over the launch
+# ncu capture of the 40 backbone tc_conv_kernel launches of one chunk (fp16x2: 148 frames; bf16x3: 128 frames): dram__bytes_read + write summed over the launch
 # group, and sm__pipe_tensor_cycles_active time-weighted over it.  fp16x2: profiles/r01_chunk_by_kernel.csv;
 # bf16x3: profiles/r01_bf16x3_backbone_tc_summary.csv
-NCU_TC = {"fp16x2": (9516.4e6 / 128, 0.700, "profiles/r01_chunk_by_kernel.csv"),
+NCU_TC = {"fp16x2": (11141.8e6 / 148, 0.720, "profiles/r01_chunk_by_kernel.csv"),
           "bf16x3": (18958.8e6 / 128, 0.712, "profiles/r01_bf16x3_backbone_tc_summary.csv")}
 CFG = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
        "n_pts": 1024, "direct_regression": True, "real_world": False}
@@ -311,7 +311,7 @@ def main():
         roof = {"bound": "tensor", "kernel": "tc_conv_kernel (tcgen05 implicit-GEMM, backbone 2-D convs)", "achieved": ach,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 "traffic": NCU_TC[eng.precision][0] * frames if eng.precision in NCU_TC else None,
-                "traffic_note": "dram__bytes_read+write summed over the launch group, ncu capture at 128 frames scaled to this chunk "
+                "traffic_note": "dram__bytes_read+write summed over the launch group, ncu capture of one chunk scaled to this chunk "
                                 f"({NCU_TC[eng.precision][2] if eng.precision in NCU_TC else 'no capture'})",
                 "tensor_pipe_active_ncu": NCU_TC[eng.precision][1] if eng.precision in NCU_TC else None,
                 "peak_source": pk["src"] + " (sustained: timed inside a long step)",
