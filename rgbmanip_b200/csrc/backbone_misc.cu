@@ -274,9 +274,26 @@ psp_fill_priors_kernel(const float* __restrict__ priors, bf16* __restrict__ out_
         const int s = c >> 7, n0 = c & 127;
         const int bins = s == 0 ? 1 : s == 1 ? 2 : s == 2 ? 3 : 6;
         const int off = s == 0 ? 0 : s == 1 ? 1 : s == 2 ? 5 : 14;
+        // one bilinear cell of the bins x bins prior map per (pixel, stage); 8 channels share its coordinates
+        int y0, y1, x0, x1;
+        float wy, wx;
+        lin_coord(y, bins, H, &y0, &y1, &wy);
+        lin_coord(x, bins, W, &x0, &x1, &wx);
+        const float* pr = spr + off * 128 + n0;
+        const float* p00 = pr + (y0 * bins + x0) * 128;
+        const float* p01 = pr + (y0 * bins + x1) * 128;
+        const float* p10 = pr + (y1 * bins + x0) * 128;
+        const float* p11 = pr + (y1 * bins + x1) * 128;
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = prior_at(spr + off * 128, bins, y, x, H, W, n0 + j);
+        for (int j = 0; j < 8; j += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(p00 + j), bq = *reinterpret_cast<const float4*>(p01 + j);
+            const float4 cq = *reinterpret_cast<const float4*>(p10 + j), d = *reinterpret_cast<const float4*>(p11 + j);
+            o[j + 0] = (1.f - wy) * ((1.f - wx) * a.x + wx * bq.x) + wy * ((1.f - wx) * cq.x + wx * d.x);
+            o[j + 1] = (1.f - wy) * ((1.f - wx) * a.y + wx * bq.y) + wy * ((1.f - wx) * cq.y + wx * d.y);
+            o[j + 2] = (1.f - wy) * ((1.f - wx) * a.z + wx * bq.z) + wy * ((1.f - wx) * cq.z + wx * d.z);
+            o[j + 3] = (1.f - wy) * ((1.f - wx) * a.w + wx * bq.w) + wy * ((1.f - wx) * cq.w + wx * d.w);
+        }
         st8(out_hi, out_lo, (((size_t)b * H + y) * W + x) * Ct + coff + c, o, f16);
     }
 }

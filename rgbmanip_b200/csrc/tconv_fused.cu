@@ -156,6 +156,9 @@ tconv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int as = 0;
         uint32_t aphase = 0;
         const int oD = 2 * p.D, oH = 2 * p.H, oW = 2 * p.W;
+        float sc[BN], sh[BN];          // folded BatchNorm, hoisted out of the tile / class loops (the epilogue is issue bound)
+#pragma unroll
+        for (int j = 0; j < BN; ++j) { sc[j] = j < p.Cout ? __ldg(p.scale + j) : 0.f; sh[j] = j < p.Cout ? __ldg(p.bias + j) : 0.f; }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int t = tile;
             const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -184,7 +187,7 @@ tconv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             float v[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                v[j] = fmaxf(fmaf(__uint_as_float(r[j0 + j]), __ldg(p.scale + j0 + j), __ldg(p.bias + j0 + j)), 0.f);
+                                v[j] = fmaxf(fmaf(__uint_as_float(r[j0 + j]), sc[j0 + j], sh[j0 + j]), 0.f);
                             if (p.res) ld8_16(p.res, ro + j0, p.f16, v, true);          // skip joins after the ReLU
                             st8_16(p.out, nullptr, o + j0, p.f16, v);
                         }
