@@ -9,8 +9,11 @@
  * Conventions: every function returns 0 on success and a negative code on failure (adp_last_error() holds the
  * message); pointers are raw CUDA device pointers unless named `host_*`; `stream` is a cudaStream_t passed as
  * void*; nothing allocates device memory except adp_conv_tc_plan (a small descriptor object on the host) and
- * nothing synchronises.  Activations are channels-last bf16 stored as a `hi` plane plus an optional `lo` plane
- * (value = hi + lo, "bf16x3" split precision); fp32 tensors are plain channels-last.  No torch types appear.
+ * nothing synchronises.  Activations are channels-last 16-bit planes: one IEEE-half plane (`f16 = 1`: the default "fp16x2"
+ * backbone and the 3-D stage) or a bf16 `hi` plane plus an optional `lo` plane (value = hi + lo, "bf16x3" split precision);
+ * fp32 tensors are plain channels-last.  `npass` of adp_conv_tc_plan selects the MMA passes per K step: 1 = A W,
+ * 2 = A W_hi + A W_lo (fp16 activations, fp16 weights split in two planes), 3 = A_hi W_hi + A_lo W_hi + A_hi W_lo (bf16).
+ * No torch types appear.
  */
 #ifndef ADAPOSE_B200_H
 #define ADAPOSE_B200_H
@@ -21,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ADP_ABI_VERSION 1
+#define ADP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ADP_API __attribute__((visibility("default")))

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     lib.adp_abi_version.restype = ctypes.c_int
-    assert lib.adp_abi_version() == 1
+    assert lib.adp_abi_version() == 2
 
 
 def test_binding_covers_the_header(lib_path):
