@@ -126,3 +126,33 @@ def test_device_actor_matches_reference(golden_dir):
     with pytest.raises(IndexError):
         actor.act_inference(accumulate_steps=6)
     est.estimator.close()
+
+
+def test_attach_rebinds_a_live_controller():
+    """view_ring.attach swaps reset_queue / add_view / get_estimation of a ControlInterface-like object and keeps the numpy
+    queue attributes that get_observation / get_reward read (rl_pose.py:156-187) in sync."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200 import view_ring
+
+    class FakeController:                     # the attributes ControlInterface.__init__ sets (rl_pose.py:22-44)
+        pass
+
+    ci = FakeController()
+    ci.estimator = _estimator(2)
+    ci.num_envs, ci.max_steps, ci.accumulate_steps = 2, 5, 3
+    ring = view_ring.attach(ci)
+    assert ci.accumulate_steps == 0 and ci.pose_queue.shape == (5, 2, 7) and ci.available.sum() == 0
+    b = synth.make_batch(2, seed=4, special=False)
+    for rgb, m, E in ((b.rgb1, b.mask1, b.E1), (b.rgb2, b.mask2, b.E2)):
+        ci.add_view({"camera0": {"Color": rgb, "Mask": m, "Intrinsic": b.K, "Extrinsic": E}}, np.full((2, 7), 0.5))
+        ci.accumulate_steps += 1
+    assert ci.available[:2].sum() == 4 and list(ci.available_num) == [2, 2]
+    assert np.all(ci.pose_queue[:2] == 0.5) and np.all(ci.bbox_queue[:2, :, 2] > ci.bbox_queue[:2, :, 0])
+    box = ci.get_estimation()
+    want = ci.estimator.estimate(b.K, b.rgb1, b.mask1, b.E1, b.rgb2, b.mask2, b.E2,
+                                 choose=(ring.choose[0].cpu().numpy(), ring.choose[1].cpu().numpy()))
+    np.testing.assert_allclose(box, want, rtol=0, atol=2e-5)
+    ci.reset_queue()
+    assert ci.available.sum() == 0 and ci.accumulate_steps == 0
+    ci.estimator.estimator.close()
