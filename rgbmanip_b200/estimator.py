@@ -63,6 +63,7 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         self._seed = int(cfg.get("sample_seed", 0))
         self._calls = 0
         self._copy_stream = None
+        self._range_checked = False
 
     # -- helpers ---------------------------------------------------------------------------------
     def _to_dev(self, a, dtype=None):
@@ -119,6 +120,14 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
                 box = eng.run_chunk(t["K"], t["rgb1"], t["m1"], t["E1"], t["rgb2"], t["m2"], t["E2"],
                                     seed=self._seed + 7919 * self._calls + lo, choose1=t["c1"], choose2=t["c2"], ransac_idx=ridx)
                 out[lo:hi].copy_(box)
+                if not self._range_checked:
+                    # fp16x2 keeps activations in IEEE half: with the first real batch make sure nothing left its range
+                    # (an overflow turns into inf/NaN features and, silently, into sentinel boxes)
+                    self._range_checked = True
+                    if eng.precision == "fp16x2" and not bool(torch.isfinite(eng.feat[:2 * (hi - lo)]).all()):
+                        from ._lib import AdpError
+                        raise AdpError("non-finite backbone features: the activations of this checkpoint exceed the fp16 range; "
+                                       "construct the estimator with precision='bf16x3'")
             if return_tensor:
                 return out
             res = out.cpu().numpy()

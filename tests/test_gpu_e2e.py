@@ -162,6 +162,27 @@ def test_empty_batch_and_all_blind_environments():
     est.estimator.close()
 
 
+def test_fp16_range_overflow_is_reported_not_silently_turned_into_sentinels():
+    """fp16x2 stores activations in IEEE half; a checkpoint whose activations leave that range must fail loudly on the
+    first batch (and run under bf16x3)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200._lib import AdpError
+    from rgbmanip_b200.estimator import AdaPoseEstimator_v5
+    sd = dict(weights.init_state_dict(0))
+    sd["img_extractor.feats.conv1.weight"] = sd["img_extractor.feats.conv1.weight"] * 3e4      # blows the stem past 65504
+    cfg = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
+           "n_pts": 1024, "direct_regression": True, "real_world": False}
+    batch = synth.make_batch(2, seed=4, special=False)
+    est = AdaPoseEstimator_v5(None, cfg, None, state_dict=sd, max_envs=2, precision="fp16x2")
+    with pytest.raises(AdpError, match="fp16 range"):
+        est.estimate(*batch.args())
+    est.estimator.close()
+    est = AdaPoseEstimator_v5(None, cfg, None, state_dict=sd, max_envs=2, precision="bf16x3")
+    assert est.estimate(*batch.args()).shape == (2, 8, 3)          # bf16's range takes it
+    est.estimator.close()
+
+
 def test_four_task_configs_share_the_path():
     """cabinet / drawer / mug / pot yamls differ only in task_name and checkpoint path (cfg/pose_estimator/adapose_*.yaml)."""
     if not torch.cuda.is_available():
