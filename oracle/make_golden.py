@@ -106,6 +106,27 @@ def golden_e2e(interface_v5, out_dir):
     print("e2e: valid", out["valid"], "boxes", out["boxes"].shape)
 
 
+def golden_e2e_seed1(interface_v5, out_dir):
+    """A second, independent end-to-end fixture: other weights (seed 1), other scenes (seed 5), boxes + pixel subsets only."""
+    torch.manual_seed(1)
+    est, cfg, _ = build_reference_estimator(interface_v5, seed=1)
+    batch = synth.make_batch(8, seed=5, special=False)
+    chooses = []
+    orig_prepare = est.prepare_model_input
+
+    def prepare(rgb, mask, K, resize_size):
+        r = orig_prepare(rgb, mask, K, resize_size)
+        chooses.append(np.asarray(r[1]))
+        return r
+
+    est.prepare_model_input = prepare
+    np.random.seed(1)
+    boxes = est.estimate(*batch.args())
+    ch = np.stack(chooses).reshape(8, 2, -1).astype(np.int32)
+    np.savez_compressed(os.path.join(out_dir, "e2e_seed1.npz"), boxes=boxes, choose1=ch[:, 0], choose2=ch[:, 1])
+    print("e2e seed 1 boxes", boxes.shape, "finite", np.isfinite(boxes).all())
+
+
 def golden_branch_b(interface_v5, out_dir):
     """direct_regression=False, use_depth=True -> RANSAC + Umeyama fit (interface_v5.py:322-338)."""
     est, cfg, _ = build_reference_estimator(interface_v5, direct_regression=False)
@@ -286,7 +307,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     interface_v5, network_v5, rotation_utils, utils, align = import_reference()
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring", "actor"]
+    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring", "actor", "e2e_seed1"]
     if "units" in what:
         golden_units(network_v5, rotation_utils, utils, align, out_dir)
     if "preprocess" in what:
@@ -295,6 +316,8 @@ def main():
         golden_e2e(interface_v5, out_dir)
     if "branch_b" in what:
         golden_branch_b(interface_v5, out_dir)
+    if "e2e_seed1" in what:
+        golden_e2e_seed1(interface_v5, out_dir)
     if "view_ring" in what:
         golden_view_ring(out_dir)
     if "actor" in what:

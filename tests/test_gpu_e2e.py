@@ -67,6 +67,26 @@ def test_estimate_matches_reference_golden(golden, max_envs, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp16x2", "bf16x3"])
+def test_estimate_matches_second_reference_fixture(golden_dir, precision):
+    """Independent fixture: other random weights (seed 1), other scenes (seed 5) -- tests/golden/e2e_seed1.npz."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200.estimator import AdaPoseEstimator_v5
+    g = np.load(os.path.join(golden_dir, "e2e_seed1.npz"))
+    cfg = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
+           "n_pts": 1024, "direct_regression": True, "real_world": False}
+    batch = synth.make_batch(8, seed=5, special=False)
+    est = AdaPoseEstimator_v5(None, cfg, None, state_dict=weights.init_state_dict(1), max_envs=8, precision=precision)
+    boxes = est.estimate(*batch.args(), choose=(g["choose1"], g["choose2"]))
+    worst = np.zeros(4)
+    for e in range(8):
+        worst = np.maximum(worst, O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e], min_z=MIN_Z))
+    print(f"{precision} second fixture worst (px, deg, mm, corner-mm):", worst)
+    assert worst[0] < TOL_PX and worst[1] < TOL_DEG and worst[2] < TOL_MM and worst[3] < TOL_MM, worst
+    est.estimator.close()
+
+
+@pytest.mark.parametrize("precision", ["fp16x2", "bf16x3"])
 def test_network_outputs_match_reference_golden(golden, precision):
     """NOCS / depth / rotation of the last processed chunk against the reference's own tensors."""
     g = golden

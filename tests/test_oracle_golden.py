@@ -140,6 +140,23 @@ def test_end_to_end_against_reference(golden_dir):
         assert px < 0.05 and deg < 0.02 and mm < 0.1 and cmm < 0.2, (px, deg, mm, cmm)
 
 
+def test_end_to_end_second_fixture(golden_dir):
+    """Independent weights (seed 1) and scenes (seed 5): tests/golden/e2e_seed1.npz, first two envs -- CPU time ~8 s."""
+    g = np.load(os.path.join(golden_dir, "e2e_seed1.npz"))
+    sd = weights.init_state_dict(1)
+    cfg = {"img_size": 224, "direct_regression": True, "use_depth": True}
+    batch = synth.make_batch(8, seed=5, special=False)
+    np.random.seed(1)
+    for e in range(2):
+        d = {}
+        box = O.predict(sd, cfg, batch.K[e], batch.rgb1[e], batch.mask1[e], batch.E1[e], batch.rgb2[e], batch.mask2[e],
+                        batch.E2[e], details=d)
+        np.testing.assert_array_equal(d["choose1"], g["choose1"][e])
+        np.testing.assert_array_equal(d["choose2"], g["choose2"][e])
+        px, deg, mm, cmm = O.parity_errors(box, g["boxes"][e], batch.K[e], batch.E1[e])
+        assert px < 0.05 and deg < 0.02 and mm < 0.1 and cmm < 0.2, (e, px, deg, mm, cmm)
+
+
 def test_branch_b_against_reference(golden_dir):
     """direct_regression=False, use_depth=True: RANSAC + Umeyama branch (interface_v5.py:322-338)."""
     g = np.load(os.path.join(golden_dir, "branch_b.npz"))
