@@ -346,7 +346,7 @@ class Engine:
         self.E1buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
         self.E2buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
         self.vol = self._act(E, S, S, 32, D=D, split=False, f16=self.vol_f16)
-        self.vol_planar = 0     # set when conv0 runs as the depth-ring kernel, which reads the chunk-planar layout
+        self.vol_planar = 0     # the volume is channels-last; the planar variant of adp_build_volume is kept for experiments only
         cr = "cost_regularization"
 
         def bn(name):
@@ -387,7 +387,6 @@ class Engine:
                 self._keep.append(w16)
                 plan = C.c_void_p()
                 va = xin.c
-                self.vol_planar = 0
                 L.check(self.lib.adp_conv0_plan_create(C.byref(plan), C.byref(va), L.ptr(w16), L.ptr(sc), L.ptr(sh), L.ptr(out.hi),
                                                        L.LAYOUT_S2D if self.l0_s2d else 0, self.num_sms), "conv0_plan")
                 self._conv0_plans.append(plan)
