@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ADP_ABI_VERSION 2
+#define ADP_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ADP_API __attribute__((visibility("default")))
@@ -76,6 +76,7 @@ typedef struct adp_epilogue { /* y = act(scale * acc + bias [+ res]) [+ res]  ->
     int32_t out_cstride;      /* channel pitch of out_hi/out_lo (0 = Cout): lets a layer write a column range of a wider tensor */
     int32_t out_coff;         /* first channel of that range (torch.cat of network_v5.py:488 without a copy) */
     int32_t bias_per_batch;   /* 1: bias is [B, Cout] (the per-env global feature term of pose_mlp2, network_v5.py:491-493) */
+    int32_t check_finite;     /* 1: OR bit 0 into err_flag[1] when an output value is inf/NaN (fp16 range guard, set on the last backbone layer) */
 } adp_epilogue;
 
 typedef struct adp_direct_conv {   /* generic CUDA-core convolution (strided / tiny-channel / transposed layers) */
@@ -105,16 +106,20 @@ ADP_API void adp_launch_count_add(uint64_t n);
 ADP_API int adp_device_info(int device, int* num_sms, int* cc_major, int* cc_minor);
 
 /* --- preprocessing: interface_v5.py:58-170 (prepare_model_input), utils.py:10-38 (get_bbox) ------------------
- * rgb [F,H,W,3] (f32|f64), mask [F,H,W] (u8|f32|f64), K [F,3,3] f64 (k_stride doubles between frames; 0 = shared).
+ * rgb [F,H,W,3] (f32|f64, or u8 = the f32 path on value / 255 like ToTensor; H, W >= 440), mask [F,H,W] (u8|f32|f64), K [F,3,3] f64 (k_stride doubles between frames; 0 = shared).
  * Outputs: win [F,4] = rmin,rmax,cmin,cmax; Kp [F,9] f64 crop intrinsics; valid [F]; crops [F,S,S,3] f32 normalised;
- * choose [F,P] i32 (written when choose_mode == 0, read-only when 1 = caller-supplied); counts [F] foreground pixels. */
+ * choose [F,P] i32 (written when choose_mode == 0, read-only when 1 = caller-supplied); counts [F] foreground pixels.
+ * The device sampler (choose_mode 0) is a counter-based hash of (seed, frame_id0 + f, pixel rank): pass the global
+ * environment index of frame 0 as frame_id0 and the subset drawn for an environment is independent of chunking / sharding. */
 ADP_API int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int mask_dtype, const double* K, int k_stride,
-                   int F, int H, int W, int S, int P, uint32_t seed, int choose_mode, int32_t* bbox_ws, int32_t* win,
-                   double* Kp, uint8_t* valid, float* crops, int32_t* choose, int32_t* counts, void* stream);
+                   int F, int H, int W, int S, int P, uint32_t seed, int choose_mode, int frame_id0, int32_t* bbox_ws,
+                   int32_t* win, double* Kp, uint8_t* valid, float* crops, int32_t* choose, int32_t* counts, void* stream);
 
 /* --- backbone: pspnet.py:33-158 ------------------------------------------------------------------------------ */
 ADP_API int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, const void* w_lo, int cout, int kd,
                      int ks, int dil, int npass, const adp_epilogue* ep, const adp_tc_geom* geom, int num_sms);
+/* err_flag: int32[2] on the device -- [0] pipeline watchdog code (a stuck barrier traps the kernel instead of hanging the GPU),
+ * [1] range flag (see adp_epilogue.check_finite).  The same two-word flag is passed to every *_run entry point. */
 ADP_API int adp_conv_tc_run(adp_conv_plan* plan, int batch, int32_t* err_flag, void* stream);
 ADP_API void adp_conv_tc_free(adp_conv_plan* plan);
 ADP_API int adp_conv_direct(const adp_direct_conv* desc, int batch, void* stream);
@@ -187,11 +192,18 @@ ADP_API int adp_rot_head(const float* psum, const uint8_t* valid, const adp_deco
 
 /* --- controller observation + actor forward: rl_pose.py:173-187 (get_observation: [N, T*11] pose/bbox
  * history ++ one_hot(step, T), from the device-resident queues of the view ring) and algo/ppo/ppo/module.py:24-34,89-91
- * (act_inference: Linear/ELU stack, torch weight layout [out][in]).  dims[0] = T*12, dims[nlayers] = action width;
- * weights / biases: host arrays of nlayers device pointers.  obs_out [N, T*12] may be NULL. */
+ * (act_inference: Linear/activation stack, torch weight layout [out][in]).  dims[0] = T*12, dims[nlayers] = action width;
+ * weights / biases: host arrays of nlayers device pointers.  activation: the hidden activation of get_activation()
+ * (module.py:110-126): ADP_ACTOR_ELU (rl.yaml), _SELU, _RELU (also "crelu"), _LRELU, _TANH, _SIGMOID.  obs_out [N, T*12] may be NULL. */
+#define ADP_ACTOR_ELU 0
+#define ADP_ACTOR_SELU 1
+#define ADP_ACTOR_RELU 2
+#define ADP_ACTOR_LRELU 3
+#define ADP_ACTOR_TANH 4
+#define ADP_ACTOR_SIGMOID 5
 ADP_API int adp_actor_forward(const double* pose_queue, const double* bbox_queue, int T, int N, int step, int nlayers,
-                              const int32_t* dims, const float* const* weights, const float* const* biases, float* obs_out,
-                              float* act_out, void* stream);
+                              const int32_t* dims, const float* const* weights, const float* const* biases, int activation,
+                              float* obs_out, float* act_out, void* stream);
 
 /* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
 /* One 4-CTA thread-block cluster per environment; the exact-median radix select recomputes the pair ratios in every pass.

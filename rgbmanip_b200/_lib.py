@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libadapose_b200.so")
 
-ADP_ABI_VERSION = 2
+ADP_ABI_VERSION = 3
 DT_U8, DT_F32, DT_F64 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_TANH = 0, 1, 2, 3
 LAYOUT_F16, LAYOUT_S2D = 1, 2          # adp_decode x11_format / adp_conv0_plan_create flags
@@ -34,7 +34,7 @@ class TcGeom(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("scale", vp), ("bias", vp), ("prelu", C.c_float), ("act", i32), ("res_after_act", i32),
                 ("res_hi", vp), ("res_lo", vp), ("res_cstride", i32), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp), ("out_h16", vp),
-                ("out_cstride", i32), ("out_coff", i32), ("bias_per_batch", i32)]
+                ("out_cstride", i32), ("out_coff", i32), ("bias_per_batch", i32), ("check_finite", i32)]
 
 
 class DirectConv(C.Structure):
@@ -63,7 +63,7 @@ SIGNATURES = {
     "adp_launch_count_add": (None, [C.c_uint64]),
     "adp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "adp_preprocess": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_uint32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
+                                 C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     "adp_conv_tc_plan": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(Epilogue), C.POINTER(TcGeom), C.c_int]),
     "adp_conv_tc_run": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -89,7 +89,7 @@ SIGNATURES = {
     "adp_colsum": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "adp_pose_gbias": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "adp_rot_head": (C.c_int, [vp, vp, C.POINTER(DecodeWeights), vp, vp, C.c_int, C.c_int, vp]),
-    "adp_actor_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "adp_actor_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
     "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "adp_fit_umeyama": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }

@@ -15,9 +15,16 @@ import torch
 from . import _lib as L
 
 
+ACTIVATIONS = {"elu": 0, "selu": 1, "relu": 2, "crelu": 2, "lrelu": 3, "tanh": 4, "sigmoid": 5}   # module.py:110-126
+
+
 class DeviceActor:
-    def __init__(self, actor_state_dict, ring):
-        """actor_state_dict: the ``actor.*`` entries of the reference's ActorCritic state dict (nn.Sequential of Linear/ELU)."""
+    def __init__(self, actor_state_dict, ring, activation="elu"):
+        """actor_state_dict: the ``actor.*`` entries of the reference's ActorCritic state dict (nn.Sequential of
+        Linear/activation); ``activation``: ``model_cfg['activation']`` of the policy (cfg/controller/rl.yaml: elu)."""
+        if activation not in ACTIVATIONS:
+            raise ValueError(f"unsupported actor activation {activation!r} (the reference's get_activation knows {sorted(ACTIVATIONS)})")
+        self.activation = ACTIVATIONS[activation]
         self.lib = L.load()
         self.ring = ring
         dev = ring.device
@@ -46,7 +53,7 @@ class DeviceActor:
             raise IndexError(f"one_hot index {step} outside [0, {r.max_steps})")       # torch.nn.functional.one_hot raises too
         st = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
         L.check(self.lib.adp_actor_forward(L.ptr(r.pose), L.ptr(r.bbox), r.max_steps, r.num_envs, step, len(self.W), self._dims,
-                                           self._wp, self._bp, L.ptr(self.obs), L.ptr(self.act), st), "actor_forward")
+                                           self._wp, self._bp, self.activation, L.ptr(self.obs), L.ptr(self.act), st), "actor_forward")
         return self.act, self.obs
 
     def get_observation(self):

@@ -18,6 +18,7 @@ struct ActorArgs {
     const double* bbox;      // [T, N, 4]
     int T, N, step;          // step = accumulate_steps - 1 (one-hot index)
     int nlayers;
+    int activation;          // hidden activation, get_activation() of module.py:110-126: 0 elu, 1 selu, 2 relu/crelu, 3 lrelu, 4 tanh, 5 sigmoid
     int dims[ACT_MAXL + 1];  // dims[0] = T * 12
     const float* W[ACT_MAXL];   // torch layout [out][in]
     const float* b[ACT_MAXL];
@@ -54,7 +55,17 @@ actor_forward_kernel(const ActorArgs a) {
             const float* w = a.W[l] + (size_t)n * din;
             float acc = __ldg(a.b[l] + n);
             for (int k = 0; k < din; ++k) acc = fmaf(buf[cur][le][k], __ldg(w + k), acc);
-            if (!last) acc = acc > 0.f ? acc : expm1f(acc);          // ELU(alpha = 1)
+            if (!last) {
+                switch (a.activation) {
+                    case 0: acc = acc > 0.f ? acc : expm1f(acc); break;                                   // nn.ELU(alpha = 1)
+                    case 1: acc = 1.0507009873554804934193349852946f *
+                                  (acc > 0.f ? acc : 1.6732632423543772848170429916717f * expm1f(acc)); break;   // nn.SELU
+                    case 2: acc = fmaxf(acc, 0.f); break;                                                  // nn.ReLU
+                    case 3: acc = acc > 0.f ? acc : 0.01f * acc; break;                                    // nn.LeakyReLU(0.01)
+                    case 4: acc = tanhf(acc); break;
+                    default: acc = 1.f / (1.f + expf(-acc)); break;                                        // nn.Sigmoid
+                }
+            }
             buf[cur ^ 1][le][n] = acc;
             if (last && e0 + le < a.N) a.act_out[(size_t)(e0 + le) * dout + n] = acc;
         }
@@ -68,6 +79,7 @@ int actor_forward(const ActorArgs& a, cudaStream_t stream) {
     ADP_CHECK_ARG(a.dims[0] == a.T * 12, "observation width must be T * 12");
     for (int l = 0; l <= a.nlayers; ++l) ADP_CHECK_ARG(a.dims[l] >= 1 && a.dims[l] <= ACT_MAXW, "layer width 1..256");
     ADP_CHECK_ARG(a.step >= -1 && a.step < a.T, "step index");
+    ADP_CHECK_ARG(a.activation >= 0 && a.activation <= 5, "activation code");
     if (a.N == 0) return ADP_OK;
     actor_forward_kernel<<<cdiv(a.N, ACT_ENVS), ACT_THREADS, 0, stream>>>(a);
     ADP_CUDA(cudaGetLastError());

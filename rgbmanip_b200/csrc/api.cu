@@ -30,7 +30,7 @@ int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batc
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream);
 int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t stream);
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
-                   int S, int P, uint32_t seed, int choose_mode, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
+                   int S, int P, uint32_t seed, int choose_mode, int frame_id0, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream);
 int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
                  int W, int C, int f16, int feat_f16, int planar, cudaStream_t stream);
@@ -61,7 +61,7 @@ int rot_head_run(const float* psum, const uint8_t* valid, float* Rout, float* r6
                  cudaStream_t stream);
 constexpr int ACT_MAXL_API = 8;
 struct ActorArgs {
-    const double* pose; const double* bbox; int T, N, step; int nlayers; int dims[ACT_MAXL_API + 1];
+    const double* pose; const double* bbox; int T, N, step; int nlayers; int activation; int dims[ACT_MAXL_API + 1];
     const float* W[ACT_MAXL_API]; const float* b[ACT_MAXL_API]; float* obs_out; float* act_out;
 };
 int actor_forward(const ActorArgs& a, cudaStream_t stream);
@@ -113,11 +113,11 @@ int adp_device_info(int device, int* num_sms, int* cc_major, int* cc_minor) {
 }
 
 int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int mask_dtype, const double* K, int k_stride, int F, int H,
-                   int W, int S, int P, uint32_t seed, int choose_mode, int32_t* bbox_ws, int32_t* win, double* Kp,
+                   int W, int S, int P, uint32_t seed, int choose_mode, int frame_id0, int32_t* bbox_ws, int32_t* win, double* Kp,
                    uint8_t* valid, float* crops, int32_t* choose, int32_t* counts, void* stream) {
     ADP_CHECK_ARG(rgb && mask && K && bbox_ws && win && Kp && valid && crops && choose && counts, "null pointer");
     g_launches += 5;
-    return preprocess_run(rgb, rgb_dtype, mask, mask_dtype, K, k_stride, F, H, W, S, P, seed, choose_mode, bbox_ws, win, Kp,
+    return preprocess_run(rgb, rgb_dtype, mask, mask_dtype, K, k_stride, F, H, W, S, P, seed, choose_mode, frame_id0, bbox_ws, win, Kp,
                           valid, crops, choose, counts, (cudaStream_t)stream);
 }
 
@@ -147,6 +147,7 @@ int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, 
     p.out_f32 = ep->out_f32;
     p.out_h16 = reinterpret_cast<__half*>(ep->out_h16);
     p.out_cs = ep->out_cstride ? ep->out_cstride : cout; p.out_coff = ep->out_coff; p.bias_per_batch = ep->bias_per_batch;
+    p.check_finite = ep->check_finite;
     {
         // coalesced epilogue stores need full accumulator chunks and a single 16-bit plane (fp32 / fp16 side outputs are fine)
         const int ch = pl->layer.BN < 32 ? pl->layer.BN : 32;
@@ -318,11 +319,12 @@ int adp_rot_head(const float* psum, const uint8_t* valid, const adp_decode_weigh
 }
 
 int adp_actor_forward(const double* pose_queue, const double* bbox_queue, int T, int N, int step, int nlayers, const int32_t* dims,
-                      const float* const* weights, const float* const* biases, float* obs_out, float* act_out, void* stream) {
+                      const float* const* weights, const float* const* biases, int activation, float* obs_out, float* act_out,
+                      void* stream) {
     ADP_CHECK_ARG(pose_queue && bbox_queue && dims && weights && biases && act_out, "null pointer");
     ADP_CHECK_ARG(nlayers >= 1 && nlayers <= ACT_MAXL_API, "1..8 layers");
     ActorArgs a{};
-    a.pose = pose_queue; a.bbox = bbox_queue; a.T = T; a.N = N; a.step = step; a.nlayers = nlayers;
+    a.pose = pose_queue; a.bbox = bbox_queue; a.T = T; a.N = N; a.step = step; a.nlayers = nlayers; a.activation = activation;
     for (int l = 0; l <= nlayers; ++l) a.dims[l] = dims[l];
     for (int l = 0; l < nlayers; ++l) { a.W[l] = weights[l]; a.b[l] = biases[l]; }
     a.obs_out = obs_out; a.act_out = act_out;

@@ -135,4 +135,20 @@ __device__ inline bool invert4x4(const double* m, double* inv) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of a kernel: one engine per GPU in the
+// same process must set it on every device it launches on.  `per_dev` is a zero-initialised static table owned by the call
+// site (one slot per device ordinal, holding the largest size configured so far on that device).
+constexpr int kMaxDevices = 64;
+template <typename Fn>
+static inline int ensure_dyn_smem(Fn* fn, int bytes, int* per_dev) {
+    int dev = 0;
+    ADP_CUDA(cudaGetDevice(&dev));
+    ADP_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "device ordinal");
+    if (bytes > per_dev[dev]) {
+        ADP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        per_dev[dev] = bytes;
+    }
+    return ADP_OK;
+}
+
 }  // namespace adp

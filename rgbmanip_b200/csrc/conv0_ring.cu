@@ -287,11 +287,8 @@ int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const flo
 
 int conv0_run(Conv0Plan* pl, int batch, int* err_flag, cudaStream_t stream) {
     ADP_CHECK_ARG(batch <= pl->p.B, "batch exceeds planned capacity");
-    static bool attr = false;
-    if (!attr) {
-        ADP_CUDA(cudaFuncSetAttribute(conv0_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM));
-        attr = true;
-    }
+    static int attr[kMaxDevices];
+    ADP_TRY(ensure_dyn_smem(conv0_ring_kernel, C0_SMEM, attr));
     pl->p.err = err_flag;
     const int units = batch * (pl->p.H / C0_R) * (pl->p.W / C0_SEG);
     if (units == 0) return ADP_OK;

@@ -296,11 +296,8 @@ int fit_umeyama_run(const float* nocs, const float* depth, const int* choose, co
     ADP_CHECK_ARG(P <= UM_MAXP, "at most 1024 points per env");
     if (B == 0) return ADP_OK;
     const size_t smem = (size_t)(6 * UM_MAXP + 13 * UM_ITERS) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        ADP_CUDA(cudaFuncSetAttribute(fit_umeyama_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    static int attr[kMaxDevices];
+    ADP_TRY(ensure_dyn_smem(fit_umeyama_kernel, (int)smem, attr));
     fit_umeyama_kernel<<<B, UM_THREADS, smem, stream>>>(nocs, depth, choose, Kp, E, valid, rand_idx, seed, bbox, scale_out, rot_out,
                                                        trans_out, P, S);
     ADP_CUDA(cudaGetLastError());

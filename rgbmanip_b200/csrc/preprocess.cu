@@ -78,10 +78,17 @@ __global__ void window_kernel(const int* __restrict__ bbox, const double* __rest
 }
 
 // ---- 3. crop + bilinear resize + normalise -> fp32 NHWC3
-template <typename T>
-__device__ __forceinline__ T ld_rgb(const void* p, size_t i) { return reinterpret_cast<const T*>(p)[i]; }
+// 8-bit frames: value / 255 in fp32, what torchvision's ToTensor (interface_v5.py:52,149) makes of a uint8 image.  The u8 path
+// is defined as "the fp32 path on rgb.float() / 255" (bit for bit); the reference callers always pass floats in [0, 1].
+struct U8AsF32 {};
+template <typename S> struct rgb_math { typedef S type; };
+template <> struct rgb_math<U8AsF32> { typedef float type; };
+template <typename S>
+__device__ __forceinline__ typename rgb_math<S>::type ld_rgb(const void* p, size_t i) { return reinterpret_cast<const S*>(p)[i]; }
+template <>
+__device__ __forceinline__ float ld_rgb<U8AsF32>(const void* p, size_t i) { return (float)reinterpret_cast<const uint8_t*>(p)[i] / 255.f; }
 
-template <typename T>   // T = float or double: OpenCV interpolates in the source float type
+template <typename SRC>   // float or double: OpenCV interpolates in the source float type; U8AsF32: see above
 __global__ void crop_resize_kernel(const void* __restrict__ rgb, const int* __restrict__ win, const uint8_t* __restrict__ valid,
                                    float* __restrict__ out, int H, int W, int S) {
     const int f = blockIdx.y;
@@ -92,6 +99,7 @@ __global__ void crop_resize_kernel(const void* __restrict__ rgb, const int* __re
     }
     const int rmin = win[4 * f], rmax = win[4 * f + 1], cmin = win[4 * f + 2];
     const int ws = rmax - rmin;
+    typedef typename rgb_math<SRC>::type T;
     const double scale = (double)ws / (double)S;
     const T mean[3] = {(T)0.485, (T)0.456, (T)0.406};
     const T stdv[3] = {(T)0.229, (T)0.224, (T)0.225};
@@ -108,8 +116,8 @@ __global__ void crop_resize_kernel(const void* __restrict__ rgb, const int* __re
         const size_t r0 = ((size_t)f * H + rmin + y0) * W + cmin, r1 = ((size_t)f * H + rmin + y1) * W + cmin;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const T a = ld_rgb<T>(rgb, (r0 + x0) * 3 + c), b = ld_rgb<T>(rgb, (r0 + x1) * 3 + c);
-            const T cc = ld_rgb<T>(rgb, (r1 + x0) * 3 + c), d = ld_rgb<T>(rgb, (r1 + x1) * 3 + c);
+            const T a = ld_rgb<SRC>(rgb, (r0 + x0) * 3 + c), b = ld_rgb<SRC>(rgb, (r0 + x1) * 3 + c);
+            const T cc = ld_rgb<SRC>(rgb, (r1 + x0) * 3 + c), d = ld_rgb<SRC>(rgb, (r1 + x1) * 3 + c);
             const T top = a * ((T)1 - wx) + b * wx, bot = cc * ((T)1 - wx) + d * wx;   // horizontal pass first
             const T v = top * ((T)1 - wy) + bot * wy;
             out[((size_t)f * S * S + i) * 3 + c] = (float)((v - mean[c]) / stdv[c]);
@@ -154,7 +162,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
 // mode 1: the caller supplies choose (exact replay of the reference RNG); only counts are produced.
 __global__ void __launch_bounds__(1024)
 choose_kernel(const void* __restrict__ mask, int dt, const int* __restrict__ win, uint8_t* __restrict__ valid,
-              int* __restrict__ choose, int* __restrict__ counts, int H, int W, int S, int P, uint32_t seed, int mode) {
+              int* __restrict__ choose, int* __restrict__ counts, int H, int W, int S, int P, uint32_t seed, int mode,
+              int frame_id0) {
     extern __shared__ int sm[];
     int* warp_sums = sm;                     // 32
     int* hist = sm + 32;                     // 256
@@ -203,7 +212,9 @@ choose_kernel(const void* __restrict__ mask, int dt, const int* __restrict__ win
         return;
     }
     // more than P candidates: keep the P smallest hash keys (ties resolved by rank), output in ascending index order
-    const uint32_t salt = mix32(seed ^ (0x9e3779b9u * (uint32_t)(f + 1)));
+    // keyed by the caller's frame id (the global environment index), not by the position inside this launch: the drawn subset
+    // of an environment does not depend on how the batch is chunked or sharded over GPUs
+    const uint32_t salt = mix32(seed ^ (0x9e3779b9u * (uint32_t)(frame_id0 + f + 1)));
     uint32_t prefix = 0, pmask = 0;
     int need = P;   // how many still to take among keys matching the prefix
     for (int shift = 24; shift >= 0; shift -= 8) {
@@ -261,9 +272,12 @@ choose_kernel(const void* __restrict__ mask, int dt, const int* __restrict__ win
 }
 
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
-                   int S, int P, uint32_t seed, int choose_mode, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
+                   int S, int P, uint32_t seed, int choose_mode, int frame_id0, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream) {
-    ADP_CHECK_ARG(rgb_dt == DT_F32 || rgb_dt == DT_F64, "rgb dtype must be f32 or f64");
+    ADP_CHECK_ARG(rgb_dt == DT_F32 || rgb_dt == DT_F64 || rgb_dt == DT_U8, "rgb dtype must be u8, f32 or f64");
+    // the crop window is a square of up to 440 pixels shifted inside the frame (utils.py:10-38 hard-codes 480 x 640): a smaller
+    // frame cannot hold it and the shifted window would start before the frame
+    ADP_CHECK_ARG(H >= 440 && W >= 440, "frames must be at least 440 x 440 (crop window of utils.py:get_bbox)");
     ADP_CHECK_ARG(mask_dt == DT_U8 || mask_dt == DT_F32 || mask_dt == DT_F64, "mask dtype must be u8, f32 or f64");
     ADP_CHECK_ARG(S * S <= 65536 && P <= S * S, "sizes");
     if (F == 0) return ADP_OK;
@@ -271,13 +285,12 @@ int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, c
     mask_bbox_kernel<<<dim3(30, F), 256, 0, stream>>>(mask, mask_dt, bbox_ws, H, W);
     window_kernel<<<cdiv(F, 128), 128, 0, stream>>>(bbox_ws, K, k_stride, win, Kp, valid, F, H, W, S);
     const size_t smem = (32 + 256 + 8) * sizeof(int) + (size_t)S * S;
-    static bool attr = false;
-    if (!attr) {
-        ADP_CUDA(cudaFuncSetAttribute(choose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        attr = true;
-    }
-    choose_kernel<<<F, 1024, smem, stream>>>(mask, mask_dt, win, valid, choose, counts, H, W, S, P, seed, choose_mode);
-    if (rgb_dt == DT_F32)
+    static int attr[kMaxDevices];
+    ADP_TRY(ensure_dyn_smem(choose_kernel, 72 * 1024, attr));
+    choose_kernel<<<F, 1024, smem, stream>>>(mask, mask_dt, win, valid, choose, counts, H, W, S, P, seed, choose_mode, frame_id0);
+    if (rgb_dt == DT_U8)
+        crop_resize_kernel<U8AsF32><<<dim3(49, F), 256, 0, stream>>>(rgb, win, valid, crops, H, W, S);
+    else if (rgb_dt == DT_F32)
         crop_resize_kernel<float><<<dim3(49, F), 256, 0, stream>>>(rgb, win, valid, crops, H, W, S);
     else
         crop_resize_kernel<double><<<dim3(49, F), 256, 0, stream>>>(rgb, win, valid, crops, H, W, S);

@@ -115,6 +115,14 @@ __device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const ui
                                     }
                                 }
                             }
+                            if (p.check_finite) {
+                                // range guard of the fp16 pipeline: an activation that left the half range upstream arrives here as
+                                // inf / NaN (the last backbone layer sees every earlier one); the host reads err[1] after every call
+                                bool bad = false;
+#pragma unroll
+                                for (int j = 0; j < CH; ++j) bad |= !(fabsf(v[j]) <= 3.0e38f);
+                                if (bad && p.err) atomicOr(p.err + 1, 1);
+                            }
 }
 
 // per-lane stores of one chunk (every lane writes its own pixel row): partial chunks, split hi + lo planes
@@ -295,10 +303,15 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = FUSED == 1 ? 2 * (A_BYTES + B_PAD) : FUSED == 2 ? (A_BYTES + 2 * B_PAD) : (A_BYTES + B_PAD);
     // small-N layers are latency bound per tile: fewer stages -> several CTAs per SM overlap their pipelines
     static constexpr int CTAS_PER_SM = FUSED ? (BN <= 64 ? 2 : 1) : (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
+    // fp16x2 with a narrow N tile: W_hi and W_lo sit back to back in the stage, so ONE MMA of N = 2 BN reads the A operand once
+    // and leaves A W_hi in columns [0, BN) and A W_lo in [BN, 2 BN) of the accumulator; the epilogue adds the two halves.  A
+    // BN <= 64 MMA is bound by the 128 B/clk shared-memory operand path (4 KB of A per MMA), not by the tensor pipe: reading A
+    // once instead of twice takes a K step from 12 KB to 8 KB of operand traffic at the same tensor work.
+    static constexpr bool NCAT = FUSED == 2 && BN <= 64 && (B_BYTES % 1024 == 0);
     static constexpr int EPI_BYTES = 4 * 2048;                  // per-epilogue-warp transpose buffers (coalesced stores)
     static constexpr int SMEM_BUDGET = (220 * 1024 - CTAS_PER_SM * (EPI_BYTES + 2048)) / CTAS_PER_SM;
     static constexpr int STAGES = (STAGE_BYTES * 6 <= SMEM_BUDGET) ? 6 : (SMEM_BUDGET / STAGE_BYTES);
-    static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns per accumulator stage
+    static constexpr int ACC_STRIDE = NCAT ? 2 * BN : (BN < 32 ? 32 : BN);   // TMEM columns per accumulator stage
     static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : (2 * ACC_STRIDE <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -412,7 +425,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint32_t phase = 0;
         int as = 0;
         uint32_t aphase = 0;
-        const uint32_t idesc = make_idesc<BN>(p.f16);
+        const uint32_t idesc = make_idesc<Cfg::NCAT ? 2 * BN : BN>(p.f16);
         const uint32_t elected = ptx::elect_one();
         const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -423,7 +436,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 ptx::mbar_wait(full_bar(stage), phase, p.err, 3);
                 ptx::tc_fence_after();
                 const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                if (FUSED == 2) {
+                if (FUSED == 2 && Cfg::NCAT) {
+                    const uint64_t ah = make_smem_desc<KC>(sa);
+                    const uint64_t whl = make_smem_desc<KC>(sa + Cfg::A_BYTES);      // rows [0, BN) = W_hi, [BN, 2 BN) = W_lo
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k)
+                        ptx::umma_bf16_elected(tmem_d, ah + (uint64_t)(2 * k), whl + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u, elected);
+                } else if (FUSED == 2) {
                     const uint64_t ah = make_smem_desc<KC>(sa);
                     const uint64_t wh = make_smem_desc<KC>(sa + Cfg::A_BYTES);
                     const uint64_t wl = make_smem_desc<KC>(sa + Cfg::A_BYTES + Cfg::B_PAD);
@@ -494,6 +513,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::ACC_STRIDE + c0);
                 ptx::tmem_ld16(taddr, r);
                 if (CH == 32) ptx::tmem_ld16(taddr + 16, r + 16);
+                if (Cfg::NCAT) {          // accumulator columns [BN, 2 BN) hold the W_lo products of the same outputs
+                    uint32_t r2[16];
+#pragma unroll
+                    for (int h = 0; h < CH / 16; ++h) {
+                        ptx::tmem_ld16(taddr + BN + 16 * h, r2);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[16 * h + j] = __float_as_uint(__uint_as_float(r[16 * h + j]) + __uint_as_float(r2[j]));
+                    }
+                }
                 ptx::tmem_ld_wait();
                 const int nbase = n0 + c0;
                 if (nbase < p.Cout) {       // Cout may be padded up to BN (e.g. 8 -> 16); uniform over the warp
@@ -911,11 +940,8 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
 template <int BN, int KC, int FUSED = 0>
 static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
     using Cfg = TcCfg<BN, KC, FUSED>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, KC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    static int attr[kMaxDevices];
+    ADP_TRY(ensure_dyn_smem(tc_conv_kernel<BN, KC, FUSED>, Cfg::SMEM_BYTES, attr));
     const TcConvParams& p = L->p;
     long long total = (long long)batch * p.D * p.tiles_y * p.tiles_x * p.tiles_n;
     const long long slots = (long long)num_sms * Cfg::CTAS_PER_SM;
@@ -932,11 +958,8 @@ static int launch_slab(const TcConvLayer* L, int batch, int num_sms, cudaStream_
     const TcConvParams& p = L->p;
     const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
     const int smem = p.slab_stages * stage_bytes + p.ntaps * Cfg::W_SLOT + Cfg::EPI_BYTES + 1024 + 512;
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        ADP_CUDA(cudaFuncSetAttribute(slab_conv_kernel<BN, KC, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    static int attr[kMaxDevices];
+    ADP_TRY(ensure_dyn_smem(slab_conv_kernel<BN, KC, CTAS>, smem, attr));
     const long long total = (long long)batch * p.D * p.tiles_y * p.tiles_x;
     const long long slots = (long long)num_sms * CTAS;
     const int grid = (int)(total < slots ? total : slots);

@@ -52,6 +52,7 @@ struct TcConvParams {
     int bias_per_batch;      // bias is [B, Cout]
     // slab mode (small-channel 3-D convs, see slab_conv_kernel): halo slab extents / origin offset, bytes per stage
     int sSX, sSY, sSZ, slox, sloy, sloz, slab_bytes, slab_stages;
+    int check_finite;        // OR bit 0 into err[1] when an output value is not finite (fp16 range guard on the feature map)
     int coalesce;            // epilogue stores go through the per-warp transpose buffers (full chunks, single 16-bit plane)
     int* err;                // device error flag (pipeline watchdog)
 };

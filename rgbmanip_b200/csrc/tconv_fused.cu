@@ -263,11 +263,8 @@ int tconv_plan(TconvPlan* pl, const Act& in, const bf16* w, int Cout, const floa
 template <int KC, int BN>
 static int tconv_launch(TconvPlan* pl, int batch, cudaStream_t stream) {
     using Cfg = TfCfg<KC, BN>;
-    static bool attr = false;
-    if (!attr) {
-        ADP_CUDA(cudaFuncSetAttribute(tconv_fused_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr = true;
-    }
+    static int attr[kMaxDevices];
+    ADP_TRY(ensure_dyn_smem(tconv_fused_kernel<KC, BN>, Cfg::SMEM, attr));
     const long long total = (long long)batch * pl->p.D * pl->p.tiles_y * pl->p.tiles_x;
     if (total == 0) return ADP_OK;
     const long long slots = 2LL * pl->num_sms;

@@ -28,9 +28,15 @@ def estimate_sharded(estimate_fn, args, n: int, group=None, device=None):
     lo, hi, per = shard_range(n, rank, world)
     local = estimate_fn(*[a[lo:hi] for a in args]) if hi > lo else None
     if device is None:
-        device = local.device if local is not None else torch.device("cpu")
+        if local is not None:
+            device = local.device
+        else:
+            # an empty shard has no result tensor to take the device from: the collective's tensors must live where the
+            # process group's backend expects them (NCCL: this rank's CUDA device; gloo: host)
+            backend = dist.get_backend(group) if dist.is_initialized() else "gloo"
+            device = torch.device("cuda", torch.cuda.current_device()) if "nccl" in str(backend) else torch.device("cpu")
     if world == 1:
-        return local
+        return local if local is not None else torch.empty((0, 8, 3), dtype=torch.float64, device=device)
     pad = torch.zeros((per, 8, 3), dtype=torch.float64, device=device)
     if local is not None:
         pad[: hi - lo].copy_(local)

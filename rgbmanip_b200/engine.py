@@ -95,9 +95,8 @@ class Engine:
         self.decode_tc = decode_tc and use_tc and int(n_pts) == 1024
         self.level0_s2d = level0_s2d
         self.use_graph = bool(use_graph) and not debug
-        self._graph = None
-        self._graph_launches = 0
-        self._full_chunks = 0
+        self._graphs = {}           # chunk size -> (CUDAGraph, launches per replay)
+        self._chunk_runs = {}       # chunk size -> eager runs so far (a size is captured on its second appearance)
         self._conv0_plans = []
         self._tconv_plans = []
         if volume_dtype not in ("fp16", "bf16"):
@@ -116,7 +115,10 @@ class Engine:
         W.check_state_dict(sd, self.regress_pose)
         self.sd = sd
         with torch.cuda.device(self.device):
-            self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            # [0] pipeline watchdog code, [1] fp16 range flag (set by the last backbone layer's epilogue on inf/NaN features)
+            self.err_flag = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._err_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._err_event = None
             self._build_backbone()
             self._build_stereo()
             torch.cuda.synchronize()
@@ -145,12 +147,12 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _epilogue(self, out: ActBuf | None, scale=None, bias=None, act=L.ACT_RELU, prelu=0.0, res: ActBuf | None = None,
-                  res_after_act=0, out_f32=None, out_h16=None, out_cstride=0, out_coff=0, bias_per_batch=0):
+                  res_after_act=0, out_f32=None, out_h16=None, out_cstride=0, out_coff=0, bias_per_batch=0, check_finite=0):
         return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act, res_after_act,
                           L.ptr(res.hi) if res else None, L.ptr(res.lo) if (res and res.lo is not None) else None,
                           res.Cn if res else 0,
                           L.ptr(out.hi) if out else None, L.ptr(out.lo) if (out and out.lo is not None) else None,
-                          L.ptr(out_f32), L.ptr(out_h16), out_cstride, out_coff, bias_per_batch)
+                          L.ptr(out_f32), L.ptr(out_h16), out_cstride, out_coff, bias_per_batch, check_finite)
 
     def _tc_plans(self, x: ActBuf, wt, cout, kd, ks, dil, npass, ep, geoms):
         """wt: fp32 [taps, CoutPad, Cin] packed weights -> callable(batch) launching one tcgen05 conv per geometry."""
@@ -328,8 +330,10 @@ class Engine:
         # fp16 twin of the feature map for the plane-sweep volume builder (the volume itself is fp16; halves its gather traffic)
         self.feat16 = torch.zeros((F, S, S, 32), dtype=torch.float16, device=self.device) if (self.vol_f16 and self.use_tc) else None
         fb = self._dev(sd["img_extractor.final.bias"])
+        # the last layer sees every earlier one: an activation that left the fp16 range upstream arrives here as inf/NaN and
+        # raises the range flag (err_flag[1]) that estimate() reads after every call
         ops.append(("final", self._conv(sd["img_extractor.final.weight"], x, None, bias=fb, act=L.ACT_NONE, out_f32=self.feat,
-                                        out_h16=self.feat16)))
+                                        out_h16=self.feat16, check_finite=1)))
         self.backbone_ops = ops
 
     def run_backbone(self, nframes):
@@ -536,21 +540,23 @@ class Engine:
             raise TypeError(f"unsupported dtype {t.dtype}")
         return code
 
-    def preprocess(self, view, rgb, mask, K, n, seed=0, choose=None, offset=None):
-        """view 0/1; rgb [n,H,W,3] f32|f64, mask [n,H,W] u8|bool|f32|f64, K [n,3,3] f64 -- device tensors.
+    def preprocess(self, view, rgb, mask, K, n, seed=0, choose=None, offset=None, frame_id0=0):
+        """view 0/1; rgb [n,H,W,3] f32|f64|u8 (u8 = value / 255), mask [n,H,W] u8|bool|f32|f64, K [n,3,3] f64 -- device tensors.
         The frames land at [offset, offset + n) of the frame buffers (default: view * max_envs)."""
         E = self.E
         o = view * E if offset is None else offset
         assert rgb.is_cuda and mask.is_cuda and K.is_cuda and K.dtype == torch.float64
         assert rgb.is_contiguous() and mask.is_contiguous() and K.is_contiguous()
+        if tuple(mask.shape) != tuple(rgb.shape[:3]) or rgb.shape[0] < n or rgb.shape[-1] != 3:
+            raise ValueError(f"rgb {tuple(rgb.shape)} / mask {tuple(mask.shape)}: expected [n,H,W,3] and [n,H,W] with n >= {n}")
         H, Wd = rgb.shape[1], rgb.shape[2]
         mode = 0
         if choose is not None:
             self.choose[o:o + n].copy_(choose.to(torch.int32))
             mode = 1
         L.check(self.lib.adp_preprocess(
-            L.ptr(rgb), self._dt(rgb, (L.DT_F32, L.DT_F64)), L.ptr(mask), self._dt(mask, (L.DT_U8, L.DT_F32, L.DT_F64)),
-            L.ptr(K), 9, n, H, Wd, self.S, self.P, (seed * 2 + view) & 0xFFFFFFFF, mode,
+            L.ptr(rgb), self._dt(rgb, (L.DT_U8, L.DT_F32, L.DT_F64)), L.ptr(mask), self._dt(mask, (L.DT_U8, L.DT_F32, L.DT_F64)),
+            L.ptr(K), 9, n, H, Wd, self.S, self.P, (seed * 2 + view) & 0xFFFFFFFF, mode, int(frame_id0),
             L.ptr(self.bbox_ws[o:]), L.ptr(self.win[o:]), L.ptr(self.Kp[o:]), L.ptr(self.valid[o:]), L.ptr(self.crops[o:]),
             L.ptr(self.choose[o:]), L.ptr(self.counts[o:]), self.stream), "preprocess")
 
@@ -599,60 +605,84 @@ class Engine:
                                         L.ptr(self.scale), L.ptr(self.rot64), L.ptr(self.trans), n, P, S, st), "fit_umeyama")
         mark("fit")
 
-    def run_chunk(self, K, rgb1, mask1, E1, rgb2, mask2, E2, seed=0, choose1=None, choose2=None, ransac_idx=None):
-        """Device tensors for n <= max_envs environments -> self.bbox[:n] ([n,8,3] f64, world frame)."""
+    def run_chunk(self, K, rgb1, mask1, E1, rgb2, mask2, E2, seed=0, choose1=None, choose2=None, ransac_idx=None, env0=0):
+        """Device tensors for n <= max_envs environments -> self.bbox[:n] ([n,8,3] f64, world frame).  ``env0``: global index
+        of the chunk's first environment (keys the device pixel sampler, so a result does not depend on the chunking)."""
         n = K.shape[0]
         assert n <= self.E
         # view 2 sits right behind view 1 (frame n): a partial chunk runs the backbone on exactly 2 n frames
-        self.preprocess(0, rgb1, mask1, K, n, seed, choose1)
-        self.preprocess(1, rgb2, mask2, K, n, seed, choose2, offset=n)
-        if n == self.E and self.use_graph and self.regress_pose:
-            # a full chunk is ~95 launches from fixed buffers: replayed as one CUDA graph (captured on the second full chunk,
-            # after every kernel has run once and set its attributes)
-            self.E1buf.copy_(E1.reshape(n, 16))
-            self.E2buf.copy_(E2.reshape(n, 16))
-            if self._graph is not None:
-                self._graph.replay()
-                self.lib.adp_launch_count_add(self._graph_launches)
+        self.preprocess(0, rgb1, mask1, K, n, seed, choose1, frame_id0=env0)
+        self.preprocess(1, rgb2, mask2, K, n, seed, choose2, offset=n, frame_id0=env0)
+        if self.use_graph and self.regress_pose:
+            # a chunk is ~95 launches from fixed buffers: replayed as one CUDA graph per chunk size (captured on the second
+            # appearance of a size, after every kernel has run once and set its attributes).  estimate() splits a batch into
+            # equal chunks, so a call sees at most two or three sizes.
+            self.E1buf[:n].copy_(E1.reshape(n, 16))
+            self.E2buf[:n].copy_(E2.reshape(n, 16))
+            g = self._graphs.get(n)
+            if g is None:
+                runs = self._chunk_runs.get(n, 0) + 1
+                self._chunk_runs[n] = runs
+                if runs == 2 and len(self._graphs) < 8:
+                    g = self._capture_graph(n)
+            if g is not None:
+                g[0].replay()
+                self.lib.adp_launch_count_add(g[1])
                 return self.bbox[:n]
-            self._full_chunks += 1
-            if self._full_chunks == 2:
-                self._capture_graph()
-                if self._graph is not None:
-                    self._graph.replay()
-                    self.lib.adp_launch_count_add(self._graph_launches)
-                    return self.bbox[:n]
-            self.run_backbone(self.F)
-            self.stereo(n, self.E1buf, self.E2buf)
+            self.run_backbone(2 * n)
+            self.stereo(n, self.E1buf, self.E2buf, o2=n)
             return self.bbox[:n]
         self.run_backbone(2 * n)
         self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed, o2=n)
         return self.bbox[:n]
 
-    def _capture_graph(self):
+    def _capture_graph(self, n):
         import warnings
         l0 = self.lib.adp_launch_count()
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.run_backbone(self.F)
-                self.stereo(self.E, self.E1buf, self.E2buf)
-            self._graph = g
-            self._graph_launches = int(self.lib.adp_launch_count() - l0)
-            self.lib.adp_launch_count_add(C.c_uint64(-self._graph_launches & 0xFFFFFFFFFFFFFFFF))   # capture itself launched nothing
+                self.run_backbone(2 * n)
+                self.stereo(n, self.E1buf, self.E2buf, o2=n)
+            launches = int(self.lib.adp_launch_count() - l0)
+            self.lib.adp_launch_count_add(C.c_uint64(-launches & 0xFFFFFFFFFFFFFFFF))   # capture itself launched nothing
+            self._graphs[n] = (g, launches)
+            return self._graphs[n]
         except Exception as e:      # stay on the eager launch path (same kernels), say so once
             warnings.warn(f"CUDA graph capture of a chunk failed ({e}); launching eagerly")
-            self._graph = None
             self.use_graph = False
+            return None
 
 
-    def check_error_flag(self):
-        v = int(self.err_flag.item())
-        if v:
-            raise L.AdpError(f"device pipeline watchdog tripped (code {v})")
+    def post_error_flag(self):
+        """Queue an asynchronous read of the device flags behind the work issued so far (no synchronisation)."""
+        self._err_host.copy_(self.err_flag, non_blocking=True)
+        self._err_event = torch.cuda.Event()
+        self._err_event.record(torch.cuda.current_stream(self.device))
+
+    def check_error_flag(self, wait=True):
+        """Raise if the watchdog or the fp16 range guard fired.  ``wait=False`` only looks at a read posted earlier by
+        :meth:`post_error_flag` that has already completed (the tensor-returning paths check one call late instead of
+        synchronising)."""
+        if self._err_event is None:
+            if not wait:
+                return
+            self.post_error_flag()
+        if not wait and not self._err_event.query():
+            return
+        self._err_event.synchronize()
+        self._err_event = None
+        code, rng = int(self._err_host[0]), int(self._err_host[1])
+        if code or rng:
+            self.err_flag.zero_()
+        if code:
+            raise L.AdpError(f"device pipeline watchdog tripped (code {code})")
+        if rng:
+            raise L.AdpError("non-finite backbone features: the activations of this checkpoint exceed the fp16 range; "
+                             "construct the estimator with precision='bf16x3'")
 
     def close(self):
-        self._graph = None           # the captured graph references the plans' parameter blocks
+        self._graphs = {}            # the captured graphs reference the plans' parameter blocks
         for p in self._plans:
             self.lib.adp_conv_tc_free(p)
         self._plans = []

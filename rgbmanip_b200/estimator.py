@@ -10,7 +10,16 @@ Deliberate deviations from the live reference, all documented in DESIGN.md:
   * inference runs in eval mode (the reference never calls ``.eval()``: SURVEY.md finding 0.3-1);
   * the random 1024-pixel subset is drawn by a counter-based hash on the device instead of the global numpy
     RNG (same distribution; pass ``choose=`` to replay the reference's stream exactly);
-  * ``draw_result`` (interface_v5.py:364) and the view-2 decode branch are dead work and are not computed.
+  * ``draw_result`` (interface_v5.py:364) and the view-2 decode branch are dead work and are not computed;
+  * float64 HOST frames are demoted to float32 while they are staged for upload.  The reference's float64 frames are the
+    simulator's float32 renders stored in ``np.zeros`` queues (rl_pose.py:94,196), for which this is lossless; for other
+    float64 data it moves the crop by <= 6e-8.  ``cfg["keep_float64"] = True`` (or passing float64 CUDA tensors) keeps
+    the cv2-in-double interpolation of interface_v5.py:148;
+  * uint8 RGB is accepted as a 4x smaller upload and means ``rgb / 255`` (torchvision ToTensor semantics).
+
+Inputs may be numpy arrays, torch host tensors (pinned or pageable) or CUDA tensors (zero-copy).  The batch is cut into equal
+chunks of at most ``max_envs`` environments; uploads of chunk i+1 overlap the kernels of chunk i, pageable host memory goes
+through pinned staging buffers, and a small first chunk (``cfg["first_chunk_envs"]``, default 16) starts the kernels early.
 """
 from __future__ import annotations
 
@@ -40,6 +49,26 @@ DEFAULT_BBOX = np.asarray([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1],
                            [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], dtype=np.float64) + 10.0
 
 
+def chunk_bounds(N, max_envs, first=0):
+    """[lo, hi) chunk boundaries of a batch of N environments: equal chunks of at most ``max_envs`` (every chunk size is replayed
+    as a CUDA graph; a short tail chunk would miss both the graph and the whole-wave sizing).  ``first`` > 0 (frames coming
+    from the host) sends a small chunk ahead, so the kernels start after ~first/N of the upload instead of a full chunk's."""
+    bounds, lo = [], 0
+    first = min(int(first), max_envs)
+    if first > 0 and N > max_envs:
+        bounds.append((0, first))
+        lo = first
+    rest = N - lo
+    if rest > 0:
+        nch = -(-rest // max_envs)
+        base, rem = divmod(rest, nch)
+        for i in range(nch):
+            hi = lo + base + (1 if i < rem else 0)
+            bounds.append((lo, hi))
+            lo = hi
+    return bounds
+
+
 class AdaPoseEstimator_v5(BasePoseEstimator):
 
     def __init__(self, env, cfg, logger, state_dict=None, device=None, max_envs=None, precision=None, **engine_kw):
@@ -63,76 +92,140 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         self._seed = int(cfg.get("sample_seed", 0))
         self._calls = 0
         self._copy_stream = None
-        self._range_checked = False
+        self._stage_bufs = {}
+        self._slot_free = [None, None]
+        self._keep_f64 = bool(cfg.get("keep_float64", False))
+        self._first_chunk = int(cfg.get("first_chunk_envs", 16))
 
     # -- helpers ---------------------------------------------------------------------------------
-    def _to_dev(self, a, dtype=None):
-        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-        if dtype is not None and t.dtype != dtype:
-            t = t.to(dtype)
-        return t.to(self.device, non_blocking=True).contiguous()
+    _RGB_OK = (torch.uint8, torch.float32, torch.float64)
+    _MASK_OK = (torch.uint8, torch.bool, torch.float32, torch.float64)
+
+    @staticmethod
+    def _as_tensor(a):
+        return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+
+    def _pinned(self, key, slot, shape, dtype):
+        """Reusable page-locked staging buffer (two slots per input: the host copy of chunk i+1 overlaps the upload of chunk i)."""
+        k = (key, slot)
+        buf = self._stage_bufs.get(k)
+        if buf is None or buf.dtype != dtype or buf.shape[1:] != tuple(shape[1:]) or buf.shape[0] < shape[0]:
+            buf = torch.empty((max(shape[0], self.estimator.E),) + tuple(shape[1:]), dtype=dtype).pin_memory()
+            self._stage_bufs[k] = buf
+        return buf[:shape[0]]
+
+    def _upload(self, key, slot, t, dtype=None):
+        """Host or device tensor -> device tensor of ``dtype`` on the current (copy) stream.  Pageable host memory goes
+        through the pinned staging buffers (a multi-threaded host copy that also converts the dtype), so the PCIe copy is
+        asynchronous and overlaps the previous chunk's kernels."""
+        if t.is_cuda:
+            t = t if dtype is None or t.dtype == dtype else t.to(dtype)
+            return t.to(self.device, non_blocking=True).contiguous()
+        dtype = dtype or t.dtype
+        if t.is_pinned() and t.dtype == dtype and t.is_contiguous():
+            return t.to(self.device, non_blocking=True)
+        buf = self._pinned(key, slot, t.shape, dtype)
+        buf.copy_(t)
+        return buf.to(self.device, non_blocking=True)
+
+    def _rgb_dtype(self, t):
+        if t.dtype == torch.float64 and not t.is_cuda and not self._keep_f64:
+            return torch.float32        # see the class docstring: float64 host frames are demoted while staging
+        if t.dtype in self._RGB_OK:
+            return t.dtype
+        if t.dtype in (torch.float16, torch.bfloat16):
+            return torch.float32
+        raise TypeError(f"unsupported image dtype {t.dtype}: pass float RGB in [0, 1] (what the simulator renders) or uint8 in [0, 255]")
 
     # -- reference API ---------------------------------------------------------------------------
-    def _stage_chunk(self, batches, choose, lo, hi, stream):
+    def _stage_chunk(self, batches, choose, lo, hi, stream, slot):
         """Issue the host->device copies of envs [lo, hi) on ``stream`` (no-ops for tensors already on the device)."""
         K_b, rgb1_b, m1_b, E1_b, rgb2_b, m2_b, E2_b = batches
+        ev_free = self._slot_free[slot]
+        if ev_free is not None:
+            ev_free.synchronize()       # the uploads that last used this slot's pinned buffers have completed
         with torch.cuda.stream(stream):
-            t = dict(K=self._to_dev(K_b[lo:hi], torch.float64), E1=self._to_dev(E1_b[lo:hi], torch.float64),
-                     E2=self._to_dev(E2_b[lo:hi], torch.float64), rgb1=self._to_dev(rgb1_b[lo:hi]),
-                     rgb2=self._to_dev(rgb2_b[lo:hi]), m1=self._to_dev(m1_b[lo:hi]), m2=self._to_dev(m2_b[lo:hi]))
-            if t["rgb1"].dtype not in (torch.float32, torch.float64):
-                t["rgb1"], t["rgb2"] = t["rgb1"].float(), t["rgb2"].float()
+            t = dict(K=self._upload("K", slot, K_b[lo:hi], torch.float64), E1=self._upload("E1", slot, E1_b[lo:hi], torch.float64),
+                     E2=self._upload("E2", slot, E2_b[lo:hi], torch.float64))
+            for name, src in (("rgb1", rgb1_b), ("rgb2", rgb2_b)):
+                t[name] = self._upload(name, slot, src[lo:hi], self._rgb_dtype(src))
+            for name, src in (("m1", m1_b), ("m2", m2_b)):
+                m = src[lo:hi]
+                if m.dtype not in self._MASK_OK:
+                    m = m != 0          # integer segmentation ids: any non-zero id is foreground (never a cast that can wrap to 0)
+                if m.dtype == torch.bool:
+                    m = m.view(torch.uint8)
+                t[name] = self._upload(name, slot, m)
             t["c1"] = t["c2"] = None
             if choose is not None:
-                t["c1"] = self._to_dev(choose[0][lo:hi], torch.int32)
-                t["c2"] = self._to_dev(choose[1][lo:hi], torch.int32)
+                t["c1"] = self._upload("c1", slot, choose[0][lo:hi], torch.int32)
+                t["c2"] = self._upload("c2", slot, choose[1][lo:hi], torch.int32)
             ev = torch.cuda.Event()
             ev.record(stream)
+            self._slot_free[slot] = ev
         return t, ev
 
+    def _chunk_bounds(self, N, on_host):
+        return chunk_bounds(N, self.estimator.E, self._first_chunk if on_host else 0)
+
     def estimate(self, camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
-                 rgb2_batch, view2_mask_batch, view2_extrinsic_batch, choose=None, return_tensor=False, ransac_idx=None):
+                 rgb2_batch, view2_mask_batch, view2_extrinsic_batch, choose=None, return_tensor=False, ransac_idx=None,
+                 env_offset=0, sample_seed=None):
+        """interface_v5.py:213-227.  Extra keyword arguments (all optional): ``choose`` / ``ransac_idx`` replay the reference's
+        random draws; ``return_tensor`` returns the CUDA tensor without the device->host copy; ``env_offset`` is the global
+        index of the first environment when the caller shards a larger batch (the device pixel sampler is keyed by
+        (seed, global env index), so shards reproduce the unsharded result); ``sample_seed`` fixes that seed for one call
+        (default: a per-call counter)."""
         eng = self.estimator
-        N = len(camera_intrinsic_batch)
+        eng.check_error_flag(wait=False)        # a flag read posted by an earlier tensor-returning call
+        batches = tuple(self._as_tensor(a) for a in (camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
+                                                     rgb2_batch, view2_mask_batch, view2_extrinsic_batch))
+        K_b, rgb1_b, m1_b, _, rgb2_b, m2_b, _ = batches
+        N = K_b.shape[0]
+        for rgb, m in ((rgb1_b, m1_b), (rgb2_b, m2_b)):
+            if rgb.dim() != 4 or rgb.shape[-1] != 3 or tuple(m.shape) != tuple(rgb.shape[:3]) or rgb.shape[0] != N:
+                raise ValueError(f"expected rgb [N,H,W,3] and mask [N,H,W] for N = {N}, got {tuple(rgb.shape)} and {tuple(m.shape)}")
+        if choose is not None:
+            choose = tuple(self._as_tensor(c) for c in choose)
+            for c in choose:
+                if c.shape[0] != N or c.shape[1] != eng.P or bool((c < 0).any()) or bool((c >= eng.S * eng.S).any()):
+                    raise ValueError(f"choose must be [N, {eng.P}] pixel indices in [0, {eng.S * eng.S})")
         out = torch.empty((N, 8, 3), dtype=torch.float64, device=self.device)
         self._calls += 1
-        batches = (camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
-                   rgb2_batch, view2_mask_batch, view2_extrinsic_batch)
+        seed = (self._seed + 7919 * self._calls) if sample_seed is None else int(sample_seed)
         with torch.cuda.device(self.device):
             compute = torch.cuda.current_stream(self.device)
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(self.device)
             copy = self._copy_stream
             copy.wait_stream(compute)
-            bounds = [(lo, min(N, lo + eng.E)) for lo in range(0, N, eng.E)]
-            nxt = self._stage_chunk(batches, choose, *bounds[0], copy) if bounds else None
+            bounds = self._chunk_bounds(N, on_host=not rgb1_b.is_cuda)
+            nxt = self._stage_chunk(batches, choose, *bounds[0], copy, 0) if bounds else None
             for i, (lo, hi) in enumerate(bounds):
                 t, ev = nxt
                 compute.wait_event(ev)
                 for v in t.values():          # allocated on the copy stream, consumed on the compute stream
                     if isinstance(v, torch.Tensor) and v.is_cuda:
                         v.record_stream(compute)
-                # the next chunk's upload overlaps this chunk's kernels
-                nxt = self._stage_chunk(batches, choose, *bounds[i + 1], copy) if i + 1 < len(bounds) else None
                 ridx = None
                 if ransac_idx is not None:      # [N,128,5] sample indices of the RANSAC fit (branch B parity replay)
-                    ridx = self._to_dev(ransac_idx[lo:hi], torch.int32)
+                    ridx = self._as_tensor(ransac_idx[lo:hi]).to(torch.int32).to(self.device)
                 box = eng.run_chunk(t["K"], t["rgb1"], t["m1"], t["E1"], t["rgb2"], t["m2"], t["E2"],
-                                    seed=self._seed + 7919 * self._calls + lo, choose1=t["c1"], choose2=t["c2"], ransac_idx=ridx)
+                                    seed=seed, choose1=t["c1"], choose2=t["c2"], ransac_idx=ridx, env0=int(env_offset) + lo)
                 out[lo:hi].copy_(box)
-                if not self._range_checked:
-                    # fp16x2 keeps activations in IEEE half: with the first real batch make sure nothing left its range
-                    # (an overflow turns into inf/NaN features and, silently, into sentinel boxes)
-                    self._range_checked = True
-                    if eng.precision == "fp16x2" and not bool(torch.isfinite(eng.feat[:2 * (hi - lo)]).all()):
-                        from ._lib import AdpError
-                        raise AdpError("non-finite backbone features: the activations of this checkpoint exceed the fp16 range; "
-                                       "construct the estimator with precision='bf16x3'")
+                # this chunk's kernels are queued: the host-side staging of the next chunk (and its upload) overlaps them
+                nxt = self._stage_chunk(batches, choose, *bounds[i + 1], copy, (i + 1) & 1) if i + 1 < len(bounds) else None
+            # watchdog + fp16 range flag (set by the last backbone layer on inf/NaN features, every chunk): read with the boxes
+            eng.post_error_flag()
             if return_tensor:
-                return out
+                return out              # checked at the next call (or by an explicit check_error_flag())
             res = out.cpu().numpy()
         eng.check_error_flag()
         return res
+
+    def check_error_flag(self):
+        """Synchronise and raise if the pipeline watchdog or the fp16 range guard fired (the tensor-returning paths defer it)."""
+        self.estimator.check_error_flag()
 
     def estimate_tensor(self, *args, **kw):
         """Same as :meth:`estimate` but returns the [N,8,3] float64 CUDA tensor without the device->host copy."""

@@ -33,4 +33,7 @@ def install():
 
 
 def uninstall():
-    sys.modules.pop(TARGET, None)
+    mod = sys.modules.pop(TARGET, None)
+    pkg = sys.modules.get("models.pose_estimator.AdaPose")
+    if pkg is not None and mod is not None and getattr(pkg, "interface_v5", None) is mod:
+        delattr(pkg, "interface_v5")      # `from models.pose_estimator.AdaPose import interface_v5` resolves to the real module again

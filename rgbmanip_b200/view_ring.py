@@ -95,11 +95,13 @@ class ViewRing:
                 hi = min(N, lo + eng.F)
                 n = hi - lo
                 rgb_d = self._dev(color[lo:hi])
-                if rgb_d.dtype not in (torch.float32, torch.float64):
+                if rgb_d.dtype not in (torch.uint8, torch.float32, torch.float64):     # uint8 = value / 255 (ToTensor), in the kernel
+                    if not rgb_d.dtype.is_floating_point:
+                        raise TypeError(f"unsupported image dtype {rgb_d.dtype}: float RGB in [0, 1] or uint8 in [0, 255]")
                     rgb_d = rgb_d.float()
                 mask_d = self._dev(mask[lo:hi])
                 if mask_d.dtype not in (torch.uint8, torch.bool, torch.float32, torch.float64):
-                    mask_d = mask_d.to(torch.uint8)
+                    mask_d = (mask_d != 0).to(torch.uint8)       # segmentation ids: a cast could wrap 256 to 0
                 K_d = self._dev(K[lo:hi], torch.float64)
                 eng.preprocess(0, rgb_d, mask_d, K_d, n, seed=(self.estimator._seed + 104729 * self._adds + lo))
                 eng.run_backbone(n)                       # ONE view: frames [0, n)

@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol(lib_path):
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     lib.adp_abi_version.restype = ctypes.c_int
-    assert lib.adp_abi_version() == 2
+    from rgbmanip_b200 import _lib
+    assert lib.adp_abi_version() == _lib.ADP_ABI_VERSION == int(re.search(r"#define ADP_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "adapose_b200.h")).read()).group(1))
 
 
 def test_binding_covers_the_header(lib_path):

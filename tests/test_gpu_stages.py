@@ -398,13 +398,14 @@ def test_maxpool_psp_upsample_fp16_planes(G):
 
 
 # ------------------------------------------------------------------------------------------------ preprocess
-def _preprocess(G, rgb, mask, K, choose=None, seed=0):
+def _preprocess(G, rgb, mask, K, choose=None, seed=0, frame_id0=0):
     lib = L.load()
     Fn = rgb.shape[0]
     dev = G.DEV
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     rgb_d, mask_d, K_d = t(rgb), t(mask), t(K.astype(np.float64))
     dt = {torch.float32: L.DT_F32, torch.float64: L.DT_F64, torch.bool: L.DT_U8, torch.uint8: L.DT_U8}
+    H, W = rgb.shape[1], rgb.shape[2]
     out = dict(bbox=torch.zeros((Fn, 4), dtype=torch.int32, device=dev), win=torch.zeros((Fn, 4), dtype=torch.int32, device=dev),
                Kp=torch.zeros((Fn, 9), dtype=torch.float64, device=dev), valid=torch.zeros(Fn, dtype=torch.uint8, device=dev),
                crops=torch.zeros((Fn, 224, 224, 3), device=dev), choose=torch.zeros((Fn, 1024), dtype=torch.int32, device=dev),
@@ -413,8 +414,8 @@ def _preprocess(G, rgb, mask, K, choose=None, seed=0):
     if choose is not None:
         out["choose"].copy_(torch.from_numpy(choose).to(torch.int32))
         mode = 1
-    L.check(lib.adp_preprocess(L.ptr(rgb_d), dt[rgb_d.dtype], L.ptr(mask_d), dt[mask_d.dtype], L.ptr(K_d), 9, Fn, 480, 640, 224,
-                               1024, seed, mode, L.ptr(out["bbox"]), L.ptr(out["win"]), L.ptr(out["Kp"]), L.ptr(out["valid"]),
+    L.check(lib.adp_preprocess(L.ptr(rgb_d), dt[rgb_d.dtype], L.ptr(mask_d), dt[mask_d.dtype], L.ptr(K_d), 9, Fn, H, W, 224,
+                               1024, seed, mode, frame_id0, L.ptr(out["bbox"]), L.ptr(out["win"]), L.ptr(out["Kp"]), L.ptr(out["valid"]),
                                L.ptr(out["crops"]), L.ptr(out["choose"]), L.ptr(out["counts"]), G.stream()), "preprocess")
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}
@@ -455,6 +456,9 @@ def test_preprocess_sampling_is_uniform_and_seeded(G):
     c = _preprocess(G, batch.rgb1, batch.mask1, batch.K, seed=2)["choose"]
     np.testing.assert_array_equal(a, b)
     assert (a != c).any()
+    # the sampler is keyed by (seed, frame id): frames 2..3 launched on their own with frame_id0 = 2 draw the same subsets
+    d = _preprocess(G, batch.rgb1[2:], batch.mask1[2:], batch.K[2:], seed=1, frame_id0=2)["choose"]
+    np.testing.assert_array_equal(d, a[2:])
     # selection probability must not depend on the position: compare the mean rank of the picks with n/2
     win = None
     for e in range(4):

@@ -1,0 +1,26 @@
+"""Host-side logic of the estimator that needs no GPU: the chunk schedule of estimate()."""
+import pytest
+
+from rgbmanip_b200.estimator import chunk_bounds
+
+
+@pytest.mark.parametrize("N,E,first", [(0, 74, 0), (1, 74, 0), (74, 74, 16), (75, 74, 0), (128, 74, 0), (128, 74, 16), (1024, 74, 0),
+                                       (1024, 74, 16), (4096, 74, 16), (40, 7, 0), (256, 48, 16), (5, 4, 16)])
+def test_chunk_bounds_cover_the_batch_in_equal_chunks(N, E, first):
+    b = chunk_bounds(N, E, first)
+    assert [lo for lo, _ in b] == [0] * (N > 0) + [hi for _, hi in b[:-1]]          # contiguous, in order
+    assert (b[-1][1] if b else 0) == N
+    sizes = [hi - lo for lo, hi in b]
+    assert all(0 < s <= E for s in sizes)
+    body = sizes[1:] if (first and N > E) else sizes
+    if first and N > E:
+        assert sizes[0] == min(first, E)                  # the small chunk that starts the kernels while the upload continues
+    assert max(body, default=0) - min(body, default=0) <= 1      # equal chunks: no short tail off the graph / whole-wave path
+    assert len(set(sizes)) <= 3                           # at most three CUDA graphs per call
+    assert len(body) == -(-sum(body) // E) if body else True     # and no more chunks than necessary
+
+
+def test_chunk_bounds_examples():
+    assert chunk_bounds(128, 74, 0) == [(0, 64), (64, 128)]                        # an 8-GPU shard of 1024 envs, device-resident
+    assert chunk_bounds(128, 74, 16) == [(0, 16), (16, 72), (72, 128)]             # the same shard uploaded from the host
+    assert chunk_bounds(8, 8, 16) == [(0, 8)]

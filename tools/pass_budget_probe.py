@@ -1,0 +1,118 @@
+"""Per-layer-group MMA pass budget of the fp16x2 backbone.
+
+Emulates the device path inside the CPU oracle: fp16 activation operands + storage everywhere, fp16 3-D stage, and for the
+backbone conv groups listed in `single` the weights rounded to ONE fp16 plane (one MMA pass) instead of hi + lo (two).
+Reports the end-to-end error against the fp32 oracle per variant, so the groups that tolerate a single pass can be read off.
+
+    python tools/pass_budget_probe.py [n_envs] [seed]
+"""
+import itertools
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import adapose_oracle as O  # noqa: E402
+from rgbmanip_b200 import synth, weights  # noqa: E402
+
+n_envs = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+sd = weights.init_state_dict(seed)
+cfg = {"img_size": 224, "direct_regression": True}
+batch = synth.make_batch(n_envs, seed=seed * 5, special=False)
+hf = torch.float16
+
+GROUPS = ["conv1", "layer1", "layer2", "layer3", "layer4", "up_1", "up_2", "up_3", "final"]
+# GFLOP per frame: what a saved pass is worth
+GFLOP = {"conv1": 0.24, "layer1": 1.39, "layer2": 1.75, "layer3": 10.69, "layer4": 20.55, "up_1": 14.80, "up_2": 3.70, "up_3": 3.70,
+         "final": 0.21}
+
+
+def group_of(x, w):
+    co, ci, kh, kw = w.shape
+    hin = x.shape[-1]
+    if kh == 7:
+        return "conv1"
+    if kh == 1 and co == 32:
+        return "final"
+    if kh == 1 and ci == 512 and co == 128:
+        return None                      # pyramid 1x1 convs: CUDA cores, fp32
+    if ci == 1024:
+        return "up_1"
+    if ci == 256 and co == 64:
+        return "up_2"
+    if ci == 64 and co == 64 and hin == 224:
+        return "up_3"
+    if co == 64:
+        return "layer1"
+    if co == 128:
+        return "layer2"
+    if co == 256:
+        return "layer3"
+    if co == 512:
+        return "layer4"
+    raise KeyError((tuple(x.shape), tuple(w.shape)))
+
+
+def run(single=(), emulate=True):
+    c2, c3, ct3 = F.conv2d, F.conv3d, F.conv_transpose3d
+
+    def conv2d(x, w, *a, **k):
+        if not emulate:
+            return c2(x, w, *a, **k)
+        g = group_of(x, w)
+        if g is None:
+            return c2(x, w, *a, **k)
+        xw = x.half().float()
+        if g in single:
+            w = w.half().float()
+        else:                            # hi + lo: 22 mantissa bits
+            wh = w.half().float()
+            w = wh + (w - wh).half().float()
+        return c2(xw, w, *a, **k)
+
+    r3 = (lambda t: t.half().float()) if emulate else (lambda t: t)
+    O.F.conv2d = conv2d
+    O.F.conv3d = lambda x, w, *a, **k: c3(r3(x), r3(w), *a, **k)
+    O.F.conv_transpose3d = lambda x, w, *a, **k: ct3(r3(x), r3(w), *a, **k)
+
+    def q(name, x):
+        if not emulate or name in ("logits", "fused_pts", "cr.prob"):
+            return x
+        return x.half().float()
+    tap = O.Taps(q=q)
+    res = []
+    try:
+        np.random.seed(0)
+        for e in range(n_envs):
+            d = {}
+            box = O.predict(sd, cfg, batch.K[e], batch.rgb1[e], batch.mask1[e], batch.E1[e], batch.rgb2[e], batch.mask2[e],
+                            batch.E2[e], both_views=False, tap=tap, details=d)
+            res.append(box)
+    finally:
+        O.F.conv2d, O.F.conv3d, O.F.conv_transpose3d = c2, c3, ct3
+    return res
+
+
+def errors(out, ref):
+    errs = np.array([O.parity_errors(b1, b0, batch.K[e], batch.E1[e], min_z=0.5) for e, (b0, b1) in enumerate(zip(ref, out))])
+    return errs.max(0), np.sqrt((errs ** 2).mean(0))
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    ref = run(emulate=False)
+    print(f"fp32 oracle: {time.time() - t0:.1f} s for {n_envs} envs (weights seed {seed})", flush=True)
+    variants = [("none (fp16x2 everywhere)", ())] + [(g, (g,)) for g in GROUPS] + [("ALL single pass", tuple(GROUPS))]
+    extra = [a for a in sys.argv[3:]]
+    for e in extra:
+        variants.append((e, tuple(e.split("+"))))
+    print(f"{'single-pass groups':34s} {'GFLOP saved':>11s} | max: px deg ctr-mm corner-mm | rms: px ctr-mm corner-mm")
+    for name, single in variants:
+        mx, rms = errors(run(single), ref)
+        saved = sum(GFLOP[g] for g in single)
+        print(f"{name:34s} {saved:11.2f} | {mx[0]:.4f} {mx[1]:.5f} {mx[2]:.4f} {mx[3]:.4f} | {rms[0]:.4f} {rms[2]:.4f} {rms[3]:.4f}", flush=True)
