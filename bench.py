@@ -1,6 +1,6 @@
 """Headline benchmark: pose estimates / second at num_envs=1024 (BASELINE.json), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--num-envs 1024] [--precision fp16x2|bf16x3|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--num-envs 1024] [--precision fp16f8|fp16x2|bf16x3|bf16]
 
 A step = one pass of the hot path (preprocess -> backbone x2 views -> plane-sweep volume -> 3-D U-Net -> decode ->
 fit) over ALL num_envs environments of synthetic input.  With N > 1 (torchrun) the environments are sharded
@@ -8,10 +8,17 @@ contiguously over the ranks (no data-path collective) and the per-env poses are 
 stays num_envs, i.e. strong scaling, as the metric is defined at num_envs=1024.
 
 `value`  : device-resident inputs, CUDA-event timing of exactly K steps, max over ranks.
-`e2e`    : the same metric through AdaPoseEstimator_v5.estimate() with pinned HOST inputs, host->device copies and the
-           device->host read of the boxes inside the timed region.
-`--impl reference`: the CPU oracle (a port of the reference's per-env loop; the reference itself does not travel to the
-           GPU box) timed on the host cores on a bounded sample of the same workload.
+`e2e`    : the same metric through AdaPoseEstimator_v5.estimate() with pinned HOST float32 inputs, host->device copies and
+           the device->host read of the boxes inside the timed region.  `e2e_variants` repeats it with what the RL caller
+           really passes (pageable float64 numpy, rl_pose.py:194-218) and with uint8 frames.
+`parity_in_bench` : before anything is timed, the 8 golden environments of tests/golden/e2e.npz (boxes produced by the
+           reference itself) run through THIS estimator object -- bench chunk size, CUDA-graph replay -- and must agree to
+           0.5 px / 0.5 deg / 1 mm.  `shard_identity`: after the timed region the sharded result (all ranks, all-gathered) is
+           compared with a one-rank run of the same environments on rank 0.
+`configs`: the other BASELINE.json configurations (single-view NOCS at N=64, the 4-view mug ring at N=256, the
+           observation + actor step of the N=4096 / 8-GPU configuration as this rank's share) -- reported beside the headline.
+`--impl reference`: the reference's own CPU implementation (oracle/_ref: a run-time copy of the unmodified reference staged
+           by __graft_entry__.build(); the oracle port if that copy is absent) timed on the host cores on a bounded sample.
 """
 from __future__ import annotations
 
@@ -32,16 +39,21 @@ sys.path.insert(0, ROOT)
 from rgbmanip_b200 import synth, weights  # noqa: E402
 
 GF_BACKBONE_PER_FRAME = 57.0177e9       # SURVEY.md A.3 (2 * MACs of every conv of the PSPNet backbone)
-GF_BACKBONE_TC_PER_FRAME = 57.0177e9 - 0.2360e9 - 0.1156e9 - 0.0128e9 - 0.0066e9   # minus conv1, layer2.0 strided convs, psp
+GF_BACKBONE_TC_PER_FRAME = 57.0177e9 - 0.0128e9 - 0.0066e9     # minus the pyramid 1x1 convs (CUDA cores); everything else is tcgen05
 GF_COSTREG_PER_VIEW = 24.4506e9
-DECODE_BYTES_PER_VIEW = 1708092
-# ncu capture of the 40 backbone tc_conv_kernel launches of one chunk (fp16x2: 148 frames; bf16x3: 128 frames): dram__bytes_read + write summed over the launch
-# group, and sm__pipe_tensor_cycles_active time-weighted over it.  fp16x2: profiles/r01_chunk_by_kernel.csv;
-# bf16x3: profiles/r01_bf16x3_backbone_tc_summary.csv
-NCU_TC = {"fp16x2": (11141.8e6 / 148, 0.720, "profiles/r01_chunk_by_kernel.csv"),
-          "bf16x3": (18958.8e6 / 128, 0.712, "profiles/r01_bf16x3_backbone_tc_summary.csv")}
+# HBM-bound stages, algorithmic bytes per environment (DESIGN.md section 5 derives them):
+#   volume + 3-D U-Net, materialised-volume variant: 302.7 MB per reference view
+#   decode gather: 3 x 3 x 26 voxels x 16 B of the last U-Net tensor per sampled pixel (the `prob` conv is evaluated only
+#   there) + 24 depths x 4 bilinear corners x 128 B of fp32 source features + 128 B reference features + outputs
+BYTES_VOLUME_COSTREG_PER_ENV = 302.7e6
+BYTES_DECODE_GATHER_PER_ENV = 1024 * (3 * 3 * 26 * 16 + 24 * 4 * 128 + 128 + 4 + 4 + 2 * 128 * 2)
+# "profile constants": figures of an ncu capture of one chunk (not of this run); the launch list they come from is committed
+NCU_PROFILE = {"fp16x2": {"dram_bytes_per_frame": 11141.8e6 / 148, "tensor_pipe_active": 0.720, "src": "profiles/r01_chunk_by_kernel.csv"},
+               "bf16x3": {"dram_bytes_per_frame": 18958.8e6 / 128, "tensor_pipe_active": 0.712, "src": "profiles/r01_bf16x3_backbone_tc_summary.csv"}}
 CFG = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
        "n_pts": 1024, "direct_regression": True, "real_world": False}
+DEFAULT_BBOX = np.asarray([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], dtype=np.float64) + 10.0
+TOL_PX, TOL_DEG, TOL_MM = 0.5, 0.5, 1.0
 
 
 def workload_name(n):
@@ -96,7 +108,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -108,18 +120,137 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
-def cpu_oracle_rate(n_envs, seed=0):
-    """The oracle's per-env loop (= the reference's algorithm) on the host cores -> (estimates/s, threads, seconds)."""
-    from oracle import adapose_oracle as O
+# ------------------------------------------------------------------------------------------------ box metrics (checker)
+def _box_pose(box):
+    c = box.mean(0)
+    ax = np.stack([box[0] - box[2], box[0] - box[4], box[0] - box[1]], 1)      # corner order of utils.py:40-58
+    return c, ax / np.maximum(np.linalg.norm(ax, axis=0, keepdims=True), 1e-12)
+
+
+def box_errors(a, b, K, E1, min_z=0.5):
+    """(keypoint reprojection error [px] of the 8 corners + centre in view 1 (points nearer than min_z to the camera plane are
+    compared in mm only: f/z diverges there, see tests/test_gpu_e2e.py MIN_Z), rotation [deg], centre [mm], max corner [mm])."""
+    ca, Ra = _box_pose(a)
+    cb, Rb = _box_pose(b)
+
+    def proj(pts):
+        pc = (E1[:3, :3] @ pts.T).T + E1[:3, 3]
+        return (K @ pc.T).T[:, :2] / pc[:, 2:3], pc[:, 2]
+    pa, za = proj(np.vstack([a, ca[None]]))
+    pb, zb = proj(np.vstack([b, cb[None]]))
+    ok = (za > min_z) & (zb > min_z)
+    px = float(np.abs(pa[ok] - pb[ok]).max()) if ok.any() else 0.0
+    cosang = np.clip((np.trace(Ra.T @ Rb) - 1.0) / 2.0, -1.0, 1.0)
+    return px, float(np.degrees(np.arccos(cosang))), float(np.linalg.norm(ca - cb) * 1e3), float(np.linalg.norm(a - b, axis=1).max() * 1e3)
+
+
+def parity_check(est, copies):
+    """The golden environments of tests/golden/e2e.npz through the bench-configured estimator (its chunk size, graph replay)."""
+    gpath = os.path.join(ROOT, "tests", "golden", "e2e.npz")
+    if not os.path.exists(gpath):
+        return {"skipped": "tests/golden/e2e.npz not found"}
+    g = np.load(gpath)
+    base = synth.make_batch(8, seed=0)
+    c1 = np.zeros((8, 1024), np.int32); c2 = np.zeros((8, 1024), np.int32)
+    for e in range(8):
+        if g["valid"][e]:
+            c1[e], c2[e] = g[f"env{e}_choose1"], g[f"env{e}_choose2"]
+    idx = np.arange(copies) % 8
+    args = [torch.from_numpy(np.ascontiguousarray(a[idx])).to(est.device) for a in base.args()]
+    args[2], args[5] = args[2].to(torch.uint8), args[5].to(torch.uint8)
+    choose = (c1[idx], c2[idx])
+    eng = est.estimator
+    for _ in range(3):                   # eager, capture, replay
+        boxes = est.estimate(*args, choose=choose)
+    worst = np.zeros(4)
+    sentinel_ok = True
+    for i, e in enumerate(idx):
+        if not g["valid"][e]:
+            sentinel_ok &= bool(np.array_equal(boxes[i], DEFAULT_BBOX))
+            continue
+        worst = np.maximum(worst, box_errors(boxes[i], g["boxes"][e], base.K[e], base.E1[e]))
+    # the gate is north_star's three quantities (keypoints, rotation, translation = box centre); the worst corner distance is
+    # reported beside them (it adds the size error of ~1 m random-init boxes)
+    ok = bool(worst[0] < TOL_PX and worst[1] < TOL_DEG and worst[2] < TOL_MM and sentinel_ok)
+    out = {"envs": int(copies), "fixture": "tests/golden/e2e.npz (boxes from the unmodified reference, 8 envs tiled)",
+           "chunk_sizes": sorted({hi - lo for lo, hi in est._chunk_bounds(copies, False)}),
+           "graph_replayed": bool(eng._graphs), "max_px": float(worst[0]), "max_deg": float(worst[1]), "max_centre_mm": float(worst[2]),
+           "max_corner_mm": float(worst[3]), "sentinels_bit_exact": sentinel_ok,
+           "tolerance": {"px": TOL_PX, "deg": TOL_DEG, "mm": TOL_MM}, "ok": ok}
+    if not ok:
+        raise SystemExit("parity_in_bench failed: " + json.dumps(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_rate(n_envs, seed=0):
+    """The reference's per-env loop on the host cores -> (estimates/s, threads, seconds, kind)."""
     torch.set_num_threads(os.cpu_count())
-    sd = weights.init_state_dict(0)
     batch = synth.make_batch(n_envs + 1, seed=seed, special=False)
+    from oracle import ref_stage
+    if ref_stage.root() is not None:
+        est, _ = ref_stage.load(seed=0)
+        with torch.no_grad():
+            np.random.seed(0)
+            est.estimate(*batch.slice(0, 1).args())          # warm-up env
+            t0 = time.perf_counter()
+            est.estimate(*batch.slice(1, n_envs + 1).args())
+            dt = time.perf_counter() - t0
+        return n_envs / dt, torch.get_num_threads(), dt, "reference"
+    from oracle import adapose_oracle as O
+    sd = weights.init_state_dict(0)
     np.random.seed(0)
-    O.estimate(sd, CFG, *batch.slice(0, 1).args())          # warm-up env
+    O.estimate(sd, CFG, *batch.slice(0, 1).args())
     t0 = time.perf_counter()
     O.estimate(sd, CFG, *batch.slice(1, n_envs + 1).args())
     dt = time.perf_counter() - t0
-    return n_envs / dt, torch.get_num_threads(), dt
+    return n_envs / dt, torch.get_num_threads(), dt, "port"
+
+
+def cpu_single_view(n_frames=3):
+    """BASELINE configs[0]: adapose_drawer forward, batch 1, ONE view, PyTorch on CPU: preprocessing + PSPNet + NOCS head of the
+    reference (the full estimate needs two views: interface_v5.py:256-257) -> frames/s."""
+    torch.set_num_threads(os.cpu_count())
+    batch = synth.make_batch(n_frames + 1, seed=3, special=False)
+    from oracle import ref_stage
+    if ref_stage.root() is None:
+        return None
+    est, _ = ref_stage.load(seed=0)
+    net = est.estimator.module
+
+    def one(e):
+        view, choose, _, _ = est.prepare_model_input(batch.rgb1[e], batch.mask1[e], batch.K[e], 224)
+        with torch.no_grad():
+            feat = net.img_extractor(view[None].float())
+            emb = feat.view(1, feat.shape[1], -1)[:, :, torch.from_numpy(np.asarray(choose)).long()]
+            return net.nocs_head(net.instance_color(emb))
+    np.random.seed(0)
+    one(0)
+    t0 = time.perf_counter()
+    for e in range(1, n_frames + 1):
+        one(e)
+    dt = time.perf_counter() - t0
+    return {"value": n_frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "what": "BASELINE configs[0]: batch 1, one 480x640 view -> crop, PSPNet, instance_color + nocs_head on the CPU", "frames": n_frames}
+
+
+def cpu_legs_subprocess(n_envs):
+    """The CPU legs run in a child process that cannot see the GPUs: the reference moves its tensors with .cuda() and wraps the
+    net in nn.DataParallel, so with a visible device it would not be the CPU arm any more."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-sample", "--cpu-sample", str(n_envs)],
+                       env=env, capture_output=True, text=True, timeout=900)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("CPU legs failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+
+
+def run_cpu_sample(args):
+    rate, threads, dt, kind = cpu_reference_rate(args.cpu_sample)
+    print(json.dumps({"rate": rate, "threads": threads, "dt": dt, "kind": kind, "single_view": cpu_single_view()}), flush=True)
 
 
 def run_reference(args, rank, world):
@@ -127,18 +258,20 @@ def run_reference(args, rank, world):
         return
     sample = 6
     vals = []
+    kind = threads = None
     for i in range(args.warmup + args.steps):
-        rate, threads, dt = cpu_oracle_rate(sample, seed=i)
+        rate, threads, dt, kind = cpu_reference_rate(sample, seed=i)
         if i >= args.warmup:
             vals.append((rate, dt))
     rate = sample * len(vals) / sum(d for _, d in vals)
+    note = ("the unmodified reference (oracle/_ref) on the CPU: per-env loop of AdaPoseEstimator_v5.estimate, eval mode"
+            if kind == "reference" else "reference's per-env CPU loop (oracle port, torch CPU fp32 eval mode)")
     line = {"metric": "pose estimates/sec at num_envs=1024", "value": rate, "unit": "estimates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in vals) / len(vals),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": workload_name(args.num_envs),
-                       "note": "reference's per-env CPU loop (oracle port, torch CPU fp32 eval mode); cost is linear in num_envs"},
-            "cpu_baseline": {"value": rate, "unit": "estimates/s", "cores": threads, "kind": "port",
+            "config": {"workload": workload_name(args.num_envs), "note": note + "; cost is linear in num_envs"},
+            "cpu_baseline": {"value": rate, "unit": "estimates/s", "cores": threads, "kind": kind,
                              "sample": f"{sample} envs per step of the {args.num_envs}-env workload (per-env loop, linear)"},
             "e2e": {"value": rate, "unit": "estimates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -157,16 +290,23 @@ def instrumented_pass(eng, n_env, E1, E2):
 
     for name, op in eng.backbone_ops:
         timed(name, getattr(op, "kind", "aux"), lambda op=op: op(2 * n_env))
-    lib, L = eng.lib, sys.modules["rgbmanip_b200._lib"]
-    timed("stereo_all", "stereo", lambda: eng.stereo(n_env, E1, E2))
-    for name, op in eng.cr_ops:
-        timed(name, getattr(op, "kind", "aux") + "3d", lambda op=op: op(n_env))
+    marks = []
+
+    def mark(name):
+        e = ev(); e.record(); marks.append((name, e))
+    start = ev(); start.record()
+    eng.stereo(n_env, E1, E2, mark=mark, o2=n_env)
     torch.cuda.synchronize()
     out = {}
     for name, kind, a, b in rec:
         d = out.setdefault(kind, {"ms": 0.0, "launches": 0})
         d["ms"] += a.elapsed_time(b); d["launches"] += 1
-    return out, {name: a.elapsed_time(b) for name, kind, a, b in rec}
+    per_op = {name: a.elapsed_time(b) for name, kind, a, b in rec}
+    prev = start
+    for name, e in marks:
+        per_op["stereo." + name] = prev.elapsed_time(e)
+        prev = e
+    return out, per_op
 
 
 def main():
@@ -178,60 +318,61 @@ def main():
     ap.add_argument("--num-envs", type=int, default=1024)
     ap.add_argument("--chunk", type=int, default=74,
                     help="envs per chunk; 74 = num_SMs / 2: 148 frames per backbone launch = whole waves of 128-row tiles on 148 SMs")
-    ap.add_argument("--precision", default="fp16x2")
+    ap.add_argument("--precision", default="fp16f8")
     ap.add_argument("--unique", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
-    ap.add_argument("--ring", action="store_true", help="also time the device view ring (one new view per controller step, "
-                                                        "cached features for the other; SURVEY 8(f)-1) and add it as `view_ring`")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU legs (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configurations and the e2e variants")
     args = ap.parse_args()
-    rank, world, local = dist_setup(args.gpus)
+    if args.impl in ("reference", "cpu-sample"):
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""         # the CPU arm must not see a GPU (see cpu_legs_subprocess); set before CUDA initialises
+    if args.impl == "cpu-sample":
+        run_cpu_sample(args)
+        return
+    rank, world, local = dist_setup()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
     import torch.distributed as dist
     from rgbmanip_b200 import _lib
+    from rgbmanip_b200.dist import shard_range
     from rgbmanip_b200.estimator import AdaPoseEstimator_v5
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     lib = _lib.load()
     N = args.num_envs
-    from rgbmanip_b200.dist import shard_range
     lo, hi, per = shard_range(N, rank, world)
     n_loc = hi - lo
-    # synthetic inputs: `unique` distinct envs tiled over this rank's shard, resident in HBM and mirrored in pinned host memory
-    base = synth.make_batch(args.unique, seed=100 + rank, special=True)
-    idx = np.arange(n_loc) % args.unique
-    host = {}
-    for name, arr in zip(("K", "rgb1", "mask1", "E1", "rgb2", "mask2", "E2"), base.args()):
+    # synthetic inputs: `unique` distinct envs (the same on every rank), global env g = unique env g % unique; this rank's shard is
+    # resident in HBM and mirrored in pinned host memory
+    base = synth.make_batch(args.unique, seed=100, special=True)
+    order = ("K", "rgb1", "mask1", "E1", "rgb2", "mask2", "E2")
+    base_t = {}
+    for name, arr in zip(order, base.args()):
         t = torch.from_numpy(np.ascontiguousarray(arr))
-        if name.startswith("mask"):
-            t = t.to(torch.uint8)
-        host[name] = t[idx].contiguous().pin_memory()
+        base_t[name] = t.to(torch.uint8) if name.startswith("mask") else t
+    idx = (lo + np.arange(n_loc)) % args.unique
+    host = {k: v[idx].contiguous().pin_memory() for k, v in base_t.items()}
     devt = {k: v.to(dev) for k, v in host.items()}
     est = AdaPoseEstimator_v5(None, dict(CFG), None, state_dict=weights.init_state_dict(0), device=dev, max_envs=args.chunk,
                               precision=args.precision)
     eng = est.estimator
-    order = ("K", "rgb1", "mask1", "E1", "rgb2", "mask2", "E2")
     gathered = torch.zeros((world * per, 8, 3), dtype=torch.float64, device=dev)
 
-    def step_device():
-        out = est.estimate(*[devt[k] for k in order], return_tensor=True)
-        if world > 1:
-            pad = out if n_loc == per else torch.cat([out, out.new_zeros((per - n_loc, 8, 3))])
-            dist.all_gather_into_tensor(gathered, pad)
-            return gathered
-        return out
+    def gather(out):
+        if world == 1:
+            return out
+        pad = out if n_loc == per else torch.cat([out, out.new_zeros((per - n_loc, 8, 3))])
+        dist.all_gather_into_tensor(gathered, pad)
+        return gathered[:N]
 
-    def step_host():
-        out = est.estimate(*[host[k] for k in order], return_tensor=True)
-        if world > 1:
-            pad = out if n_loc == per else torch.cat([out, out.new_zeros((per - n_loc, 8, 3))])
-            dist.all_gather_into_tensor(gathered, pad)
-            out = gathered
-        return out.cpu()
+    def step_device():
+        return gather(est.estimate(*[devt[k] for k in order], return_tensor=True, env_offset=lo))
+
+    def step_host(src=host):
+        return gather(est.estimate(*[src[k] for k in order], return_tensor=True, env_offset=lo)).cpu()
 
     def barrier():
         if world > 1:
@@ -259,6 +400,10 @@ def main():
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall, launches
 
+    # ---- parity gate inside the measurement: the golden envs through this very estimator (chunk size, graph replay)
+    parity = parity_check(est, 2 * args.chunk) if rank == 0 else None
+    barrier()
+
     sampler = ClockSampler(local)
     sampler.start()
     ms, wall, launches = timed(step_device, args.steps, args.warmup)
@@ -267,83 +412,194 @@ def main():
     eng.check_error_flag()
 
     e2e = None
+    h2d = sum(host[k].numel() * host[k].element_size() for k in order)
     if not args.no_e2e:
-        ms_h, wall_h, _ = timed(step_host, max(1, args.steps), 1)
-        h2d = sum(host[k].numel() * host[k].element_size() for k in order)
+        ms_h, wall_h, _ = timed(step_host, max(1, args.steps), 2)
         e2e = {"value": N * max(1, args.steps) / wall_h, "unit": "estimates/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(n_loc * 24 * 8), "timed": "host wall clock around estimate(); pinned host inputs"}
+               "d2h_bytes_per_step": int(n_loc * 24 * 8), "timed": "host wall clock around estimate() + all-gather + D2H; pinned fp32 host inputs",
+               "chunks": [h - l for l, h in est._chunk_bounds(n_loc, True)]}
 
-    ring_info = None
-    if args.ring:
-        from rgbmanip_b200.view_ring import ViewRing
-        ring = ViewRing(est, n_loc, 5)
-        views = [{"camera0": {"Color": devt["rgb1"], "Mask": devt["mask1"], "Intrinsic": devt["K"], "Extrinsic": devt["E1"]}},
-                 {"camera0": {"Color": devt["rgb2"], "Mask": devt["mask2"], "Intrinsic": devt["K"], "Extrinsic": devt["E2"]}}]
-        pose = torch.zeros((n_loc, 7), dtype=torch.float64, device=dev)
-        state = {"t": 0}
-
-        def step_ring():
-            ring.add_view(views[state["t"] % 2], pose)
-            ring.accumulate_steps += 1
-            state["t"] += 1
-            return ring.get_estimation(return_tensor=True)
-
-        ms_r, _, _ = timed(step_ring, max(2, args.steps), 3)
-        ring_info = {"value": N * max(2, args.steps) / (ms_r / 1e3), "unit": "estimates/s", "ms_per_step": ms_r / max(2, args.steps),
-                     "what": "controller step = add_view (1 new frame per env: preprocess + backbone) + get_estimation (stereo head on "
-                             "cached features), frames resident in HBM", "cache_gb": ring.feat.numel() * 6 / 1e9}
-        del ring
+    # ---- sharded result == one-rank result (same sampler seed; the sampler is keyed by the global env index)
+    SEED = 424242
+    mine = gather(est.estimate(*[devt[k] for k in order], return_tensor=True, env_offset=lo, sample_seed=SEED)).clone()
+    identity = None
+    if rank == 0:
+        if world > 1:
+            gidx = np.arange(N) % args.unique
+            full = [base_t[k][gidx].to(dev) for k in order]
+            alone = est.estimate(*full, return_tensor=True, sample_seed=SEED)
+            del full
+            what = f"{world}-rank sharded + all-gathered boxes vs a 1-rank run of the same {N} envs on rank 0"
+        else:
+            alone = est.estimate(*[host[k] for k in order], return_tensor=True, sample_seed=SEED)     # other chunking (host path)
+            what = ("device-resident run (equal chunks) vs the host-input run (small first chunk + equal chunks) of the same "
+                    f"{N} envs: an environment's box does not depend on how the batch is cut")
+        diff = (mine - alone).abs()
+        diff = torch.where(torch.isnan(diff), torch.zeros_like(diff), diff)
+        identity = {"what": what, "envs": int(N), "bit_identical_envs": int((diff.reshape(N, -1).max(1).values == 0).sum()),
+                    "max_abs_diff_m": float(diff.max()), "checksum": float(torch.nan_to_num(mine).sum())}
         torch.cuda.empty_cache()
+    barrier()
 
-    # per-kernel-class timing of one chunk, live, on the launching stream
+    variants, configs = {}, {}
+    if not args.no_extra:
+        # ---- e2e with the RL caller's real input format: pageable float64 numpy (rl_pose.py:194-218), bounded to 256 envs
+        nv = min(n_loc, 256)
+        if nv:
+            f64 = {k: (host[k][:nv].numpy().astype(np.float64) if k.startswith(("rgb", "mask")) else host[k][:nv].numpy().copy()) for k in order}
+            run = lambda: est.estimate(*[f64[k] for k in order])
+            run()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                run()
+            dt = (time.perf_counter() - t0) / 2
+            variants["pageable_float64_numpy"] = {"value": nv * world / dt, "unit": "estimates/s", "num_envs": nv * world, "host_bytes_per_step": int(sum(v.nbytes for v in f64.values())),
+                                                  "note": "what rl_pose.py passes; staged through pinned buffers and demoted to float32 on the way (host-copy bound)"}
+            del f64
+            u8 = {k: ((host[k] * 255).round().to(torch.uint8).pin_memory() if k.startswith("rgb") else host[k]) for k in order}
+            ms_u, wall_u, _ = timed(lambda: step_host(u8), 2, 1)
+            variants["pinned_uint8"] = {"value": N * 2 / wall_u, "unit": "estimates/s", "num_envs": N,
+                                        "h2d_bytes_per_step": int(sum(u8[k].numel() * u8[k].element_size() for k in order))}
+            del u8
+        # ---- BASELINE configs[1]: N = 64, one view per env: backbone + NOCS
+        n64 = min(64, n_loc)
+        if n64:
+            a = [devt["K"][:n64], devt["rgb1"][:n64], devt["mask1"][:n64]]
+            f = lambda: est.estimate_nocs_single_view(*a)
+            f(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                f()
+            dt = (time.perf_counter() - t0) / 5
+            configs["single_view_nocs_n64"] = {"value": n64 / dt, "unit": "frames/s", "ms_per_step": dt * 1e3, "num_envs": n64,
+                                               "what": "BASELINE configs[1]: 64 envs, one view each: preprocess + PSPNet + NOCS head, device-resident frames, NOCS read back"}
+        # ---- BASELINE configs[2] (N = 256 mug ring, 4 views) and configs[4] (this rank's share of the N = 4096 observation step)
+        from rgbmanip_b200.actor import DeviceActor
+        from rgbmanip_b200.view_ring import ViewRing
+
+        def ring_bench(n_ring, task, with_actor):
+            est.cfg["task_name"] = task
+            ring = ViewRing(est, n_ring, 5)
+            ridx = torch.arange(n_ring, device=dev) % n_loc
+            views = [{"camera0": {"Color": devt[f"rgb{v}"][ridx], "Mask": devt[f"mask{v}"][ridx], "Intrinsic": devt["K"][ridx],
+                                  "Extrinsic": devt[f"E{v}"][ridx]}} for v in (1, 2)]
+            pose = torch.zeros((n_ring, 7), dtype=torch.float64, device=dev)
+            actor = None
+            if with_actor:
+                g = torch.Generator().manual_seed(0)
+                dims = [60, 96, 96, 32, 12]                    # cfg/controller/rl.yaml pi_hid_sizes, 12 actions
+                sd = {}
+                for i, (a_, b_) in enumerate(zip(dims[:-1], dims[1:])):
+                    sd[f"actor.{2 * i}.weight"] = torch.randn((b_, a_), generator=g) / a_ ** 0.5
+                    sd[f"actor.{2 * i}.bias"] = torch.zeros(b_)
+                actor = DeviceActor(sd, ring, activation="elu")
+            state = {"t": 0}
+
+            def step():
+                ring.add_view(views[state["t"] % 2], pose)
+                ring.accumulate_steps = min(ring.accumulate_steps + 1, ring.max_steps)
+                state["t"] += 1
+                out = ring.get_estimation(return_tensor=True)
+                if actor is not None:
+                    actor.act_inference()
+                return out
+            for _ in range(4):
+                step()                               # 4 views in the ring
+            ms_r, _, _ = timed(step, 3, 0)
+            pairs = ring.pair_slots()
+            res = {"ms_per_step": ms_r / 3, "value": n_ring * world * 3 / (ms_r / 1e3), "unit": "estimates/s", "num_envs": n_ring * world,
+                   "views_in_ring": int((ring.avail > 0).sum(0).max()), "cache_gb": ring.feat.numel() * 6 / 1e9}
+            if not with_actor:       # the reference-equivalent cost: both paired views through the whole network again
+                a2 = [views[0]["camera0"]["Intrinsic"], views[0]["camera0"]["Color"], views[0]["camera0"]["Mask"], views[0]["camera0"]["Extrinsic"],
+                      views[1]["camera0"]["Color"], views[1]["camera0"]["Mask"], views[1]["camera0"]["Extrinsic"]]
+                rec = lambda: est.estimate(*a2, return_tensor=True)[:, [0, 2, 4, 6, 1, 3, 5, 7]]
+                ms_c, _, _ = timed(rec, 3, 2)
+                res["recomputed"] = {"ms_per_step": ms_c / 3, "value": n_ring * world * 3 / (ms_c / 1e3), "unit": "estimates/s"}
+            del ring, actor, views
+            torch.cuda.empty_cache()
+            est.cfg["task_name"] = CFG["task_name"]
+            return res
+        n_mug = max(1, 256 // world)
+        configs["mug_ring_n256"] = dict(ring_bench(n_mug, "mugs", False),
+                                        what="BASELINE configs[2]: adapose_mug, 4 views per env in the device ring, pairing rule of rl_pose.py:199-208, "
+                                             "stereo estimate + fit + mug corner permutation; `value` = one new frame per env with the cached "
+                                             "features of the other view, `recomputed` = both paired frames through the whole network (reference-equivalent)")
+        n_obs = 4096 // 8                               # per-GPU share of the 8-GPU configuration
+        configs["obs_step_n4096_share"] = dict(ring_bench(n_obs, "one_drawer_cabinet", True),
+                                               what=f"BASELINE configs[4]: open_drawer observation step at num_envs=4096 on 8 GPUs = {n_obs} envs per GPU; this line "
+                                                    f"runs that share on each of the {world} rank(s): add_view (preprocess + backbone of the new frame) + "
+                                                    "get_estimation (stereo head on cached features) + get_observation + actor forward (60-96-96-32-12 ELU)")
+
+    # ---- per-kernel-class timing of one chunk, live, on the launching stream
     n_chunk = min(eng.E, n_loc)
     E1c = devt["E1"][:n_chunk].contiguous(); E2c = devt["E2"][:n_chunk].contiguous()
-    est.estimate(*[devt[k][:n_chunk] for k in order], return_tensor=True)
-    # three instrumented passes, per-op median: a single pass right after the e2e leg catches the GPU mid clock ramp
+    eng.run_chunk(devt["K"][:n_chunk], devt["rgb1"][:n_chunk], devt["mask1"][:n_chunk], E1c, devt["rgb2"][:n_chunk], devt["mask2"][:n_chunk], E2c)
+    # three instrumented passes, per-op median: a single pass right after the previous leg catches the GPU mid clock ramp
     passes = [instrumented_pass(eng, n_chunk, E1c, E2c) for _ in range(3)]
     per_op = {k: float(np.median([p[1][k] for p in passes])) for k in passes[0][1]}
     classes = {k: {"ms": float(np.median([p[0][k]["ms"] for p in passes])), "launches": passes[0][0][k]["launches"]} for k in passes[0][0]}
     pk = peaks()
     frames = 2 * n_chunk
-    npass = eng.npass
+    npass = {"fp16f8": 1.5, "fp16x2": 2, "bf16x3": 3, "bf16": 1}[eng.precision]
     tc_ms = classes.get("tc", {}).get("ms", 0.0)
     tc_flops = GF_BACKBONE_TC_PER_FRAME * frames
     roof = None
+    prof = NCU_PROFILE.get(eng.precision)
     if tc_ms > 0:
         ach = tc_flops / (tc_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "tc_conv_kernel (tcgen05 implicit-GEMM, backbone 2-D convs)", "achieved": ach,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": NCU_TC[eng.precision][0] * frames if eng.precision in NCU_TC else None,
-                "traffic_note": "dram__bytes_read+write summed over the launch group, ncu capture of one chunk scaled to this chunk "
-                                f"({NCU_TC[eng.precision][2] if eng.precision in NCU_TC else 'no capture'})",
-                "tensor_pipe_active_ncu": NCU_TC[eng.precision][1] if eng.precision in NCU_TC else None,
+                "traffic": prof["dram_bytes_per_frame"] * frames if prof else None,
+                "traffic_note": ("PROFILE CONSTANT, not measured in this run: dram__bytes_read+write of the launch group in the ncu capture "
+                                 f"{prof['src']}, scaled to this chunk") if prof else "no ncu capture of this precision mode committed yet",
+                "tensor_pipe_active_ncu": prof["tensor_pipe_active"] if prof else None,
                 "peak_source": pk["src"] + " (sustained: timed inside a long step)",
                 "algorithmic_flops_per_launch_group": tc_flops, "launches": classes["tc"]["launches"],
                 "tensor_pipe_work_frac": ach * npass / pk["tf_sustained"],
                 "note": f"algorithmic FLOPs (SURVEY A.3) / summed CUDA-event time of the {classes['tc']['launches']} launches of one chunk "
-                        f"({frames} frames); precision {eng.precision} issues {npass} MMA pass(es) per algorithmic FLOP"}
-    dec_ms = per_op.get("stereo_all", 0.0) - sum(v for k, v in per_op.items() if k.startswith("cr."))
+                        f"({frames} frames); precision {eng.precision} issues {npass} fp16-equivalent MMA pass(es) per algorithmic FLOP"
+                        + (" (the wide layers run the low-order weight term as an fp8 MMA at twice the rate)" if eng.precision == "fp16f8" else "")}
+    cr_ms = sum(v for k, v in per_op.items() if k.startswith("stereo.cr."))
+    vol_ms = per_op.get("stereo.volume", 0.0)
+    dg_ms = per_op.get("stereo.decode_gather", 0.0)
+    hbm = {}
+    if cr_ms + vol_ms > 0:
+        gbs = BYTES_VOLUME_COSTREG_PER_ENV * n_chunk / ((cr_ms + vol_ms) / 1e3) / 1e9
+        hbm["volume_costreg"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                 "ms_per_chunk": cr_ms + vol_ms, "algorithmic_bytes_per_env": BYTES_VOLUME_COSTREG_PER_ENV,
+                                 "variant": "materialised fp16 volume (SURVEY 8(d): 302.7 MB per reference view)"}
+    if dg_ms > 0:
+        gbs = BYTES_DECODE_GATHER_PER_ENV * n_chunk / (dg_ms / 1e3) / 1e9
+        hbm["decode_gather"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                "ms_per_chunk": dg_ms, "algorithmic_bytes_per_env": BYTES_DECODE_GATHER_PER_ENV,
+                                "note": "bytes the gather formulation must touch (16 B voxels of the last U-Net tensor, fp32 feature corners); "
+                                        "most of it is L2-resident, so this is an L2-path figure quoted against the HBM peak"}
     kernels = {k: {"ms_per_chunk": v["ms"], "launches": v["launches"]} for k, v in classes.items()}
     kernels["chunk_envs"] = n_chunk
-    kernels["costreg_tflops"] = (GF_COSTREG_PER_VIEW * n_chunk / (sum(v for k, v in per_op.items() if k.startswith("cr.")) / 1e3) / 1e12
-                                 if any(k.startswith("cr.") for k in per_op) else None)
-    kernels["volume_decode_fit_ms"] = dec_ms
+    kernels["costreg_tflops"] = GF_COSTREG_PER_VIEW * n_chunk / (cr_ms / 1e3) / 1e12 if cr_ms > 0 else None
+    kernels["stereo_ms"] = {k[7:]: v for k, v in per_op.items() if k.startswith("stereo.")}
 
     if rank == 0:
-        cpu_rate, threads, cpu_dt = (0.0, 0, 0.0) if args.no_cpu else cpu_oracle_rate(args.cpu_sample)
+        cpu = {"value": 0.0, "unit": "estimates/s", "cores": 0, "kind": "skipped", "sample": "--no-cpu"}
+        if not args.no_cpu:
+            c = cpu_legs_subprocess(args.cpu_sample)
+            cpu = {"value": c["rate"], "unit": "estimates/s", "cores": c["threads"], "kind": c["kind"],
+                   "sample": f"{args.cpu_sample} envs of the workload through the reference's per-env loop on the host cores ({c['dt']:.1f} s)"}
+            if c.get("single_view") is not None:
+                configs["cpu_single_view_b1"] = c["single_view"]
         line = {"metric": "pose estimates/sec at num_envs=1024", "value": value, "unit": "estimates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "fp16" if eng.precision == "fp16x2" else "bf16", "data": f"synthetic ({args.unique} seeded envs tiled to {N})",
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if eng.precision.startswith("bf16") else "fp16",
+                "data": f"synthetic ({args.unique} seeded envs tiled to {N})",
                 "config": {"workload": workload_name(N),
                            "precision": eng.precision, "chunk_envs": eng.E, "sharding": f"env-sharded dp{world}, NCCL all-gather of poses",
                            "l2": "inputs (>= 8 GB per step) exceed the 126 MB L2; no explicit flush needed",
-                           "sampling": "device hash sampler for the 1024-pixel subset"},
-                "roofline": roof, "cpu_baseline": {"value": cpu_rate, "unit": "estimates/s", "cores": threads, "kind": "port",
-                                                   "sample": f"{args.cpu_sample} envs of the workload through the oracle's per-env loop ({cpu_dt:.1f} s)"},
+                           "sampling": "device hash sampler for the 1024-pixel subset, keyed by the global env index"},
+                "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels,
+                "parity_in_bench": parity, "shard_identity": identity, "e2e_variants": variants, "configs": configs,
                 "wall_s_timed_region": wall}
-        if ring_info is not None:
-            line["view_ring"] = ring_info
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

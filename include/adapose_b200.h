@@ -12,7 +12,9 @@
  * nothing synchronises.  Activations are channels-last 16-bit planes: one IEEE-half plane (`f16 = 1`: the default "fp16x2"
  * backbone and the 3-D stage) or a bf16 `hi` plane plus an optional `lo` plane (value = hi + lo, "bf16x3" split precision);
  * fp32 tensors are plain channels-last.  `npass` of adp_conv_tc_plan selects the MMA passes per K step: 1 = A W,
- * 2 = A W_hi + A W_lo (fp16 activations, fp16 weights split in two planes), 3 = A_hi W_hi + A_lo W_hi + A_hi W_lo (bf16).
+ * 2 = A W_hi + A W_lo (fp16 activations, fp16 weights split in two planes), 3 = A_hi W_hi + A_lo W_hi + A_hi W_lo (bf16),
+ * 4 = A W_hi in fp16 + the low-order term as an fp8 MMA at twice the rate: e4m3(A / 2) (the activation's q8 twin) x
+ * e4m3(W_lo 2^16) (passed as w_lo, one byte per weight), joined through the MMA's 2^-15 accumulator scale.
  * No torch types appear.
  */
 #ifndef ADAPOSE_B200_H
@@ -48,6 +50,8 @@ typedef struct adp_act {      /* channels-last activation [B, D, H, W, C]; D == 
     void* lo;                 /* bf16 or NULL */
     int32_t B, D, H, W, C;
     int32_t f16;              /* 1: 16-bit planes are IEEE half (3-D cost-regularisation stage), no lo plane */
+    void* q8;                 /* optional fp8 (e4m3) twin of an f16 activation holding value / 2, or NULL: the A operand of the
+                                 low-order pass of npass = 4 layers; written by the producing layer (adp_epilogue.out_q8) */
 } adp_act;
 
 typedef struct adp_tc_geom {  /* non-default geometry of a tcgen05 conv: explicit tap table and grid mapping */
@@ -76,18 +80,9 @@ typedef struct adp_epilogue { /* y = act(scale * acc + bias [+ res]) [+ res]  ->
     int32_t out_cstride;      /* channel pitch of out_hi/out_lo (0 = Cout): lets a layer write a column range of a wider tensor */
     int32_t out_coff;         /* first channel of that range (torch.cat of network_v5.py:488 without a copy) */
     int32_t bias_per_batch;   /* 1: bias is [B, Cout] (the per-env global feature term of pose_mlp2, network_v5.py:491-493) */
+    void* out_q8;             /* optional fp8 (e4m3) twin of out_hi holding value / 2 (same channel pitch / offset), or NULL: see adp_act.q8 */
     int32_t check_finite;     /* 1: OR bit 0 into err_flag[1] when an output value is inf/NaN (fp16 range guard, set on the last backbone layer) */
 } adp_epilogue;
-
-typedef struct adp_direct_conv {   /* generic CUDA-core convolution (strided / tiny-channel / transposed layers) */
-    const void* in_hi; const void* in_lo; const float* in_f32;   /* exactly one of in_hi / in_f32 */
-    int32_t B, Di, Hi, Wi, Cin;
-    int32_t Do, Ho, Wo, Cout;
-    int32_t kd, kh, kw, sd, sh, sw, pd, ph, pw, dil, transposed;
-    int32_t f16;              /* 16-bit planes (in/res/out) are IEEE half instead of bf16 */
-    const float* w;           /* fp32 [taps][Cin][Cout] */
-    adp_epilogue ep;
-} adp_direct_conv;
 
 typedef struct adp_decode_weights {   /* fp32, each matrix transposed to [K][N]; names follow the reference state_dict */
     const float *ic_w, *ic_b, *nh0_w, *nh0_b, *nh1_w, *nh1_b, *nh2_w, *nh2_b, *np0_w, *np0_b, *np1_w, *np1_b;
@@ -122,13 +117,11 @@ ADP_API int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void
  * [1] range flag (see adp_epilogue.check_finite).  The same two-word flag is passed to every *_run entry point. */
 ADP_API int adp_conv_tc_run(adp_conv_plan* plan, int batch, int32_t* err_flag, void* stream);
 ADP_API void adp_conv_tc_free(adp_conv_plan* plan);
-ADP_API int adp_conv_direct(const adp_direct_conv* desc, int batch, void* stream);
 ADP_API int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, void* stream);                 /* pspnet.py:39 */
 /* feat_cstride: channel pitch of feat (0 = dense); the engine lets layer4's last conv write straight into the first 512
  * channels of the 1024-channel concat tensor, adp_psp_fill_priors writes the resized priors behind them (:92-94). */
 ADP_API int adp_psp_priors(const adp_act* feat, int feat_cstride, const float* w, float* pooled, float* priors, int batch, void* stream); /* :84-90 */
 ADP_API int adp_psp_fill_priors(const float* priors, const adp_act* out, int coff, int batch, void* stream);
-ADP_API int adp_psp_concat_up(const adp_act* feat, const float* priors, const adp_act* out, int batch, void* stream);   /* :92-94,105 */
 ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream);                   /* pspnet.py:105 */
 /* fp32 crops [F,S,S,3] -> space-to-depth(2) activation [F,S/2,S/2,16] (channel = (py*2+px)*3 + c, 12 used): the 7x7/2
  * stem conv (pspnet.py:37) then is a 4x4 stride-1 conv over 16 channels and runs on the tcgen05 kernel. */
@@ -163,23 +156,19 @@ ADP_API void adp_tconv_free(adp_tconv_plan* plan);
 ADP_API int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src,
                               float* Mw, const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B,
                               void* stream);
-/* feat_*: [B,H,W,32] fp32, or IEEE half when feat_f16 != 0.  vol: [B,D,H,W,32], or the channel-chunk-planar layout
- * [B,D,H,4,W,8] when planar != 0 (what adp_conv0_run reads: one contiguous 16-byte-per-pixel run per chunk and row). */
+/* feat_*: [B,H,W,32] IEEE half (the fp16 twin of the feature map written by the last backbone layer, adp_epilogue.out_h16).
+ * vol: [B,D,H,W,32], IEEE half when f16 != 0 else bf16. */
 ADP_API int adp_build_volume(const void* feat_ref, const void* feat_src, const float* Mw, const float* depths, void* vol,
-                     int B, int D, int H, int W, int C, int f16, int feat_f16, int planar, void* stream);
+                     int B, int D, int H, int W, int C, int f16, void* stream);
 
 /* --- decode + heads: network_v5.py:432-465,486-499; rotation_utils.py:4-27 ----------------------------------- */
-/* x11_format: ADP_LAYOUT_F16 (IEEE half instead of bf16) | ADP_LAYOUT_S2D (x11 stored [B,D/2,S/2,S/2,64], see adp_conv0_plan_create) */
-ADP_API int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
-               const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth,
-               float* pf1, float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused,
-               int B, int S, int D, int P, int regress_pose, int x11_format, void* stream);
-
-/* decode split for the tensor-core MLP path: adp_decode_gather = the gather-bound part (depth logits at the sampled pixels,
+/* adp_decode_gather = the gather-bound part (depth logits at the sampled pixels = the `prob` conv evaluated only there,
  * softmax / soft-argmax, depth-guided fusion; network_v5.py:449-465) writing the MLP inputs as bf16 hi/lo
  * (xfeat [B,P,32], xcat [B,P,96] columns 0..31); the per-point MLPs (network_v5.py:432-444,486-493) then run as 1x1
- * convolutions through adp_conv_tc_*; adp_colsum = mean over points (sums), adp_pose_gbias = per-env bias of pose_mlp2's
- * first layer, adp_rot_head = rotation MLP + Ortho6d2Mat (rotation_utils.py:18-27). */
+ * convolutions through adp_conv_tc_*; adp_colsum = sum over points (fixed-order, no atomics), adp_pose_gbias = per-env bias of
+ * pose_mlp2's first layer, adp_rot_head = rotation MLP + Ortho6d2Mat (rotation_utils.py:18-27).
+ * x11_format: ADP_LAYOUT_F16 (IEEE half instead of bf16) | ADP_LAYOUT_S2D (x11 stored [B,D/2,S/2,S/2,64], see adp_conv0_plan_create).
+ * x11 == NULL selects the single-view mode (backbone + NOCS of one frame, network_v5.py:432-444): only xfeat is written. */
 ADP_API int adp_decode_gather(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                       const int32_t* choose, const uint8_t* valid, const float* prob_w, float* depth, void* xfeat_hi,
                       void* xfeat_lo, void* xcat_hi, void* xcat_lo, float* dbg_logits, float* dbg_fused, int B, int S, int D,

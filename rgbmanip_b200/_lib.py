@@ -22,7 +22,7 @@ class AdpError(RuntimeError):
 
 
 class Act(C.Structure):
-    _fields_ = [("hi", vp), ("lo", vp), ("B", i32), ("D", i32), ("H", i32), ("W", i32), ("C", i32), ("f16", i32)]
+    _fields_ = [("hi", vp), ("lo", vp), ("B", i32), ("D", i32), ("H", i32), ("W", i32), ("C", i32), ("f16", i32), ("q8", vp)]
 
 
 class TcGeom(C.Structure):
@@ -34,16 +34,7 @@ class TcGeom(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("scale", vp), ("bias", vp), ("prelu", C.c_float), ("act", i32), ("res_after_act", i32),
                 ("res_hi", vp), ("res_lo", vp), ("res_cstride", i32), ("out_hi", vp), ("out_lo", vp), ("out_f32", vp), ("out_h16", vp),
-                ("out_cstride", i32), ("out_coff", i32), ("bias_per_batch", i32), ("check_finite", i32)]
-
-
-class DirectConv(C.Structure):
-    _fields_ = [("in_hi", vp), ("in_lo", vp), ("in_f32", vp),
-                ("B", i32), ("Di", i32), ("Hi", i32), ("Wi", i32), ("Cin", i32),
-                ("Do", i32), ("Ho", i32), ("Wo", i32), ("Cout", i32),
-                ("kd", i32), ("kh", i32), ("kw", i32), ("sd", i32), ("sh", i32), ("sw", i32),
-                ("pd", i32), ("ph", i32), ("pw", i32), ("dil", i32), ("transposed", i32), ("f16", i32),
-                ("w", vp), ("ep", Epilogue)]
+                ("out_cstride", i32), ("out_coff", i32), ("bias_per_batch", i32), ("out_q8", vp), ("check_finite", i32)]
 
 
 DECODE_FIELDS = ["ic_w", "ic_b", "nh0_w", "nh0_b", "nh1_w", "nh1_b", "nh2_w", "nh2_b", "np0_w", "np0_b", "np1_w", "np1_b",
@@ -68,11 +59,9 @@ SIGNATURES = {
                                    C.POINTER(Epilogue), C.POINTER(TcGeom), C.c_int]),
     "adp_conv_tc_run": (C.c_int, [vp, C.c_int, vp, vp]),
     "adp_conv_tc_free": (None, [vp]),
-    "adp_conv_direct": (C.c_int, [C.POINTER(DirectConv), C.c_int, vp]),
     "adp_maxpool3x3s2": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
     "adp_psp_priors": (C.c_int, [C.POINTER(Act), C.c_int, vp, vp, vp, C.c_int, vp]),
     "adp_psp_fill_priors": (C.c_int, [vp, C.POINTER(Act), C.c_int, C.c_int, vp]),
-    "adp_psp_concat_up": (C.c_int, [C.POINTER(Act), vp, C.POINTER(Act), C.c_int, vp]),
     "adp_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
     "adp_pack_s2d": (C.c_int, [vp, C.POINTER(Act), C.c_int, C.c_int, vp]),
     "adp_conv0_plan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, vp, vp, C.c_int, C.c_int]),
@@ -82,9 +71,7 @@ SIGNATURES = {
     "adp_tconv_run": (C.c_int, [vp, C.c_int, vp, vp]),
     "adp_tconv_free": (None, [vp]),
     "adp_warp_matrices": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
-    "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
-    "adp_decode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DecodeWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_build_volume": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "adp_decode_gather": (C.c_int, [vp] * 15 + [C.c_int] * 5 + [vp]),
     "adp_colsum": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "adp_pose_gbias": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),

@@ -7,7 +7,6 @@
 #include "../../include/adapose_b200.h"
 #include "common.cuh"
 #include <stdlib.h>
-#include "direct_conv.cuh"
 #include "tc_conv.cuh"
 
 namespace adp {
@@ -26,14 +25,13 @@ void set_last_error(const char* fmt, ...) {
 int maxpool3x3s2(const Act& in, const Act& out, int batch, cudaStream_t stream);
 int psp_priors(const Act& feat, int feat_cs, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream);
 int psp_fill_priors(const float* priors, const Act& out, int coff, int batch, cudaStream_t stream);
-int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream);
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream);
 int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t stream);
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
                    int S, int P, uint32_t seed, int choose_mode, int frame_id0, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream);
 int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, int f16, int feat_f16, int planar, cudaStream_t stream);
+                 int W, int C, int f16, cudaStream_t stream);
 int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
                   const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream);
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
@@ -72,18 +70,12 @@ int tconv_plan(TconvPlan* pl, const Act& in, const bf16* w, int Cout, const floa
                int res_cs, bf16* out, int flags, int num_sms);
 int tconv_run(TconvPlan* pl, int batch, int* err_flag, cudaStream_t stream);
 
-struct DecodeWeights;
-struct DecodeArgs;
-int decode_run_c(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
-                 const int* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth, float* pf1,
-                 float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P,
-                 int regress_pose, int x11_f16, cudaStream_t stream);
-
 static Act to_act(const adp_act* a) {
     Act r;
     r.hi = reinterpret_cast<bf16*>(a->hi);
     r.lo = reinterpret_cast<bf16*>(a->lo);
     r.B = a->B; r.D = a->D; r.H = a->H; r.W = a->W; r.C = a->C; r.f16 = a->f16;
+    r.q8 = reinterpret_cast<uint8_t*>(a->q8);
     return r;
 }
 
@@ -146,6 +138,12 @@ int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, 
     p.out_hi = reinterpret_cast<bf16*>(ep->out_hi); p.out_lo = reinterpret_cast<bf16*>(ep->out_lo);
     p.out_f32 = ep->out_f32;
     p.out_h16 = reinterpret_cast<__half*>(ep->out_h16);
+    p.out_q8 = reinterpret_cast<uint8_t*>(ep->out_q8);
+    if (p.out_q8 && (pl->layer.BN < 32 || cout % 32 != 0 || ep->out_lo || !in->f16)) {
+        set_last_error("out_q8 needs fp16 activations and Cout %% 32 == 0 (coalesced epilogue, 32-channel chunks)");
+        delete pl;
+        return ADP_ERR_ARG;
+    }
     p.out_cs = ep->out_cstride ? ep->out_cstride : cout; p.out_coff = ep->out_coff; p.bias_per_batch = ep->bias_per_batch;
     p.check_finite = ep->check_finite;
     {
@@ -168,23 +166,6 @@ int adp_conv_tc_run(adp_conv_plan* plan, int batch, int32_t* err_flag, void* str
 
 void adp_conv_tc_free(adp_conv_plan* plan) { delete plan; }
 
-int adp_conv_direct(const adp_direct_conv* d, int batch, void* stream) {
-    ADP_CHECK_ARG(d, "null descriptor");
-    DirectConvParams p;
-    p.in_hi = reinterpret_cast<const bf16*>(d->in_hi); p.in_lo = reinterpret_cast<const bf16*>(d->in_lo); p.in_f32 = d->in_f32;
-    p.B = d->B; p.Di = d->Di; p.Hi = d->Hi; p.Wi = d->Wi; p.Cin = d->Cin;
-    p.Do = d->Do; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
-    p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
-    p.pd = d->pd; p.ph = d->ph; p.pw = d->pw; p.dil = d->dil; p.transposed = d->transposed; p.f16 = d->f16;
-    p.w = d->w;
-    p.scale = d->ep.scale; p.bias = d->ep.bias; p.prelu = d->ep.prelu; p.act = d->ep.act; p.res_after_act = d->ep.res_after_act;
-    p.res_hi = reinterpret_cast<const bf16*>(d->ep.res_hi); p.res_lo = reinterpret_cast<const bf16*>(d->ep.res_lo);
-    p.res_cs = d->ep.res_cstride;
-    p.out_hi = reinterpret_cast<bf16*>(d->ep.out_hi); p.out_lo = reinterpret_cast<bf16*>(d->ep.out_lo); p.out_f32 = d->ep.out_f32;
-    g_launches += 1;
-    return direct_conv_launch(p, batch, (cudaStream_t)stream);
-}
-
 int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, void* stream) {
     ADP_CHECK_ARG(in && out, "null pointer");
     g_launches += 1;
@@ -195,12 +176,6 @@ int adp_psp_priors(const adp_act* feat, int feat_cstride, const float* w, float*
     ADP_CHECK_ARG(feat && w && pooled && priors, "null pointer");
     g_launches += 2;
     return psp_priors(to_act(feat), feat_cstride, w, pooled, priors, batch, (cudaStream_t)stream);
-}
-
-int adp_psp_concat_up(const adp_act* feat, const float* priors, const adp_act* out, int batch, void* stream) {
-    ADP_CHECK_ARG(feat && priors && out, "null pointer");
-    g_launches += 1;
-    return psp_concat_up(to_act(feat), priors, to_act(out), batch, (cudaStream_t)stream);
 }
 
 int adp_psp_fill_priors(const float* priors, const adp_act* out, int coff, int batch, void* stream) {
@@ -266,10 +241,10 @@ int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void*
 }
 
 int adp_build_volume(const void* feat_ref, const void* feat_src, const float* Mw, const float* depths, void* vol, int B, int D,
-                     int H, int W, int C, int f16, int feat_f16, int planar, void* stream) {
+                     int H, int W, int C, int f16, void* stream) {
     ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && vol, "null pointer");
     g_launches += 1;
-    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, f16, feat_f16, planar, (cudaStream_t)stream);
+    return build_volume(feat_ref, feat_src, Mw, depths, reinterpret_cast<bf16*>(vol), B, D, H, W, C, f16, (cudaStream_t)stream);
 }
 
 int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
@@ -279,22 +254,12 @@ int adp_warp_matrices(const double* Kp_ref, const double* E_ref, const double* K
     return warp_matrices(Kp_ref, E_ref, Kp_src, E_src, Mw, valid_ref, valid_src, valid_env, B, (cudaStream_t)stream);
 }
 
-int adp_decode(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
-               const int32_t* choose, const uint8_t* valid, const adp_decode_weights* w, float* nocs, float* depth, float* pf1,
-               float* gsum, float* psum, float* R, float* r6, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P,
-               int regress_pose, int x11_f16, void* stream) {
-    ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && x11 && choose && w && nocs && depth && pf1 && gsum && psum && R,
-                  "null pointer");
-    g_launches += regress_pose ? 3 : 1;
-    return decode_run_c(feat_ref, feat_src, Mw, depths, x11, choose, valid, w, nocs, depth, pf1, gsum, psum, R, r6, dbg_logits,
-                        dbg_fused, B, S, D, P, regress_pose, x11_f16, (cudaStream_t)stream);
-}
-
 int adp_decode_gather(const float* feat_ref, const float* feat_src, const float* Mw, const float* depths, const void* x11,
                       const int32_t* choose, const uint8_t* valid, const float* prob_w, float* depth, void* xfeat_hi, void* xfeat_lo,
                       void* xcat_hi, void* xcat_lo, float* dbg_logits, float* dbg_fused, int B, int S, int D, int P, int x11_f16,
                       void* stream) {
-    ADP_CHECK_ARG(feat_ref && feat_src && Mw && depths && x11 && choose && prob_w && depth && xfeat_hi && xcat_hi, "null pointer");
+    ADP_CHECK_ARG(feat_ref && choose && xfeat_hi, "null pointer");
+    ADP_CHECK_ARG(!x11 || (feat_src && Mw && depths && prob_w && depth && xcat_hi), "null pointer (stereo mode)");
     g_launches += 1;
     return decode_gather_c(feat_ref, feat_src, Mw, depths, x11, choose, valid, prob_w, depth, xfeat_hi, xfeat_lo, xcat_hi, xcat_lo,
                            dbg_logits, dbg_fused, B, S, D, P, x11_f16, (cudaStream_t)stream);

@@ -63,7 +63,7 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in_hi, const bf16* 
                 float v[8];
                 ld8(in_hi, in_lo, (((size_t)b * Hi + iy) * Wi + ix) * C + c, v, f16);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+                for (int j = 0; j < 8; ++j) m[j] = max_nan(m[j], v[j]);
             }
         }
         st8(out_hi, out_lo, (((size_t)b * Ho + oy) * Wo + ox) * C + c, m, f16);
@@ -140,7 +140,7 @@ __global__ void psp_conv_kernel(const float* __restrict__ pooled, const float* _
     const float* ws = w + (size_t)stage * Cin * 128;
     float acc = 0.f;
     for (int c = 0; c < Cin; ++c) acc = fmaf(sv[c], ws[(size_t)c * 128 + n], acc);
-    priors[((size_t)b * 50 + cell) * 128 + n] = fmaxf(acc, 0.f);
+    priors[((size_t)b * 50 + cell) * 128 + n] = max_nan(acc, 0.f);
 }
 
 int psp_priors(const Act& feat, int feat_cs, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream) {
@@ -167,93 +167,6 @@ __device__ __forceinline__ void lin_coord(int o, int in_size, int out_size, int*
     *i0 = a;
     *i1 = a + (a < in_size - 1 ? 1 : 0);
     *w1 = s - (float)a;
-}
-
-__device__ __forceinline__ float prior_at(const float* __restrict__ pr, int bins, int y, int x, int H, int W, int n) {
-    // value of the stage's b x b prior map, bilinearly resized (align_corners=True) to H x W, at (y, x)
-    int y0, y1, x0, x1;
-    float wy, wx;
-    lin_coord(y, bins, H, &y0, &y1, &wy);
-    lin_coord(x, bins, W, &x0, &x1, &wx);
-    const float v00 = pr[(y0 * bins + x0) * 128 + n], v01 = pr[(y0 * bins + x1) * 128 + n];
-    const float v10 = pr[(y1 * bins + x0) * 128 + n], v11 = pr[(y1 * bins + x1) * 128 + n];
-    return (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
-}
-
-// one block = one output row of one frame; the frame's 50 x 128 prior table sits in shared memory
-__global__ void __launch_bounds__(256)
-psp_concat_up_kernel(const bf16* __restrict__ f_hi, const bf16* __restrict__ f_lo, const float* __restrict__ priors,
-                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int H, int W, int C, int f16) {
-    __shared__ __align__(16) float spr[50 * 128];
-    const int Ho = 2 * H, Wo = 2 * W, Ct = C + 512, C8 = Ct >> 3;
-    const int b = blockIdx.y, Y = blockIdx.x;
-    for (int i = threadIdx.x; i < 50 * 128 / 4; i += blockDim.x)
-        reinterpret_cast<float4*>(spr)[i] = __ldg(reinterpret_cast<const float4*>(priors + (size_t)b * 50 * 128) + i);
-    __syncthreads();
-    int y0, y1;
-    float wy;
-    lin_coord(Y, H, Ho, &y0, &y1, &wy);
-    const size_t base = (size_t)b * H * W;
-    for (int it = threadIdx.x; it < Wo * C8; it += blockDim.x) {
-        const int X = it / C8, c = (it - X * C8) * 8;
-        int x0, x1;
-        float wx;
-        lin_coord(X, W, Wo, &x0, &x1, &wx);
-        float v00[8], v01[8], v10[8], v11[8], o[8];
-        if (c < C) {
-            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x0) * C + c, v00, f16);
-            ld8(f_hi, f_lo, (base + (size_t)y0 * W + x1) * C + c, v01, f16);
-            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x0) * C + c, v10, f16);
-            ld8(f_hi, f_lo, (base + (size_t)y1 * W + x1) * C + c, v11, f16);
-        } else {
-            const int s = (c - C) / 128, n0 = (c - C) % 128;
-            const int bins = s == 0 ? 1 : s == 1 ? 2 : s == 2 ? 3 : 6;
-            const int off = s == 0 ? 0 : s == 1 ? 1 : s == 2 ? 5 : 14;
-            const float* pr = spr + off * 128 + n0;
-            // prior map value at the four (H x W)-grid corners: each is itself a bilinear read of the bins x bins map
-            const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
-            int py0[2], py1[2], px0[2], px1[2];
-            float pwy[2], pwx[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                lin_coord(ys[q], bins, H, &py0[q], &py1[q], &pwy[q]);
-                lin_coord(xs[q], bins, W, &px0[q], &px1[q], &pwx[q]);
-            }
-            float* dst[4] = {v00, v01, v10, v11};
-#pragma unroll
-            for (int qy = 0; qy < 2; ++qy)
-#pragma unroll
-                for (int qx = 0; qx < 2; ++qx) {
-                    const float* a00 = pr + (py0[qy] * bins + px0[qx]) * 128;
-                    const float* a01 = pr + (py0[qy] * bins + px1[qx]) * 128;
-                    const float* a10 = pr + (py1[qy] * bins + px0[qx]) * 128;
-                    const float* a11 = pr + (py1[qy] * bins + px1[qx]) * 128;
-                    const float wy_ = pwy[qy], wx_ = pwx[qx];
-                    float* d = dst[qy * 2 + qx];
-#pragma unroll
-                    for (int j = 0; j < 8; j += 4) {
-                        const float4 p00 = *reinterpret_cast<const float4*>(a00 + j), p01 = *reinterpret_cast<const float4*>(a01 + j);
-                        const float4 p10 = *reinterpret_cast<const float4*>(a10 + j), p11 = *reinterpret_cast<const float4*>(a11 + j);
-                        d[j + 0] = (1.f - wy_) * ((1.f - wx_) * p00.x + wx_ * p01.x) + wy_ * ((1.f - wx_) * p10.x + wx_ * p11.x);
-                        d[j + 1] = (1.f - wy_) * ((1.f - wx_) * p00.y + wx_ * p01.y) + wy_ * ((1.f - wx_) * p10.y + wx_ * p11.y);
-                        d[j + 2] = (1.f - wy_) * ((1.f - wx_) * p00.z + wx_ * p01.z) + wy_ * ((1.f - wx_) * p10.z + wx_ * p11.z);
-                        d[j + 3] = (1.f - wy_) * ((1.f - wx_) * p00.w + wx_ * p01.w) + wy_ * ((1.f - wx_) * p10.w + wx_ * p11.w);
-                    }
-                }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            o[j] = (1.f - wy) * ((1.f - wx) * v00[j] + wx * v01[j]) + wy * ((1.f - wx) * v10[j] + wx * v11[j]);
-        st8(out_hi, out_lo, (((size_t)b * Ho + Y) * Wo + X) * Ct + c, o, f16);
-    }
-}
-
-int psp_concat_up(const Act& feat, const float* priors, const Act& out, int batch, cudaStream_t stream) {
-    ADP_CHECK_ARG(out.C == feat.C + 512 && out.H == 2 * feat.H && out.W == 2 * feat.W && feat.C % 8 == 0 && feat.f16 == out.f16, "psp concat shapes");
-    if (batch == 0) return ADP_OK;
-    psp_concat_up_kernel<<<dim3(out.H, batch), 256, 0, stream>>>(feat.hi, feat.lo, priors, out.hi, out.lo, feat.H, feat.W, feat.C, feat.f16);
-    ADP_CUDA(cudaGetLastError());
-    return ADP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -332,7 +245,7 @@ __device__ __forceinline__ void up_unpack8(const uint4& u, float* v, bool f16) {
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
-                  bf16* __restrict__ out_lo, int H, int W, int C, int tiles_x, int f16) {
+                  bf16* __restrict__ out_lo, uint8_t* __restrict__ out_q8, int H, int W, int C, int tiles_x, int f16) {
     __shared__ uint4 tile[(SPLIT ? 2 : 1) * UP_IN * UP_IN * (UP_CS / 8)];      // raw 16-bit values, 16 B per (pixel, 8 channels)
     constexpr int PLANE = UP_IN * UP_IN * (UP_CS / 8);
     const int Ho = 2 * H, Wo = 2 * W;
@@ -393,7 +306,9 @@ upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             o[j] = (1.f - wy) * ((1.f - wx) * a[j] + wx * bq[j]) + wy * ((1.f - wx) * c[j] + wx * d[j]);
-        st8(out_hi, out_lo, (((size_t)b * Ho + Y) * Wo + X) * C + c0 + g * 8, o, f16);
+        const size_t oo = (((size_t)b * Ho + Y) * Wo + X) * C + c0 + g * 8;
+        st8(out_hi, out_lo, oo, o, f16);
+        if (out_q8) *reinterpret_cast<uint2*>(out_q8 + oo) = pack8_q8(o);      // fp8 twin for the consumer's low-order pass
     }
 }
 
@@ -402,8 +317,8 @@ int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
     if (batch == 0) return ADP_OK;
     const int tiles_x = (out.W + UP_T - 1) / UP_T, tiles_y = (out.H + UP_T - 1) / UP_T;
     const dim3 grid(tiles_x * tiles_y, in.C / UP_CS, batch);
-    if (in.lo && !in.f16) upsample2x_kernel<true><<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, in.H, in.W, in.C, tiles_x, 0);
-    else upsample2x_kernel<false><<<grid, 256, 0, stream>>>(in.hi, nullptr, out.hi, out.lo, in.H, in.W, in.C, tiles_x, in.f16);
+    if (in.lo && !in.f16) upsample2x_kernel<true><<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, nullptr, in.H, in.W, in.C, tiles_x, 0);
+    else upsample2x_kernel<false><<<grid, 256, 0, stream>>>(in.hi, nullptr, out.hi, out.lo, out.f16 ? out.q8 : nullptr, in.H, in.W, in.C, tiles_x, in.f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -50,6 +51,7 @@ struct Act {
     bf16* lo = nullptr;   // nullptr -> single bf16
     int B = 0, D = 1, H = 0, W = 0, C = 0;
     int f16 = 0;          // 1: the planes hold IEEE half instead of bf16 (3-D stage; no lo plane)
+    uint8_t* q8 = nullptr;   // optional fp8 (e4m3) twin holding value / 2: the A operand of the fp8 low-order pass ("fp16+fp8lo" layers)
     size_t numel() const { return (size_t)B * D * H * W * C; }
 };
 
@@ -131,6 +133,26 @@ __device__ inline bool invert4x4(const double* m, double* inv) {
     }
     for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) inv[4 * r + c] = a[r][4 + c];
     return true;
+}
+
+// 8 fp32 values -> 8 e4m3 bytes of (value * 0.5), saturating (cvt.rn.satfinite.e4m3x2.f32): the fp8 twin of an fp16 activation
+__device__ __forceinline__ uint2 pack8_q8(const float* v) {
+    uint32_t w[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint32_t a = __nv_cvt_float2_to_fp8x2(make_float2(0.5f * v[4 * q], 0.5f * v[4 * q + 1]), __NV_SATFINITE, __NV_E4M3);
+        const uint32_t b = __nv_cvt_float2_to_fp8x2(make_float2(0.5f * v[4 * q + 2], 0.5f * v[4 * q + 3]), __NV_SATFINITE, __NV_E4M3);
+        w[q] = a | (b << 16);
+    }
+    return make_uint2(w[0], w[1]);
+}
+
+// max that PROPAGATES NaN (fmaxf returns the non-NaN operand): a ReLU / max-pool built on fmaxf would launder the NaNs that an
+// fp16 overflow turns into (inf - inf) back into zeros and hide it from the range guard at the end of the backbone.
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

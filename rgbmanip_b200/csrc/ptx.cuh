@@ -114,6 +114,28 @@ __device__ __forceinline__ void umma_bf16_elected(uint32_t tmem_d, uint64_t ades
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(elected)
         : "memory");
 }
+// fp8 (e4m3 x e4m3 -> fp32) MMA, K = 32 per instruction: twice the rate of kind::f16
+__device__ __forceinline__ void umma_f8_elected(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                                uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(elected)
+        : "memory");
+}
+// kind::f16 MMA with scale-input-d = 15: D = A B + D * 2^-15.  Joins an accumulator that was built with operands pre-scaled by
+// 2^15 in total (the fp8 low-order pass) to the unscaled fp16 pass.
+__device__ __forceinline__ void umma_f16_scale15_elected(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "setp.ne.b32 e, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 15;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(elected)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_elected(uint32_t bar, uint32_t elected) {
     asm volatile(
         "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"

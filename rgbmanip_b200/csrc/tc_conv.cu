@@ -92,7 +92,7 @@ __device__ __forceinline__ void tc_epilogue_math(const TcConvParams& p, const ui
                             }
                             if (p.act == 1) {
 #pragma unroll
-                                for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+                                for (int j = 0; j < CH; ++j) v[j] = max_nan(v[j], 0.f);
                             } else if (p.act == 2) {
 #pragma unroll
                                 for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.prelu;
@@ -288,6 +288,15 @@ __device__ __forceinline__ void tc_epilogue_store_warp(const TcConvParams& p, co
         tc_store_rows<NP16>(wbuf, lane, pc, pix, validmask, reinterpret_cast<uint8_t*>(p.out_hi), (size_t)p.out_cs * 2,
                             (size_t)(p.out_coff + nbase) * 2);
     }
+    if (CH == 32 && p.out_q8) {       // fp8 twin (value / 2, e4m3) for the low-order pass of the consuming layer: 32 bytes per row
+        uint4 pc[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint2 a = pack8_q8(v + 16 * j), b = pack8_q8(v + 16 * j + 8);
+            pc[j] = make_uint4(a.x, a.y, b.x, b.y);
+        }
+        tc_store_rows<2>(wbuf, lane, pc, pix, validmask, p.out_q8, (size_t)p.out_cs, (size_t)(p.out_coff + nbase));
+    }
 }
 
 constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
@@ -295,19 +304,27 @@ constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + 
 // FUSED = 1: split-precision bf16x3 layers keep A_hi, A_lo, W_hi, W_lo of one (tap, K chunk) in the same stage and issue the
 // three MMA groups (hi*hi, lo*hi, hi*lo) from it: 2x the bytes of a single pass instead of 3x.
 // FUSED = 2: "fp16x2" -- one fp16 activation plane against fp16 hi + lo weights: stage = [A | W_hi | W_lo], two MMA groups.
-template <int BN, int KC, int FUSED = 0>
+// FUSED = 3: "fp16 + fp8 lo" (npass 4) -- the low-order term A W_lo only needs ~4 significant bits (W_lo <= 2^-12 |W|), so it runs
+//            as an e4m3 x e4m3 MMA at twice the fp16 rate: first a sweep over K with [A8 | W8] stages (A8 = e4m3(A / 2), the
+//            producer's fp8 twin; W8 = e4m3(W_lo 2^16); 128 channels per stage, K = 32 per MMA), then the fp16 sweep with
+//            [A | W_hi] stages whose first MMA scales the accumulator by 2^-15 (scale-input-d).  1.5 MMA passes per
+//            algorithmic FLOP instead of 2, same stage size (48 KB at BN = 256: 4 stages instead of 2).
+template <int BN, int KC, int FUSED = 0, bool NCAT_EN = false>
 struct TcCfg {
     static constexpr int A_BYTES = 128 * KC * 2;
     static constexpr int B_BYTES = BN * KC * 2;
     static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
+    static_assert(FUSED != 3 || KC == 64, "the fp8 low-order sweep moves 128 one-byte channels per stage = the bytes of 64 fp16 channels");
     static constexpr int STAGE_BYTES = FUSED == 1 ? 2 * (A_BYTES + B_PAD) : FUSED == 2 ? (A_BYTES + 2 * B_PAD) : (A_BYTES + B_PAD);
     // small-N layers are latency bound per tile: fewer stages -> several CTAs per SM overlap their pipelines
-    static constexpr int CTAS_PER_SM = FUSED ? (BN <= 64 ? 2 : 1) : (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
+    static constexpr int CTAS_PER_SM = FUSED ? ((BN <= 64 && FUSED != 3) ? 2 : 1) : (BN <= 16 && KC <= 32) ? 5 : BN <= 32 ? 3 : (BN <= 64 ? 2 : 1);
     // fp16x2 with a narrow N tile: W_hi and W_lo sit back to back in the stage, so ONE MMA of N = 2 BN reads the A operand once
     // and leaves A W_hi in columns [0, BN) and A W_lo in [BN, 2 BN) of the accumulator; the epilogue adds the two halves.  A
     // BN <= 64 MMA is bound by the 128 B/clk shared-memory operand path (4 KB of A per MMA), not by the tensor pipe: reading A
-    // once instead of twice takes a K step from 12 KB to 8 KB of operand traffic at the same tensor work.
-    static constexpr bool NCAT = FUSED == 2 && BN <= 64 && (B_BYTES % 1024 == 0);
+    // once instead of twice takes a K step from 12 KB to 8 KB of operand traffic at the same tensor work.  The epilogue reads
+    // twice the accumulator columns, so this pays only for layers with a long K loop (>= 18 K steps per tile: up_2 0.96 ->
+    // 0.86 ms per 148 frames; the 9-step layers layer1 / up_3 are epilogue bound and lose 5-10 %): tc_conv_plan decides.
+    static constexpr bool NCAT = NCAT_EN && FUSED == 2 && BN <= 64 && (B_BYTES % 1024 == 0);
     static constexpr int EPI_BYTES = 4 * 2048;                  // per-epilogue-warp transpose buffers (coalesced stores)
     static constexpr int SMEM_BUDGET = (220 * 1024 - CTAS_PER_SM * (EPI_BYTES + 2048)) / CTAS_PER_SM;
     static constexpr int STAGES = (STAGE_BYTES * 6 <= SMEM_BUDGET) ? 6 : (SMEM_BUDGET / STAGE_BYTES);
@@ -316,12 +333,12 @@ struct TcCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int KC, int FUSED>
-__global__ void __launch_bounds__(kTcThreads, TcCfg<BN, KC, FUSED>::CTAS_PER_SM)
+template <int BN, int KC, int FUSED, bool NCAT_EN>
+__global__ void __launch_bounds__(kTcThreads, TcCfg<BN, KC, FUSED, NCAT_EN>::CTAS_PER_SM)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                const TcConvParams p, int batch) {
-    using Cfg = TcCfg<BN, KC, FUSED>;
+    using Cfg = TcCfg<BN, KC, FUSED, NCAT_EN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -367,7 +384,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     const int taps = p.ntaps;
     const int npass_loop = FUSED ? 1 : p.npass;
-    const int k_iters = npass_loop * taps * p.kchunks;
+    const int lo_iters = FUSED == 3 ? taps * (p.kchunks >> 1) : 0;      // fp8 sweep: 128 channels per stage
+    const int k_iters = npass_loop * taps * p.kchunks + lo_iters;
     const int tiles_per_img = p.D * p.tiles_y * p.tiles_x * p.tiles_n;
     const int total_tiles = batch * tiles_per_img;
     const int rows_valid = p.TW * p.TH;
@@ -387,6 +405,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int d = t % p.D;
                 const int b = t / p.D;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
+                if (FUSED == 3) {      // low-order sweep first: [A8 | W8] stages from the fp8 twins (maps tmA_lo / tmW_lo)
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const int cx = x0 * p.in_mul + p.tdx[tap], cy = y0 * p.in_mul + p.tdy[tap];
+                        const int cz = d * p.in_mul + p.tdz[tap], wt = p.twt[tap];
+                        for (int kc = 0; kc < (p.kchunks >> 1); ++kc) {
+                            ptx::mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
+                            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                            ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+                            ptx::tma_load_5d(&tmA_lo, full_bar(stage), sa, kc * 128, cx, cy, cz, b);
+                            ptx::tma_load_3d(&tmW_lo, full_bar(stage), sa + Cfg::A_BYTES, kc * 128, n0, wt);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
                 for (int pass = 0; pass < npass_loop; ++pass) {
                     // npass 3: (A_hi W_hi, A_lo W_hi, A_hi W_lo); npass 2: (A W_hi, A W_lo)
                     const CUtensorMap* mapA = (p.npass == 3 && pass == 1) ? &tmA_lo : &tmA_hi;
@@ -461,6 +493,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         ptx::umma_bf16_elected(tmem_d, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u, elected);
                         ptx::umma_bf16_elected(tmem_d, al + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, 1u, elected);
                         ptx::umma_bf16_elected(tmem_d, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u, elected);
+                    }
+                } else if (FUSED == 3) {
+                    const uint64_t adesc = make_smem_desc<KC>(sa);
+                    const uint64_t bdesc = make_smem_desc<KC>(sa + Cfg::A_BYTES);
+                    if (it < lo_iters) {            // e4m3 x e4m3, K = 32 (32 bytes of each 128-byte row) per MMA
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_f8_elected(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u, elected);
+                    } else if (it == lo_iters) {    // first fp16 step: the accumulator holds 2^15 x (A W_lo) -> scale it down while adding
+                        ptx::umma_f16_scale15_elected(tmem_d, adesc, bdesc, idesc, elected);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k)
+                            ptx::umma_bf16_elected(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u, elected);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16_elected(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u, elected);
                     }
                 } else {
                     const uint64_t adesc = make_smem_desc<KC>(sa);
@@ -780,15 +829,18 @@ static CUtensorMapSwizzle swizzle_for(int KC) {
     return KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
-static int encode_act_map(CUtensorMap* tm, const bf16* ptr, const Act& a, int KC, int TW, int TH, int in_mul, int f16) {
+// esize 2: 16-bit plane (f16 selects half / bf16), KC channels per box; esize 1: the fp8 twin, 128 one-byte channels per box (the
+// rows are 128 bytes either way -> SWIZZLE_128B)
+static int encode_act_map(CUtensorMap* tm, const void* ptr, const Act& a, int KC, int TW, int TH, int in_mul, int f16, int esize = 2) {
     cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B};
-    cuuint64_t strides[4] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2,
-                             (cuuint64_t)a.D * a.H * a.W * a.C * 2};
+    cuuint64_t strides[4] = {(cuuint64_t)a.C * esize, (cuuint64_t)a.W * a.C * esize, (cuuint64_t)a.H * a.W * a.C * esize,
+                             (cuuint64_t)a.D * a.H * a.W * a.C * esize};
     // with an element stride s the unit loads ceil(box / s) elements: a box of (T-1)*s+1 yields exactly T
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)((TW - 1) * in_mul + 1), (cuuint32_t)((TH - 1) * in_mul + 1), 1, 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)in_mul, (cuuint32_t)in_mul, (cuuint32_t)(a.D > 1 ? in_mul : 1), 1};
-    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const CUtensorMapDataType dt = esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = g_encode(tm, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, esize == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d D=%d B=%d box=%dx%dx%d) failed: %d", a.C, a.W, a.H,
@@ -798,13 +850,14 @@ static int encode_act_map(CUtensorMap* tm, const bf16* ptr, const Act& a, int KC
     return ADP_OK;
 }
 
-static int encode_w_map(CUtensorMap* tm, const bf16* ptr, int Cin, int CoutPad, int taps, int KC, int BN, int f16) {
+static int encode_w_map(CUtensorMap* tm, const void* ptr, int Cin, int CoutPad, int taps, int KC, int BN, int f16, int esize = 2) {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)CoutPad, (cuuint64_t)taps};
-    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)CoutPad * Cin * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * esize, (cuuint64_t)CoutPad * Cin * esize};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const CUtensorMapDataType dt = esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = g_encode(tm, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, esize == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(weights Cin=%d Cout=%d taps=%d box=%dx%d) failed: %d", Cin, CoutPad, taps, KC,
@@ -837,7 +890,9 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     ADP_TRY(tc_conv_init_driver());
     int KC = in.C % 64 == 0 ? 64 : in.C % 32 == 0 ? 32 : in.C % 16 == 0 ? 16 : 0;
     ADP_CHECK_ARG(KC != 0, "Cin must be a multiple of 16 for the tcgen05 path");
-    ADP_CHECK_ARG(npass >= 1 && npass <= 3, "npass");
+    ADP_CHECK_ARG(npass >= 1 && npass <= 4, "npass");
+    ADP_CHECK_ARG(npass != 4 || (f16 && in.q8 && w_lo && in.C % 128 == 0),
+                  "fp16 + fp8 low-order pass needs fp16 activations with an fp8 twin, packed e4m3 low-order weights and Cin % 128 == 0");
     ADP_CHECK_ARG(npass != 3 || (in.lo && w_lo && !f16), "bf16x3 needs bf16 lo planes of activations and weights");
     ADP_CHECK_ARG(npass != 2 || (w_lo && f16), "fp16x2 needs fp16 activations and a lo plane of the weights");
     int coutPad = (Cout + 15) / 16 * 16;
@@ -884,6 +939,7 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
         g_fuse_max_bn = e ? atoi(e) : 256;
     }
     L->fused = (npass >= 2) && (BN <= g_fuse_max_bn) && KC >= 16;
+    ADP_CHECK_ARG(npass != 4 || (BN == 256 || BN == 128 || BN == 64), "fp16 + fp8 low-order pass: Cout tile of 64, 128 or 256");
     // slab mode: single K chunk, single pass, small N, unit strides, a tap window of at most 3 per axis, 8 | W
     L->slab = false;
     {
@@ -930,24 +986,29 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
         }
     }
     ADP_TRY(encode_act_map(&L->tmA_hi, in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
-    ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
     ADP_TRY(encode_w_map(&L->tmW_hi, w_hi, in.C, coutPad, w_taps, KC, BN, f16));
-    ADP_TRY(encode_w_map(&L->tmW_lo, w_lo ? w_lo : w_hi, in.C, coutPad, w_taps, KC, BN, f16));
+    if (npass == 4) {        // the "lo" maps address the fp8 twins: 128 one-byte channels per box
+        ADP_TRY(encode_act_map(&L->tmA_lo, in.q8, in, 128, p.TW, p.TH, p.in_mul, f16, 1));
+        ADP_TRY(encode_w_map(&L->tmW_lo, w_lo, in.C, coutPad, w_taps, 128, BN, f16, 1));
+    } else {
+        ADP_TRY(encode_act_map(&L->tmA_lo, in.lo ? in.lo : in.hi, in, KC, p.TW, p.TH, p.in_mul, f16));
+        ADP_TRY(encode_w_map(&L->tmW_lo, w_lo ? w_lo : w_hi, in.C, coutPad, w_taps, KC, BN, f16));
+    }
     L->ready = true;
     return ADP_OK;
 }
 
-template <int BN, int KC, int FUSED = 0>
+template <int BN, int KC, int FUSED = 0, bool NCAT_EN = false>
 static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
-    using Cfg = TcCfg<BN, KC, FUSED>;
+    using Cfg = TcCfg<BN, KC, FUSED, NCAT_EN>;
     static int attr[kMaxDevices];
-    ADP_TRY(ensure_dyn_smem(tc_conv_kernel<BN, KC, FUSED>, Cfg::SMEM_BYTES, attr));
+    ADP_TRY(ensure_dyn_smem(tc_conv_kernel<BN, KC, FUSED, NCAT_EN>, Cfg::SMEM_BYTES, attr));
     const TcConvParams& p = L->p;
     long long total = (long long)batch * p.D * p.tiles_y * p.tiles_x * p.tiles_n;
     const long long slots = (long long)num_sms * Cfg::CTAS_PER_SM;
     int grid = (int)(total < slots ? total : slots);
     if (grid <= 0) return ADP_OK;
-    tc_conv_kernel<BN, KC, FUSED><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(L->tmA_hi, L->tmA_lo, L->tmW_hi, L->tmW_lo, p, batch);
+    tc_conv_kernel<BN, KC, FUSED, NCAT_EN><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(L->tmA_hi, L->tmA_lo, L->tmW_hi, L->tmW_lo, p, batch);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }
@@ -987,7 +1048,15 @@ int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t st
         if (L->BN == 128 && L->KC == 64) return launch_impl<128, 64, 1>(L, batch, num_sms, stream);
         if (L->BN == 256 && L->KC == 64) return launch_impl<256, 64, 1>(L, batch, num_sms, stream);
     }
+    if (L->p.npass == 4) {               // fp16 pass + fp8 low-order pass
+        if (L->BN == 256 && L->KC == 64) return launch_impl<256, 64, 3>(L, batch, num_sms, stream);
+        if (L->BN == 128 && L->KC == 64) return launch_impl<128, 64, 3>(L, batch, num_sms, stream);
+        if (L->BN == 64 && L->KC == 64) return launch_impl<64, 64, 3>(L, batch, num_sms, stream);
+        set_last_error("no fp16 + fp8lo instantiation for BN=%d KC=%d", L->BN, L->KC);
+        return ADP_ERR_ARG;
+    }
     if (L->p.npass == 2 && L->fused) {   // fp16x2: one stage carries A, W_hi, W_lo
+        if (L->BN == 64 && L->KC == 64 && L->p.ntaps * L->p.kchunks >= 18) return launch_impl<64, 64, 2, true>(L, batch, num_sms, stream);
         if (L->BN == 64 && L->KC == 64) return launch_impl<64, 64, 2>(L, batch, num_sms, stream);
         if (L->BN == 32 && L->KC == 64) return launch_impl<32, 64, 2>(L, batch, num_sms, stream);
         if (L->BN == 64 && L->KC == 16) return launch_impl<64, 16, 2>(L, batch, num_sms, stream);

@@ -34,7 +34,7 @@ struct TcConvParams {
     int TW, TH;              // spatial tile; TW * TH <= 128
     int tiles_x, tiles_y, tiles_n;
     int kchunks;             // Cin / KC
-    int npass;               // 1 = single pass, 2 = fp16x2 (A W_hi + A W_lo), 3 = bf16x3
+    int npass;               // 1 = single pass, 2 = fp16x2 (A W_hi + A W_lo), 3 = bf16x3, 4 = fp16 + fp8 low-order pass
     // epilogue
     const float* bias;       // [Cout] or nullptr (BatchNorm shift is passed here too)
     const float* scale;      // [Cout] or nullptr (folded BatchNorm scale)
@@ -47,6 +47,7 @@ struct TcConvParams {
     bf16* out_hi;
     bf16* out_lo;
     float* out_f32;
+    uint8_t* out_q8;         // optional fp8 twin of out_hi (value / 2, e4m3; same channel pitch / offset): see Act::q8
     __half* out_h16;         // optional extra fp16 copy
     int out_cs, out_coff;    // channel pitch / first channel of out_hi, out_lo
     int bias_per_batch;      // bias is [B, Cout]

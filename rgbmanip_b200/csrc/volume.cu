@@ -8,130 +8,13 @@
 
 namespace adp {
 
-// 8 consecutive feature channels as fp32, from an fp32 or an fp16 feature map
-template <typename FT> __device__ __forceinline__ void ld_feat8(const FT* p, float* v);
-template <> __device__ __forceinline__ void ld_feat8<float>(const float* p, float* v) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <> __device__ __forceinline__ void ld_feat8<__half>(const __half* p, float* v) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        v[2 * q] = __half2float(__ushort_as_half((unsigned short)(w[q] & 0xffffu)));
-        v[2 * q + 1] = __half2float(__ushort_as_half((unsigned short)(w[q] >> 16)));
-    }
-}
-
-// one thread = one voxel x 8 channels (C == 32 -> 4 threads per voxel, coalesced 64/128 B per corner)
-template <typename FT>
-__global__ void __launch_bounds__(256)
-build_volume_kernel(const FT* __restrict__ f_ref, const FT* __restrict__ f_src, const float* __restrict__ Mw,
-                    const float* __restrict__ depths, bf16* __restrict__ vol, int B, int D, int H, int W, int f16, int planar) {
-    constexpr int C = 32;
-    const size_t total = (size_t)B * D * H * W * 4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int cg, x;
-        size_t t;
-        if (planar) {      // consecutive threads = consecutive x of one channel chunk (coalesced 16 B stores per chunk plane)
-            x = (int)(i % W); t = i / W;
-            cg = (int)(t & 3); t >>= 2;
-        } else {
-            cg = (int)(i & 3); t = i >> 2;
-            x = (int)(t % W); t /= W;
-        }
-        const int y = (int)(t % H); t /= H;
-        const int d = (int)(t % D);
-        const int b = (int)(t / D);
-        float ix, iy;
-        warp_coords(Mw + 12 * b, (float)x, (float)y, depths[d], W, H, &ix, &iy);
-        const Bilin bl = bilin_setup(ix, iy, W, H);
-        float v[8];
-        ld_feat8<FT>(f_ref + (((size_t)b * H + y) * W + x) * C + cg * 8, v);
-        if (bl.any) {
-            const FT* src = f_src + (size_t)b * H * W * C + cg * 8;
-            const float wts[4] = {bl.w00, bl.w01, bl.w10, bl.w11};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (wts[k] != 0.f) {
-                    const int yy = bl.y0 + (k >> 1), xx = bl.x0 + (k & 1);
-                    float s8[8];
-                    ld_feat8<FT>(src + ((size_t)yy * W + xx) * C, s8);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaf(wts[k], s8[j], v[j]);
-                }
-            }
-        }
-        uint32_t o[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (f16)
-                o[u] = (uint32_t)__half_as_ushort(__float2half_rn(v[2 * u])) | ((uint32_t)__half_as_ushort(__float2half_rn(v[2 * u + 1])) << 16);
-            else
-                o[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u])) |
-                       ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * u + 1])) << 16);
-        }
-        const size_t off = planar ? (((((size_t)b * D + d) * H + y) * 4 + cg) * W + x) * 8
-                                  : ((((size_t)b * D + d) * H + y) * W + x) * C + cg * 8;
-        *reinterpret_cast<uint4*>(vol + off) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-}
-
-// one block = one volume row (b, d, y), one thread = one voxel with all 32 channels: the homography is evaluated once per
-// voxel and the row index needs no per-thread division (the 4-threads-per-voxel kernel above is issue bound on exactly that)
-__global__ void __launch_bounds__(256)
-build_volume_row_kernel(const __half* __restrict__ f_ref, const __half* __restrict__ f_src, const float* __restrict__ Mw,
-                        const float* __restrict__ depths, bf16* __restrict__ vol, int D, int H, int W, int f16, int planar) {
-    constexpr int C = 32;
-    const int row = blockIdx.x;
-    const int y = row % H, d = (row / H) % D, b = row / (H * D);
-    const float dep = depths[d];
-    const float* M = Mw + 12 * b;
-    for (int x = threadIdx.x; x < W; x += blockDim.x) {
-        float ix, iy;
-        warp_coords(M, (float)x, (float)y, dep, W, H, &ix, &iy);
-        const Bilin bl = bilin_setup(ix, iy, W, H);
-        float v[C];
-        const __half* ref = f_ref + (((size_t)b * H + y) * W + x) * C;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ld_feat8<__half>(ref + 8 * q, v + 8 * q);
-        if (bl.any) {
-            const __half* src = f_src + (size_t)b * H * W * C;
-            const float wts[4] = {bl.w00, bl.w01, bl.w10, bl.w11};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (wts[k] != 0.f) {
-                    const __half* p = src + ((size_t)(bl.y0 + (k >> 1)) * W + bl.x0 + (k & 1)) * C;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float s8[8];
-                        ld_feat8<__half>(p + 8 * q, s8);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[8 * q + j] = fmaf(wts[k], s8[j], v[8 * q + j]);
-                    }
-                }
-            }
-        }
-        if (planar) {     // [B,D,H,4,W,8]: consecutive threads write consecutive 16-byte pieces of each chunk plane
-            bf16* dst = vol + ((((size_t)b * D + d) * H + y) * 4 * W + x) * 8;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) st8_16(dst, nullptr, (size_t)q * W * 8, f16, v + 8 * q);
-        } else {
-            bf16* dst = vol + ((((size_t)b * D + d) * H + y) * W + x) * C;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) st8_16(dst, nullptr, 8 * q, f16, v + 8 * q);
-        }
-    }
-}
-
 // Tiled builder (fp16 features): one block = a 16 x 16 tile of reference pixels for VT_DG consecutive depth planes.
 // The plane-sweep gather reads every source pixel ~4 times (once per bilinear footprint that covers it); done per voxel
 // from global memory that is 256 B of L2 traffic per 64 B written, and the kernel is L2-bandwidth bound.  Here the
 // source footprint of the tile at one depth (the bounding box of its 256 sample cells, found with a block min/max) is
 // staged in shared memory once and the four corners are read from there; the reference features stay in registers
 // across the depth loop.  A footprint larger than the staging buffer (strong rotation / scale between the views) falls
-// back to the direct gather for that (tile, depth).  Arithmetic (and its order) is the row kernel's, so results are equal.
+// back to the direct gather for that (tile, depth).
 constexpr int VT_T = 16;
 constexpr int VT_DG = 8;
 constexpr int VT_MAXPX = 480;                 // staged source pixels (x 64 B = 30 KB; + 16 KB of transpose buffers < 48 KB static)
@@ -307,32 +190,12 @@ build_volume_tile_kernel(const __half* __restrict__ f_ref, const __half* __restr
 }
 
 int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
-                 int W, int C, int f16, int feat_f16, int planar, cudaStream_t stream) {
+                 int W, int C, int f16, cudaStream_t stream) {
     ADP_CHECK_ARG(C == 32, "feature channels must be 32");
-    size_t total = (size_t)B * D * H * W * 4;
-    if (total == 0) return ADP_OK;
-    if (feat_f16 && !planar) {
-        const int tiles_x = cdiv(W, VT_T), tiles_y = cdiv(H, VT_T);
-        build_volume_tile_kernel<<<dim3(tiles_x * tiles_y, cdiv(D, VT_DG), B), 256, 0, stream>>>(
-            reinterpret_cast<const __half*>(f_ref), reinterpret_cast<const __half*>(f_src), Mw, depths, vol, D, H, W, tiles_x, f16);
-        ADP_CUDA(cudaGetLastError());
-        return ADP_OK;
-    }
-    if (feat_f16) {
-        build_volume_row_kernel<<<B * D * H, W <= 128 ? 128 : 256, 0, stream>>>(reinterpret_cast<const __half*>(f_ref),
-                                                                               reinterpret_cast<const __half*>(f_src), Mw, depths, vol, D,
-                                                                               H, W, f16, planar);
-        ADP_CUDA(cudaGetLastError());
-        return ADP_OK;
-    }
-    size_t blocks = (total + 255) / 256;
-    int grid = (int)(blocks < (size_t)148 * 32 ? blocks : (size_t)148 * 32);
-    if (feat_f16)
-        build_volume_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(f_ref), reinterpret_cast<const __half*>(f_src),
-                                                              Mw, depths, vol, B, D, H, W, f16, planar);
-    else
-        build_volume_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(f_ref), reinterpret_cast<const float*>(f_src),
-                                                             Mw, depths, vol, B, D, H, W, f16, planar);
+    if ((size_t)B * D * H * W == 0) return ADP_OK;
+    const int tiles_x = cdiv(W, VT_T), tiles_y = cdiv(H, VT_T);
+    build_volume_tile_kernel<<<dim3(tiles_x * tiles_y, cdiv(D, VT_DG), B), 256, 0, stream>>>(
+        reinterpret_cast<const __half*>(f_ref), reinterpret_cast<const __half*>(f_src), Mw, depths, vol, D, H, W, tiles_x, f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

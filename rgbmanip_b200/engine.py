@@ -40,10 +40,11 @@ class ActBuf:
     Cn: int
     f16: int = 0
     s2d: bool = False        # level-0 U-Net tensor stored space-to-depth(2): logical [B, 2D, 2H, 2W, C/8]
+    q8: torch.Tensor | None = None   # fp8 (e4m3) twin holding value / 2: A operand of the fp8 low-order pass of the consumer
 
     @property
     def c(self):
-        return L.Act(L.ptr(self.hi), L.ptr(self.lo), self.B, self.D, self.H, self.W, self.Cn, self.f16)
+        return L.Act(L.ptr(self.hi), L.ptr(self.lo), self.B, self.D, self.H, self.W, self.Cn, self.f16, L.ptr(self.q8))
 
     def value(self, n=None):
         """fp32 torch view [B,(D,)H,W,C] (debug / tests)."""
@@ -64,13 +65,12 @@ def _split_bf16(w: torch.Tensor):
 class Engine:
     """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
 
-    def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="fp16x2", regress_pose=True, use_tc=True,
-                 use_tc_3d=True, tc_strided=True, tc_transposed=True, conv0_ring=True, tconv_fused=True, volume_dtype="fp16", debug=False,
-                 img_size=IMG_SIZE, n_pts=N_PTS, decode_tc=True, level0_s2d=True, use_graph=True):
+    def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="fp16f8", regress_pose=True, debug=False,
+                 img_size=IMG_SIZE, n_pts=N_PTS, use_graph=True):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
-        if precision not in ("bf16", "bf16x3", "fp16x2"):
-            raise ValueError("precision must be 'fp16x2', 'bf16x3' or 'bf16'")
+        if precision not in ("bf16", "bf16x3", "fp16x2", "fp16f8"):
+            raise ValueError("precision must be 'fp16f8', 'fp16x2', 'bf16x3' or 'bf16'")
         self.lib = L.load()
         self.device = torch.device(device)
         self.E = int(max_envs)
@@ -81,27 +81,22 @@ class Engine:
         #   fp16x2  one fp16 activation plane x (fp16 hi + lo) weights, 2 MMA passes
         #   bf16x3  (bf16 hi + lo) activations x (bf16 hi + lo) weights, 3 MMA passes
         #   bf16    single pass (fast, outside the parity tolerance)
+        #   fp16f8  fp16x2, except that the wide layers (layer3, layer4, up_1: 81 % of the FLOPs) run the low-order term A W_lo
+        #           as an e4m3 x e4m3 MMA at twice the rate (1.5 passes); W_lo <= 2^-12 |W| needs ~4 significant bits
         self.split = precision == "bf16x3"
-        self.act_f16 = 1 if precision == "fp16x2" else 0
-        self.npass = {"bf16": 1, "fp16x2": 2, "bf16x3": 3}[precision]
+        self.act_f16 = 1 if precision in ("fp16x2", "fp16f8") else 0
+        self.fp8lo = precision == "fp16f8"
+        self.npass = {"bf16": 1, "fp16x2": 2, "fp16f8": 2, "bf16x3": 3}[precision]
         self.precision = precision
         self.regress_pose = bool(regress_pose)
-        self.use_tc = use_tc
-        self.use_tc_3d = use_tc_3d
-        self.tc_strided = tc_strided
-        self.tc_transposed = tc_transposed
-        self.conv0_ring = conv0_ring and use_tc_3d
-        self.tconv_fused = tconv_fused and use_tc_3d and tc_transposed
-        self.decode_tc = decode_tc and use_tc and int(n_pts) == 1024
-        self.level0_s2d = level0_s2d
+        if int(n_pts) != 1024 or int(img_size) % 224 != 0:
+            raise ValueError("the device pipeline is built for n_pts = 1024 and img_size = 224 (every shipped adapose_* yaml)")
         self.use_graph = bool(use_graph) and not debug
         self._graphs = {}           # chunk size -> (CUDAGraph, launches per replay)
         self._chunk_runs = {}       # chunk size -> eager runs so far (a size is captured on its second appearance)
         self._conv0_plans = []
         self._tconv_plans = []
-        if volume_dtype not in ("fp16", "bf16"):
-            raise ValueError("volume_dtype must be 'fp16' or 'bf16'")
-        self.vol_f16 = 1 if volume_dtype == "fp16" else 0
+        self.vol_f16 = 1            # the 3-D stage (volume, U-Net) stores IEEE half: BatchNorm keeps its activations O(10)
         self.debug = debug
         self._keep = []
         self._plans = []
@@ -129,7 +124,7 @@ class Engine:
         self._keep.append(t)
         return t
 
-    def _act(self, B, H, Wd, Cn, D=1, split=None, f16=None):
+    def _act(self, B, H, Wd, Cn, D=1, split=None, f16=None, q8=False):
         if split is None and f16 is None:      # a backbone activation in the engine's precision
             f16 = self.act_f16
         f16 = int(f16 or 0)
@@ -139,6 +134,8 @@ class Engine:
         hi = torch.zeros(shape, dtype=dt, device=self.device)
         lo = torch.zeros(shape, dtype=dt, device=self.device) if (split and not f16) else None
         buf = ActBuf(hi, lo, B, D, H, Wd, Cn, f16)
+        if q8 and f16:
+            buf.q8 = torch.zeros(shape, dtype=torch.uint8, device=self.device)
         self._keep.append(buf)   # layer plans hold raw pointers: the tensors must outlive them
         return buf
 
@@ -152,7 +149,8 @@ class Engine:
                           L.ptr(res.hi) if res else None, L.ptr(res.lo) if (res and res.lo is not None) else None,
                           res.Cn if res else 0,
                           L.ptr(out.hi) if out else None, L.ptr(out.lo) if (out and out.lo is not None) else None,
-                          L.ptr(out_f32), L.ptr(out_h16), out_cstride, out_coff, bias_per_batch, check_finite)
+                          L.ptr(out_f32), L.ptr(out_h16), out_cstride, out_coff, bias_per_batch,
+                          L.ptr(out.q8) if (out is not None and out.q8 is not None) else None, check_finite)
 
     def _tc_plans(self, x: ActBuf, wt, cout, kd, ks, dil, npass, ep, geoms):
         """wt: fp32 [taps, CoutPad, Cin] packed weights -> callable(batch) launching one tcgen05 conv per geometry."""
@@ -160,6 +158,8 @@ class Engine:
             hi, lo = wt.to(torch.float16), None
             if npass == 2:
                 lo = (wt - hi.float()).to(torch.float16).to(self.device).contiguous()
+            elif npass == 4:     # low-order term for the fp8 pass: e4m3(W_lo * 2^16), one byte per weight (see tc_conv.cu FUSED = 3)
+                lo = ((wt - hi.float()) * 65536.0).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8).to(self.device).contiguous()
         else:
             hi, lo = _split_bf16(wt)
             lo = lo.to(self.device).contiguous()
@@ -181,27 +181,25 @@ class Engine:
         run.kind = "tc"
         return run
 
-    def _conv(self, w_np, x: ActBuf, out: ActBuf | None, *, stride=1, dil=1, transposed=False, npass=None, tc=None, **ep_kw):
+    def _conv(self, w_np, x: ActBuf, out: ActBuf | None, *, stride=1, dil=1, transposed=False, npass=None, **ep_kw):
         """Returns a callable(batch) running the convolution x -> out.  w_np: torch layout
         [Cout,Cin,(kd,)kh,kw] or, transposed, [Cin,Cout,kd,kh,kw]."""
         w = torch.as_tensor(np.ascontiguousarray(w_np)).float()
         three_d = w.dim() == 5
         if transposed:
             cin, cout = w.shape[0], w.shape[1]
-            w_tcin_cout = w.reshape(cin, cout, -1).permute(2, 0, 1).contiguous()        # [taps, Cin, Cout]
             w_tcout_cin = w.reshape(cin, cout, -1).permute(2, 1, 0).contiguous()        # [taps, Cout, Cin]
         else:
             cout, cin = w.shape[0], w.shape[1]
-            w_tcin_cout = w.reshape(cout, cin, -1).permute(2, 1, 0).contiguous()        # [taps, Cin, Cout]
             w_tcout_cin = w.reshape(cout, cin, -1).permute(2, 0, 1).contiguous()        # [taps, Cout, Cin]
         kd = w.shape[2] if three_d else 1
         ks = w.shape[-1]
         assert cin == x.Cn
         npass = self.npass if npass is None else npass
-        if tc is None:
-            tc = self.use_tc_3d if three_d else self.use_tc
-        can_tc = (tc and cin % 16 == 0 and ks in (1, 3) and (ks == w.shape[-2]) and (npass == 1 or (npass == 2 and x.f16) or (npass == 3 and x.lo is not None))
-                  and (stride == 1 or (stride == 2 and (self.tc_transposed if transposed else self.tc_strided))))
+        if npass == 2 and self.fp8lo and x.q8 is not None and cin % 128 == 0 and not three_d and stride == 1 and not transposed:
+            npass = 4
+        can_tc = (cin % 16 == 0 and ks in (1, 3) and (ks == w.shape[-2]) and stride in (1, 2)
+                  and (npass == 1 or (npass in (2, 4) and x.f16) or (npass == 3 and x.lo is not None)))
         ep = self._epilogue(out, **ep_kw)
         if three_d:
             Do, Ho, Wo = (x.D * 2, x.H * 2, x.W * 2) if transposed else ((x.D + stride - 1) // stride,
@@ -224,19 +222,8 @@ class Engine:
             else:
                 geoms = [None]
             return self._tc_plans(x, wt, cout, kd, ks, dil, npass, ep, geoms)
-        wd = w_tcin_cout.to(self.device).contiguous()
-        self._keep.append(wd)
-        pd = 1 if three_d else 0
-        pad = dil * (ks // 2)
-        d = L.DirectConv(L.ptr(x.hi), L.ptr(x.lo), None, x.B, x.D, x.H, x.W, cin, Do, Ho, Wo, cout,
-                         kd, ks, ks, stride if three_d else 1, stride, stride, pd, pad, pad, dil, 1 if transposed else 0,
-                         x.f16, L.ptr(wd), ep)
-        self._keep.append(d)
-
-        def run(batch, d=d):
-            L.check(self.lib.adp_conv_direct(C.byref(d), batch, self.stream), "conv_direct")
-        run.kind = "direct"
-        return run
+        raise L.AdpError(f"no tcgen05 plan for this convolution (Cin {cin}, Cout {cout}, k {ks}, stride {stride}, npass {npass}): "
+                         "the library has no CUDA-core fallback")
 
     # ------------------------------------------------------------------ backbone (pspnet.py)
     def _build_backbone(self):
@@ -244,23 +231,15 @@ class Engine:
         ops = []
         p = "img_extractor.feats"
         self.crops = torch.zeros((F, S, S, 3), dtype=torch.float32, device=self.device)
-        # conv1 7x7/2 on the fp32 crop (Cin = 3: CUDA cores)
+        # conv1 7x7/2
         c1 = self._act(F, S // 2, S // 2, 64)
         w = torch.as_tensor(sd[f"{p}.conv1.weight"]).float()
-        if self.use_tc:
-            # stem on tensor cores: space-to-depth(2) repack of the crop, then a 4x4 stride-1 window over 16 channels
-            s2d = self._act(F, S // 2, S // 2, 16)
-            ops.append(("pack_s2d", lambda b, o=s2d: L.check(
-                self.lib.adp_pack_s2d(L.ptr(self.crops), C.byref(o.c), b, S, self.stream), "pack_s2d")))
-            ops.append(("conv1", self._tc_plans(s2d, G.stem_s2d_weights(w), 64, 1, 4, 1, self.npass,
-                                                self._epilogue(c1, act=L.ACT_RELU), [G.stem_s2d(S)])))
-        else:
-            wd = w.reshape(64, 3, 49).permute(2, 1, 0).contiguous().to(self.device)
-            self._keep.append(wd)
-            d = L.DirectConv(None, None, L.ptr(self.crops), F, 1, S, S, 3, 1, S // 2, S // 2, 64, 1, 7, 7, 1, 2, 2, 0, 3, 3, 1, 0,
-                             0, L.ptr(wd), self._epilogue(c1, act=L.ACT_RELU))
-            self._keep.append(d)
-            ops.append(("conv1", lambda b, d=d: L.check(self.lib.adp_conv_direct(C.byref(d), b, self.stream), "conv1")))
+        # stem on tensor cores: space-to-depth(2) repack of the crop, then a 4x4 stride-1 window over 16 channels
+        s2d = self._act(F, S // 2, S // 2, 16)
+        ops.append(("pack_s2d", lambda b, o=s2d: L.check(
+            self.lib.adp_pack_s2d(L.ptr(self.crops), C.byref(o.c), b, S, self.stream), "pack_s2d")))
+        ops.append(("conv1", self._tc_plans(s2d, G.stem_s2d_weights(w), 64, 1, 4, 1, self.npass,
+                                            self._epilogue(c1, act=L.ACT_RELU), [G.stem_s2d(S)])))
         mp = self._act(F, S // 4, S // 4, 64)
         ops.append(("maxpool", lambda b, a=c1, o=mp: L.check(
             self.lib.adp_maxpool3x3s2(C.byref(a.c), C.byref(o.c), b, self.stream), "maxpool")))
@@ -274,20 +253,22 @@ class Engine:
                 pre = f"{p}.layer{li}.{bi}"
                 s_b = stride if bi == 0 else 1
                 d_b = 1 if bi == 0 else dil
-                t = self._act(F, Hn, Hn, planes)
+                # fp16f8: every activation that feeds a wide (layer3 / layer4) conv carries an fp8 twin written by its producer
+                wide = self.fp8lo and li >= 2
+                t = self._act(F, Hn, Hn, planes, q8=wide)
                 ops.append((f"{pre}.conv1", self._conv(sd[f"{pre}.conv1.weight"], x, t, stride=s_b, dil=d_b, act=L.ACT_RELU)))
                 res = x
                 if f"{pre}.downsample.0.weight" in sd:
                     res = self._act(F, Hn, Hn, planes)
                     ops.append((f"{pre}.down", self._conv(sd[f"{pre}.downsample.0.weight"], x, res, stride=s_b, dil=1,
                                                           act=L.ACT_NONE)))
-                last = (li == 4 and bi == blocks - 1) and self.use_tc
+                last = li == 4 and bi == blocks - 1
                 if last:
                     o = ActBuf(cat.hi[..., :planes], cat.lo[..., :planes] if cat.lo is not None else None, F, 1, Hn, Hn, planes, cat.f16)
                     ops.append((f"{pre}.conv2", self._conv(sd[f"{pre}.conv2.weight"], t, o, stride=1, dil=d_b, act=L.ACT_RELU,
                                                            res=res, out_cstride=1024)))
                 else:
-                    o = self._act(F, Hn, Hn, planes)
+                    o = self._act(F, Hn, Hn, planes, q8=wide)
                     ops.append((f"{pre}.conv2", self._conv(sd[f"{pre}.conv2.weight"], t, o, stride=1, dil=d_b, act=L.ACT_RELU,
                                                            res=res)))
                 self.taps[pre] = o
@@ -299,19 +280,13 @@ class Engine:
         self.pooled = torch.zeros((F, 50, 512), dtype=torch.float32, device=self.device)
         self.priors = torch.zeros((F, 50, 128), dtype=torch.float32, device=self.device)
         l4 = x
-        u1 = self._act(F, 2 * l4.H, 2 * l4.W, 1024)
-        if self.use_tc:
-            ops.append(("psp_priors", lambda b, a=l4: L.check(
-                self.lib.adp_psp_priors(C.byref(a.c), 1024, L.ptr(wpsp), L.ptr(self.pooled), L.ptr(self.priors), b, self.stream), "psp")))
-            ops.append(("psp_fill_priors", lambda b, o=cat: L.check(
-                self.lib.adp_psp_fill_priors(L.ptr(self.priors), C.byref(o.c), 512, b, self.stream), "psp_fill")))
-            ops.append(("psp_upsample", lambda b, a=cat, o=u1: L.check(
-                self.lib.adp_upsample2x(C.byref(a.c), C.byref(o.c), b, self.stream), "psp_upsample")))
-        else:
-            ops.append(("psp_priors", lambda b, a=l4: L.check(
-                self.lib.adp_psp_priors(C.byref(a.c), 0, L.ptr(wpsp), L.ptr(self.pooled), L.ptr(self.priors), b, self.stream), "psp")))
-            ops.append(("psp_concat_up", lambda b, a=l4, o=u1: L.check(
-                self.lib.adp_psp_concat_up(C.byref(a.c), L.ptr(self.priors), C.byref(o.c), b, self.stream), "psp_concat_up")))
+        u1 = self._act(F, 2 * l4.H, 2 * l4.W, 1024, q8=self.fp8lo)
+        ops.append(("psp_priors", lambda b, a=l4: L.check(
+            self.lib.adp_psp_priors(C.byref(a.c), 1024, L.ptr(wpsp), L.ptr(self.pooled), L.ptr(self.priors), b, self.stream), "psp")))
+        ops.append(("psp_fill_priors", lambda b, o=cat: L.check(
+            self.lib.adp_psp_fill_priors(L.ptr(self.priors), C.byref(o.c), 512, b, self.stream), "psp_fill")))
+        ops.append(("psp_upsample", lambda b, a=cat, o=u1: L.check(
+            self.lib.adp_upsample2x(C.byref(a.c), C.byref(o.c), b, self.stream), "psp_upsample")))
         x = u1
         for nm, cout in (("up_1", 256), ("up_2", 64), ("up_3", 64)):
             o = self._act(F, x.H, x.W, cout)
@@ -328,7 +303,7 @@ class Engine:
                 x = o
         self.feat = torch.zeros((F, S, S, 32), dtype=torch.float32, device=self.device)
         # fp16 twin of the feature map for the plane-sweep volume builder (the volume itself is fp16; halves its gather traffic)
-        self.feat16 = torch.zeros((F, S, S, 32), dtype=torch.float16, device=self.device) if (self.vol_f16 and self.use_tc) else None
+        self.feat16 = torch.zeros((F, S, S, 32), dtype=torch.float16, device=self.device)
         fb = self._dev(sd["img_extractor.final.bias"])
         # the last layer sees every earlier one: an activation that left the fp16 range upstream arrives here as inf/NaN and
         # raises the range flag (err_flag[1]) that estimate() reads after every call
@@ -349,8 +324,7 @@ class Engine:
         self.valid_env = torch.zeros(E, dtype=torch.uint8, device=dev)
         self.E1buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
         self.E2buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
-        self.vol = self._act(E, S, S, 32, D=D, split=False, f16=self.vol_f16)
-        self.vol_planar = 0     # the volume is channels-last; the planar variant of adp_build_volume is kept for experiments only
+        self.vol = self._act(E, S, S, 32, D=D, split=False, f16=1)
         cr = "cost_regularization"
 
         def bn(name):
@@ -362,86 +336,73 @@ class Engine:
 
         def act3(level, Cn):
             d, s = dims[level]
-            return self._act(E, s, s, Cn, D=d, split=False, f16=self.vol_f16)
+            return self._act(E, s, s, Cn, D=d, split=False, f16=1)
 
-        pad0 = 16 if self.use_tc_3d else 8    # conv0's output carries 8 zero channels so that conv1 (Cin = 8) fits the K=16 MMA
-        # With the depth-ring conv0 the two full-resolution tensors (conv0 output, conv11 output) live in space-to-depth(2)
-        # layout [E, D/2, S/2, S/2, 64]: conv1 (stride 2) and conv11 (transposed, + skip) become stride-1 2x2x2-tap convs.
-        self.l0_s2d = bool(self.conv0_ring and S % 224 == 0 and pad0 == 16 and self.level0_s2d)
-        if self.l0_s2d:
-            c0 = act3(1, 64); c0.s2d = True
-            x11 = act3(1, 64); x11.s2d = True
-        else:
-            c0 = act3(0, pad0); x11 = act3(0, 8)
+        # The two full-resolution tensors (conv0 output, conv11 output) live in space-to-depth(2) layout [E, D/2, S/2, S/2, 64]
+        # (channel = parity * 8 + c): conv1 (stride 2) and conv11 (transposed, + skip) become stride-1 2x2x2-tap convs.
+        c0 = act3(1, 64); c0.s2d = True
+        x11 = act3(1, 64); x11.s2d = True
         c1 = act3(1, 16); c2 = act3(1, 16); c3 = act3(2, 32); c4 = act3(2, 32)
         c5 = act3(3, 64); c6 = act3(3, 64); x7 = act3(2, 32); x9 = act3(1, 16)
-        chain = [("conv0", self.vol, c0, 1), ("conv1", c0, c1, 2), ("conv2", c1, c2, 1), ("conv3", c2, c3, 2),
-                 ("conv4", c3, c4, 1), ("conv5", c4, c5, 2), ("conv6", c5, c6, 1)]
-        for nm, xin, out, stride in chain:
-            sc, sh = bn(nm)
-            wgt = torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float()
-            if nm == "conv0" and pad0 == 16:      # zero output channels 8..15
-                wgt = torch.cat([wgt, torch.zeros(8, *wgt.shape[1:])], 0)
-                sc = self._dev(torch.cat([sc.cpu(), torch.zeros(8)])); sh = self._dev(torch.cat([sh.cpu(), torch.zeros(8)]))
-            if nm == "conv1" and pad0 == 16:      # zero input channels 8..15
-                wgt = torch.cat([wgt, torch.zeros(wgt.shape[0], 8, 3, 3, 3)], 1)
-            if nm == "conv0" and self.conv0_ring and S % 112 == 0 and pad0 == 16:
-                w16 = G.conv0_ring_weights(torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float())
-                w16 = w16.to(torch.float16 if self.vol_f16 else torch.bfloat16).to(self.device).contiguous()
-                self._keep.append(w16)
-                plan = C.c_void_p()
-                va = xin.c
-                L.check(self.lib.adp_conv0_plan_create(C.byref(plan), C.byref(va), L.ptr(w16), L.ptr(sc), L.ptr(sh), L.ptr(out.hi),
-                                                       L.LAYOUT_S2D if self.l0_s2d else 0, self.num_sms), "conv0_plan")
-                self._conv0_plans.append(plan)
+        wcr = lambda nm: torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float()
+        # conv0: depth-ring tcgen05 kernel (csrc/conv0_ring.cu), output written space-to-depth
+        sc, sh = bn("conv0")
+        w16 = G.conv0_ring_weights(wcr("conv0")).to(torch.float16).to(self.device).contiguous()
+        self._keep.append(w16)
+        plan = C.c_void_p()
+        va = self.vol.c
+        L.check(self.lib.adp_conv0_plan_create(C.byref(plan), C.byref(va), L.ptr(w16), L.ptr(sc), L.ptr(sh), L.ptr(c0.hi),
+                                               L.LAYOUT_S2D, self.num_sms), "conv0_plan")
+        self._conv0_plans.append(plan)
 
-                def run0(batch, plan=plan):
-                    L.check(self.lib.adp_conv0_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv0_run")
-                run0.kind = "tc"
-                ops.append((f"cr.{nm}", run0))
-                continue
-            if nm == "conv1" and self.l0_s2d:
-                w_s2d = G.strided_s2d_weights(torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float())
-                ep = self._epilogue(out, scale=sc, bias=sh, act=L.ACT_RELU)
-                ops.append((f"cr.{nm}", self._tc_plans(xin, w_s2d, 16, 1, 1, 1, 1, ep, [G.strided_s2d(xin.D, xin.H, xin.W)])))
-                continue
-            ops.append((f"cr.{nm}", self._conv(wgt.numpy(), xin, out, stride=stride, npass=1, scale=sc, bias=sh, act=L.ACT_RELU)))
-        for nm, xin, skip, out in (("conv7", c6, c4, x7), ("conv9", x7, c2, x9), ("conv11", x9, c0, x11)):
+        def run0(batch, plan=plan):
+            L.check(self.lib.adp_conv0_run(plan, batch, L.ptr(self.err_flag), self.stream), "conv0_run")
+        run0.kind = "tc"
+        ops.append(("cr.conv0", run0))
+        # conv1 on the s2d tensor: a stride-1 2x2x2-tap conv over 64 channels
+        sc, sh = bn("conv1")
+        ops.append(("cr.conv1", self._tc_plans(c0, G.strided_s2d_weights(wcr("conv1")), 16, 1, 1, 1, 1,
+                                               self._epilogue(c1, scale=sc, bias=sh, act=L.ACT_RELU), [G.strided_s2d(c0.D, c0.H, c0.W)])))
+        for nm, xin, out, stride in (("conv2", c1, c2, 1), ("conv3", c2, c3, 2), ("conv4", c3, c4, 1), ("conv5", c4, c5, 2),
+                                     ("conv6", c5, c6, 1)):
             sc, sh = bn(nm)
-            if nm == "conv11" and self.l0_s2d:    # stride-1 2x2x2-tap conv writing s2d layout: the slab tcgen05 kernel
-                w_s2d = G.transposed_s2d_weights(torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float())
-                sc8, sh8 = self._dev(sc.cpu().repeat(8)), self._dev(sh.cpu().repeat(8))
-                ep = self._epilogue(out, scale=sc8, bias=sh8, act=L.ACT_RELU, res=skip, res_after_act=1)
-                ops.append((f"cr.{nm}", self._tc_plans(xin, w_s2d, 64, 1, 1, 1, 1, ep, [G.transposed_s2d(xin.D, xin.H, xin.W)])))
-                continue
-            if self.tconv_fused and xin.Cn in (16, 32) and xin.lo is None:
-                wgt = torch.as_tensor(sd[f"{cr}.{nm}.conv.weight"]).float()            # [Cin, Cout, 3,3,3]
-                cin, cout = wgt.shape[0], wgt.shape[1]
-                bn_pad = 16 if cout <= 16 else 32
-                wt = wgt.reshape(cin, cout, 27).permute(2, 1, 0).contiguous()            # [27, Cout, Cin]
-                if bn_pad != cout:
-                    wt = torch.cat([wt, torch.zeros(27, bn_pad - cout, cin)], 1).contiguous()
-                w16 = wt.to(torch.float16 if xin.f16 else torch.bfloat16).to(self.device).contiguous()
-                self._keep.append(w16)
-                plan = C.c_void_p()
-                xa = xin.c
-                L.check(self.lib.adp_tconv_plan_create(C.byref(plan), C.byref(xa), L.ptr(w16), cout, L.ptr(sc), L.ptr(sh),
-                                                       L.ptr(skip.hi), skip.Cn, L.ptr(out.hi),
-                                                       L.LAYOUT_S2D if out.s2d else 0, self.num_sms), "tconv_plan")
-                self._tconv_plans.append(plan)
+            ops.append((f"cr.{nm}", self._conv(wcr(nm).numpy(), xin, out, stride=stride, npass=1, scale=sc, bias=sh, act=L.ACT_RELU)))
+        # conv7 (64 -> 32 at the coarsest level: 8 parity-class launches of the generic kernel) and conv9 (32 -> 16: the 8
+        # parity classes fused in one kernel, csrc/tconv_fused.cu)
+        sc, sh = bn("conv7")
+        ops.append(("cr.conv7", self._conv(sd[f"{cr}.conv7.conv.weight"], c6, x7, stride=2, transposed=True, npass=1,
+                                           scale=sc, bias=sh, act=L.ACT_RELU, res=c4, res_after_act=1)))
+        for nm, xin, skip, out in (("conv9", x7, c2, x9),):
+            sc, sh = bn(nm)
+            wgt = wcr(nm)                                                              # [Cin, Cout, 3,3,3]
+            cin, cout = wgt.shape[0], wgt.shape[1]
+            bn_pad = 16 if cout <= 16 else 32
+            wt = wgt.reshape(cin, cout, 27).permute(2, 1, 0).contiguous()              # [27, Cout, Cin]
+            if bn_pad != cout:
+                wt = torch.cat([wt, torch.zeros(27, bn_pad - cout, cin)], 1).contiguous()
+            w16 = wt.to(torch.float16).to(self.device).contiguous()
+            self._keep.append(w16)
+            plan = C.c_void_p()
+            xa = xin.c
+            L.check(self.lib.adp_tconv_plan_create(C.byref(plan), C.byref(xa), L.ptr(w16), cout, L.ptr(sc), L.ptr(sh),
+                                                   L.ptr(skip.hi), skip.Cn, L.ptr(out.hi), 0, self.num_sms), "tconv_plan")
+            self._tconv_plans.append(plan)
 
-                def runt(batch, plan=plan):
-                    L.check(self.lib.adp_tconv_run(plan, batch, L.ptr(self.err_flag), self.stream), "tconv_run")
-                runt.kind = "tc"
-                ops.append((f"cr.{nm}", runt))
-                continue
-            ops.append((f"cr.{nm}", self._conv(sd[f"{cr}.{nm}.conv.weight"], xin, out, stride=2, transposed=True, npass=1,
-                                               scale=sc, bias=sh, act=L.ACT_RELU, res=skip, res_after_act=1)))
+            def runt(batch, plan=plan):
+                L.check(self.lib.adp_tconv_run(plan, batch, L.ptr(self.err_flag), self.stream), "tconv_run")
+            runt.kind = "tc"
+            ops.append((f"cr.{nm}", runt))
+        # conv11 (+ conv0 skip) writing the s2d layout: a stride-1 2x2x2-tap conv on the slab tcgen05 kernel
+        sc, sh = bn("conv11")
+        sc8, sh8 = self._dev(sc.cpu().repeat(8)), self._dev(sh.cpu().repeat(8))
+        ep = self._epilogue(x11, scale=sc8, bias=sh8, act=L.ACT_RELU, res=c0, res_after_act=1)
+        ops.append(("cr.conv11", self._tc_plans(x9, G.transposed_s2d_weights(wcr("conv11")), 64, 1, 1, 1, 1, ep,
+                                                [G.transposed_s2d(x9.D, x9.H, x9.W)])))
         self.cr_ops = ops
         self.cr_taps = {"conv0": c0, "conv1": c1, "conv2": c2, "conv3": c3, "conv4": c4, "conv5": c5, "conv6": c6,
                         "conv7": x7, "conv9": x9, "conv11": x11}
         self.x11 = x11
-        self.x11_format = (L.LAYOUT_F16 if self.vol_f16 else 0) | (L.LAYOUT_S2D if self.l0_s2d else 0)
+        self.x11_format = L.LAYOUT_F16 | L.LAYOUT_S2D
         # decode weights, transposed to [K][N]
         def tw(name):
             w = torch.as_tensor(sd[name]).float()
@@ -462,7 +423,6 @@ class Engine:
         f32 = dict(dtype=torch.float32, device=dev)
         self.nocs = torch.zeros((E, P, 3), **f32)
         self.depth = torch.zeros((E, P), **f32)
-        self.pf1 = torch.zeros((E, P, 128), **f32)
         self.gsum = torch.zeros((E, 128), **f32)
         self.psum = torch.zeros((E, 256), **f32)
         self.R = torch.zeros((E, 9), **f32)
@@ -481,8 +441,7 @@ class Engine:
         self.scale = torch.zeros(E, dtype=torch.float64, device=dev)
         self.trans = torch.zeros((E, 3), dtype=torch.float64, device=dev)
         self.rot64 = torch.zeros((E, 9), dtype=torch.float64, device=dev)
-        if self.decode_tc:
-            self._build_decode_tc()
+        self._build_decode_tc()
 
     def _build_decode_tc(self):
         """Per-point MLPs (network_v5.py:432-444,486-493) as 1x1 convolutions on the tcgen05 kernel: the P = 1024 sampled
@@ -571,29 +530,19 @@ class Engine:
         L.check(lib.adp_warp_matrices(L.ptr(self.Kp), L.ptr(E1), L.ptr(self.Kp[E:]), L.ptr(E2), L.ptr(self.Mw),
                                       L.ptr(self.valid), L.ptr(self.valid[E:]), L.ptr(self.valid_env), n, st), "warp_matrices")
         f1, f2 = self.feat, self.feat[E:]
-        if self.feat16 is not None and not getattr(self, "force_f32_volume_feats", False):
-            L.check(lib.adp_build_volume(L.ptr(self.feat16), L.ptr(self.feat16[E:]), L.ptr(self.Mw), L.ptr(self.depths),
-                                         L.ptr(self.vol.hi), n, D, S, S, 32, self.vol_f16, 1, self.vol_planar, st), "build_volume")
-        else:
-            L.check(lib.adp_build_volume(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.vol.hi), n, D, S, S,
-                                         32, self.vol_f16, 0, self.vol_planar, st), "build_volume")
+        L.check(lib.adp_build_volume(L.ptr(self.feat16), L.ptr(self.feat16[E:]), L.ptr(self.Mw), L.ptr(self.depths),
+                                     L.ptr(self.vol.hi), n, D, S, S, 32, 1, st), "build_volume")
         mark("volume")
         for name, op in self.cr_ops:
             op(n)
             mark(name)
-        if self.decode_tc:
-            L.check(lib.adp_decode_gather(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi),
-                                          L.ptr(self.choose), L.ptr(self.valid_env), self.dw.prob_w, L.ptr(self.depth),
-                                          L.ptr(self.xfeat.hi), L.ptr(self.xfeat.lo), L.ptr(self.xcat.hi), L.ptr(self.xcat.lo),
-                                          L.ptr(self.dbg_logits), L.ptr(self.dbg_fused), n, S, D, P, self.x11_format, st), "decode_gather")
-            mark("decode_gather")
-            for name, op in self.dec_ops:
-                op(n)
-        else:
-            L.check(lib.adp_decode(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi), L.ptr(self.choose),
-                                   L.ptr(self.valid_env), C.byref(self.dw), L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.pf1),
-                                   L.ptr(self.gsum), L.ptr(self.psum), L.ptr(self.R), L.ptr(self.r6), L.ptr(self.dbg_logits),
-                                   L.ptr(self.dbg_fused), n, S, D, P, 1 if self.regress_pose else 0, self.x11_format, st), "decode")
+        L.check(lib.adp_decode_gather(L.ptr(f1), L.ptr(f2), L.ptr(self.Mw), L.ptr(self.depths), L.ptr(self.x11.hi),
+                                      L.ptr(self.choose), L.ptr(self.valid_env), self.dw.prob_w, L.ptr(self.depth),
+                                      L.ptr(self.xfeat.hi), L.ptr(self.xfeat.lo), L.ptr(self.xcat.hi), L.ptr(self.xcat.lo),
+                                      L.ptr(self.dbg_logits), L.ptr(self.dbg_fused), n, S, D, P, self.x11_format, st), "decode_gather")
+        mark("decode_gather")
+        for name, op in self.dec_ops:
+            op(n)
         mark("decode")
         if self.regress_pose:
             L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
@@ -604,6 +553,21 @@ class Engine:
                                         L.ptr(self.valid_env), L.ptr(ransac_idx), seed & 0xFFFFFFFF, L.ptr(self.bbox),
                                         L.ptr(self.scale), L.ptr(self.rot64), L.ptr(self.trans), n, P, S, st), "fit_umeyama")
         mark("fit")
+
+    def single_view_nocs(self, rgb, mask, K, n, seed=0, choose=None, env0=0):
+        """One view per environment (BASELINE configs[0..1]): preprocess -> backbone -> features at the sampled pixels ->
+        instance_color -> nocs_head (network_v5.py:432-444; what the reference evaluates per view before any stereo term).
+        n <= max_envs frames -> (self.nocs[:n] [n,P,3], self.choose[:n], self.valid[:n])."""
+        assert n <= self.E
+        self.preprocess(0, rgb, mask, K, n, seed, choose, frame_id0=env0)
+        self.run_backbone(n)
+        self.valid_env[:n].copy_(self.valid[:n])
+        L.check(self.lib.adp_decode_gather(L.ptr(self.feat), None, None, None, None, L.ptr(self.choose), L.ptr(self.valid_env), None,
+                                           None, L.ptr(self.xfeat.hi), L.ptr(self.xfeat.lo), None, None, None, None, n, self.S,
+                                           N_DEPTH, self.P, 0, self.stream), "decode_gather(single view)")
+        for _, op in self.dec_ops[:4]:          # instance_color, nocs_head x 3
+            op(n)
+        return self.nocs[:n], self.choose[:n], self.valid[:n]
 
     def run_chunk(self, K, rgb1, mask1, E1, rgb2, mask2, E2, seed=0, choose1=None, choose2=None, ransac_idx=None, env0=0):
         """Device tensors for n <= max_envs environments -> self.bbox[:n] ([n,8,3] f64, world frame).  ``env0``: global index

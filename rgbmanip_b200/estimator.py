@@ -87,7 +87,7 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         device = device or cfg.get("device", "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0")
         self.device = torch.device(device)
         self.estimator = Engine(state_dict, device=self.device, max_envs=int(max_envs or cfg.get("max_envs_per_chunk", 16)),
-                                precision=precision or cfg.get("precision", "fp16x2"), regress_pose=regress,
+                                precision=precision or cfg.get("precision", "fp16f8"), regress_pose=regress,
                                 img_size=int(cfg.get("img_size", 224)), **engine_kw)
         self._seed = int(cfg.get("sample_seed", 0))
         self._calls = 0
@@ -222,6 +222,34 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             res = out.cpu().numpy()
         eng.check_error_flag()
         return res
+
+    def estimate_nocs_single_view(self, camera_intrinsic_batch, rgb_batch, mask_batch, choose=None):
+        """BASELINE configs[0..1]: one view per environment -> (nocs [N,1024,3] float32, choose [N,1024] int32, valid [N] bool)
+        as numpy arrays.  This is the per-view part of the reference forward (preprocessing, PSPNet, ``instance_color`` +
+        ``nocs_head``, network_v5.py:432-444); a full pose needs two views (interface_v5.py:256-257)."""
+        eng = self.estimator
+        K_b, rgb_b, m_b = (self._as_tensor(a) for a in (camera_intrinsic_batch, rgb_batch, mask_batch))
+        N = K_b.shape[0]
+        nocs = torch.empty((N, eng.P, 3), dtype=torch.float32, device=self.device)
+        chs = torch.empty((N, eng.P), dtype=torch.int32, device=self.device)
+        val = torch.empty((N,), dtype=torch.uint8, device=self.device)
+        self._calls += 1
+        with torch.cuda.device(self.device):
+            for lo, hi in chunk_bounds(N, eng.E):
+                m = m_b[lo:hi]
+                if m.dtype not in self._MASK_OK:
+                    m = m != 0
+                if m.dtype == torch.bool:
+                    m = m.view(torch.uint8)
+                c = None if choose is None else self._as_tensor(choose[lo:hi]).to(torch.int32).to(self.device)
+                n_, c_, v_ = eng.single_view_nocs(self._upload("rgb1", 0, rgb_b[lo:hi], self._rgb_dtype(rgb_b)),
+                                                  self._upload("m1", 0, m), self._upload("K", 0, K_b[lo:hi], torch.float64), hi - lo,
+                                                  seed=self._seed + 7919 * self._calls, choose=c, env0=lo)
+                nocs[lo:hi].copy_(n_); chs[lo:hi].copy_(c_); val[lo:hi].copy_(v_)
+                torch.cuda.current_stream(self.device).synchronize()       # the pinned staging slot is reused by the next chunk
+            out = (nocs.cpu().numpy(), chs.cpu().numpy(), val.cpu().numpy().astype(bool))
+        eng.check_error_flag()
+        return out
 
     def check_error_flag(self):
         """Synchronise and raise if the pipeline watchdog or the fp16 range guard fired (the tensor-returning paths defer it)."""

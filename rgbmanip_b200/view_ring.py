@@ -94,11 +94,10 @@ class ViewRing:
             for lo in range(0, N, eng.F):                 # the frame buffers hold 2 x max_envs frames: full-size backbone launches
                 hi = min(N, lo + eng.F)
                 n = hi - lo
-                rgb_d = self._dev(color[lo:hi])
-                if rgb_d.dtype not in (torch.uint8, torch.float32, torch.float64):     # uint8 = value / 255 (ToTensor), in the kernel
-                    if not rgb_d.dtype.is_floating_point:
-                        raise TypeError(f"unsupported image dtype {rgb_d.dtype}: float RGB in [0, 1] or uint8 in [0, 255]")
-                    rgb_d = rgb_d.float()
+                c = color[lo:hi]
+                c = c if isinstance(c, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(c))
+                # same staging policy as estimate(): float64 host frames are demoted to float32, uint8 means value / 255
+                rgb_d = self._dev(c, self.estimator._rgb_dtype(c))
                 mask_d = self._dev(mask[lo:hi])
                 if mask_d.dtype not in (torch.uint8, torch.bool, torch.float32, torch.float64):
                     mask_d = (mask_d != 0).to(torch.uint8)       # segmentation ids: a cast could wrap 256 to 0

@@ -20,8 +20,17 @@ def split(x: torch.Tensor, with_lo=True):
     return hi.to(DEV).contiguous(), (lo.to(DEV).contiguous() if with_lo else None)
 
 
-def act(hi, lo, B, D, H, W, Cn, f16=0):
-    return L.Act(L.ptr(hi), L.ptr(lo), B, D, H, W, Cn, f16)
+def act(hi, lo, B, D, H, W, Cn, f16=0, q8=None):
+    return L.Act(L.ptr(hi), L.ptr(lo), B, D, H, W, Cn, f16, L.ptr(q8))
+
+
+def to_e4m3(x):
+    """fp32 -> e4m3 bytes (saturating), as a uint8 tensor; from_e4m3 is the inverse."""
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def from_e4m3(u):
+    return u.view(torch.float8_e4m3fn).float()
 
 
 def val(hi, lo):
@@ -43,9 +52,9 @@ def from_cl(x):
 
 
 def epilogue(out_hi=None, out_lo=None, out_f32=None, scale=None, bias=None, act_code=L.ACT_NONE, prelu=0.0, res_hi=None,
-             res_lo=None, res_after_act=0):
+             res_lo=None, res_after_act=0, out_q8=None):
     return L.Epilogue(L.ptr(scale), L.ptr(bias), float(prelu), act_code, res_after_act, L.ptr(res_hi), L.ptr(res_lo), 0,
-                      L.ptr(out_hi), L.ptr(out_lo), L.ptr(out_f32), None)
+                      L.ptr(out_hi), L.ptr(out_lo), L.ptr(out_f32), None, 0, 0, 0, L.ptr(out_q8), 0)
 
 
 def rel_err(a, b):
@@ -54,7 +63,7 @@ def rel_err(a, b):
 
 
 def tc_conv(x_cl, w, *, dil=1, npass=3, bias=None, scale=None, act_code=L.ACT_NONE, prelu=0.0, res_cl=None, res_after_act=0,
-            batch=None, stride=1, transposed=False, f16=0):
+            batch=None, stride=1, transposed=False, f16=0, q8_out=None):
     """x_cl: fp32 [B,(D,)H,W,Cin] cpu; w: torch layout [Cout,Cin,(kd,)k,k] ([Cin,Cout,3,3,3] when transposed).
     Returns (fp32 output, 16-bit output as fp32), cpu, channels-last."""
     from rgbmanip_b200 import geometry
@@ -87,13 +96,18 @@ def tc_conv(x_cl, w, *, dil=1, npass=3, bias=None, scale=None, act_code=L.ACT_NO
         xh, xl = x_cl.to(torch.float16).to(DEV).contiguous(), None
         wh16 = wt.to(torch.float16)
         wh, wl = wh16.to(DEV).contiguous(), None
+        xq = None
         if npass == 2:      # fp16x2: the rounding residual of the weights rides in a second fp16 plane
             wl = (wt - wh16.float()).to(torch.float16).to(DEV).contiguous()
+        elif npass == 4:    # fp16 + fp8 low-order pass: e4m3(W_lo 2^16) against the activation's e4m3(x / 2) twin
+            wl = to_e4m3((wt - wh16.float()) * 65536.0).to(DEV).contiguous()
+            xq = to_e4m3(x_cl.to(torch.float16).float() * 0.5).to(DEV).contiguous()
         dt16 = torch.float16
     else:
         xh, xl = split(x_cl, npass == 3)
         wh, wl = split(wt, npass == 3)
         dt16 = torch.bfloat16
+        xq = None
     out_f32 = torch.full(oshape, float("nan"), dtype=torch.float32, device=DEV)
     out_hi = torch.zeros(out_f32.shape, dtype=dt16, device=DEV)
     out_lo = torch.zeros_like(out_hi) if not f16 else None
@@ -105,9 +119,10 @@ def tc_conv(x_cl, w, *, dil=1, npass=3, bias=None, scale=None, act_code=L.ACT_NO
             rh, rl = split(res_cl, True)
     b_d = bias.to(DEV) if bias is not None else None
     s_d = scale.to(DEV) if scale is not None else None
-    ep = epilogue(out_hi, out_lo, out_f32, s_d, b_d, act_code, prelu, rh, rl, res_after_act)
-    a = act(xh, xl, B, D, H, Wd, Cin, f16)
-    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out_q8 = torch.zeros(out_f32.shape, dtype=torch.uint8, device=DEV) if q8_out is not None else None
+    ep = epilogue(out_hi, out_lo, out_f32, s_d, b_d, act_code, prelu, rh, rl, res_after_act, out_q8=out_q8)
+    a = act(xh, xl, B, D, H, Wd, Cin, f16, xq)
+    err = torch.zeros(2, dtype=torch.int32, device=DEV)
     for g in geoms:
         plan = C.c_void_p()
         L.check(lib.adp_conv_tc_plan(C.byref(plan), C.byref(a), L.ptr(wh), L.ptr(wl), Cout, kd, ks, dil, npass, C.byref(ep),
@@ -115,46 +130,7 @@ def tc_conv(x_cl, w, *, dil=1, npass=3, bias=None, scale=None, act_code=L.ACT_NO
         L.check(lib.adp_conv_tc_run(plan, B if batch is None else batch, L.ptr(err), stream()), "run")
         torch.cuda.synchronize()
         lib.adp_conv_tc_free(plan)
-    assert int(err.item()) == 0, f"watchdog code {int(err.item())}"
+    assert int(err[0].item()) == 0, f"watchdog code {int(err[0].item())}"
+    if q8_out is not None:
+        q8_out.append(from_e4m3(out_q8.cpu()) * 2.0)
     return out_f32.cpu(), val(out_hi, out_lo).cpu()
-
-
-def direct_conv(x_cl, w, *, stride=1, dil=1, transposed=False, bias=None, scale=None, act_code=L.ACT_NONE, res_cl=None,
-                res_after_act=0, f32_input=False):
-    lib = L.load()
-    three_d = x_cl.dim() == 5
-    B = x_cl.shape[0]
-    D = x_cl.shape[1] if three_d else 1
-    H, Wd, Cin = x_cl.shape[-3], x_cl.shape[-2], x_cl.shape[-1]
-    if transposed:
-        Cout = w.shape[1]
-        wp = w.reshape(Cin, Cout, -1).permute(2, 0, 1).contiguous().to(DEV)
-        Do, Ho, Wo = 2 * D, 2 * H, 2 * Wd
-    else:
-        Cout = w.shape[0]
-        wp = w.reshape(Cout, Cin, -1).permute(2, 1, 0).contiguous().to(DEV)
-        Do = (D + stride - 1) // stride if three_d else 1
-        Ho, Wo = (H + stride - 1) // stride, (Wd + stride - 1) // stride
-    kd = w.shape[2] if three_d else 1
-    ks = w.shape[-1]
-    pad = dil * (ks // 2)
-    shape = (B, Do, Ho, Wo, Cout) if three_d else (B, Ho, Wo, Cout)
-    out_f32 = torch.full(shape, float("nan"), dtype=torch.float32, device=DEV)
-    rh = rl = None
-    if res_cl is not None:
-        rh, rl = split(res_cl, True)
-    b_d = bias.to(DEV) if bias is not None else None
-    s_d = scale.to(DEV) if scale is not None else None
-    ep = epilogue(None, None, out_f32, s_d, b_d, act_code, 0.0, rh, rl, res_after_act)
-    if f32_input:
-        xin = x_cl.to(DEV).contiguous()
-        xh = xl = None
-    else:
-        xin = None
-        xh, xl = split(x_cl, True)
-    d = L.DirectConv(L.ptr(xh), L.ptr(xl), L.ptr(xin), B, D, H, Wd, Cin, Do, Ho, Wo, Cout, kd, ks, ks,
-                     stride if three_d else 1, stride, stride, 1 if three_d else 0, pad, pad, dil, 1 if transposed else 0,
-                     0, L.ptr(wp), ep)
-    L.check(lib.adp_conv_direct(C.byref(d), B, stream()), "direct")
-    torch.cuda.synchronize()
-    return out_f32.cpu()

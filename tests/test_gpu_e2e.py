@@ -46,7 +46,7 @@ def _make(cfg_extra=None, **kw):
     return AdaPoseEstimator_v5(None, cfg, None, state_dict=weights.init_state_dict(0), **kw)
 
 
-@pytest.mark.parametrize("precision", ["fp16x2", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp16f8", "fp16x2", "bf16x3"])
 @pytest.mark.parametrize("max_envs", [8, 3])
 def test_estimate_matches_reference_golden(golden, max_envs, precision):
     g = golden
@@ -66,7 +66,7 @@ def test_estimate_matches_reference_golden(golden, max_envs, precision):
     est.estimator.close()
 
 
-@pytest.mark.parametrize("precision", ["fp16x2", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp16f8", "fp16x2", "bf16x3"])
 def test_estimate_matches_second_reference_fixture(golden_dir, precision):
     """Independent fixture: other random weights (seed 1), other scenes (seed 5) -- tests/golden/e2e_seed1.npz."""
     if not torch.cuda.is_available():
@@ -86,7 +86,7 @@ def test_estimate_matches_second_reference_fixture(golden_dir, precision):
     est.estimator.close()
 
 
-@pytest.mark.parametrize("precision", ["fp16x2", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp16f8", "fp16x2", "bf16x3"])
 def test_network_outputs_match_reference_golden(golden, precision):
     """NOCS / depth / rotation of the last processed chunk against the reference's own tensors."""
     g = golden
@@ -97,7 +97,8 @@ def test_network_outputs_match_reference_golden(golden, precision):
     for e in range(8):
         if not g["valid"][e]:
             continue
-        assert float(np.abs(eng.nocs[e].cpu().numpy() - g[f"env{e}_view1_nocs"]).max()) < 2e-3
+        # NOCS coordinates (unit cube): fp16f8 carries the e4m3 rounding of the low-order weight term on top of fp16x2
+        assert float(np.abs(eng.nocs[e].cpu().numpy() - g[f"env{e}_view1_nocs"]).max()) < (3e-3 if precision == "fp16f8" else 2e-3)
         d = np.abs(eng.depth[e].cpu().numpy() - g[f"env{e}_view1_depth"])
         assert d.mean() < 1e-3 and d.max() < 8e-3           # metres; per-pixel soft-argmax through the bf16 U-Net
         assert O.rotation_angle_deg(eng.R[e].cpu().numpy().reshape(3, 3), g[f"env{e}_view1_r"]) < 0.1
@@ -304,3 +305,24 @@ def test_size_independent_properties_at_scale(golden):
     boxes_c = est2.estimate(*[a[:40] for a in args], choose=(choose[0][:40], choose[1][:40]))
     np.testing.assert_allclose(boxes_c, boxes[:40], rtol=0, atol=2e-5)
     est2.estimator.close()
+
+
+def test_single_view_nocs_matches_reference_golden(golden):
+    """BASELINE configs[0..1] (one view per env: backbone + NOCS head) against the reference's own per-view NOCS maps, for the
+    frames of both views of the golden environments."""
+    g = golden
+    batch = synth.make_batch(8, seed=0)
+    est = _make(max_envs=3)                     # chunks of 3, 3, 2
+    for view, (rgb, mask) in enumerate(((batch.rgb1, batch.mask1), (batch.rgb2, batch.mask2)), 1):
+        ch = np.zeros((8, 1024), np.int32)
+        for e in range(8):
+            if g["valid"][e]:
+                ch[e] = g[f"env{e}_choose{view}"]
+        nocs, choose, valid = est.estimate_nocs_single_view(batch.K, rgb, mask, choose=ch)
+        assert nocs.shape == (8, 1024, 3) and nocs.dtype == np.float32
+        for e in range(8):
+            if g["valid"][e]:
+                assert valid[e]
+                np.testing.assert_array_equal(choose[e], ch[e])
+                assert float(np.abs(nocs[e] - g[f"env{e}_view{view}_nocs"]).max()) < 3e-3, (view, e)
+    est.estimator.close()

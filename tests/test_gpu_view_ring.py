@@ -30,7 +30,9 @@ def test_queue_state_matches_reference_controller(golden_dir):
     ring = ViewRing(est, 3, 5)
     q = V.ViewQueues(3, 5)
     for t, (color, mask, K, E, pose) in enumerate(V.view_ring_script()):
-        ring.add_view({"camera0": {"Color": color, "Mask": mask, "Intrinsic": K, "Extrinsic": E}}, pose)
+        # the script's frames are constant images whose value (10 .. 92) encodes (step, env); the queue state does not depend
+        # on them, and as images they would leave the fp16 range of the backbone (the per-call range guard reports that)
+        ring.add_view({"camera0": {"Color": color / 100.0, "Mask": mask, "Intrinsic": K, "Extrinsic": E}}, pose)
         ring.accumulate_steps += 1
         q.add_view(color, mask, K, E, pose)
         q.accumulate_steps += 1

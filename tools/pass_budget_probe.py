@@ -58,7 +58,15 @@ def group_of(x, w):
     raise KeyError((tuple(x.shape), tuple(w.shape)))
 
 
-def run(single=(), emulate=True):
+def e4m3(x):
+    """Round to fp8 e4m3 (saturating, like cvt.rn.satfinite.e4m3x2.f32)."""
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+
+
+A8_SCALE, W8_SCALE = 0.5, 2.0 ** 16      # A8 = e4m3(A / 2), W8 = e4m3(W_lo * 2^16): the product carries 2^15 (scale-input-d = 15)
+
+
+def run(single=(), emulate=True, fp8lo=()):
     c2, c3, ct3 = F.conv2d, F.conv3d, F.conv_transpose3d
 
     def conv2d(x, w, *a, **k):
@@ -68,6 +76,13 @@ def run(single=(), emulate=True):
         if g is None:
             return c2(x, w, *a, **k)
         xw = x.half().float()
+        if g in fp8lo:                   # hi pass in fp16, lo pass in fp8 (e4m3 x e4m3) at twice the MMA rate
+            wh = w.half().float()
+            wl8 = e4m3((w - wh) * W8_SCALE) / W8_SCALE
+            a8 = e4m3(xw * A8_SCALE) / A8_SCALE
+            bias = k.pop("bias", None) if "bias" in k else (a[0] if a else None)
+            rest = a[1:] if a else a
+            return c2(xw, wh, bias, *rest, **k) + c2(a8, wl8, None, *rest, **k)
         if g in single:
             w = w.half().float()
         else:                            # hi + lo: 22 mantissa bits
@@ -107,12 +122,21 @@ if __name__ == "__main__":
     t0 = time.time()
     ref = run(emulate=False)
     print(f"fp32 oracle: {time.time() - t0:.1f} s for {n_envs} envs (weights seed {seed})", flush=True)
-    variants = [("none (fp16x2 everywhere)", ())] + [(g, (g,)) for g in GROUPS] + [("ALL single pass", tuple(GROUPS))]
-    extra = [a for a in sys.argv[3:]]
+    variants = [("none (fp16x2 everywhere)", ())]
+    if "--only-extra" not in sys.argv:
+        variants += [(g, (g,)) for g in GROUPS] + [("ALL single pass", tuple(GROUPS))]
+    extra = [a for a in sys.argv[3:] if not a.startswith("--")]
     for e in extra:
-        variants.append((e, tuple(e.split("+"))))
+        if e.startswith("fp8lo:"):
+            variants.append((e, ("fp8lo", tuple(e[6:].split("+")))))
+        else:
+            variants.append((e, tuple(e.split("+"))))
     print(f"{'single-pass groups':34s} {'GFLOP saved':>11s} | max: px deg ctr-mm corner-mm | rms: px ctr-mm corner-mm")
     for name, single in variants:
-        mx, rms = errors(run(single), ref)
-        saved = sum(GFLOP[g] for g in single)
+        if single and single[0] == "fp8lo":
+            mx, rms = errors(run(fp8lo=single[1]), ref)
+            saved = 0.5 * sum(GFLOP[g] for g in single[1])
+        else:
+            mx, rms = errors(run(single), ref)
+            saved = sum(GFLOP[g] for g in single)
         print(f"{name:34s} {saved:11.2f} | {mx[0]:.4f} {mx[1]:.5f} {mx[2]:.4f} {mx[3]:.4f} | {rms[0]:.4f} {rms[2]:.4f} {rms[3]:.4f}", flush=True)
