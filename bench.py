@@ -462,6 +462,24 @@ def main():
             variants["pinned_uint8"] = {"value": N * 2 / wall_u, "unit": "estimates/s", "num_envs": N,
                                         "h2d_bytes_per_step": int(sum(u8[k].numel() * u8[k].element_size() for k in order))}
             del u8
+        # ---- the whole box from ONE process (cfg["devices"]): what an unmodified vec-env host gets without torchrun
+        if world == 1 and torch.cuda.device_count() > 1:
+            ndev = torch.cuda.device_count()
+            est_m = AdaPoseEstimator_v5(None, dict(CFG, devices=list(range(ndev))), None, state_dict=weights.init_state_dict(0),
+                                        max_envs=args.chunk, precision=args.precision)
+            run = lambda: est_m.estimate(*[host[k] for k in order])
+            for _ in range(3):
+                run()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                out_m = run()
+            dt = (time.perf_counter() - t0) / 3
+            ref_m = est.estimate(*[host[k] for k in order], sample_seed=est_m._seed + 7919 * est_m._calls)
+            variants["single_process_all_gpus"] = {"value": N / dt, "unit": "estimates/s", "devices": ndev, "num_envs": N,
+                                                   "bit_identical_to_one_gpu": bool(np.array_equal(out_m, ref_m)),
+                                                   "note": "AdaPoseEstimator_v5(cfg['devices']=[0..n)): one engine per GPU, one host thread each, pinned fp32 host inputs"}
+            del est_m
+            torch.cuda.empty_cache()
         # ---- BASELINE configs[1]: N = 64, one view per env: backbone + NOCS
         n64 = min(64, n_loc)
         if n64:

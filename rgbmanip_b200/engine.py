@@ -15,6 +15,7 @@ Stage map (reference lines relative to models/pose_estimator/AdaPose):
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -27,6 +28,7 @@ from . import weights as W
 IMG_SIZE = 224
 N_PTS = 1024
 N_DEPTH = 24
+_CAPTURE_LOCK = threading.Lock()        # one CUDA-graph capture at a time per process
 
 
 @dataclass
@@ -92,6 +94,7 @@ class Engine:
         if int(n_pts) != 1024 or int(img_size) % 224 != 0:
             raise ValueError("the device pipeline is built for n_pts = 1024 and img_size = 224 (every shipped adapose_* yaml)")
         self.use_graph = bool(use_graph) and not debug
+        self._capture_stream = None
         self._graphs = {}           # chunk size -> (CUDAGraph, launches per replay)
         self._chunk_runs = {}       # chunk size -> eager runs so far (a size is captured on its second appearance)
         self._conv0_plans = []
@@ -605,7 +608,13 @@ class Engine:
         l0 = self.lib.adp_launch_count()
         try:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread-local capture mode: with one engine per GPU driven by one host thread each (single-process multi-GPU), the
+            # other threads keep issuing copies / allocations on their own devices while this one captures
+            # (and an explicit capture stream on THIS device: torch caches one process-wide default capture stream, created on
+            # whichever device captured first, and would switch the current device to it)
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(self.device)
+            with _CAPTURE_LOCK, torch.cuda.graph(g, stream=self._capture_stream, capture_error_mode="thread_local"):
                 self.run_backbone(2 * n)
                 self.stereo(n, self.E1buf, self.E2buf, o2=n)
             launches = int(self.lib.adp_launch_count() - l0)

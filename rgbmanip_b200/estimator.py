@@ -71,9 +71,10 @@ def chunk_bounds(N, max_envs, first=0):
 
 class AdaPoseEstimator_v5(BasePoseEstimator):
 
-    def __init__(self, env, cfg, logger, state_dict=None, device=None, max_envs=None, precision=None, **engine_kw):
+    def __init__(self, env, cfg, logger, state_dict=None, device=None, max_envs=None, precision=None, devices=None, **engine_kw):
         super().__init__(env, cfg, logger)
         self.cfg = cfg
+        self._replicas = None
         regress = bool(cfg.get("direct_regression", True))
         if not regress and not cfg.get("use_depth", True):
             # branch C (interface_v5.py:339-349) lives inside OpenCV (triangulatePoints / solvePnPRansac): parity unpinned
@@ -84,6 +85,27 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
                 state_dict = W.load_checkpoint(cfg["checkpoint_path"], regress_pose=regress)
             else:
                 state_dict = W.init_state_dict(int(cfg.get("seed", 0)), regress_pose=regress)
+        devices = devices if devices is not None else cfg.get("devices")
+        if devices == "all":
+            devices = list(range(torch.cuda.device_count()))
+        if devices is not None and len(devices) > 1:
+            # Single-process multi-GPU: the reference builds ONE estimator in ONE process (train.py:238-240), so
+            # an unmodified vec-env host reaches every GPU of the box through this object -- no torchrun.  One replica (engine,
+            # weights, workspace, streams) per device, each driven by its own host thread; the ctypes calls and torch's CUDA calls
+            # release the GIL, and a chunk is one CUDA-graph replay, so the host threads stay out of each other's way.
+            from concurrent.futures import ThreadPoolExecutor
+            devs = [torch.device(d if isinstance(d, (str, torch.device)) else f"cuda:{int(d)}") for d in devices]
+            self._pool = ThreadPoolExecutor(max_workers=len(devs), thread_name_prefix="adapose-gpu")
+            mk = lambda d: AdaPoseEstimator_v5(env, {k: v for k, v in cfg.items() if k != "devices"}, logger, state_dict=state_dict,
+                                               device=d, max_envs=max_envs, precision=precision, **engine_kw)
+            self._replicas = list(self._pool.map(mk, devs))
+            self.device = devs[0]
+            self.estimator = self._replicas[0].estimator     # the attribute the reference exposes (interface_v5.py:48)
+            self._seed = int(cfg.get("sample_seed", 0))
+            self._calls = 0
+            return
+        if devices is not None and len(devices) == 1:
+            device = devices[0] if isinstance(devices[0], (str, torch.device)) else f"cuda:{int(devices[0])}"
         device = device or cfg.get("device", "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0")
         self.device = torch.device(device)
         self.estimator = Engine(state_dict, device=self.device, max_envs=int(max_envs or cfg.get("max_envs_per_chunk", 16)),
@@ -176,6 +198,10 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         index of the first environment when the caller shards a larger batch (the device pixel sampler is keyed by
         (seed, global env index), so shards reproduce the unsharded result); ``sample_seed`` fixes that seed for one call
         (default: a per-call counter)."""
+        if self._replicas is not None:
+            return self._estimate_multi((camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
+                                         rgb2_batch, view2_mask_batch, view2_extrinsic_batch), choose, return_tensor, ransac_idx,
+                                        env_offset, sample_seed)
         eng = self.estimator
         eng.check_error_flag(wait=False)        # a flag read posted by an earlier tensor-returning call
         batches = tuple(self._as_tensor(a) for a in (camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
@@ -251,9 +277,38 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         eng.check_error_flag()
         return out
 
+    def _estimate_multi(self, batches, choose, return_tensor, ransac_idx, env_offset, sample_seed):
+        """Contiguous blocks of environments, one per replica / device, run concurrently; the [n,8,3] results come back to the
+        first device (peer copies) or the host.  Same sampler seed and global env indices on every replica: the result equals
+        the one-GPU result of the same call bit for bit."""
+        from .dist import shard_range
+        N = len(batches[0])
+        world = len(self._replicas)
+        self._calls += 1
+        seed = (self._seed + 7919 * self._calls) if sample_seed is None else int(sample_seed)
+
+        def run(r):
+            lo, hi, _ = shard_range(N, r, world)
+            if hi <= lo:
+                return None
+            rep = self._replicas[r]
+            sl = lambda a: None if a is None else a[lo:hi]
+            ch = None if choose is None else (choose[0][lo:hi], choose[1][lo:hi])
+            return rep.estimate(*[a[lo:hi] for a in batches], choose=ch, return_tensor=True, ransac_idx=sl(ransac_idx),
+                                env_offset=int(env_offset) + lo, sample_seed=seed)
+        parts = [p for p in self._pool.map(run, range(world)) if p is not None]
+        if return_tensor:
+            if not parts:
+                return torch.empty((0, 8, 3), dtype=torch.float64, device=self.device)
+            return torch.cat([p.to(self.device) for p in parts])
+        res = np.concatenate([p.cpu().numpy() for p in parts]) if parts else np.zeros((0, 8, 3))
+        self.check_error_flag()
+        return res
+
     def check_error_flag(self):
         """Synchronise and raise if the pipeline watchdog or the fp16 range guard fired (the tensor-returning paths defer it)."""
-        self.estimator.check_error_flag()
+        for rep in (self._replicas or [self]):
+            rep.estimator.check_error_flag()
 
     def estimate_tensor(self, *args, **kw):
         """Same as :meth:`estimate` but returns the [N,8,3] float64 CUDA tensor without the device->host copy."""

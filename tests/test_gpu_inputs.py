@@ -156,3 +156,21 @@ def test_one_engine_per_device_in_one_process():
     a = _make(max_envs=2, device="cuda:0").estimate(*b.args(), choose=ch)
     c = _make(max_envs=2, device="cuda:1").estimate(*b.args(), choose=ch)
     np.testing.assert_allclose(a, c, rtol=0, atol=2e-5)
+
+
+def test_single_process_multi_gpu_equals_one_gpu():
+    """cfg["devices"] = [0, 1]: one estimator object in one process (what train.py:238-240 builds) drives one engine per GPU from
+    its own host thread; the boxes equal the one-GPU result of the same call bit for bit."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    b = synth.make_batch(9, seed=18, special=True)
+    one = _make(max_envs=2)
+    multi = _make(max_envs=2, cfg_extra={"devices": list(range(min(torch.cuda.device_count(), 4)))})
+    for call in range(3):                     # eager, graph capture, graph replay
+        a = one.estimate(*b.args(), sample_seed=77 + call)
+        c = multi.estimate(*b.args(), sample_seed=77 + call)
+        np.testing.assert_array_equal(a, c)
+    t = multi.estimate(*b.args(), sample_seed=79, return_tensor=True)
+    assert t.device == multi.device and tuple(t.shape) == (9, 8, 3)
+    np.testing.assert_array_equal(t.cpu().numpy(), a)
+    multi.check_error_flag()
