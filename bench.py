@@ -341,6 +341,8 @@ def main():
     from rgbmanip_b200.estimator import AdaPoseEstimator_v5
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    from rgbmanip_b200.dist import bind_to_gpu_numa
+    numa_bound = bind_to_gpu_numa(dev) if world > 1 else False     # pinned host frames on the GPU's own NUMA node
     lib = _lib.load()
     N = args.num_envs
     lo, hi, per = shard_range(N, rank, world)
@@ -414,8 +416,12 @@ def main():
     e2e = None
     h2d = sum(host[k].numel() * host[k].element_size() for k in order)
     if not args.no_e2e:
+        b0 = est.h2d_bytes
         ms_h, wall_h, _ = timed(step_host, max(1, args.steps), 2)
-        e2e = {"value": N * max(1, args.steps) / wall_h, "unit": "estimates/s", "h2d_bytes_per_step": int(h2d),
+        h2d_real = (est.h2d_bytes - b0) // (max(1, args.steps) + 2)
+        e2e = {"value": N * max(1, args.steps) / wall_h, "unit": "estimates/s", "h2d_bytes_per_step": int(h2d_real),
+               "host_input_bytes_per_step": int(h2d),
+               "h2d_note": "of every host frame only the rows under its crop window are uploaded (masks first, windows read back from the device)",
                "d2h_bytes_per_step": int(n_loc * 24 * 8), "timed": "host wall clock around estimate() + all-gather + D2H; pinned fp32 host inputs",
                "chunks": [h - l for l, h in est._chunk_bounds(n_loc, True)]}
 
@@ -458,9 +464,17 @@ def main():
                                                   "note": "what rl_pose.py passes; staged through pinned buffers and demoted to float32 on the way (host-copy bound)"}
             del f64
             u8 = {k: ((host[k] * 255).round().to(torch.uint8).pin_memory() if k.startswith("rgb") else host[k]) for k in order}
+            b0 = est.h2d_bytes
             ms_u, wall_u, _ = timed(lambda: step_host(u8), 2, 1)
             variants["pinned_uint8"] = {"value": N * 2 / wall_u, "unit": "estimates/s", "num_envs": N,
-                                        "h2d_bytes_per_step": int(sum(u8[k].numel() * u8[k].element_size() for k in order))}
+                                        "h2d_bytes_per_step": int((est.h2d_bytes - b0) // 3)}
+            est._window_upload = False
+            b0 = est.h2d_bytes
+            ms_w, wall_w, _ = timed(step_host, 2, 1)
+            est._window_upload = True
+            variants["pinned_float32_whole_frames"] = {"value": N * 2 / wall_w, "unit": "estimates/s", "num_envs": N,
+                                                       "h2d_bytes_per_step": int((est.h2d_bytes - b0) // 3),
+                                                       "note": "window_upload off: every frame uploaded whole (the round-1 behaviour)"}
             del u8
         # ---- the whole box from ONE process (cfg["devices"]): what an unmodified vec-env host gets without torchrun
         if world == 1 and torch.cuda.device_count() > 1:
@@ -613,7 +627,8 @@ def main():
                 "config": {"workload": workload_name(N),
                            "precision": eng.precision, "chunk_envs": eng.E, "sharding": f"env-sharded dp{world}, NCCL all-gather of poses",
                            "l2": "inputs (>= 8 GB per step) exceed the 126 MB L2; no explicit flush needed",
-                           "sampling": "device hash sampler for the 1024-pixel subset, keyed by the global env index"},
+                           "sampling": "device hash sampler for the 1024-pixel subset, keyed by the global env index",
+                           "host_threads_bound_to_gpu_numa_node": bool(numa_bound)},
                 "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels,
                 "parity_in_bench": parity, "shard_identity": identity, "e2e_variants": variants, "configs": configs,

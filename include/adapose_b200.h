@@ -110,6 +110,12 @@ ADP_API int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int
                    int F, int H, int W, int S, int P, uint32_t seed, int choose_mode, int frame_id0, int32_t* bbox_ws,
                    int32_t* win, double* Kp, uint8_t* valid, float* crops, int32_t* choose, int32_t* counts, void* stream);
 
+/* Crop windows alone (the mask pass of adp_preprocess: utils.py:10-38): win [F,4] = rmin,rmax,cmin,cmax, valid [F].  The host
+ * mirror uploads the masks first, reads the windows back and then uploads only the image rows a window covers (a 480 x 640 fp32
+ * frame is 3.7 MB, the rows of a typical 160-pixel window 1.2 MB); adp_preprocess reads nothing outside the window. */
+ADP_API int adp_mask_windows(const void* mask, int mask_dtype, int F, int H, int W, int32_t* bbox_ws, int32_t* win, uint8_t* valid,
+                             void* stream);
+
 /* --- backbone: pspnet.py:33-158 ------------------------------------------------------------------------------ */
 ADP_API int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, const void* w_lo, int cout, int kd,
                      int ks, int dil, int npass, const adp_epilogue* ep, const adp_tc_geom* geom, int num_sms);

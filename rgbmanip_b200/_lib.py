@@ -55,6 +55,7 @@ SIGNATURES = {
     "adp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "adp_preprocess": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "adp_mask_windows": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "adp_conv_tc_plan": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(Epilogue), C.POINTER(TcGeom), C.c_int]),
     "adp_conv_tc_run": (C.c_int, [vp, C.c_int, vp, vp]),

@@ -30,6 +30,7 @@ int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t 
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
                    int S, int P, uint32_t seed, int choose_mode, int frame_id0, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
                    float* crops, int* choose, int* counts, cudaStream_t stream);
+int mask_windows_run(const void* mask, int mask_dt, int F, int H, int W, int* bbox_ws, int* win, uint8_t* valid, cudaStream_t stream);
 int build_volume(const void* f_ref, const void* f_src, const float* Mw, const float* depths, bf16* vol, int B, int D, int H,
                  int W, int C, int f16, cudaStream_t stream);
 int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
@@ -111,6 +112,12 @@ int adp_preprocess(const void* rgb, int rgb_dtype, const void* mask, int mask_dt
     g_launches += 5;
     return preprocess_run(rgb, rgb_dtype, mask, mask_dtype, K, k_stride, F, H, W, S, P, seed, choose_mode, frame_id0, bbox_ws, win, Kp,
                           valid, crops, choose, counts, (cudaStream_t)stream);
+}
+
+int adp_mask_windows(const void* mask, int mask_dtype, int F, int H, int W, int32_t* bbox_ws, int32_t* win, uint8_t* valid, void* stream) {
+    ADP_CHECK_ARG(mask && bbox_ws && win && valid, "null pointer");
+    g_launches += 3;
+    return mask_windows_run(mask, mask_dtype, F, H, W, bbox_ws, win, valid, (cudaStream_t)stream);
 }
 
 int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, const void* w_lo, int cout, int kd, int ks,

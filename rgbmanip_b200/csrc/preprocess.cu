@@ -54,7 +54,7 @@ __global__ void window_kernel(const int* __restrict__ bbox, const double* __rest
     if (y2 < 0) {
         valid[f] = 0;
         win[4 * f] = 0; win[4 * f + 1] = 40; win[4 * f + 2] = 0; win[4 * f + 3] = 40;
-        for (int i = 0; i < 9; ++i) Kp[9 * f + i] = (i % 4 == 0) ? 1.0 : 0.0;
+        if (Kp) for (int i = 0; i < 9; ++i) Kp[9 * f + i] = (i % 4 == 0) ? 1.0 : 0.0;
         return;
     }
     int ws = (max(y2 - y1, x2 - x1) / 40 + 1) * 40;
@@ -67,6 +67,7 @@ __global__ void window_kernel(const int* __restrict__ bbox, const double* __rest
     if (cmax > W) { cmin -= cmax - W; cmax = W; }
     win[4 * f] = rmin; win[4 * f + 1] = rmax; win[4 * f + 2] = cmin; win[4 * f + 3] = cmax;
     valid[f] = 1;
+    if (!Kp) return;
     const double* k = K + (size_t)f * k_stride;
     const double ratio = (double)S / (double)(rmax - rmin);
     const double ccx = (double)(cmin + cmax) / 2, ccy = (double)(rmin + rmax) / 2;
@@ -269,6 +270,18 @@ choose_kernel(const void* __restrict__ mask, int dt, const int* __restrict__ win
                 ++r;
             }
     }
+}
+
+// crop windows only (the first three kernels of preprocess_run): lets the host upload just the image rows a window covers
+int mask_windows_run(const void* mask, int mask_dt, int F, int H, int W, int* bbox_ws, int* win, uint8_t* valid, cudaStream_t stream) {
+    ADP_CHECK_ARG(mask_dt == DT_U8 || mask_dt == DT_F32 || mask_dt == DT_F64, "mask dtype must be u8, f32 or f64");
+    ADP_CHECK_ARG(H >= 440 && W >= 440, "frames must be at least 440 x 440 (crop window of utils.py:get_bbox)");
+    if (F == 0) return ADP_OK;
+    mask_bbox_init_kernel<<<cdiv(F, 256), 256, 0, stream>>>(bbox_ws, F, H, W);
+    mask_bbox_kernel<<<dim3(30, F), 256, 0, stream>>>(mask, mask_dt, bbox_ws, H, W);
+    window_kernel<<<cdiv(F, 128), 128, 0, stream>>>(bbox_ws, nullptr, 0, win, nullptr, valid, F, H, W, 224);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
 }
 
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,

@@ -43,3 +43,22 @@ def estimate_sharded(estimate_fn, args, n: int, group=None, device=None):
     out = torch.empty((world * per, 8, 3), dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return out[:n]
+
+
+def bind_to_gpu_numa(device) -> bool:
+    """Pin the calling host thread to the CPU cores nearest to ``device`` (NVML's ideal affinity for that GPU).
+
+    Host->device copies of a rank run at PCIe speed only if the pinned staging memory sits on the GPU's own NUMA node; memory is
+    placed on the node of the thread that first touches it, and neither torchrun nor a plain thread pool binds anything.  With
+    8 ranks pulling ~1 GB of frames each per step this is the difference between ~25 and ~50 GB/s per GPU.  Call it before
+    allocating pinned buffers.  Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+        dev = torch.device(device)
+        prop = torch.cuda.get_device_properties(dev)
+        pynvml.nvmlInit()
+        bus = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+        return True
+    except Exception:
+        return False

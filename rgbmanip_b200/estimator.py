@@ -19,7 +19,9 @@ Deliberate deviations from the live reference, all documented in DESIGN.md:
 
 Inputs may be numpy arrays, torch host tensors (pinned or pageable) or CUDA tensors (zero-copy).  The batch is cut into equal
 chunks of at most ``max_envs`` environments; uploads of chunk i+1 overlap the kernels of chunk i, pageable host memory goes
-through pinned staging buffers, and a small first chunk (``cfg["first_chunk_envs"]``, default 16) starts the kernels early.
+through pinned staging buffers, a small first chunk (``cfg["first_chunk_envs"]``, default 16) followed by doubling ones starts
+the kernels early, and of every host frame only the rows under its crop window are uploaded (``cfg["window_upload"]``, default
+on: the masks go first, the device returns the windows, see ``_upload_window_rows``).
 """
 from __future__ import annotations
 
@@ -52,12 +54,16 @@ DEFAULT_BBOX = np.asarray([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1],
 def chunk_bounds(N, max_envs, first=0):
     """[lo, hi) chunk boundaries of a batch of N environments: equal chunks of at most ``max_envs`` (every chunk size is replayed
     as a CUDA graph; a short tail chunk would miss both the graph and the whole-wave sizing).  ``first`` > 0 (frames coming
-    from the host) sends a small chunk ahead, so the kernels start after ~first/N of the upload instead of a full chunk's."""
+    from the host): a small chunk goes ahead and the following ones double in size (first, 2 first, 4 first, ...) until the
+    equal split takes over -- the upload of chunk i+1 then fits under the kernels of chunk i, so only the first small upload is
+    exposed instead of a full chunk's (at 8 GPUs a shard is 128 envs = 1 GB of fp32 frames against 43 ms of kernels)."""
     bounds, lo = [], 0
-    first = min(int(first), max_envs)
-    if first > 0 and N > max_envs:
-        bounds.append((0, first))
-        lo = first
+    size = min(int(first), max_envs)
+    if size > 0 and N > max_envs:
+        while size < max_envs and N - lo - size >= size:
+            bounds.append((lo, lo + size))
+            lo += size
+            size = min(2 * size, max_envs)
     rest = N - lo
     if rest > 0:
         nch = -(-rest // max_envs)
@@ -95,9 +101,14 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             # release the GIL, and a chunk is one CUDA-graph replay, so the host threads stay out of each other's way.
             from concurrent.futures import ThreadPoolExecutor
             devs = [torch.device(d if isinstance(d, (str, torch.device)) else f"cuda:{int(d)}") for d in devices]
+            import threading
+            self._tls = threading.local()
             self._pool = ThreadPoolExecutor(max_workers=len(devs), thread_name_prefix="adapose-gpu")
-            mk = lambda d: AdaPoseEstimator_v5(env, {k: v for k, v in cfg.items() if k != "devices"}, logger, state_dict=state_dict,
-                                               device=d, max_envs=max_envs, precision=precision, **engine_kw)
+            def mk(d):
+                from .dist import bind_to_gpu_numa
+                bind_to_gpu_numa(d)          # this replica's pinned staging buffers land on the GPU's NUMA node
+                return AdaPoseEstimator_v5(env, {k: v for k, v in cfg.items() if k != "devices"}, logger, state_dict=state_dict,
+                                           device=d, max_envs=max_envs, precision=precision, **engine_kw)
             self._replicas = list(self._pool.map(mk, devs))
             self.device = devs[0]
             self.estimator = self._replicas[0].estimator     # the attribute the reference exposes (interface_v5.py:48)
@@ -116,6 +127,9 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         self._copy_stream = None
         self._stage_bufs = {}
         self._slot_free = [None, None]
+        self._win_state = {}
+        self._window_upload = bool(cfg.get("window_upload", True))
+        self.h2d_bytes = 0          # bytes copied host -> device so far (bench.py reports the per-step figure)
         self._keep_f64 = bool(cfg.get("keep_float64", False))
         self._first_chunk = int(cfg.get("first_chunk_envs", 16))
 
@@ -169,8 +183,6 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         with torch.cuda.stream(stream):
             t = dict(K=self._upload("K", slot, K_b[lo:hi], torch.float64), E1=self._upload("E1", slot, E1_b[lo:hi], torch.float64),
                      E2=self._upload("E2", slot, E2_b[lo:hi], torch.float64))
-            for name, src in (("rgb1", rgb1_b), ("rgb2", rgb2_b)):
-                t[name] = self._upload(name, slot, src[lo:hi], self._rgb_dtype(src))
             for name, src in (("m1", m1_b), ("m2", m2_b)):
                 m = src[lo:hi]
                 if m.dtype not in self._MASK_OK:
@@ -178,6 +190,13 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
                 if m.dtype == torch.bool:
                     m = m.view(torch.uint8)
                 t[name] = self._upload(name, slot, m)
+            if rgb1_b.is_cuda or not self._window_upload or hi == lo:
+                for name, src in (("rgb1", rgb1_b), ("rgb2", rgb2_b)):
+                    t[name] = self._upload(name, slot, src[lo:hi], self._rgb_dtype(src))
+                    self.h2d_bytes += 0 if src.is_cuda else t[name].numel() * t[name].element_size()
+            else:
+                self._upload_window_rows(t, (rgb1_b, rgb2_b), lo, hi, stream, slot)
+            self.h2d_bytes += sum(t[k].numel() * t[k].element_size() for k in ("m1", "m2") if not (m1_b.is_cuda))
             t["c1"] = t["c2"] = None
             if choose is not None:
                 t["c1"] = self._upload("c1", slot, choose[0][lo:hi], torch.int32)
@@ -186,6 +205,60 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             ev.record(stream)
             self._slot_free[slot] = ev
         return t, ev
+
+    def _upload_window_rows(self, t, rgbs, lo, hi, stream, slot):
+        """Host frames: upload only the image rows the crop window of each frame covers.  The masks (already queued on ``stream``)
+        give the windows on the device (adp_mask_windows = the mask pass of the preprocessing); they are read back (a few
+        hundred bytes) and every frame contributes rows [rmin, rmax) -- a contiguous block of the host frame -- to a persistent
+        device frame buffer.  adp_preprocess reads nothing outside the window, so the stale rest of the buffer is never seen.
+        A 480 x 640 fp32 frame is 3.7 MB, the rows of a typical 160-pixel window 1.2 MB."""
+        from . import _lib as L
+        eng = self.estimator
+        n = hi - lo
+        st = self._win_state.get(slot)
+        if st is None:
+            st = dict(win=torch.zeros((2 * eng.E, 4), dtype=torch.int32, device=self.device),
+                      ws=torch.zeros((2 * eng.E, 4), dtype=torch.int32, device=self.device),
+                      valid=torch.zeros(2 * eng.E, dtype=torch.uint8, device=self.device),
+                      host=torch.zeros((2 * eng.E, 5), dtype=torch.int32).pin_memory(), frames={}, done=None)
+            self._win_state[slot] = st
+        cs = L.C.c_void_p(stream.cuda_stream)
+        for v, key in enumerate(("m1", "m2")):
+            m = t[key]
+            code = {torch.uint8: L.DT_U8, torch.float32: L.DT_F32, torch.float64: L.DT_F64}[m.dtype]
+            L.check(eng.lib.adp_mask_windows(L.ptr(m), code, n, m.shape[1], m.shape[2], L.ptr(st["ws"][v * n:]), L.ptr(st["win"][v * n:]),
+                                             L.ptr(st["valid"][v * n:]), cs), "mask_windows")
+        st["host"][:2 * n, :4].copy_(st["win"][:2 * n], non_blocking=True)
+        st["host"][:2 * n, 4].copy_(st["valid"][:2 * n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        if st["done"] is not None:
+            stream.wait_event(st["done"])        # the preprocessing that last read this slot's frame buffers has run
+        ev.synchronize()
+        wins = st["host"][:2 * n].tolist()
+        for v, (name, src) in enumerate((("rgb1", rgbs[0]), ("rgb2", rgbs[1]))):
+            dt = self._rgb_dtype(src)
+            key = (v, dt, tuple(src.shape[1:]))
+            buf = st["frames"].get(key)
+            if buf is None:
+                buf = torch.zeros((eng.E,) + tuple(src.shape[1:]), dtype=dt, device=self.device)
+                st["frames"] = {k: b for k, b in st["frames"].items() if k[0] != v}      # one buffer per view and slot
+                st["frames"][key] = buf
+            direct = src.is_pinned() and src.dtype == dt
+            stage = None if direct else self._pinned(name, slot, (n,) + tuple(src.shape[1:]), dt)
+            row_bytes = src.shape[2] * src.shape[3] * buf.element_size()
+            for f in range(n):
+                r0, r1, _, _, ok = wins[v * n + f]
+                if not ok:
+                    continue
+                if direct:
+                    buf[f, r0:r1].copy_(src[lo + f, r0:r1], non_blocking=True)
+                else:        # pageable (or float64) source: only these rows pass through the pinned staging buffer
+                    stage[f, r0:r1].copy_(src[lo + f, r0:r1])
+                    buf[f, r0:r1].copy_(stage[f, r0:r1], non_blocking=True)
+                self.h2d_bytes += (r1 - r0) * row_bytes
+            t[name] = buf[:n]
+        t["_slot"] = slot
 
     def _chunk_bounds(self, N, on_host):
         return chunk_bounds(N, self.estimator.E, self._first_chunk if on_host else 0)
@@ -232,13 +305,17 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
                 compute.wait_event(ev)
                 for v in t.values():          # allocated on the copy stream, consumed on the compute stream
                     if isinstance(v, torch.Tensor) and v.is_cuda:
-                        v.record_stream(compute)
+                        v.record_stream(compute)          # (harmless for the persistent window-upload frame buffers)
                 ridx = None
                 if ransac_idx is not None:      # [N,128,5] sample indices of the RANSAC fit (branch B parity replay)
                     ridx = self._as_tensor(ransac_idx[lo:hi]).to(torch.int32).to(self.device)
                 box = eng.run_chunk(t["K"], t["rgb1"], t["m1"], t["E1"], t["rgb2"], t["m2"], t["E2"],
                                     seed=seed, choose1=t["c1"], choose2=t["c2"], ransac_idx=ridx, env0=int(env_offset) + lo)
                 out[lo:hi].copy_(box)
+                if "_slot" in t:          # the slot's persistent frame buffers may be overwritten once this chunk's kernels ran
+                    done = torch.cuda.Event()
+                    done.record(compute)
+                    self._win_state[t["_slot"]]["done"] = done
                 # this chunk's kernels are queued: the host-side staging of the next chunk (and its upload) overlaps them
                 nxt = self._stage_chunk(batches, choose, *bounds[i + 1], copy, (i + 1) & 1) if i + 1 < len(bounds) else None
             # watchdog + fp16 range flag (set by the last backbone layer on inf/NaN features, every chunk): read with the boxes
@@ -292,6 +369,10 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             if hi <= lo:
                 return None
             rep = self._replicas[r]
+            if getattr(self._tls, "bound", None) != r:      # pool threads are not tied to a replica: re-pin when it changes
+                from .dist import bind_to_gpu_numa
+                bind_to_gpu_numa(rep.device)
+                self._tls.bound = r
             sl = lambda a: None if a is None else a[lo:hi]
             ch = None if choose is None else (choose[0][lo:hi], choose[1][lo:hi])
             return rep.estimate(*[a[lo:hi] for a in batches], choose=ch, return_tensor=True, ransac_idx=sl(ransac_idx),

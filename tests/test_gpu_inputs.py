@@ -174,3 +174,24 @@ def test_single_process_multi_gpu_equals_one_gpu():
     assert t.device == multi.device and tuple(t.shape) == (9, 8, 3)
     np.testing.assert_array_equal(t.cpu().numpy(), a)
     multi.check_error_flag()
+
+
+def test_window_row_upload_equals_whole_frame_upload():
+    """Host frames: only the rows under each frame's crop window are uploaded (cfg['window_upload'], default on).  Same boxes as
+    uploading the frames whole, bit for bit, over several chunks and with blind / border / small-mask environments in the batch;
+    the bytes copied drop by the ratio of window rows to frame rows."""
+    b = synth.make_batch(12, seed=19, special=True)
+    m1 = b.mask1.copy(); m1[5] = 0
+    a_est = _make(max_envs=4, cfg_extra={"first_chunk_envs": 2})
+    w_est = _make(max_envs=4, cfg_extra={"first_chunk_envs": 2, "window_upload": False})
+    args = (b.K, b.rgb1, m1, b.E1, b.rgb2, b.mask2, b.E2)
+    pinned = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in args]
+    for call in range(3):
+        a = a_est.estimate(*args, sample_seed=5 + call)                 # pageable numpy -> staged rows
+        p = a_est.estimate(*pinned, sample_seed=5 + call)               # pinned -> direct row copies
+        w = w_est.estimate(*args, sample_seed=5 + call)
+        np.testing.assert_array_equal(a, w)
+        np.testing.assert_array_equal(p, w)
+    np.testing.assert_array_equal(a[5], O.DEFAULT_BBOX)
+    assert a_est.h2d_bytes < 0.75 * w_est.h2d_bytes * 2, (a_est.h2d_bytes, w_est.h2d_bytes)     # a_est ran twice as many calls
+    a_est.estimator.close(); w_est.estimator.close()

@@ -12,15 +12,19 @@ def test_chunk_bounds_cover_the_batch_in_equal_chunks(N, E, first):
     assert (b[-1][1] if b else 0) == N
     sizes = [hi - lo for lo, hi in b]
     assert all(0 < s <= E for s in sizes)
-    body = sizes[1:] if (first and N > E) else sizes
-    if first and N > E:
-        assert sizes[0] == min(first, E)                  # the small chunk that starts the kernels while the upload continues
+    ramp = 0
+    if first and N > E:      # the ramp: first, 2 first, 4 first ... while as much again remains behind each ramp chunk
+        while ramp < len(sizes) and sizes[ramp] == min(first << ramp, E) and sizes[ramp] < E and sum(sizes[ramp + 1:]) >= sizes[ramp]:
+            ramp += 1
+        assert min(first, E) == E or (ramp >= 1 and sizes[0] == first)
+    body = sizes[ramp:]
     assert max(body, default=0) - min(body, default=0) <= 1      # equal chunks: no short tail off the graph / whole-wave path
-    assert len(set(sizes)) <= 3                           # at most three CUDA graphs per call
+    assert len(set(sizes)) <= 8                           # CUDA graphs per call (the engine keeps at most 8)
     assert len(body) == -(-sum(body) // E) if body else True     # and no more chunks than necessary
 
 
 def test_chunk_bounds_examples():
     assert chunk_bounds(128, 74, 0) == [(0, 64), (64, 128)]                        # an 8-GPU shard of 1024 envs, device-resident
-    assert chunk_bounds(128, 74, 16) == [(0, 16), (16, 72), (72, 128)]             # the same shard uploaded from the host
+    assert chunk_bounds(128, 74, 16) == [(0, 16), (16, 48), (48, 88), (88, 128)]   # the same shard uploaded from the host
+    assert [h - l for l, h in chunk_bounds(1024, 74, 16)][:4] == [16, 32, 64, 71]
     assert chunk_bounds(8, 8, 16) == [(0, 8)]
