@@ -202,10 +202,23 @@ ADP_API int adp_actor_forward(const double* pose_queue, const double* bbox_queue
 
 /* --- pose fit + box: utils.py:40-119, interface_v5.py:318-321,354-374 ---------------------------------------- */
 /* One 4-CTA thread-block cluster per environment; the exact-median radix select recomputes the pair ratios in every pass.
- * scratch: unused (kept for ABI stability), may be NULL. */
+ * Points mode (pts_cam != NULL; branch C): the camera-frame points are given ([B,P,3], the first pts_count[b] valid, `nocs` in
+ * the same order) instead of being back-projected from depth / choose / Kp; `scale` is the result of interest. */
 ADP_API int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R,
-            const double* E, const uint8_t* valid, double* bbox, double* scale, double* trans, float* scratch, int B, int P,
-            int S, void* stream);
+            const double* E, const uint8_t* valid, double* bbox, double* scale, double* trans, const float* pts_cam,
+            const int32_t* pts_count, int B, int P, int S, void* stream);
+
+/* --- pose fit, branch C, device part: utils.py:121-195 (depth_estimation_from_nocs_matches) -------------------------------
+ * Per env: mutual nearest neighbours of the two views' NOCS maps (1024 x 1024, np.argmin tie rule), distance < 0.01, epipolar
+ * filter |x1^T F x2| < 1 px (F from the UNCROPPED K and the two extrinsics, interface_v5.py:340-343), linear triangulation
+ * (the DLT of cv2.triangulatePoints) and the transform into the view-1 camera frame.  Outputs: pts2d1 [B,P,2] (image
+ * coordinates of every sampled view-1 pixel, interface_v5.py:136-145: the 2-D side of the PnP), pts_cam / nocs_m [B,P,3]
+ * (matched points, compacted in ascending view-1 index), count [B], match_ids [B,P,2] (view-1 / view-2 index pairs; optional).
+ * The median scale then comes from adp_fit in points mode; cv2.solvePnPRansac (align.py:104-115) stays a host call. */
+ADP_API int adp_nocs_match(const float* nocs1, const float* nocs2, const int32_t* choose1, const int32_t* choose2,
+                           const int32_t* win1, const int32_t* win2, const double* K, const double* E1, const double* E2,
+                           const uint8_t* valid, int S, float* pts2d1, float* pts_cam, float* nocs_m, int32_t* count,
+                           int32_t* match_ids, int B, int P, void* stream);
 
 /* --- pose fit, branch B: align.py:44-102 (RANSAC + Umeyama), interface_v5.py:322-338 --------------------------
  * rand_idx: [B,128,5] sample indices (NULL = counter-based hash of `seed`); rot [B,9], trans [B,3], scale [B] optional. */

@@ -133,7 +133,9 @@ def prepare_model_input(rgb, mask, intrinsic, resize_size=IMG_SIZE, rng=np.rando
     ratio = resize_size / crop_w
     xm = (choose % resize_size).astype(np.float32)[:, None]
     ym = (choose // resize_size).astype(np.float32)[:, None]
-    pts2d = np.concatenate((xm / ratio + cmin, ym / ratio + rmin), axis=-1)
+    # the window bounds are numpy integers in the reference, so ``ratio`` is a np.float64 scalar: under NumPy >= 2 promotion
+    # (this image, where the goldens were made) float32 / float64-scalar is float64; NumPy 1.x kept float32 (differs by < 2e-5 px)
+    pts2d = np.concatenate((xm.astype(np.float64) / ratio + cmin, ym.astype(np.float64) / ratio + rmin), axis=-1)
     crop = resize_linear(np.asarray(rgb[rmin:rmax, cmin:cmax, :]), resize_size)
     # transforms.ToTensor on a float ndarray = HWC->CHW without rescaling; Normalize (interface_v5.py:52-54)
     mean = np.asarray(IMAGENET_MEAN, crop.dtype)[:, None, None]
@@ -432,6 +434,73 @@ def similarity_ransac(source, target, rng=np.random, rand_idx=None):
         return None, None, None, None
     return umeyama(S[:, best_idx], T[:, best_idx])
 
+def prepare_pts2d(choose, rmin, rmax, cmin, img_size=IMG_SIZE):
+    """interface_v5.py:136-145: image coordinates of the sampled crop pixels, x / ratio + cmin, y / ratio + rmin (float64 under
+    NumPy >= 2, see prepare_model_input)."""
+    ratio = img_size / (int(rmax) - int(rmin))
+    x = (choose % img_size)[:, None].astype(np.float64) / ratio + int(cmin)
+    y = (choose // img_size)[:, None].astype(np.float64) / ratio + int(rmin)
+    return np.concatenate((x, y), axis=-1)
+
+
+def triangulate_dlt(P1, P2, x1, x2):
+    """cv2.triangulatePoints (OpenCV calib3d triangulate.cpp, icvTriangulatePoints): per point the 4 x 4 system
+    rows x P[2] - P[0], y P[2] - P[1] of both views, solution = right singular vector of the smallest singular value.
+    x1, x2: [2, N].  Returns homogeneous [4, N] (sign / norm of each column are arbitrary; callers divide by X[3])."""
+    out = np.zeros((4, x1.shape[1]))
+    for i in range(x1.shape[1]):
+        A = np.stack([x1[0, i] * P1[2] - P1[0], x1[1, i] * P1[2] - P1[1],
+                      x2[0, i] * P2[2] - P2[0], x2[1, i] * P2[2] - P2[1]])
+        out[:, i] = np.linalg.svd(A)[2][3]
+    return out
+
+
+def nocs_matches(left_pts2d, left_nocs, left_proj, left_pose, right_pts2d, right_nocs, right_proj, right_pose, intrinsic,
+                 details=None):
+    """utils.py:121-195 (depth_estimation_from_nocs_matches): mutual nearest neighbours in NOCS space, distance < 0.01,
+    epipolar filter < 1 px, triangulation, median scale per view.  -> (left_scale, right_scale, left_pts2d_m, right_pts2d_m)."""
+    dis = np.linalg.norm(left_nocs[:, None, :] - right_nocs[None, :, :], axis=-1)
+    l2r, r2l = np.argmin(dis, axis=1), np.argmin(dis, axis=0)
+    lid = np.arange(left_nocs.shape[0])
+    lm = lid[r2l[l2r] == lid]
+    rm = l2r[lm]
+    keep = dis[lm, rm] < 0.01
+    lm, rm = lm[keep], rm[keep]
+    rel = left_pose @ np.linalg.inv(right_pose)
+    t = rel[:3, 3]
+    tx = np.zeros((3, 3), np.float32)                       # float32 like the reference
+    tx[0, 1], tx[1, 0], tx[0, 2], tx[2, 0], tx[1, 2], tx[2, 1] = -t[2], t[2], t[1], -t[1], -t[0], t[0]
+    Ki = np.linalg.inv(intrinsic)
+    f21 = Ki.T @ tx @ rel[:3, :3] @ Ki
+    hl = np.vstack([left_pts2d[lm].T.astype(np.float64), np.ones(len(lm))])
+    hr = np.vstack([right_pts2d[rm].T.astype(np.float64), np.ones(len(rm))])
+    epi = np.abs(np.einsum("in,ij,jn->n", hl, f21, hr))     # the diagonal of hl^T f21 hr
+    keep = epi < 1.0
+    lm, rm = lm[keep], rm[keep]
+    hl, hr = hl[:, keep], hr[:, keep]
+    X = triangulate_dlt(left_proj[:3], right_proj[:3], hl[:2], hr[:2])
+    X = X / X[3]
+    lp, rp = left_pose @ X, right_pose @ X
+    ls = compute_scale(lp[:3].T, left_nocs[lm])
+    rs = compute_scale(rp[:3].T, right_nocs[rm])
+    if details is not None:
+        details.update(left_id=lm, right_id=rm, left_cam=lp[:3].T, right_cam=rp[:3].T, f21=f21)
+    return ls, rs, left_pts2d[lm], right_pts2d[rm]
+
+
+def pnp_ransac(nocs, pts2d, size, intrinsic):
+    """align.py:104-115 (estimatePnPRansac): the reference's own OpenCV calls (solvePnPRansac with EPnP, 3 px, then VVS
+    refinement).  The algorithm lives inside OpenCV (the image's cv2, same on the GPU box): "parity unpinned" below this call;
+    what the product shares with the reference is the call itself, so the comparison is on its inputs."""
+    import cv2
+    tmp = nocs * size
+    ok, r, t, _ = cv2.solvePnPRansac(tmp, pts2d, intrinsic, np.zeros(4), flags=cv2.SOLVEPNP_EPNP, reprojectionError=3.0)
+    if ok:
+        crit = (cv2.TERM_CRITERIA_MAX_ITER + cv2.TERM_CRITERIA_EPS, 20, 1e-6)
+        r, t = cv2.solvePnPRefineVVS(tmp, pts2d, intrinsic, None, r, t, criteria=crit)
+    R, _ = cv2.Rodrigues(r)
+    return ok, size, R, t
+
 
 def get_3d_bbox(size):
     """utils.py:40-58: corner order (+++,++-,-++,-+-,+-+,+--,--+,---) * size/2, returned [3,8]."""
@@ -488,8 +557,14 @@ def predict(sd, cfg, K, rgb1, mask1, E1, rgb2, mask2, E2, rng=np.random, both_vi
     elif cfg.get("use_depth", True):
         cam = back_project(depth.flatten(), ch1, K1, S)
         s, R, t, _ = similarity_ransac(nocs, cam, rng, rand_idx)
-    else:
-        raise NotImplementedError("branch C (NOCS matching + cv2 PnP) is outside the oracle: parity unpinned")
+    else:                                                   # interface_v5.py:339-349
+        P1, P2 = np.eye(4), np.eye(4)
+        P1[:3], P2[:3] = K @ E1[:3], K @ E2[:3]
+        md = {}
+        res = nocs_matches(pts1, nocs, P1, E1, pts2, pred["view2_nocs"][0].numpy(), P2, E2, K, details=md)
+        _, s, R, t = pnp_ransac(nocs.astype(np.float32), pts1.astype(np.float32), res[0], K)
+        if details is not None:
+            details.update(matches=md, pts2d1=pts1, pts2d2=pts2, right_scale=res[1])
     if details is not None:
         details.update(view1_rgb=v1, view2_rgb=v2, choose1=ch1, choose2=ch2, K1=K1, K2=K2, nocs=nocs,
                        depth=depth, R=R, t=t, s=s, pred=pred)

@@ -137,6 +137,136 @@ def golden_branch_b(interface_v5, out_dir):
     print("branch B boxes", boxes.shape, np.isfinite(boxes).all())
 
 
+def branch_c_unit_case(seed, n_shared=700, noise=0.0015, focal=None, world_scale=1.0):
+    """Two views of one rigid object with partly shared surface points: NOCS maps of both views, sampled crop pixels
+    (choose + window -> pts2d exactly as interface_v5.py:136-145), intrinsics, extrinsics.  ``focal`` overrides fx = fy (a
+    short focal length or a scene in other units (``world_scale``) makes the algebraic epipolar test of utils.py:160-166
+    actually reject pairs: with metres and the 440 px focal length it passes everything)."""
+    rng = np.random.default_rng(seed)
+    P, S = 1024, 224
+    K = synth.intrinsics()
+    if focal is not None:
+        K[0, 0] = K[1, 1] = focal
+    E1, E2 = synth._camera_pair(rng)
+    target = -E1[:3, :3].T @ E1[:3, 3] + E1[2, :3] * 0.7            # a point 0.7 m in front of camera 1
+    Rw = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    size = rng.uniform(0.15, 0.3)
+    obj = rng.uniform(-0.5, 0.5, (2 * P - n_shared, 3))
+    ids1 = np.arange(P)
+    ids2 = np.concatenate([rng.permutation(P)[:n_shared], np.arange(P, 2 * P - n_shared)])
+    rng.shuffle(ids2)
+    out = {}
+    for v, (ids, E) in enumerate(((ids1, E1), (ids2, E2)), 1):
+        world = (size * obj[ids]) @ Rw.T + target
+        cam = world @ E[:3, :3].T + E[:3, 3]
+        uv = (cam @ K.T)
+        uv = uv[:, :2] / uv[:, 2:3]
+        crop = 40 * int(rng.integers(4, 9))                           # window sizes of get_bbox
+        rmin = int(np.clip(np.median(uv[:, 1]) - crop / 2, 0, 480 - crop))
+        cmin = int(np.clip(np.median(uv[:, 0]) - crop / 2, 0, 640 - crop))
+        ratio = S / crop
+        cx = np.clip(np.round((uv[:, 0] - cmin) * ratio), 0, S - 1).astype(np.int64)
+        cy = np.clip(np.round((uv[:, 1] - rmin) * ratio), 0, S - 1).astype(np.int64)
+        out[f"choose{v}"] = (cy * S + cx).astype(np.int32)
+        out[f"win{v}"] = np.array([rmin, rmin + crop, cmin, cmin + crop], np.int32)
+        out[f"nocs{v}"] = (obj[ids] + rng.normal(0, noise, (P, 3))).astype(np.float32)
+    if world_scale != 1.0:          # the same images seen in other length units: only the translations change
+        E1, E2 = E1.copy(), E2.copy()
+        E1[:3, 3] *= world_scale
+        E2[:3, 3] *= world_scale
+    out.update(K=K, E1=E1, E2=E2)
+    return out
+
+
+def golden_branch_c_units(utils, align, out_dir):
+    """utils.depth_estimation_from_nocs_matches + align.estimatePnPRansac of the reference on synthetic two-view cases."""
+    import contextlib
+    import io
+    from oracle import adapose_oracle as orc
+    out = {}
+    cases = [dict(seed=11), dict(seed=12, n_shared=300, noise=0.004), dict(seed=13, focal=6.0), dict(seed=14, n_shared=1024, noise=0.0),
+             dict(seed=15, world_scale=400.0)]
+    for ci, kw in enumerate(cases):
+        c = branch_c_unit_case(**kw)
+        pts1 = orc.prepare_pts2d(c["choose1"].astype(np.int64), *c["win1"][:3])
+        pts2 = orc.prepare_pts2d(c["choose2"].astype(np.int64), *c["win2"][:3])
+        P1, P2 = np.eye(4), np.eye(4)
+        P1[:3], P2[:3] = c["K"] @ c["E1"][:3], c["K"] @ c["E2"][:3]
+        with contextlib.redirect_stdout(io.StringIO()):
+            ls, rs, lp, rp = utils.depth_estimation_from_nocs_matches(pts1, c["nocs1"], P1, c["E1"], pts2, c["nocs2"], P2, c["E2"], c["K"])
+            if np.isfinite(ls):
+                ok, size, R, t, _ = align.estimatePnPRansac(c["nocs1"].astype(np.float32), pts1.astype(np.float32), ls, c["K"])
+            else:
+                ok, R, t = False, np.full((3, 3), np.nan), np.full((3, 1), np.nan)
+        for k, v in c.items():
+            out[f"case{ci}_{k}"] = v
+        out.update({f"case{ci}_pts2d1": pts1, f"case{ci}_pts2d2": pts2, f"case{ci}_left_scale": ls, f"case{ci}_right_scale": rs,
+                    f"case{ci}_left_pts": lp, f"case{ci}_right_pts": rp, f"case{ci}_pnp_ok": ok, f"case{ci}_pnp_R": R,
+                    f"case{ci}_pnp_t": t})
+        print(f"branch C unit case {ci}: matches {len(lp)}, scales {ls:.6f} {rs:.6f}, pnp ok {ok}")
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(out_dir, "branch_c_units.npz"), **out)
+
+
+def golden_branch_c(interface_v5, out_dir):
+    """direct_regression=False, use_depth=False -> NOCS matching + triangulation + cv2 PnP (interface_v5.py:339-349)."""
+    import contextlib
+    import io
+    est, cfg, _ = build_reference_estimator(interface_v5, direct_regression=False)
+    est.cfg["use_depth"] = False
+    batch = synth.make_batch(4, seed=3, special=False)
+    rec = {"match": [], "pnp": [], "prep": [], "pred": []}
+    orig_match, orig_pnp = interface_v5.depth_estimation_from_nocs_matches, interface_v5.estimatePnPRansac
+    orig_prepare, orig_forward = est.prepare_model_input, est.estimator.module.forward
+
+    def match(*a):
+        r = orig_match(*a)
+        rec["match"].append(r)
+        return r
+
+    def pnp(*a):
+        r = orig_pnp(*a)
+        rec["pnp"].append(r)
+        return r
+
+    def prepare(rgb, mask, K, resize_size):
+        r = orig_prepare(rgb, mask, K, resize_size)
+        rec["prep"].append(r)
+        return r
+
+    def forward(*a, **k):
+        o = orig_forward(*a, **k)
+        rec["pred"].append({kk: v.detach().cpu().numpy() for kk, v in o.items()})
+        return o
+
+    interface_v5.depth_estimation_from_nocs_matches, interface_v5.estimatePnPRansac = match, pnp
+    est.prepare_model_input, est.estimator.module.forward = prepare, forward
+    np.random.seed(7)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            boxes = est.estimate(*batch.args())
+    finally:
+        interface_v5.depth_estimation_from_nocs_matches, interface_v5.estimatePnPRansac = orig_match, orig_pnp
+    n = len(batch)
+    out = dict(boxes=boxes,
+               choose1=np.stack([rec["prep"][2 * e][1] for e in range(n)]).astype(np.int32),
+               choose2=np.stack([rec["prep"][2 * e + 1][1] for e in range(n)]).astype(np.int32),
+               pts2d1=np.stack([rec["prep"][2 * e][2] for e in range(n)]),
+               pts2d2=np.stack([rec["prep"][2 * e + 1][2] for e in range(n)]),
+               nocs1=np.stack([rec["pred"][e]["view1_nocs"][0] for e in range(n)]),
+               nocs2=np.stack([rec["pred"][e]["view2_nocs"][0] for e in range(n)]),
+               left_scale=np.array([rec["match"][e][0] for e in range(n)]),
+               right_scale=np.array([rec["match"][e][1] for e in range(n)]),
+               n_match=np.array([len(rec["match"][e][2]) for e in range(n)]),
+               pnp_ok=np.array([bool(rec["pnp"][e][0]) for e in range(n)]),
+               pnp_R=np.stack([rec["pnp"][e][2] for e in range(n)]), pnp_t=np.stack([np.asarray(rec["pnp"][e][3]).flatten() for e in range(n)]))
+    for e in range(n):
+        out[f"env{e}_left_pts"] = rec["match"][e][2]
+        out[f"env{e}_right_pts"] = rec["match"][e][3]
+    np.savez_compressed(os.path.join(out_dir, "branch_c.npz"), **out)
+    print("branch C boxes", boxes.shape, "finite", np.isfinite(boxes).all(), "matches", out["n_match"], "scales", out["left_scale"])
+
+
 def golden_view_ring(out_dir):
     """Caller-side queues of the RL controller (models/controller/rl_pose.py:85-97,118-150,189-223), executed unmodified."""
     for m in ["tensorboard", "torch.utils.tensorboard", "ipdb", "open3d", "sapien.utils.viewer"]:
@@ -307,7 +437,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     interface_v5, network_v5, rotation_utils, utils, align = import_reference()
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring", "actor", "e2e_seed1"]
+    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring", "actor", "e2e_seed1", "branch_c_units", "branch_c"]
     if "units" in what:
         golden_units(network_v5, rotation_utils, utils, align, out_dir)
     if "preprocess" in what:
@@ -316,6 +446,10 @@ def main():
         golden_e2e(interface_v5, out_dir)
     if "branch_b" in what:
         golden_branch_b(interface_v5, out_dir)
+    if "branch_c_units" in what:
+        golden_branch_c_units(utils, align, out_dir)
+    if "branch_c" in what:
+        golden_branch_c(interface_v5, out_dir)
     if "e2e_seed1" in what:
         golden_e2e_seed1(interface_v5, out_dir)
     if "view_ring" in what:

@@ -78,7 +78,8 @@ SIGNATURES = {
     "adp_pose_gbias": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "adp_rot_head": (C.c_int, [vp, vp, C.POINTER(DecodeWeights), vp, vp, C.c_int, C.c_int, vp]),
     "adp_actor_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
-    "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "adp_nocs_match": (C.c_int, [vp] * 10 + [C.c_int] + [vp] * 5 + [C.c_int, C.c_int, vp]),
     "adp_fit_umeyama": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }
 

@@ -36,8 +36,11 @@ int build_volume(const void* f_ref, const void* f_src, const float* Mw, const fl
 int warp_matrices(const double* Kp_ref, const double* E_ref, const double* Kp_src, const double* E_src, float* Mw,
                   const uint8_t* valid_ref, const uint8_t* valid_src, uint8_t* valid_env, int B, cudaStream_t stream);
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
-            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, float* scratch, int B, int P, int S,
-            cudaStream_t stream);
+            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, const float* pts_cam, const int* pts_count,
+            int B, int P, int S, cudaStream_t stream);
+int nocs_match_run(const float* nocs1, const float* nocs2, const int* choose1, const int* choose2, const int* win1, const int* win2,
+                   const double* K, const double* E1, const double* E2, const uint8_t* valid, int S, float* pts2d1, float* pts_cam,
+                   float* nocs_m, int* count, int* match_ids, int B, int P, cudaStream_t stream);
 
 int fit_umeyama_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const double* E, const uint8_t* valid,
                     const int* rand_idx, uint32_t seed, double* bbox, double* scale_out, double* rot_out, double* trans_out, int B,
@@ -305,10 +308,21 @@ int adp_actor_forward(const double* pose_queue, const double* bbox_queue, int T,
 }
 
 int adp_fit(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const float* R, const double* E,
-            const uint8_t* valid, double* bbox, double* scale, double* trans, float* scratch, int B, int P, int S, void* stream) {
-    ADP_CHECK_ARG(nocs && depth && choose && Kp && R && E && bbox, "null pointer");
+            const uint8_t* valid, double* bbox, double* scale, double* trans, const float* pts_cam, const int32_t* pts_count, int B,
+            int P, int S, void* stream) {
+    ADP_CHECK_ARG(nocs && Kp && R && E && bbox && (pts_cam || (depth && choose)), "null pointer");
     g_launches += 1;
-    return fit_run(nocs, depth, choose, Kp, R, E, valid, bbox, scale, trans, scratch, B, P, S, (cudaStream_t)stream);
+    return fit_run(nocs, depth, choose, Kp, R, E, valid, bbox, scale, trans, pts_cam, pts_count, B, P, S, (cudaStream_t)stream);
+}
+
+int adp_nocs_match(const float* nocs1, const float* nocs2, const int32_t* choose1, const int32_t* choose2, const int32_t* win1,
+                   const int32_t* win2, const double* K, const double* E1, const double* E2, const uint8_t* valid, int S,
+                   float* pts2d1, float* pts_cam, float* nocs_m, int32_t* count, int32_t* match_ids, int B, int P, void* stream) {
+    ADP_CHECK_ARG(nocs1 && nocs2 && choose1 && choose2 && win1 && win2 && K && E1 && E2 && pts2d1 && pts_cam && nocs_m && count,
+                  "null pointer");
+    g_launches += 1;
+    return nocs_match_run(nocs1, nocs2, choose1, choose2, win1, win2, K, E1, E2, valid, S, pts2d1, pts_cam, nocs_m, count, match_ids,
+                          B, P, (cudaStream_t)stream);
 }
 
 int adp_fit_umeyama(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const double* E,

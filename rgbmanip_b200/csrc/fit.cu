@@ -110,8 +110,8 @@ __device__ __forceinline__ void fit_for_each_ratio(int P, int rank, const float4
 __global__ void __cluster_dims__(FIT_G, 1, 1) __launch_bounds__(FIT_THREADS, 2)
 fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, const int* __restrict__ choose,
            const double* __restrict__ Kp, const float* __restrict__ R, const double* __restrict__ E, const uint8_t* __restrict__ valid,
-           double* __restrict__ bbox, double* __restrict__ scale_out, double* __restrict__ trans_out, float* __restrict__ scratch,
-           int P, int S) {
+           double* __restrict__ bbox, double* __restrict__ scale_out, double* __restrict__ trans_out,
+           const float* __restrict__ pts_cam, const int* __restrict__ pts_count, int P, int S) {
     __shared__ float4 pa[FIT_MAXP];              // (cx, cy, cz, nx): camera-frame point + first NOCS coordinate
     __shared__ float2 pb[FIT_MAXP];              // (ny, nz)
     __shared__ unsigned int hist[FIT_BINS];      // this CTA's digit histogram (read by the whole cluster)
@@ -133,7 +133,19 @@ fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, cons
         return;
     }
     const double* k = Kp + 9 * b;
-    const double fx = k[0], fy = k[4], pcx = k[2], pcy = k[5];
+    const double fx = k[0], fy = k[4], pcx = k[2], pcy = k[5];     // (unused in points mode)
+    if (pts_cam) {
+        // points mode (branch C, utils.py:189-193): camera-frame points come from the triangulation of the matched pixels,
+        // `nocs` holds their NOCS coordinates in the same (compacted) order, the first pts_count[b] entries are valid.  The rest
+        // is parked far apart: every pair with one of them fails the |dc| < 0.3 filter.
+        const int cnt = pts_count[b];
+        for (int i = tid; i < P; i += FIT_THREADS) {
+            const float* pp = pts_cam + ((size_t)b * P + i) * 3;
+            const float* nn = nocs + ((size_t)b * P + i) * 3;
+            if (i < cnt) { pa[i] = make_float4(pp[0], pp[1], pp[2], nn[0]); pb[i] = make_float2(nn[1], nn[2]); }
+            else { pa[i] = make_float4(1.0e6f * (float)(i + 1), 0.f, 0.f, 0.f); pb[i] = make_float2(0.f, 0.f); }
+        }
+    } else
     for (int i = tid; i < P; i += FIT_THREADS) {
         const int pix = choose[(size_t)b * P + i];
         const double z = (double)depth[(size_t)b * P + i];
@@ -301,12 +313,12 @@ fit_kernel(const float* __restrict__ nocs, const float* __restrict__ depth, cons
 }
 
 int fit_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const float* R, const double* E,
-            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, float* scratch, int B, int P, int S,
-            cudaStream_t stream) {
+            const uint8_t* valid, double* bbox, double* scale_out, double* trans_out, const float* pts_cam, const int* pts_count,
+            int B, int P, int S, cudaStream_t stream) {
     ADP_CHECK_ARG(P <= FIT_MAXP, "at most 1024 points per env");
-    (void)scratch;     // kept in the signature for ABI stability: the pair ratios are recomputed, not parked
+    ADP_CHECK_ARG(!pts_cam || pts_count, "points mode needs the per-env point counts");
     if (B == 0) return ADP_OK;
-    fit_kernel<<<B * FIT_G, FIT_THREADS, 0, stream>>>(nocs, depth, choose, Kp, R, E, valid, bbox, scale_out, trans_out, scratch, P, S);
+    fit_kernel<<<B * FIT_G, FIT_THREADS, 0, stream>>>(nocs, depth, choose, Kp, R, E, valid, bbox, scale_out, trans_out, pts_cam, pts_count, P, S);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

@@ -68,7 +68,7 @@ class Engine:
     """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
 
     def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="fp16f8", regress_pose=True, debug=False,
-                 img_size=IMG_SIZE, n_pts=N_PTS, use_graph=True):
+                 img_size=IMG_SIZE, n_pts=N_PTS, use_graph=True, use_depth=True):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
         if precision not in ("bf16", "bf16x3", "fp16x2", "fp16f8"):
@@ -91,6 +91,9 @@ class Engine:
         self.npass = {"bf16": 1, "fp16x2": 2, "fp16f8": 2, "bf16x3": 3}[precision]
         self.precision = precision
         self.regress_pose = bool(regress_pose)
+        # branch C (direct_regression = False, use_depth = False; interface_v5.py:339-349): NOCS of both views -> matching,
+        # triangulation and median scale on the device, cv2 PnP on the host (estimator._pnp_tail); no volume / U-Net at all
+        self.branch_c = (not self.regress_pose) and not bool(use_depth)
         if int(n_pts) != 1024 or int(img_size) % 224 != 0:
             raise ValueError("the device pipeline is built for n_pts = 1024 and img_size = 224 (every shipped adapose_* yaml)")
         self.use_graph = bool(use_graph) and not debug
@@ -424,7 +427,7 @@ class Engine:
         self.dw = dw
         P = self.P
         f32 = dict(dtype=torch.float32, device=dev)
-        self.nocs = torch.zeros((E, P, 3), **f32)
+        self.nocs = torch.zeros((self.F if self.branch_c else E, P, 3), **f32)
         self.depth = torch.zeros((E, P), **f32)
         self.gsum = torch.zeros((E, 128), **f32)
         self.psum = torch.zeros((E, 256), **f32)
@@ -444,13 +447,22 @@ class Engine:
         self.scale = torch.zeros(E, dtype=torch.float64, device=dev)
         self.trans = torch.zeros((E, 3), dtype=torch.float64, device=dev)
         self.rot64 = torch.zeros((E, 9), dtype=torch.float64, device=dev)
+        if self.branch_c:
+            self.valid_f = torch.zeros(F, dtype=torch.uint8, device=dev)
+            self.pts2d1 = torch.zeros((E, P, 2), **f32)
+            self.pts_cam = torch.zeros((E, P, 3), **f32)
+            self.nocs_m = torch.zeros((E, P, 3), **f32)
+            self.match_count = torch.zeros(E, dtype=torch.int32, device=dev)
+            self.match_ids = torch.zeros((E, P, 2), dtype=torch.int32, device=dev)
+            self.R.copy_(torch.eye(3, device=dev).reshape(1, 9).expand(E, 9))
         self._build_decode_tc()
 
     def _build_decode_tc(self):
         """Per-point MLPs (network_v5.py:432-444,486-493) as 1x1 convolutions on the tcgen05 kernel: the P = 1024 sampled
         pixels of an env form a 32x32 "image", every layer is one split-precision (bf16x3) launch over all envs."""
-        sd, E, P = self.sd, self.E, self.P
+        sd, P = self.sd, self.P
         assert P == 1024
+        E = self.F if self.branch_c else self.E          # branch C decodes the frames of both views
         pt = lambda Cn: self._act(E, 32, 32, Cn, split=True)
         self.xfeat, self.xcat = pt(32), pt(96)
         h_ic, h_n0, h_n1, self.nocs16 = pt(64), pt(128), pt(64), pt(16)
@@ -550,7 +562,7 @@ class Engine:
         if self.regress_pose:
             L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
                                 L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans),
-                                None, n, P, S, st), "fit")
+                                None, None, n, P, S, st), "fit")
         else:   # direct_regression = False, use_depth = True: RANSAC + Umeyama (interface_v5.py:322-338)
             L.check(lib.adp_fit_umeyama(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(E1),
                                         L.ptr(self.valid_env), L.ptr(ransac_idx), seed & 0xFFFFFFFF, L.ptr(self.bbox),
@@ -600,8 +612,32 @@ class Engine:
             self.stereo(n, self.E1buf, self.E2buf, o2=n)
             return self.bbox[:n]
         self.run_backbone(2 * n)
+        if self.branch_c:
+            return self.match_branch_c(n, K, E1, E2)
         self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed, o2=n)
         return self.bbox[:n]
+
+    def match_branch_c(self, n, K, E1, E2):
+        """Frames [0,n) = view 1, [n,2n) = view 2 (features present).  -> dict of device tensors for the host PnP tail:
+        nocs1 [n,P,3], pts2d1 [n,P,2], scale [n] (median scale of the triangulated matches), count [n], valid [n]."""
+        lib, st, P, S = self.lib, self.stream, self.P, self.S
+        self.valid_f[:2 * n].copy_(self.valid[:2 * n])
+        L.check(lib.adp_decode_gather(L.ptr(self.feat), None, None, None, None, L.ptr(self.choose), L.ptr(self.valid_f), None,
+                                      None, L.ptr(self.xfeat.hi), L.ptr(self.xfeat.lo), None, None, None, None, 2 * n, S,
+                                      N_DEPTH, P, 0, st), "decode_gather(branch C)")
+        for _, op in self.dec_ops[:4]:
+            op(2 * n)
+        self.valid_env[:n].copy_(self.valid[:n] & self.valid[n:2 * n])
+        Kc = K.reshape(n, 9).contiguous()
+        L.check(lib.adp_nocs_match(L.ptr(self.nocs), L.ptr(self.nocs[n:]), L.ptr(self.choose), L.ptr(self.choose[n:]), L.ptr(self.win),
+                                   L.ptr(self.win[n:]), L.ptr(Kc), L.ptr(E1), L.ptr(E2), L.ptr(self.valid_env), S, L.ptr(self.pts2d1),
+                                   L.ptr(self.pts_cam), L.ptr(self.nocs_m), L.ptr(self.match_count), L.ptr(self.match_ids), n, P, st),
+                "nocs_match")
+        L.check(lib.adp_fit(L.ptr(self.nocs_m), None, None, L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1), L.ptr(self.valid_env),
+                            L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans), L.ptr(self.pts_cam), L.ptr(self.match_count),
+                            n, P, S, st), "fit(points mode)")
+        return dict(nocs1=self.nocs[:n], pts2d1=self.pts2d1[:n], scale=self.scale[:n], count=self.match_count[:n],
+                    valid=self.valid_env[:n], match_ids=self.match_ids[:n], pts_cam=self.pts_cam[:n])
 
     def _capture_graph(self, n):
         import warnings

@@ -75,6 +75,46 @@ def chunk_bounds(N, max_envs, first=0):
     return bounds
 
 
+_BOX_SIGNS = np.array([[1, 1, 1], [1, 1, -1], [-1, 1, 1], [-1, 1, -1], [1, -1, 1], [1, -1, -1], [-1, -1, 1], [-1, -1, -1]], np.float64)
+
+
+def pnp_box_tail(nocs, pts2d, scale, valid, K, E1):
+    """Host tail of branch C, per environment as the reference runs it: ``estimatePnPRansac`` (align.py:104-115) with size = the
+    median scale of the triangulated matches, then the box + world transform + finite check of interface_v5.py:350-374.  The
+    PnP is the reference's own OpenCV call (its RANSAC lives inside cv2); everything before it ran on the device.
+    nocs [n,P,3] f32, pts2d [n,P,2] f32, scale [n] f64, valid [n], K [n,3,3], E1 [n,4,4] -> [n,8,3] float64."""
+    import cv2
+    out = np.empty((len(scale), 8, 3))
+    crit = (cv2.TERM_CRITERIA_MAX_ITER + cv2.TERM_CRITERIA_EPS, 20, 1e-6)
+    for e in range(len(scale)):
+        out[e] = DEFAULT_BBOX
+        ts = np.float64(scale[e])
+        if not valid[e] or not np.isfinite(ts):
+            continue          # NaN scale: the reference's box is NaN too and fails its finite check -> sentinel
+        temp = nocs[e] * ts                                  # float32 array * np.float64 scalar, as in the reference
+        try:
+            ok, rv, tv, _ = cv2.solvePnPRansac(temp, pts2d[e], K[e], np.zeros(4), flags=cv2.SOLVEPNP_EPNP, reprojectionError=3.0)
+            if ok:
+                rv, tv = cv2.solvePnPRefineVVS(temp, pts2d[e], K[e], None, rv, tv, criteria=crit)
+            Rm, _ = cv2.Rodrigues(rv)
+        except cv2.error:
+            continue
+        size = 2 * np.max(np.abs(nocs[e]), axis=0) * ts
+        sRT = np.eye(4).astype(np.float32)                   # float32 matrix, no scale in it (interface_v5.py:359-361)
+        sRT[:3, :3] = Rm
+        sRT[:3, 3] = np.asarray(tv).flatten()
+        cam = sRT @ np.vstack([(_BOX_SIGNS * (size / 2)).T, np.ones((1, 8), np.float32)])
+        cam = cam[:3] / cam[3]
+        with np.errstate(all="ignore"):
+            try:
+                inv = np.linalg.inv(E1[e])
+            except np.linalg.LinAlgError:
+                continue
+        if np.isfinite(inv).all() and np.isfinite(cam).all():
+            out[e] = (inv[:3, :3] @ cam + inv[:3, 3:4]).T
+    return out
+
+
 class AdaPoseEstimator_v5(BasePoseEstimator):
 
     def __init__(self, env, cfg, logger, state_dict=None, device=None, max_envs=None, precision=None, devices=None, **engine_kw):
@@ -82,9 +122,12 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         self.cfg = cfg
         self._replicas = None
         regress = bool(cfg.get("direct_regression", True))
-        if not regress and not cfg.get("use_depth", True):
-            # branch C (interface_v5.py:339-349) lives inside OpenCV (triangulatePoints / solvePnPRansac): parity unpinned
-            raise NotImplementedError("direct_regression=False with use_depth=False (NOCS matching + cv2 PnP) is not supported")
+        self._branch_c = (not regress) and not cfg.get("use_depth", True)
+        if self._branch_c:
+            # branch C (interface_v5.py:339-349): matching / triangulation / median scale run on the device, the PnP tail is the
+            # reference's own OpenCV call on the host (align.py:104-115; its RANSAC lives inside cv2: "parity unpinned" there)
+            import cv2  # noqa: F401  (fail at construction, not in the middle of an episode)
+            engine_kw = dict(engine_kw, use_depth=False)
         if state_dict is None:
             if cfg.get("load", False):
                 # same failure mode as the reference: a missing checkpoint raises from torch.load (interface_v5.py:55-56)
@@ -311,7 +354,10 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
                     ridx = self._as_tensor(ransac_idx[lo:hi]).to(torch.int32).to(self.device)
                 box = eng.run_chunk(t["K"], t["rgb1"], t["m1"], t["E1"], t["rgb2"], t["m2"], t["E2"],
                                     seed=seed, choose1=t["c1"], choose2=t["c2"], ransac_idx=ridx, env0=int(env_offset) + lo)
-                out[lo:hi].copy_(box)
+                if self._branch_c:
+                    out[lo:hi].copy_(self._pnp_tail(box, t["K"], t["E1"]))
+                else:
+                    out[lo:hi].copy_(box)
                 if "_slot" in t:          # the slot's persistent frame buffers may be overwritten once this chunk's kernels ran
                     done = torch.cuda.Event()
                     done.record(compute)
@@ -325,6 +371,12 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             res = out.cpu().numpy()
         eng.check_error_flag()
         return res
+
+    def _pnp_tail(self, r, K, E1):
+        """Host tail of branch C for one chunk of environments -> [n,8,3] float64 boxes on the device."""
+        box = pnp_box_tail(r["nocs1"].cpu().numpy(), r["pts2d1"].cpu().numpy(), r["scale"].cpu().numpy(), r["valid"].cpu().numpy(),
+                           K.cpu().numpy().reshape(-1, 3, 3), E1.cpu().numpy().reshape(-1, 4, 4))
+        return torch.from_numpy(box).to(self.device)
 
     def estimate_nocs_single_view(self, camera_intrinsic_batch, rgb_batch, mask_batch, choose=None):
         """BASELINE configs[0..1]: one view per environment -> (nocs [N,1024,3] float32, choose [N,1024] int32, valid [N] bool)

@@ -646,8 +646,7 @@ def test_fit_median_is_exact_and_sentinel(G):
     scale = torch.zeros(B, dtype=torch.float64, device=dev)
     trans = torch.zeros((B, 3), dtype=torch.float64, device=dev)
     args = [t(nocs), t(depth), t(choose), t(Kp), t(R), t(E), t(valid)]
-    scratch = None
-    L.check(lib.adp_fit(*[L.ptr(a) for a in args], L.ptr(bbox), L.ptr(scale), L.ptr(trans), L.ptr(scratch), B, P, 224, G.stream()), "fit")
+    L.check(lib.adp_fit(*[L.ptr(a) for a in args], L.ptr(bbox), L.ptr(scale), L.ptr(trans), None, None, B, P, 224, G.stream()), "fit")
     torch.cuda.synchronize()
     for e in (0, 1):
         cam = O.back_project(depth[e], choose[e], Kp[e].reshape(3, 3))

@@ -28,3 +28,20 @@ def test_chunk_bounds_examples():
     assert chunk_bounds(128, 74, 16) == [(0, 16), (16, 48), (48, 88), (88, 128)]   # the same shard uploaded from the host
     assert [h - l for l, h in chunk_bounds(1024, 74, 16)][:4] == [16, 32, 64, 71]
     assert chunk_bounds(8, 8, 16) == [(0, 8)]
+
+
+def test_branch_c_host_tail_equals_reference(golden_dir):
+    """The host tail of branch C (cv2 PnP + box, estimator.pnp_box_tail) on the reference's own NOCS / scale -> its boxes."""
+    import os
+    import numpy as np
+    from rgbmanip_b200 import synth
+    from rgbmanip_b200.estimator import DEFAULT_BBOX, pnp_box_tail
+    g = np.load(os.path.join(golden_dir, "branch_c.npz"))
+    b = synth.make_batch(4, seed=3, special=False)
+    scale = g["left_scale"].copy()
+    valid = np.array([1, 1, 1, 0], bool)
+    box = pnp_box_tail(g["nocs1"], g["pts2d1"].astype(np.float32), scale, valid, b.K, b.E1)
+    np.testing.assert_allclose(box[:3], g["boxes"][:3], rtol=1e-9, atol=1e-9)
+    np.testing.assert_array_equal(box[3], DEFAULT_BBOX)
+    scale[0] = np.nan
+    np.testing.assert_array_equal(pnp_box_tail(g["nocs1"], g["pts2d1"].astype(np.float32), scale, valid, b.K, b.E1)[0], DEFAULT_BBOX)
