@@ -141,7 +141,12 @@ def box_errors(a, b, K, E1, min_z=0.5):
     ok = (za > min_z) & (zb > min_z)
     px = float(np.abs(pa[ok] - pb[ok]).max()) if ok.any() else 0.0
     cosang = np.clip((np.trace(Ra.T @ Rb) - 1.0) / 2.0, -1.0, 1.0)
+    box_errors.compared += int(ok.sum())
+    box_errors.total += int(ok.size)
     return px, float(np.degrees(np.arccos(cosang))), float(np.linalg.norm(ca - cb) * 1e3), float(np.linalg.norm(a - b, axis=1).max() * 1e3)
+
+
+box_errors.compared = box_errors.total = 0      # keypoints that entered the pixel metric / all keypoints seen (the rest: mm only)
 
 
 def parity_check(est, copies):
@@ -164,6 +169,7 @@ def parity_check(est, copies):
         boxes = est.estimate(*args, choose=choose)
     worst = np.zeros(4)
     sentinel_ok = True
+    box_errors.compared = box_errors.total = 0
     for i, e in enumerate(idx):
         if not g["valid"][e]:
             sentinel_ok &= bool(np.array_equal(boxes[i], DEFAULT_BBOX))
@@ -176,6 +182,7 @@ def parity_check(est, copies):
            "chunk_sizes": sorted({hi - lo for lo, hi in est._chunk_bounds(copies, False)}),
            "graph_replayed": bool(eng._graphs), "max_px": float(worst[0]), "max_deg": float(worst[1]), "max_centre_mm": float(worst[2]),
            "max_corner_mm": float(worst[3]), "sentinels_bit_exact": sentinel_ok,
+           "keypoints_in_px_metric": box_errors.compared, "keypoints_total": box_errors.total,
            "tolerance": {"px": TOL_PX, "deg": TOL_DEG, "mm": TOL_MM}, "ok": ok}
     if not ok:
         raise SystemExit("parity_in_bench failed: " + json.dumps(out))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ADP_ABI_VERSION 3
+#define ADP_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define ADP_API __attribute__((visibility("default")))
@@ -219,6 +219,19 @@ ADP_API int adp_nocs_match(const float* nocs1, const float* nocs2, const int32_t
                            const int32_t* win1, const int32_t* win2, const double* K, const double* E1, const double* E2,
                            const uint8_t* valid, int S, float* pts2d1, float* pts_cam, float* nocs_m, int32_t* count,
                            int32_t* match_ids, int B, int P, void* stream);
+
+/* --- transformer variant: lib/fusion.py:11-82 (ViewFusion, 4 cross-view attention blocks, d = 32, 4 heads, 1024 tokens per view)
+ * and the depth MLP of lib/network_baseline.py:555-562,631-643 (StereoPoseNet_with_depth_baseline; train.py:242-244) -----------
+ * feat1/feat2 [B,S*S,32] fp32 channels-last feature maps, choose1/choose2 [B,P] sampled pixels (tokens = gathered features,
+ * network_baseline.py:616-626).  blocks: [n_blocks][2 directions (fusion1, fusion2)][4 linears (q,k,v,out)][32*32 weight (out,in)
+ * + 32 bias] fp32; depth_w: depth_head.0 weight [64][32], bias [64], depth_head.2 weight TRANSPOSED [64][32], bias [32],
+ * depth_head.4 weight [32], bias [1].  scratch: 4 * B*P*32 floats.  Outputs: depth1 [B,P] (metres; required), depth2 / fused1 /
+ * fused2 ([B,P,32] fp32 tokens after the last block) optional, xcat_hi/lo optional bf16 planes [B,P,96] whose columns 0..31 receive
+ * the view-1 tokens (input of pose_mlp1).  Environments with valid[b] == 0 get zeros. */
+ADP_API int adp_view_fusion(const float* feat1, const float* feat2, const int32_t* choose1, const int32_t* choose2,
+                            const uint8_t* valid, const float* blocks, const float* depth_w, float* scratch, float* depth1,
+                            float* depth2, void* xcat_hi, void* xcat_lo, float* fused1, float* fused2, int B, int S, int P,
+                            int n_blocks, void* stream);
 
 /* --- pose fit, branch B: align.py:44-102 (RANSAC + Umeyama), interface_v5.py:322-338 --------------------------
  * rand_idx: [B,128,5] sample indices (NULL = counter-based hash of `seed`); rot [B,9], trans [B,3], scale [B] optional. */

@@ -366,6 +366,60 @@ def network_forward(sd, img1, choose1, img2, choose2, P1, P2, depth_values, regr
 
 
 # ----------------------------------------------------------------------------------------------
+# transformer variant: StereoPoseNet_with_depth_baseline (ADA/lib/network_baseline.py:523-669, ADA/lib/fusion.py:11-82)
+# ----------------------------------------------------------------------------------------------
+def multi_head_attention(sd, name, query, key, value, heads=4):
+    """fusion.py:28-51 (MultiHeadedAttention.forward; mask / dropout / position embedding are None on this path) with
+    fusion.py:11-26 (scores = q k^T / sqrt(d_k), softmax over the keys).  query/key/value: [B, N, d_model]."""
+    B, d = query.shape[0], query.shape[-1]
+    dk = d // heads
+    lin = lambda i, x: F.linear(x, _w(sd, f"{name}.linears.{i}.weight"), _w(sd, f"{name}.linears.{i}.bias"))
+    q, k, v = (lin(i, x).view(B, -1, heads, dk).transpose(1, 2) for i, x in enumerate((query, key, value)))
+    p = F.softmax(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk), dim=-1)
+    x = torch.matmul(p, v).transpose(1, 2).contiguous().view(B, -1, d)
+    return lin(3, x), p
+
+
+def view_fusion(sd, f1, f2, depth=4, heads=4, tap=_NOTAP):
+    """fusion.py:53-82: per block, view 1 attends to view 2 (fusion1) and view 2 to view 1 (fusion2), both from the block's
+    INPUTS, each added to its own input.  f1, f2: [B, d, N]."""
+    for b in range(depth):
+        q, k = f1.transpose(2, 1), f2.transpose(2, 1)
+        x, p1 = multi_head_attention(sd, f"view_fusion.blocks.{b}.fusion1", q, k, k, heads)
+        y, _ = multi_head_attention(sd, f"view_fusion.blocks.{b}.fusion2", k, q, q, heads)
+        tap(f"attn{b}", p1)
+        f1, f2 = x.transpose(2, 1) + f1, y.transpose(2, 1) + f2
+    return f1, f2
+
+
+def network_forward_baseline(sd, img1, choose1, img2, choose2, regress_pose=True, tap=_NOTAP):
+    """StereoPoseNet_with_depth_baseline.forward (network_baseline.py:606-669): PSPNet features at the sampled pixels ->
+    NOCS head per view; 4 cross-view attention blocks on the raw 32-channel point features -> depth MLP (metres, ReLU) and
+    the pose heads of network_v5 on cat(fused features, nocs_pts_mlp(nocs))."""
+    f1, f2 = pspnet(sd, img1, tap), pspnet(sd, img2, tap)
+    B, C = f1.shape[:2]
+    out = {"feat1": f1, "feat2": f2}
+    emb = {}
+    for v, (f, ch) in enumerate(((f1, choose1), (f2, choose2)), 1):
+        emb[v] = torch.gather(f.view(B, C, -1), 2, ch[:, None, :].repeat(1, C, 1)).contiguous()
+        h = _mlp1d(sd, "nocs_head", (0, 2), _mlp1d(sd, "instance_color", (0,), emb[v]))
+        out[f"view{v}_nocs_cf"] = torch.tanh(F.conv1d(h, _w(sd, "nocs_head.4.weight"), _w(sd, "nocs_head.4.bias")))
+        out[f"view{v}_nocs"] = out[f"view{v}_nocs_cf"].permute(0, 2, 1).contiguous()
+    fused = dict(zip((1, 2), view_fusion(sd, emb[1], emb[2], tap=tap)))
+    for v in (1, 2):
+        out[f"view{v}_fused"] = fused[v]
+        out[f"view{v}_depth"] = _mlp1d(sd, "depth_head", (0, 2, 4), fused[v]).squeeze(1)
+        if regress_pose:
+            pts = _mlp1d(sd, "nocs_pts_mlp", (0, 2), out[f"view{v}_nocs_cf"])
+            pf = _mlp1d(sd, "pose_mlp1", (0, 2), torch.cat((fused[v], pts), dim=1))
+            g = torch.mean(pf, 2, keepdim=True)
+            pf2 = _mlp1d(sd, "pose_mlp2", (0, 2), torch.cat([pf, g.expand_as(pf)], 1)).mean(2)
+            r6 = _mlp1d(sd, "rotation_estimator", (0, 2, 4), pf2, last_act=False)
+            out[f"view{v}_r"] = ortho6d_to_mat(r6[:, :3].contiguous(), r6[:, 3:].contiguous()).view(-1, 3, 3)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # pose fit  (ADA/lib/utils.py:40-119, ADA/lib/align.py:10-102) and box (ADA/interface_v5.py:318-374)
 # ----------------------------------------------------------------------------------------------
 def back_project(depth, choose, Kp, img_size=IMG_SIZE):
@@ -546,9 +600,13 @@ def predict(sd, cfg, K, rgb1, mask1, E1, rgb2, mask2, E2, rng=np.random, both_vi
     dv = torch.from_numpy(depth_hypotheses())[None]
     regress = bool(cfg.get("direct_regression", True))
     with torch.no_grad():
-        pred = network_forward(sd, t32(v1), torch.from_numpy(ch1)[None], t32(v2), torch.from_numpy(ch2)[None],
-                               t32(projection(K1, E1)), t32(projection(K2, E2)), dv, regress_pose=regress,
-                               both_views=both_views, tap=tap)
+        if cfg.get("name", "adapose") == "adapose_baseline":      # train.py:242-244 -> interface_baseline.py (same interface)
+            pred = network_forward_baseline(sd, t32(v1), torch.from_numpy(ch1)[None], t32(v2), torch.from_numpy(ch2)[None],
+                                            regress_pose=regress, tap=tap)
+        else:
+            pred = network_forward(sd, t32(v1), torch.from_numpy(ch1)[None], t32(v2), torch.from_numpy(ch2)[None],
+                                   t32(projection(K1, E1)), t32(projection(K2, E2)), dv, regress_pose=regress,
+                                   both_views=both_views, tap=tap)
     nocs = pred["view1_nocs"][0].numpy()
     depth = pred["view1_depth"][0].numpy()
     if regress:
@@ -618,3 +676,11 @@ def parity_errors(box_a, box_b, K, E1, min_z=0.2):
     px = float(np.abs(pa[ok] - pb[ok]).max()) if ok.any() else 0.0
     return (px, rotation_angle_deg(Ra, Rb), float(np.linalg.norm(ca - cb) * 1e3),
             float(np.linalg.norm(box_a - box_b, axis=1).max() * 1e3))
+
+
+def keypoints_compared(box_a, box_b, K, E1, min_z=0.2):
+    """(number of keypoints -- 8 corners + centre -- whose reprojection enters :func:`parity_errors`, total).  The others lie
+    nearer than ``min_z`` to the camera plane in one of the two boxes and are compared in millimetres only."""
+    _, za = project_points(np.vstack([box_a, box_a.mean(axis=0)[None]]), K, E1)
+    _, zb = project_points(np.vstack([box_b, box_b.mean(axis=0)[None]]), K, E1)
+    return int(((za > min_z) & (zb > min_z)).sum()), 9

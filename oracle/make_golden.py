@@ -11,6 +11,7 @@ can regenerate them; inputs come from ``rgbmanip_b200.synth``.
 from __future__ import annotations
 
 import logging
+import math
 import os
 import sys
 from unittest.mock import MagicMock
@@ -26,6 +27,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 
 from rgbmanip_b200 import synth, weights  # noqa: E402
+
+# init gains of the transformer-variant fixtures (weights.init_state_dict docstring); tests regenerate the weights with these
+BASELINE_INIT = dict(attn_gain=5.0, depth_bias=0.8)
 from oracle.view_ring_oracle import view_ring_script  # noqa: E402
 
 
@@ -267,6 +271,53 @@ def golden_branch_c(interface_v5, out_dir):
     print("branch C boxes", boxes.shape, "finite", np.isfinite(boxes).all(), "matches", out["n_match"], "scales", out["left_scale"])
 
 
+def golden_baseline(out_dir):
+    """The transformer variant (train.py:242-244: name = adapose_baseline -> interface_baseline.AdaPoseEstimator_baseline, the v5
+    interface around StereoPoseNet_with_depth_baseline): 4 envs end to end, plus the attention statistics the init gains aim at."""
+    from models.pose_estimator.AdaPose import interface_baseline
+    cfg = yaml.safe_load(open(f"{REF}/cfg/pose_estimator/adapose_drawer.yaml"))
+    cfg.update(load=False, name="adapose_baseline")
+    torch.manual_seed(0)
+    est = interface_baseline.AdaPoseEstimator_baseline(None, cfg, logging.getLogger("golden"))
+    sd = weights.init_state_dict(0, arch="baseline", **BASELINE_INIT)
+    est.estimator.load_state_dict({"module." + k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    est.estimator.eval()
+    batch = synth.make_batch(4, seed=9, special=False)
+    rec = {"prep": [], "pred": [], "fused": [], "attn": []}
+    orig_prepare, orig_forward = est.prepare_model_input, est.estimator.module.forward
+
+    def prepare(rgb, mask, K, resize_size):
+        r = orig_prepare(rgb, mask, K, resize_size)
+        rec["prep"].append(r)
+        return r
+
+    def forward(*a, **k):
+        o = orig_forward(*a, **k)
+        rec["pred"].append({kk: v.detach().cpu().numpy() for kk, v in o.items()})
+        return o
+
+    est.prepare_model_input, est.estimator.module.forward = prepare, forward
+    est.estimator.module.view_fusion.register_forward_hook(lambda m, i, o: rec["fused"].append([t.detach().numpy().copy() for t in o]))
+    blk0 = est.estimator.module.view_fusion.blocks[0].fusion1
+    est.estimator.module.view_fusion.blocks[0].register_forward_hook(lambda m, i, o: rec["attn"].append(blk0.attn.detach().numpy().copy()))
+    np.random.seed(11)
+    boxes = est.estimate(*batch.args())
+    n = len(batch)
+    p = rec["attn"][0][0]                                  # [heads, N, N] of env 0, block 0
+    ent = -(p * np.log(np.maximum(p, 1e-30))).sum(-1)
+    print("baseline: attention entropy (block 0, env 0) mean %.3f of max %.3f; row max prob mean %.3f" % (ent.mean(), math.log(p.shape[-1]), p.max(-1).mean()))
+    out = dict(boxes=boxes,
+               choose1=np.stack([rec["prep"][2 * e][1] for e in range(n)]).astype(np.int32),
+               choose2=np.stack([rec["prep"][2 * e + 1][1] for e in range(n)]).astype(np.int32),
+               fused1=np.stack([rec["fused"][e][0][0] for e in range(n)]), fused2=np.stack([rec["fused"][e][1][0] for e in range(n)]),
+               attn_entropy=ent.astype(np.float32))
+    for k in ("view1_nocs", "view2_nocs", "view1_depth", "view2_depth", "view1_r", "view2_r"):
+        out[k] = np.stack([rec["pred"][e][k][0] for e in range(n)])
+    np.savez_compressed(os.path.join(out_dir, "baseline.npz"), **out)
+    print("baseline boxes", boxes.shape, "finite", np.isfinite(boxes).all(), "depth range", out["view1_depth"].min(), out["view1_depth"].max(),
+          "fused range", np.abs(out["fused1"]).max())
+
+
 def golden_view_ring(out_dir):
     """Caller-side queues of the RL controller (models/controller/rl_pose.py:85-97,118-150,189-223), executed unmodified."""
     for m in ["tensorboard", "torch.utils.tensorboard", "ipdb", "open3d", "sapien.utils.viewer"]:
@@ -437,7 +488,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     interface_v5, network_v5, rotation_utils, utils, align = import_reference()
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring", "actor", "e2e_seed1", "branch_c_units", "branch_c"]
+    what = sys.argv[1:] or ["units", "preprocess", "e2e", "branch_b", "view_ring", "actor", "e2e_seed1", "branch_c_units", "branch_c", "baseline"]
     if "units" in what:
         golden_units(network_v5, rotation_utils, utils, align, out_dir)
     if "preprocess" in what:
@@ -450,6 +501,8 @@ def main():
         golden_branch_c_units(utils, align, out_dir)
     if "branch_c" in what:
         golden_branch_c(interface_v5, out_dir)
+    if "baseline" in what:
+        golden_baseline(out_dir)
     if "e2e_seed1" in what:
         golden_e2e_seed1(interface_v5, out_dir)
     if "view_ring" in what:

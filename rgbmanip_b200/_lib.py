@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libadapose_b200.so")
 
-ADP_ABI_VERSION = 3
+ADP_ABI_VERSION = 4
 DT_U8, DT_F32, DT_F64 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_TANH = 0, 1, 2, 3
 LAYOUT_F16, LAYOUT_S2D = 1, 2          # adp_decode x11_format / adp_conv0_plan_create flags
@@ -80,6 +80,7 @@ SIGNATURES = {
     "adp_actor_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
     "adp_fit": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "adp_nocs_match": (C.c_int, [vp] * 10 + [C.c_int] + [vp] * 5 + [C.c_int, C.c_int, vp]),
+    "adp_view_fusion": (C.c_int, [vp] * 14 + [C.c_int] * 4 + [vp]),
     "adp_fit_umeyama": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadapose_b200.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "build")
-SOURCES = ["api.cu", "tc_conv.cu", "conv0_ring.cu", "tconv_fused.cu", "backbone_misc.cu", "preprocess.cu", "volume.cu", "decode.cu", "fit.cu", "fit_umeyama.cu", "nocs_match.cu", "actor.cu"]
+SOURCES = ["api.cu", "tc_conv.cu", "conv0_ring.cu", "tconv_fused.cu", "backbone_misc.cu", "preprocess.cu", "volume.cu", "decode.cu", "fit.cu", "fit_umeyama.cu", "nocs_match.cu", "view_fusion.cu", "actor.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -41,6 +41,9 @@ int fit_run(const float* nocs, const float* depth, const int* choose, const doub
 int nocs_match_run(const float* nocs1, const float* nocs2, const int* choose1, const int* choose2, const int* win1, const int* win2,
                    const double* K, const double* E1, const double* E2, const uint8_t* valid, int S, float* pts2d1, float* pts_cam,
                    float* nocs_m, int* count, int* match_ids, int B, int P, cudaStream_t stream);
+int view_fusion_run(const float* feat1, const float* feat2, const int* choose1, const int* choose2, const uint8_t* valid,
+                    const float* blocks, const float* depth_w, float* scratch, float* depth1, float* depth2, bf16* xcat_hi,
+                    bf16* xcat_lo, float* fused1, float* fused2, int B, int S, int P, int n_blocks, cudaStream_t stream);
 
 int fit_umeyama_run(const float* nocs, const float* depth, const int* choose, const double* Kp, const double* E, const uint8_t* valid,
                     const int* rand_idx, uint32_t seed, double* bbox, double* scale_out, double* rot_out, double* trans_out, int B,
@@ -323,6 +326,17 @@ int adp_nocs_match(const float* nocs1, const float* nocs2, const int32_t* choose
     g_launches += 1;
     return nocs_match_run(nocs1, nocs2, choose1, choose2, win1, win2, K, E1, E2, valid, S, pts2d1, pts_cam, nocs_m, count, match_ids,
                           B, P, (cudaStream_t)stream);
+}
+
+int adp_view_fusion(const float* feat1, const float* feat2, const int32_t* choose1, const int32_t* choose2, const uint8_t* valid,
+                    const float* blocks, const float* depth_w, float* scratch, float* depth1, float* depth2, void* xcat_hi,
+                    void* xcat_lo, float* fused1, float* fused2, int B, int S, int P, int n_blocks, void* stream) {
+    ADP_CHECK_ARG(feat1 && feat2 && choose1 && choose2 && blocks && depth_w && scratch && depth1, "null pointer");
+    ADP_CHECK_ARG((xcat_hi == nullptr) == (xcat_lo == nullptr), "xcat planes come in pairs");
+    g_launches += n_blocks;
+    return view_fusion_run(feat1, feat2, choose1, choose2, valid, blocks, depth_w, scratch, depth1, depth2,
+                           reinterpret_cast<bf16*>(xcat_hi), reinterpret_cast<bf16*>(xcat_lo), fused1, fused2, B, S, P, n_blocks,
+                           (cudaStream_t)stream);
 }
 
 int adp_fit_umeyama(const float* nocs, const float* depth, const int32_t* choose, const double* Kp, const double* E,

@@ -68,7 +68,7 @@ class Engine:
     """One per device.  ``max_envs`` environments (2 x max_envs frames) are processed per chunk."""
 
     def __init__(self, state_dict, device="cuda:0", max_envs=16, precision="fp16f8", regress_pose=True, debug=False,
-                 img_size=IMG_SIZE, n_pts=N_PTS, use_graph=True, use_depth=True):
+                 img_size=IMG_SIZE, n_pts=N_PTS, use_graph=True, use_depth=True, arch="v5"):
         if not torch.cuda.is_available():
             raise L.AdpError("no CUDA device: the AdaPose B200 path has no CPU fallback")
         if precision not in ("bf16", "bf16x3", "fp16x2", "fp16f8"):
@@ -94,6 +94,12 @@ class Engine:
         # branch C (direct_regression = False, use_depth = False; interface_v5.py:339-349): NOCS of both views -> matching,
         # triangulation and median scale on the device, cv2 PnP on the host (estimator._pnp_tail); no volume / U-Net at all
         self.branch_c = (not self.regress_pose) and not bool(use_depth)
+        # arch "baseline" = StereoPoseNet_with_depth_baseline (network_baseline.py:523-669): same backbone and NOCS head, 4 blocks of
+        # cross-view attention + a depth MLP (csrc/view_fusion.cu) in place of the cost volume and its 3-D U-Net
+        if arch not in ("v5", "baseline"):
+            raise ValueError("arch must be 'v5' or 'baseline'")
+        self.arch = arch
+        self.need_volume = arch == "v5" and not self.branch_c
         if int(n_pts) != 1024 or int(img_size) % 224 != 0:
             raise ValueError("the device pipeline is built for n_pts = 1024 and img_size = 224 (every shipped adapose_* yaml)")
         self.use_graph = bool(use_graph) and not debug
@@ -113,7 +119,7 @@ class Engine:
         if self.cc[0] != 10:
             raise L.AdpError(f"device compute capability {self.cc} is not sm_100: this library ships sm_100a code only")
         sd = W.to_numpy_state_dict(state_dict)
-        W.check_state_dict(sd, self.regress_pose)
+        W.check_state_dict(sd, self.regress_pose, arch)
         self.sd = sd
         with torch.cuda.device(self.device):
             # [0] pipeline watchdog code, [1] fp16 range flag (set by the last backbone layer's epilogue on inf/NaN features)
@@ -330,6 +336,12 @@ class Engine:
         self.valid_env = torch.zeros(E, dtype=torch.uint8, device=dev)
         self.E1buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
         self.E2buf = torch.zeros((E, 16), dtype=torch.float64, device=dev)
+        if self.need_volume:
+            self._build_cost_volume_stage()
+        self._build_decode()
+
+    def _build_cost_volume_stage(self):
+        sd, E, S, D = self.sd, self.E, self.S, N_DEPTH
         self.vol = self._act(E, S, S, 32, D=D, split=False, f16=1)
         cr = "cost_regularization"
 
@@ -409,6 +421,10 @@ class Engine:
                         "conv7": x7, "conv9": x9, "conv11": x11}
         self.x11 = x11
         self.x11_format = L.LAYOUT_F16 | L.LAYOUT_S2D
+
+    def _build_decode(self):
+        sd, E, D, dev = self.sd, self.E, N_DEPTH, self.device
+        cr = "cost_regularization"
         # decode weights, transposed to [K][N]
         def tw(name):
             w = torch.as_tensor(sd[name]).float()
@@ -422,8 +438,9 @@ class Engine:
         for short, full in names.items():
             setattr(dw, f"{short}_w", L.ptr(tw(f"{full}.weight")))
             setattr(dw, f"{short}_b", L.ptr(self._dev(sd[f"{full}.bias"])))
-        pw = torch.as_tensor(sd[f"{cr}.prob.weight"]).float()[0].permute(1, 2, 3, 0).contiguous()    # [kz,ky,kx,c]
-        dw.prob_w = L.ptr(self._dev(pw.reshape(27, 8)))
+        if self.need_volume:
+            pw = torch.as_tensor(sd[f"{cr}.prob.weight"]).float()[0].permute(1, 2, 3, 0).contiguous()    # [kz,ky,kx,c]
+            dw.prob_w = L.ptr(self._dev(pw.reshape(27, 8)))
         self.dw = dw
         P = self.P
         f32 = dict(dtype=torch.float32, device=dev)
@@ -455,6 +472,23 @@ class Engine:
             self.match_count = torch.zeros(E, dtype=torch.int32, device=dev)
             self.match_ids = torch.zeros((E, P, 2), dtype=torch.int32, device=dev)
             self.R.copy_(torch.eye(3, device=dev).reshape(1, 9).expand(E, 9))
+        elif self.arch == "baseline":
+            # fusion.py:28-82 weights packed per block / direction / linear as [32 x 32 weight (out, in) | 32 bias]
+            blocks = []
+            for b in range(W.FUSION_DEPTH):
+                for f in ("fusion1", "fusion2"):
+                    for l in range(4):
+                        nm = f"view_fusion.blocks.{b}.{f}.linears.{l}"
+                        blocks += [np.asarray(sd[f"{nm}.weight"], np.float32).reshape(-1), np.asarray(sd[f"{nm}.bias"], np.float32)]
+            self.fusion_w = self._dev(np.concatenate(blocks))
+            g = lambda nm: np.asarray(sd[nm], np.float32)
+            self.depth_w = self._dev(np.concatenate([g("depth_head.0.weight").reshape(64, 32).reshape(-1), g("depth_head.0.bias"),
+                                                     g("depth_head.2.weight").reshape(32, 64).T.reshape(-1), g("depth_head.2.bias"),
+                                                     g("depth_head.4.weight").reshape(-1), g("depth_head.4.bias")]))
+            self.fusion_scratch = torch.zeros((4, E, P, 32), **f32)
+            self.fused1 = torch.zeros((E, P, 32), **f32) if self.debug else None
+            self.fused2 = torch.zeros((E, P, 32), **f32) if self.debug else None
+            self.depth2 = torch.zeros((E, P), **f32) if self.debug else None
         self._build_decode_tc()
 
     def _build_decode_tc(self):
@@ -592,7 +626,7 @@ class Engine:
         # view 2 sits right behind view 1 (frame n): a partial chunk runs the backbone on exactly 2 n frames
         self.preprocess(0, rgb1, mask1, K, n, seed, choose1, frame_id0=env0)
         self.preprocess(1, rgb2, mask2, K, n, seed, choose2, offset=n, frame_id0=env0)
-        if self.use_graph and self.regress_pose:
+        if self.use_graph and self.regress_pose and self.arch == "v5":
             # a chunk is ~95 launches from fixed buffers: replayed as one CUDA graph per chunk size (captured on the second
             # appearance of a size, after every kernel has run once and set its attributes).  estimate() splits a batch into
             # equal chunks, so a call sees at most two or three sizes.
@@ -614,8 +648,38 @@ class Engine:
         self.run_backbone(2 * n)
         if self.branch_c:
             return self.match_branch_c(n, K, E1, E2)
-        self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed, o2=n)
+        if self.arch == "baseline":
+            self.stereo_attention(n, E1, ransac_idx=ransac_idx, seed=seed, o2=n)
+        else:
+            self.stereo(n, E1, E2, ransac_idx=ransac_idx, seed=seed, o2=n)
         return self.bbox[:n]
+
+    def stereo_attention(self, n, E1, ransac_idx=None, seed=0, o2=None):
+        """The transformer variant behind the backbone (network_baseline.py:616-669): view-1 NOCS head, 4 cross-view attention
+        blocks on the sampled point features of both views + depth MLP (adp_view_fusion), pose heads, fit.  Frames [0,n) are
+        view 1, [o2,o2+n) view 2."""
+        lib, st, P, S = self.lib, self.stream, self.P, self.S
+        o2 = self.E if o2 is None else o2
+        self.valid_env[:n].copy_(self.valid[:n] & self.valid[o2:o2 + n])
+        L.check(lib.adp_decode_gather(L.ptr(self.feat), None, None, None, None, L.ptr(self.choose), L.ptr(self.valid_env), None,
+                                      None, L.ptr(self.xfeat.hi), L.ptr(self.xfeat.lo), None, None, None, None, n, S,
+                                      N_DEPTH, P, 0, st), "decode_gather(view 1)")
+        for _, op in self.dec_ops[:4]:          # instance_color, nocs_head x 3
+            op(n)
+        L.check(lib.adp_view_fusion(L.ptr(self.feat), L.ptr(self.feat[o2:]), L.ptr(self.choose), L.ptr(self.choose[o2:]),
+                                    L.ptr(self.valid_env), L.ptr(self.fusion_w), L.ptr(self.depth_w), L.ptr(self.fusion_scratch),
+                                    L.ptr(self.depth), L.ptr(self.depth2), L.ptr(self.xcat.hi), L.ptr(self.xcat.lo),
+                                    L.ptr(self.fused1), L.ptr(self.fused2), n, S, P, W.FUSION_DEPTH, st), "view_fusion")
+        for _, op in self.dec_ops[4:]:          # nocs_pts_mlp, pose_mlp1 / 2, rotation head (regress_pose only)
+            op(n)
+        if self.regress_pose:
+            L.check(lib.adp_fit(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(self.R), L.ptr(E1),
+                                L.ptr(self.valid_env), L.ptr(self.bbox), L.ptr(self.scale), L.ptr(self.trans),
+                                None, None, n, P, S, st), "fit")
+        else:
+            L.check(lib.adp_fit_umeyama(L.ptr(self.nocs), L.ptr(self.depth), L.ptr(self.choose), L.ptr(self.Kp), L.ptr(E1),
+                                        L.ptr(self.valid_env), L.ptr(ransac_idx), seed & 0xFFFFFFFF, L.ptr(self.bbox),
+                                        L.ptr(self.scale), L.ptr(self.rot64), L.ptr(self.trans), n, P, S, st), "fit_umeyama")
 
     def match_branch_c(self, n, K, E1, E2):
         """Frames [0,n) = view 1, [n,2n) = view 2 (features present).  -> dict of device tensors for the host PnP tail:

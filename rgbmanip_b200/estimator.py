@@ -116,11 +116,13 @@ def pnp_box_tail(nocs, pts2d, scale, valid, K, E1):
 
 
 class AdaPoseEstimator_v5(BasePoseEstimator):
+    ARCH = "v5"          # which network sits behind the interface (weights.param_table)
 
     def __init__(self, env, cfg, logger, state_dict=None, device=None, max_envs=None, precision=None, devices=None, **engine_kw):
         super().__init__(env, cfg, logger)
         self.cfg = cfg
         self._replicas = None
+        engine_kw = dict(engine_kw, arch=self.ARCH)
         regress = bool(cfg.get("direct_regression", True))
         self._branch_c = (not regress) and not cfg.get("use_depth", True)
         if self._branch_c:
@@ -131,9 +133,9 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         if state_dict is None:
             if cfg.get("load", False):
                 # same failure mode as the reference: a missing checkpoint raises from torch.load (interface_v5.py:55-56)
-                state_dict = W.load_checkpoint(cfg["checkpoint_path"], regress_pose=regress)
+                state_dict = W.load_checkpoint(cfg["checkpoint_path"], regress_pose=regress, arch=self.ARCH)
             else:
-                state_dict = W.init_state_dict(int(cfg.get("seed", 0)), regress_pose=regress)
+                state_dict = W.init_state_dict(int(cfg.get("seed", 0)), regress_pose=regress, arch=self.ARCH)
         devices = devices if devices is not None else cfg.get("devices")
         if devices == "all":
             devices = list(range(torch.cuda.device_count()))
@@ -150,8 +152,9 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             def mk(d):
                 from .dist import bind_to_gpu_numa
                 bind_to_gpu_numa(d)          # this replica's pinned staging buffers land on the GPU's NUMA node
-                return AdaPoseEstimator_v5(env, {k: v for k, v in cfg.items() if k != "devices"}, logger, state_dict=state_dict,
-                                           device=d, max_envs=max_envs, precision=precision, **engine_kw)
+                kw = {k: v for k, v in engine_kw.items() if k != "arch"}
+                return type(self)(env, {k: v for k, v in cfg.items() if k != "devices"}, logger, state_dict=state_dict,
+                                  device=d, max_envs=max_envs, precision=precision, **kw)
             self._replicas = list(self._pool.map(mk, devs))
             self.device = devs[0]
             self.estimator = self._replicas[0].estimator     # the attribute the reference exposes (interface_v5.py:48)
@@ -452,3 +455,11 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         f = lambda a: (a if isinstance(a, torch.Tensor) else np.asarray(a))[None]
         return self.estimate(f(camera_intrinsic), f(rgb1), f(view1_mask), f(view1_extrinsic),
                              f(rgb2), f(view2_mask), f(view2_extrinsic))[0]
+
+
+class AdaPoseEstimator_baseline(AdaPoseEstimator_v5):
+    """``name: adapose_baseline`` (train.py:242-244 -> interface_baseline.py:37-56): the same interface, preprocessing and pose
+    fit around StereoPoseNet_with_depth_baseline (network_baseline.py:523-669), whose stereo term is 4 blocks of cross-view
+    attention over the sampled point features (fusion.py:53-82) followed by a per-point depth MLP instead of the plane-sweep
+    cost volume and its 3-D U-Net."""
+    ARCH = "baseline"

@@ -15,6 +15,7 @@ import sys
 import types
 
 TARGET = "models.pose_estimator.AdaPose.interface_v5"
+TARGET_BASELINE = "models.pose_estimator.AdaPose.interface_baseline"      # train.py:38,242-244 (name: adapose_baseline)
 
 
 def install():
@@ -24,9 +25,14 @@ def install():
     mod.AdaPoseEstimator_v5 = estimator.AdaPoseEstimator_v5
     mod.StereoPoseNet_with_depth = None
     sys.modules[TARGET] = mod
+    modb = types.ModuleType(TARGET_BASELINE)
+    modb.__doc__ = mod.__doc__
+    modb.AdaPoseEstimator_baseline = estimator.AdaPoseEstimator_baseline
+    sys.modules[TARGET_BASELINE] = modb
     try:   # make `from models.pose_estimator.AdaPose import interface_v5` resolve to the same object
         pkg = importlib.import_module("models.pose_estimator.AdaPose")
         setattr(pkg, "interface_v5", mod)
+        setattr(pkg, "interface_baseline", modb)
     except Exception:
         pass
     return mod
@@ -34,6 +40,9 @@ def install():
 
 def uninstall():
     mod = sys.modules.pop(TARGET, None)
+    modb = sys.modules.pop(TARGET_BASELINE, None)
     pkg = sys.modules.get("models.pose_estimator.AdaPose")
+    if pkg is not None and modb is not None and getattr(pkg, "interface_baseline", None) is modb:
+        delattr(pkg, "interface_baseline")
     if pkg is not None and mod is not None and getattr(pkg, "interface_v5", None) is mod:
         delattr(pkg, "interface_v5")      # `from models.pose_estimator.AdaPose import interface_v5` resolves to the real module again

@@ -52,8 +52,12 @@ def _bn(name, c):
             (f"{name}.num_batches_tracked", (), "bn_n")]
 
 
-def param_table(regress_pose: bool = True):
-    """[(name, shape, init-kind)] in the reference's state_dict order."""
+def param_table(regress_pose: bool = True, arch: str = "v5"):
+    """[(name, shape, init-kind)] in the reference's state_dict order.  ``arch``: "v5" = StereoPoseNet_with_depth
+    (network_v5.py:260-376); "baseline" = StereoPoseNet_with_depth_baseline (network_baseline.py:523-620: the cost volume and
+    CostRegNet are replaced by 4 cross-view attention blocks, fusion.py:53-82, and a per-point depth MLP)."""
+    if arch not in ("v5", "baseline"):
+        raise ValueError(f"unknown architecture {arch!r}")
     ent = _resnet_entries()
     for s in range(4):
         ent.append((f"img_extractor.psp.stages.{s}.1.weight", (128, 512, 1, 1), "default"))
@@ -62,6 +66,8 @@ def param_table(regress_pose: bool = True):
         ent.append((f"img_extractor.{nm}.conv.1.weight", (1,), "prelu"))
     ent += _conv_default("img_extractor.final", (32, 64, 1, 1))
     ent += _conv_default("instance_color.0", (64, 32, 1))
+    if arch == "baseline":
+        return ent + _baseline_tail(regress_pose)
     cr = "cost_regularization"
     for nm, cout, cin in (("conv0", 8, 32), ("conv1", 16, 8), ("conv2", 16, 16), ("conv3", 32, 16),
                           ("conv4", 32, 32), ("conv5", 64, 32), ("conv6", 64, 64)):
@@ -76,21 +82,47 @@ def param_table(regress_pose: bool = True):
     ent += _conv_default("nocs_head.2", (64, 128, 1))
     ent += _conv_default("nocs_head.4", (3, 64, 1))
     if regress_pose:
-        ent += _conv_default("nocs_pts_mlp.0", (32, 3, 1))
-        ent += _conv_default("nocs_pts_mlp.2", (64, 32, 1))
-        ent += _conv_default("pose_mlp1.0", (128, 96, 1))
-        ent += _conv_default("pose_mlp1.2", (128, 128, 1))
-        ent += _conv_default("pose_mlp2.0", (256, 256, 1))
-        ent += _conv_default("pose_mlp2.2", (256, 256, 1))
-        for head, nout in (("rotation_estimator", 6), ("translation_estimator", 3), ("size_estimator", 3)):
-            ent += _conv_default(f"{head}.0", (256, 256))
-            ent += _conv_default(f"{head}.2", (128, 256))
-            ent += _conv_default(f"{head}.4", (nout, 128))
+        ent += _pose_entries()
+    return ent
+
+
+def _pose_entries():
+    ent = _conv_default("nocs_pts_mlp.0", (32, 3, 1))
+    ent += _conv_default("nocs_pts_mlp.2", (64, 32, 1))
+    ent += _conv_default("pose_mlp1.0", (128, 96, 1))
+    ent += _conv_default("pose_mlp1.2", (128, 128, 1))
+    ent += _conv_default("pose_mlp2.0", (256, 256, 1))
+    ent += _conv_default("pose_mlp2.2", (256, 256, 1))
+    for head, nout in (("rotation_estimator", 6), ("translation_estimator", 3), ("size_estimator", 3)):
+        ent += _conv_default(f"{head}.0", (256, 256))
+        ent += _conv_default(f"{head}.2", (128, 256))
+        ent += _conv_default(f"{head}.4", (nout, 128))
+    return ent
+
+
+FUSION_DEPTH, FUSION_HEADS, FUSION_DIM = 4, 4, 32      # ViewFusion(embed_dim=32, num_heads=4, depth=4), network_baseline.py:553
+
+
+def _baseline_tail(regress_pose):
+    """Everything behind ``instance_color`` of StereoPoseNet_with_depth_baseline, in constructor order."""
+    ent = _conv_default("nocs_head.0", (128, 64, 1))
+    ent += _conv_default("nocs_head.2", (64, 128, 1))
+    ent += _conv_default("nocs_head.4", (3, 64, 1))
+    for b in range(FUSION_DEPTH):
+        for f in ("fusion1", "fusion2"):
+            for l in range(4):        # q, k, v, output projections (fusion.py:33)
+                ent += _conv_default(f"view_fusion.blocks.{b}.{f}.linears.{l}", (FUSION_DIM, FUSION_DIM))
+    ent += _conv_default("depth_head.0", (64, 32, 1))
+    ent += _conv_default("depth_head.2", (32, 64, 1))
+    ent += _conv_default("depth_head.4", (1, 32, 1))
+    if regress_pose:
+        ent += _pose_entries()
     return ent
 
 
 def init_state_dict(seed: int = 0, regress_pose: bool = True, randomize_bn: bool = True,
-                    nocs_gain: float = 16.0, prob_gain: float = 4.0):
+                    nocs_gain: float = 16.0, prob_gain: float = 4.0, arch: str = "v5", attn_gain: float = 1.0,
+                    depth_bias: float = 0.8):
     """Random-init weights of the AdaPose architecture as ``OrderedDict[str, np.ndarray]``.
 
     ``randomize_bn`` perturbs the BatchNorm3d affine parameters and running statistics so that BN
@@ -101,11 +133,13 @@ def init_state_dict(seed: int = 0, regress_pose: bool = True, randomize_bn: bool
     the pair filter at utils.py:83) and the depth softmax is flat, so the scale fit divides by ~0 and
     amplifies any rounding by 1/|dNOCS|: box-level parity would measure that conditioning, not the
     kernels.  The default gains give NOCS a spread of a few tenths and a peaked depth distribution, like a
-    trained network, while staying a seeded random init of the same architecture.
+    trained network, while staying a seeded random init of the same architecture.  For ``arch="baseline"`` the same
+    reasoning gives ``attn_gain`` (multiplies the query / key projections of every attention block, so the softmax is peaked
+    rather than uniform) and ``depth_bias`` (added to the last depth-MLP bias: the head ends in a ReLU and predicts metres).
     """
     rng = np.random.default_rng(seed)
     sd = OrderedDict()
-    for name, shape, kind in param_table(regress_pose):
+    for name, shape, kind in param_table(regress_pose, arch):
         if kind == "resnet":
             n = shape[2] * shape[3] * shape[0]
             w = rng.standard_normal(shape, dtype=np.float32) * np.float32(math.sqrt(2.0 / n))
@@ -134,6 +168,10 @@ def init_state_dict(seed: int = 0, regress_pose: bool = True, randomize_bn: bool
             w = w * np.float32(nocs_gain)
         elif name == "cost_regularization.prob.weight":
             w = w * np.float32(prob_gain)
+        elif name.startswith("view_fusion.") and (".linears.0." in name or ".linears.1." in name):
+            w = w * np.float32(attn_gain)
+        elif name == "depth_head.4.bias":
+            w = w + np.float32(depth_bias)
         sd[name] = w
     return sd
 
@@ -155,9 +193,9 @@ def to_numpy_state_dict(sd):
     return out
 
 
-def check_state_dict(sd, regress_pose: bool = True):
+def check_state_dict(sd, regress_pose: bool = True, arch: str = "v5"):
     """Strict check (the reference uses ``load_state_dict(strict=True)``, interface_v5.py:56)."""
-    table = param_table(regress_pose)
+    table = param_table(regress_pose, arch)
     want = {n: s for n, s, _ in table}
     missing = [n for n in want if n not in sd]
     extra = [n for n in sd if n not in want]
@@ -168,11 +206,11 @@ def check_state_dict(sd, regress_pose: bool = True):
             raise ValueError(f"{n}: shape {np.shape(sd[n])} != {s}")
 
 
-def load_checkpoint(path: str, regress_pose: bool = True):
+def load_checkpoint(path: str, regress_pose: bool = True, arch: str = "v5"):
     """Read a reference ``.pth`` (torch.save of a DataParallel state_dict)."""
     import torch
     sd = to_numpy_state_dict(torch.load(path, map_location="cpu"))
-    check_state_dict(sd, regress_pose)
+    check_state_dict(sd, regress_pose, arch)
     return sd
 
 

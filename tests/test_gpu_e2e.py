@@ -55,6 +55,7 @@ def test_estimate_matches_reference_golden(golden, max_envs, precision):
     boxes = est.estimate(*batch.args(), choose=_golden_choose(g, 8))
     assert boxes.shape == (8, 8, 3) and boxes.dtype == np.float64
     worst = np.zeros(3)
+    compared = total = 0
     for e in range(8):
         if not g["valid"][e]:
             np.testing.assert_array_equal(boxes[e], O.DEFAULT_BBOX)      # sentinel: bit exact
@@ -62,7 +63,12 @@ def test_estimate_matches_reference_golden(golden, max_envs, precision):
         px, deg, mm, cmm = O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e], min_z=MIN_Z)
         worst = np.maximum(worst, (px, deg, mm))
         assert px < TOL_PX and deg < TOL_DEG and mm < TOL_MM and cmm < TOL_MM, (e, px, deg, mm, cmm)
-    print(f"{precision} worst (px, deg, mm):", worst)
+        k, t = O.keypoints_compared(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e], min_z=MIN_Z)
+        compared, total = compared + k, total + t
+    # the MIN_Z exemption (corners nearer than 0.5 m to the camera plane are held to 1 mm instead of 0.5 px) must stay the
+    # exception: every keypoint is held to the millimetre bound, and most of them to the pixel bound as well
+    print(f"{precision} worst (px, deg, mm):", worst, f"keypoints in the pixel metric: {compared} of {total}")
+    assert compared >= 0.6 * total, (compared, total)
     est.estimator.close()
 
 
@@ -325,4 +331,30 @@ def test_single_view_nocs_matches_reference_golden(golden):
                 assert valid[e]
                 np.testing.assert_array_equal(choose[e], ch[e])
                 assert float(np.abs(nocs[e] - g[f"env{e}_view{view}_nocs"]).max()) < 3e-3, (view, e)
+    est.estimator.close()
+
+
+def test_plain_constructor_init_stage_level():
+    """weights.init_state_dict conditions the random init (NOCS x16, depth logits x4) so that box-level parity measures the
+    kernels and not a division by ~0.  This test drops the conditioning (gains 1 = the distributions of the reference
+    constructor) and checks what is well defined there: the network outputs (NOCS, soft-argmax depth, rotation) of one
+    environment against the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200.estimator import AdaPoseEstimator_v5
+    sd = weights.init_state_dict(3, nocs_gain=1.0, prob_gain=1.0)
+    cfg = {"name": "adapose_v5", "load": False, "img_size": 224, "use_depth": True, "n_pts": 1024, "direct_regression": True}
+    batch = synth.make_batch(1, seed=21, special=False)
+    np.random.seed(3)
+    d = {}
+    O.predict(sd, cfg, batch.K[0], batch.rgb1[0], batch.mask1[0], batch.E1[0], batch.rgb2[0], batch.mask2[0], batch.E2[0],
+              both_views=False, details=d)
+    est = AdaPoseEstimator_v5(None, cfg, None, state_dict=sd, max_envs=1, precision="fp16f8")
+    est.estimate(*batch.args(), choose=(d["choose1"][None].astype(np.int32), d["choose2"][None].astype(np.int32)))
+    eng = est.estimator
+    nocs, depth, R = eng.nocs[0].cpu().numpy(), eng.depth[0].cpu().numpy(), eng.R[0].cpu().numpy().reshape(3, 3)
+    assert np.abs(d["nocs"]).std() < 0.05                              # the unconditioned NOCS map really is nearly constant
+    assert np.abs(nocs - d["nocs"]).max() < 5e-4, np.abs(nocs - d["nocs"]).max()
+    assert np.abs(depth - d["depth"]).max() < 1e-3, np.abs(depth - d["depth"]).max()
+    assert O.rotation_angle_deg(R, d["R"]) < 0.1
     est.estimator.close()

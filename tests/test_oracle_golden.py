@@ -235,3 +235,30 @@ def test_branch_c_against_reference(golden_dir):
         # with random-init NOCS the PnP is ill-posed (boxes hundreds of metres away): relative agreement only
         np.testing.assert_allclose(bx, g["boxes"][e], rtol=1e-5, atol=1e-5)
     assert abs(d["s"] - g["left_scale"][0]) < 0.02 * g["left_scale"][0]
+
+
+def test_transformer_variant_against_reference(golden_dir):
+    """name = adapose_baseline (train.py:242-244): StereoPoseNet_with_depth_baseline, cross-view attention instead of the cost
+    volume.  First env of tests/golden/baseline.npz end to end; strict weight table."""
+    from oracle.make_golden import BASELINE_INIT
+    g = np.load(os.path.join(golden_dir, "baseline.npz"))
+    sd = weights.init_state_dict(0, arch="baseline", **BASELINE_INIT)
+    assert len(sd) == 159
+    weights.check_state_dict(sd, arch="baseline")
+    with pytest.raises(KeyError):
+        weights.check_state_dict(sd, arch="v5")
+    cfg = {"img_size": 224, "direct_regression": True, "use_depth": True, "name": "adapose_baseline"}
+    batch = synth.make_batch(4, seed=9, special=False)
+    np.random.seed(11)
+    d = {}
+    box = O.predict(sd, cfg, batch.K[0], batch.rgb1[0], batch.mask1[0], batch.E1[0], batch.rgb2[0], batch.mask2[0], batch.E2[0],
+                    details=d)
+    np.testing.assert_array_equal(d["choose1"], g["choose1"][0])
+    np.testing.assert_allclose(d["pred"]["view1_fused"][0].numpy(), g["fused1"][0], atol=2e-4)
+    np.testing.assert_allclose(d["pred"]["view2_fused"][0].numpy(), g["fused2"][0], atol=2e-4)
+    np.testing.assert_allclose(d["nocs"], g["view1_nocs"][0], atol=2e-4)
+    np.testing.assert_allclose(d["depth"], g["view1_depth"][0], atol=2e-5)
+    np.testing.assert_allclose(d["R"], g["view1_r"][0], atol=1e-4)
+    px, deg, mm, cmm = O.parity_errors(box, g["boxes"][0], batch.K[0], batch.E1[0])
+    assert px < 0.05 and deg < 0.02 and mm < 0.1 and cmm < 0.2, (px, deg, mm, cmm)
+    assert 3.0 < float(g["attn_entropy"].mean()) < 5.0          # the fixture's softmax is peaked, not uniform
