@@ -129,6 +129,11 @@ ADP_API int adp_maxpool3x3s2(const adp_act* in, const adp_act* out, int batch, v
 ADP_API int adp_psp_priors(const adp_act* feat, int feat_cstride, const float* w, float* pooled, float* priors, int batch, void* stream); /* :84-90 */
 ADP_API int adp_psp_fill_priors(const float* priors, const adp_act* out, int coff, int batch, void* stream);
 ADP_API int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* stream);                   /* pspnet.py:105 */
+/* PSPUpsample (pspnet.py:97-107: bilinear x2, align_corners=True -> Conv2d 3x3 pad 1 -> PReLU), second half of its restructured
+ * form: q [B,h,w,9*C] holds the nine per-tap 1x1 products W_tap x of the LOW-resolution input (channel = (ky*3+kx)*C + c, one
+ * adp_conv_tc GEMM); this call blends them (9 taps x 4 bilinear neighbours, zero padding of the upsampled image), adds the bias and
+ * applies the PReLU -> out [B,2h,2w,C].  Equal to conv(upsample(x)) up to fp32 summation order. */
+ADP_API int adp_upconv_blend(const adp_act* q, const adp_act* out, const float* bias, float prelu_slope, int batch, void* stream);
 /* fp32 crops [F,S,S,3] -> space-to-depth(2) activation [F,S/2,S/2,16] (channel = (py*2+px)*3 + c, 12 used): the 7x7/2
  * stem conv (pspnet.py:37) then is a 4x4 stride-1 conv over 16 channels and runs on the tcgen05 kernel. */
 ADP_API int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream);

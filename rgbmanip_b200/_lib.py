@@ -64,6 +64,7 @@ SIGNATURES = {
     "adp_psp_priors": (C.c_int, [C.POINTER(Act), C.c_int, vp, vp, vp, C.c_int, vp]),
     "adp_psp_fill_priors": (C.c_int, [vp, C.POINTER(Act), C.c_int, C.c_int, vp]),
     "adp_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, vp]),
+    "adp_upconv_blend": (C.c_int, [vp, vp, vp, C.c_float, C.c_int, vp]),
     "adp_pack_s2d": (C.c_int, [vp, C.POINTER(Act), C.c_int, C.c_int, vp]),
     "adp_conv0_plan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Act), vp, vp, vp, vp, C.c_int, C.c_int]),
     "adp_conv0_run": (C.c_int, [vp, C.c_int, vp, vp]),

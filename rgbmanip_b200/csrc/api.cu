@@ -26,6 +26,7 @@ int maxpool3x3s2(const Act& in, const Act& out, int batch, cudaStream_t stream);
 int psp_priors(const Act& feat, int feat_cs, const float* w, float* pooled, float* priors, int batch, cudaStream_t stream);
 int psp_fill_priors(const float* priors, const Act& out, int coff, int batch, cudaStream_t stream);
 int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream);
+int upconv_blend(const Act& q, const Act& out, const float* bias, float slope, int batch, cudaStream_t stream);
 int pack_s2d(const float* crops, const Act& out, int batch, int S, cudaStream_t stream);
 int preprocess_run(const void* rgb, int rgb_dt, const void* mask, int mask_dt, const double* K, int k_stride, int F, int H, int W,
                    int S, int P, uint32_t seed, int choose_mode, int frame_id0, int* bbox_ws, int* win, double* Kp, uint8_t* valid,
@@ -201,6 +202,12 @@ int adp_upsample2x(const adp_act* in, const adp_act* out, int batch, void* strea
     ADP_CHECK_ARG(in && out, "null pointer");
     g_launches += 1;
     return upsample2x(to_act(in), to_act(out), batch, (cudaStream_t)stream);
+}
+
+int adp_upconv_blend(const adp_act* q, const adp_act* out, const float* bias, float prelu_slope, int batch, void* stream) {
+    ADP_CHECK_ARG(q && out && bias, "null pointer");
+    g_launches += 1;
+    return upconv_blend(to_act(q), to_act(out), bias, prelu_slope, batch, (cudaStream_t)stream);
 }
 
 int adp_conv0_plan_create(adp_conv0_plan** plan, const adp_act* vol, const void* w_packed, const float* scale, const float* shift,

@@ -175,8 +175,8 @@ __device__ __forceinline__ void lin_coord(int o, int in_size, int out_size, int*
 // producing convolution itself (epilogue channel pitch), so the concat never exists as a separate pass.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-psp_fill_priors_kernel(const float* __restrict__ priors, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int H, int W, int Ct,
-                       int coff, int f16) {
+psp_fill_priors_kernel(const float* __restrict__ priors, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                       uint8_t* __restrict__ out_q8, int H, int W, int Ct, int coff, int f16) {
     __shared__ __align__(16) float spr[50 * 128];
     const int b = blockIdx.y, y = blockIdx.x;
     for (int i = threadIdx.x; i < 50 * 128 / 4; i += blockDim.x)
@@ -207,14 +207,17 @@ psp_fill_priors_kernel(const float* __restrict__ priors, bf16* __restrict__ out_
             o[j + 2] = (1.f - wy) * ((1.f - wx) * a.z + wx * bq.z) + wy * ((1.f - wx) * cq.z + wx * d.z);
             o[j + 3] = (1.f - wy) * ((1.f - wx) * a.w + wx * bq.w) + wy * ((1.f - wx) * cq.w + wx * d.w);
         }
-        st8(out_hi, out_lo, (((size_t)b * H + y) * W + x) * Ct + coff + c, o, f16);
+        const size_t oo = (((size_t)b * H + y) * W + x) * Ct + coff + c;
+        st8(out_hi, out_lo, oo, o, f16);
+        if (out_q8) *reinterpret_cast<uint2*>(out_q8 + oo) = pack8_q8(o);      // fp8 twin for the consumer's low-order pass
     }
 }
 
 int psp_fill_priors(const float* priors, const Act& out, int coff, int batch, cudaStream_t stream) {
     ADP_CHECK_ARG(coff % 8 == 0 && coff + 512 <= out.C, "psp prior channel range");
     if (batch == 0) return ADP_OK;
-    psp_fill_priors_kernel<<<dim3(out.H, batch), 256, 0, stream>>>(priors, out.hi, out.lo, out.H, out.W, out.C, coff, out.f16);
+    psp_fill_priors_kernel<<<dim3(out.H, batch), 256, 0, stream>>>(priors, out.hi, out.lo, out.f16 ? out.q8 : nullptr, out.H, out.W, out.C,
+                                                                   coff, out.f16);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }
@@ -319,6 +322,145 @@ int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
     const dim3 grid(tiles_x * tiles_y, in.C / UP_CS, batch);
     if (in.lo && !in.f16) upsample2x_kernel<true><<<grid, 256, 0, stream>>>(in.hi, in.lo, out.hi, out.lo, nullptr, in.H, in.W, in.C, tiles_x, 0);
     else upsample2x_kernel<false><<<grid, 256, 0, stream>>>(in.hi, nullptr, out.hi, out.lo, out.f16 ? out.q8 : nullptr, in.H, in.W, in.C, tiles_x, in.f16);
+    ADP_CUDA(cudaGetLastError());
+    return ADP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PSPUpsample (pspnet.py:97-107) = bilinear x2 (align_corners=True) -> Conv2d 3x3 pad 1 -> PReLU, restructured.
+// Interpolation and the conv's channel mixing are both linear and act on different axes, so
+//     conv3x3(up(x))[Y,X] = bias + sum_{dy,dx} [ (Y+dy, X+dx) inside ] up(q_{dy,dx})[Y+dy, X+dx],      q_tap = W_tap x  (a 1x1 conv at LOW resolution)
+// The nine q_tap come out of ONE tensor-core GEMM over the low-resolution map (N = 9 Cout, K = Cin: a quarter of the FLOPs of the
+// 3x3 conv over the upsampled map, and the upsampled tensor never exists).  This kernel is the second half: per output pixel the
+// 9 taps x 4 bilinear neighbours of q, + bias, PReLU.  A thread owns (output column X, 8 channels) and walks down a strip of
+// output rows: per low-resolution row r it folds the horizontal part once, H_dy[r] = sum_{dx,j} wx_j(X+dx) q_{dy,dx}[r, x_j(X+dx)]
+// (18 16-byte loads), keeps H of the three low-resolution rows a 3-row output window can touch in registers, and every output
+// row is 27 FMAs per channel with coefficients that hold the vertical weights (zero where a tap falls outside the image:
+// the conv's zero padding applies to the UPSAMPLED image).
+// q: [B, h, w, 9 C] (channel = tap * C + c, tap = ky * 3 + kx), out: [B, 2h, 2w, C].
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__device__ __forceinline__ void upconv_fold_row(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, size_t row_base, int C9,
+                                                int tap0, int C, const int (&xo)[3][2], const float (&xw)[3][2], int f16, float* H) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) H[j] = 0.f;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const size_t off = row_base + (size_t)xo[dx][j] * C9 + (size_t)(tap0 + dx) * C;
+            float v[8];
+            up_unpack8(__ldg(reinterpret_cast<const uint4*>(q_hi + off)), v, !SPLIT && f16);
+            if (SPLIT) {
+                float t[8];
+                up_unpack8(__ldg(reinterpret_cast<const uint4*>(q_lo + off)), t, false);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += t[e];
+            }
+            const float wgt = xw[dx][j];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) H[e] = fmaf(wgt, v[e], H[e]);
+        }
+    }
+}
+
+constexpr int UPB_MAX_STRIP = 64;      // output rows a block walks at most (shared-memory coefficient table)
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 2)
+upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                    uint8_t* __restrict__ out_q8, const float* __restrict__ bias, float slope, int h, int w, int C, int f16, int strip) {
+    // per output row of the strip: 9 vertical coefficients [dy][window row] and the first low-resolution row of its window;
+    // the rows are the same for every thread of the block, so they are worked out once
+    __shared__ float s_cf[UPB_MAX_STRIP][9];
+    __shared__ int s_rb[UPB_MAX_STRIP];
+    const int C8 = C >> 3, Ho = 2 * h, Wo = 2 * w, C9 = 9 * C;
+    const int Y0 = blockIdx.y * strip, Y1 = min(Y0 + strip, Ho);
+    for (int i = threadIdx.x; i < (Y1 - Y0) * 3; i += 256) {
+        const int yy = i / 3, dy = i - yy * 3, Y = Y0 + yy;
+        int rb, y0, y1, dummy;
+        float wy, wdummy;
+        lin_coord(max(Y - 1, 0), h, Ho, &rb, &dummy, &wdummy);
+        const int Yt = Y + dy - 1;
+        const bool in = Yt >= 0 && Yt < Ho;
+        lin_coord(in ? Yt : Y, h, Ho, &y0, &y1, &wy);
+        const int k0 = y0 - rb, k1 = y1 - rb;          // k0 in {0, 1}, k1 in {k0, k0 + 1}: rows Y - 1 .. Y + 1 span < 1 low-resolution row
+        for (int k = 0; k < 3; ++k) s_cf[yy][dy * 3 + k] = in ? ((k == k0 ? 1.f - wy : 0.f) + (k == k1 ? wy : 0.f)) : 0.f;
+        if (dy == 0) s_rb[yy] = rb;
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int cg = idx % C8, X = idx / C8;
+    if (X >= Wo) return;
+    const int b = blockIdx.z;
+    // horizontal taps of this column: low-resolution columns and weights of X - 1, X, X + 1 (weight 0 outside the image)
+    int xo[3][2];
+    float xw[3][2];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+        const int Xt = X + dx - 1;
+        const bool in = Xt >= 0 && Xt < Wo;
+        int x0, x1;
+        float wx;
+        lin_coord(in ? Xt : X, w, Wo, &x0, &x1, &wx);
+        xo[dx][0] = x0; xo[dx][1] = x1;
+        xw[dx][0] = in ? 1.f - wx : 0.f; xw[dx][1] = in ? wx : 0.f;
+    }
+    const size_t img = (size_t)b * h * w * C9 + (size_t)cg * 8;
+    float bv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bv[e] = __ldg(bias + cg * 8 + e);
+    int rb = s_rb[0];
+    float H[3][3][8];          // [dy][window row k = low-resolution row rb + k][channel]
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const size_t rbase = img + (size_t)min(rb + k, h - 1) * w * C9;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) upconv_fold_row<SPLIT>(q_hi, q_lo, rbase, C9, dy * 3, C, xo, xw, f16, H[dy][k]);
+    }
+    size_t oo = (((size_t)b * Ho + Y0) * Wo + X) * C + cg * 8;
+    const size_t ostep = (size_t)Wo * C;
+    for (int yy = 0; yy < Y1 - Y0; ++yy, oo += ostep) {
+        if (s_rb[yy] != rb) {        // the window moves down by one low-resolution row
+            rb = s_rb[yy];
+            const size_t rbase = img + (size_t)min(rb + 2, h - 1) * w * C9;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { H[dy][0][e] = H[dy][1][e]; H[dy][1][e] = H[dy][2][e]; }
+                upconv_fold_row<SPLIT>(q_hi, q_lo, rbase, C9, dy * 3, C, xo, xw, f16, H[dy][2]);
+            }
+        }
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = bv[e];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float cf = s_cf[yy][dy * 3 + k];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(cf, H[dy][k][e], acc[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = acc[e] >= 0.f ? acc[e] : slope * acc[e];
+        st8(out_hi, out_lo, oo, acc, f16);
+        if (out_q8) *reinterpret_cast<uint2*>(out_q8 + oo) = pack8_q8(acc);
+    }
+}
+
+int upconv_blend(const Act& q, const Act& out, const float* bias, float slope, int batch, cudaStream_t stream) {
+    ADP_CHECK_ARG(q.C == 9 * out.C && out.H == 2 * q.H && out.W == 2 * q.W && out.C % 8 == 0 && q.f16 == out.f16, "upconv_blend shapes");
+    ADP_CHECK_ARG((q.lo != nullptr) == (out.lo != nullptr) || q.f16, "upconv_blend: q and out must use the same plane format");
+    if (batch == 0) return ADP_OK;
+    const int cols = out.W * (out.C / 8);
+    // strips of output rows: long enough to amortise the 3-row window fill, short enough to fill the GPU
+    int strip = out.H < UPB_MAX_STRIP ? out.H : UPB_MAX_STRIP;
+    while (strip > 8 && (size_t)batch * ((cols + 255) / 256) * ((out.H + strip - 1) / strip) < 4 * 148) strip = (strip + 1) / 2;
+    const dim3 grid((cols + 255) / 256, (out.H + strip - 1) / strip, batch);
+    if (q.lo && !q.f16) upconv_blend_kernel<true><<<grid, 256, 0, stream>>>(q.hi, q.lo, out.hi, out.lo, nullptr, bias, slope, q.H, q.W, out.C, 0, strip);
+    else upconv_blend_kernel<false><<<grid, 256, 0, stream>>>(q.hi, nullptr, out.hi, out.lo, out.f16 ? out.q8 : nullptr, bias, slope, q.H, q.W, out.C, q.f16, strip);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

@@ -67,13 +67,13 @@ def test_view_fusion_kernel_matches_oracle(G, gain):
     r1, r2 = r1.permute(0, 2, 1).numpy(), r2.permute(0, 2, 1).numpy()
     scale = np.abs(r1).max()
     for got, ref in ((fused1, r1), (fused2, r2)):
-        np.testing.assert_allclose(got.cpu().numpy()[:2], ref[:2], rtol=0, atol=2e-5 * scale)
+        np.testing.assert_allclose(got.cpu().numpy()[:2], ref[:2], rtol=0, atol=5e-5 * scale)   # 4 stacked softmax blocks, fp32 both sides
         assert (got[2] == 0).all()
     np.testing.assert_allclose(depth1.cpu().numpy()[:2], dref[0][:2], rtol=0, atol=5e-5)
     np.testing.assert_allclose(depth2.cpu().numpy()[:2], dref[1][:2], rtol=0, atol=5e-5)
     assert (depth1[2] == 0).all()
     planes = (xh.float() + xl.float()).cpu().numpy()
-    np.testing.assert_allclose(planes[:2, :, :32], r1[:2], rtol=2e-5, atol=2e-5 * scale)
+    np.testing.assert_allclose(planes[:2, :, :32], r1[:2], rtol=2e-5, atol=5e-5 * scale)
     assert (planes[:, :, 32:] == 0).all()
     # the last block's view-2 direction is skipped when nobody asks for it: view-1 results must not change
     depth1b = torch.zeros_like(depth1)
@@ -96,10 +96,11 @@ def test_baseline_estimator_matches_reference(G, golden_dir, precision):
     batch = synth.make_batch(4, seed=9, special=False)
     boxes = est.estimate(*batch.args(), choose=(g["choose1"], g["choose2"]))
     eng = est.estimator
-    # the last chunk (env 3) is still in the engine's buffers
-    assert np.abs(eng.nocs[0].cpu().numpy() - g["view1_nocs"][3]).max() < 3e-3
-    assert np.abs(eng.depth[0].cpu().numpy() - g["view1_depth"][3]).max() < 2e-3
-    assert np.abs(eng.fused1[0].cpu().numpy().T - g["fused1"][3]).max() < 2e-2 * np.abs(g["fused1"][3]).max()
+    # 4 envs in chunks of at most 3 = two equal chunks: the last one (envs 2, 3) is still in the engine's buffers
+    for slot, e in ((0, 2), (1, 3)):
+        assert np.abs(eng.nocs[slot].cpu().numpy() - g["view1_nocs"][e]).max() < 3e-3
+        assert np.abs(eng.depth[slot].cpu().numpy() - g["view1_depth"][e]).max() < 2e-3
+        assert np.abs(eng.fused1[slot].cpu().numpy().T - g["fused1"][e]).max() < 2e-2 * np.abs(g["fused1"][e]).max()
     worst = np.zeros(4)
     for e in range(4):
         worst = np.maximum(worst, O.parity_errors(boxes[e], g["boxes"][e], batch.K[e], batch.E1[e], min_z=0.5))

@@ -369,6 +369,40 @@ def test_maxpool_psp_upsample(G):
     assert G.rel_err(G.from_cl(G.val(zh, zl).cpu()), ref) < 5e-5
 
 
+@pytest.mark.parametrize("case", [(2, 12, 20, 32, 64, 1), (1, 28, 28, 64, 16, 1), (2, 7, 9, 32, 8, 0), (1, 5, 30, 16, 64, 0)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_upconv_restructured_matches_oracle(G, case):
+    """PSPUpsample (pspnet.py:97-107) as per-tap 1x1 GEMM at low resolution (adp_conv_tc) + adp_upconv_blend against
+    conv3x3(interpolate(x, 2, bilinear, align_corners=True)) + PReLU in torch fp32: fp16 planes and bf16 hi/lo planes, odd sizes,
+    borders (the conv's zero padding applies to the upsampled image)."""
+    lib = L.load()
+    B, h, w, Cin, Cout, f16 = case
+    rng = _rng(31)
+    x = _t(rng, B, Cin, h, w)
+    wgt = _t(rng, Cout, Cin, 3, 3, scale=1.0 / np.sqrt(9 * Cin))
+    bias = _t(rng, Cout)
+    slope = 0.25
+    ref = F.prelu(F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True), wgt, bias, padding=1),
+                  torch.tensor([slope]))
+    w1 = wgt.permute(2, 3, 0, 1).reshape(9 * Cout, Cin, 1, 1).contiguous()        # channel = (ky*3+kx)*Cout + co
+    q32, _ = G.tc_conv(G.to_cl(x), w1, npass=2 if f16 else 3, f16=f16)
+    dev = G.DEV
+    if f16:
+        qh, ql = q32.to(torch.float16).to(dev).contiguous(), None
+        oh, ol = torch.zeros((B, 2 * h, 2 * w, Cout), dtype=torch.float16, device=dev), None
+    else:
+        qh, ql = G.split(q32)
+        oh = torch.zeros((B, 2 * h, 2 * w, Cout), dtype=torch.bfloat16, device=dev)
+        ol = torch.zeros_like(oh)
+    bd = bias.to(dev)
+    L.check(lib.adp_upconv_blend(C.byref(G.act(qh, ql, B, 1, h, w, 9 * Cout, f16)), C.byref(G.act(oh, ol, B, 1, 2 * h, 2 * w, Cout, f16)),
+                                 L.ptr(bd), slope, B, G.stream()), "upconv_blend")
+    torch.cuda.synchronize()
+    got = G.from_cl(G.val(oh, ol).cpu())
+    # fp16 planes: q and the result are rounded to 11 bits; bf16 hi/lo: 16 bits
+    assert G.rel_err(got, ref) < (2e-3 if f16 else 1e-4), G.rel_err(got, ref)
+
+
 def test_maxpool_psp_upsample_fp16_planes(G):
     """Same helpers on a single fp16 activation plane (the fp16x2 backbone)."""
     lib = L.load()
