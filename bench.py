@@ -40,6 +40,8 @@ from rgbmanip_b200 import synth, weights  # noqa: E402
 
 GF_BACKBONE_PER_FRAME = 57.0177e9       # SURVEY.md A.3 (2 * MACs of every conv of the PSPNet backbone)
 GF_BACKBONE_TC_PER_FRAME = 57.0177e9 - 0.0128e9 - 0.0066e9     # minus the pyramid 1x1 convs (CUDA cores); everything else is tcgen05
+# executed on the tensor cores: up_1 / up_2 run as low-resolution per-tap GEMMs (engine._build_backbone), a quarter of their 3x3 FLOPs
+GF_BACKBONE_EXECUTED_PER_FRAME = GF_BACKBONE_TC_PER_FRAME - 0.75 * (14.7968e9 + 3.6992e9)
 GF_COSTREG_PER_VIEW = 24.4506e9
 # HBM-bound stages, algorithmic bytes per environment (DESIGN.md section 5 derives them):
 #   volume + 3-D U-Net, materialised-volume variant: 302.7 MB per reference view
@@ -48,7 +50,8 @@ GF_COSTREG_PER_VIEW = 24.4506e9
 BYTES_VOLUME_COSTREG_PER_ENV = 302.7e6
 BYTES_DECODE_GATHER_PER_ENV = 1024 * (3 * 3 * 26 * 16 + 24 * 4 * 128 + 128 + 4 + 4 + 2 * 128 * 2)
 # "profile constants": figures of an ncu capture of one chunk (not of this run); the launch list they come from is committed
-NCU_PROFILE = {"fp16x2": {"dram_bytes_per_frame": 11141.8e6 / 148, "tensor_pipe_active": 0.720, "src": "profiles/r01_chunk_by_kernel.csv"},
+NCU_PROFILE = {"fp16f8": {"dram_bytes_per_frame": 13394.9e6 / 148, "tensor_pipe_active": 0.628, "src": "profiles/r02b_chunk_by_kernel.csv"},
+               "fp16x2": {"dram_bytes_per_frame": 11141.8e6 / 148, "tensor_pipe_active": 0.720, "src": "profiles/r01_chunk_by_kernel.csv"},
                "bf16x3": {"dram_bytes_per_frame": 18958.8e6 / 128, "tensor_pipe_active": 0.712, "src": "profiles/r01_bf16x3_backbone_tc_summary.csv"}}
 CFG = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
        "n_pts": 1024, "direct_regression": True, "real_world": False}
@@ -587,7 +590,8 @@ def main():
     prof = NCU_PROFILE.get(eng.precision)
     if tc_ms > 0:
         ach = tc_flops / (tc_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "tc_conv_kernel (tcgen05 implicit-GEMM, backbone 2-D convs)", "achieved": ach,
+        roof = {"bound": "tensor", "kernel": "tc_conv_kernel (tcgen05 implicit-GEMM, backbone 2-D convs) + the two upconv_blend launches that "
+                                             "complete the restructured up_1 / up_2 stages", "achieved": ach,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 "traffic": prof["dram_bytes_per_frame"] * frames if prof else None,
                 "traffic_note": ("PROFILE CONSTANT, not measured in this run: dram__bytes_read+write of the launch group in the ncu capture "
@@ -595,10 +599,13 @@ def main():
                 "tensor_pipe_active_ncu": prof["tensor_pipe_active"] if prof else None,
                 "peak_source": pk["src"] + " (sustained: timed inside a long step)",
                 "algorithmic_flops_per_launch_group": tc_flops, "launches": classes["tc"]["launches"],
-                "tensor_pipe_work_frac": ach * npass / pk["tf_sustained"],
+                "executed_flops_per_launch_group": GF_BACKBONE_EXECUTED_PER_FRAME * frames,
+                "tensor_pipe_work_frac": ach * npass / pk["tf_sustained"] * GF_BACKBONE_EXECUTED_PER_FRAME / GF_BACKBONE_TC_PER_FRAME,
                 "note": f"algorithmic FLOPs (SURVEY A.3) / summed CUDA-event time of the {classes['tc']['launches']} launches of one chunk "
                         f"({frames} frames); precision {eng.precision} issues {npass} fp16-equivalent MMA pass(es) per algorithmic FLOP"
-                        + (" (the wide layers run the low-order weight term as an fp8 MMA at twice the rate)" if eng.precision == "fp16f8" else "")}
+                        + (" (the wide layers run the low-order weight term as an fp8 MMA at twice the rate)" if eng.precision == "fp16f8" else "")
+                        + "; `achieved` counts the reference's FLOPs (conv 3x3 over the upsampled maps), `executed_flops...` what the GEMMs "
+                          "really issue after up_1 / up_2 were restructured (upsampling and channel mixing commute)"}
     cr_ms = sum(v for k, v in per_op.items() if k.startswith("stereo.cr."))
     vol_ms = per_op.get("stereo.volume", 0.0)
     dg_ms = per_op.get("stereo.decode_gather", 0.0)
