@@ -339,21 +339,23 @@ int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
 // the conv's zero padding applies to the UPSAMPLED image).
 // q: [B, h, w, 9 C] (channel = tap * C + c, tap = ky * 3 + kx), out: [B, 2h, 2w, C].
 // ---------------------------------------------------------------------------------------------
+// One low-resolution row of q, columns [col0, col0 + ncols), staged in shared memory: [col][9 C channels] 16-bit, column pitch padded
+// by 16 bytes (9 C * 2 is a multiple of 128: without the pad the columns of different threads would share banks).
 template <bool SPLIT>
-__device__ __forceinline__ void upconv_fold_row(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, size_t row_base, int C9,
-                                                int tap0, int C, const int (&xo)[3][2], const float (&xw)[3][2], int f16, float* H) {
+__device__ __forceinline__ void upconv_fold_row(const uint4* __restrict__ st_hi, const uint4* __restrict__ st_lo, int pitch16, int tap0, int C8,
+                                                int cg, const int (&xo)[3][2], const float (&xw)[3][2], int f16, float* H) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) H[j] = 0.f;
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const size_t off = row_base + (size_t)xo[dx][j] * C9 + (size_t)(tap0 + dx) * C;
+            const int off = xo[dx][j] * pitch16 + (tap0 + dx) * C8 + cg;
             float v[8];
-            up_unpack8(__ldg(reinterpret_cast<const uint4*>(q_hi + off)), v, !SPLIT && f16);
+            up_unpack8(st_hi[off], v, !SPLIT && f16);
             if (SPLIT) {
                 float t[8];
-                up_unpack8(__ldg(reinterpret_cast<const uint4*>(q_lo + off)), t, false);
+                up_unpack8(st_lo[off], t, false);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] += t[e];
             }
@@ -364,19 +366,32 @@ __device__ __forceinline__ void upconv_fold_row(const bf16* __restrict__ q_hi, c
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 constexpr int UPB_MAX_STRIP = 64;      // output rows a block walks at most (shared-memory coefficient table)
 
+// Block = 256 threads = (256 / (C/8)) consecutive output columns x C/8 channel groups; it walks a strip of output rows.  The q rows
+// it needs come through a two-deep shared-memory ring filled with cp.async: every q element is fetched once per block (the
+// direct version had each of them fetched by ~4 threads of different warps: 7 TB/s of L2 traffic, the kernel's bound).
 template <bool SPLIT>
 __global__ void __launch_bounds__(256, 2)
 upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
-                    uint8_t* __restrict__ out_q8, const float* __restrict__ bias, float slope, int h, int w, int C, int f16, int strip) {
+                    uint8_t* __restrict__ out_q8, const float* __restrict__ bias, float slope, int h, int w, int C, int f16, int strip,
+                    int ncols_max) {
+    extern __shared__ uint4 upb_stage[];
     // per output row of the strip: 9 vertical coefficients [dy][window row] and the first low-resolution row of its window;
     // the rows are the same for every thread of the block, so they are worked out once
     __shared__ float s_cf[UPB_MAX_STRIP][9];
     __shared__ int s_rb[UPB_MAX_STRIP];
     const int C8 = C >> 3, Ho = 2 * h, Wo = 2 * w, C9 = 9 * C;
     const int Y0 = blockIdx.y * strip, Y1 = min(Y0 + strip, Ho);
-    for (int i = threadIdx.x; i < (Y1 - Y0) * 3; i += 256) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (Y1 - Y0) * 3; i += 256) {
         const int yy = i / 3, dy = i - yy * 3, Y = Y0 + yy;
         int rb, y0, y1, dummy;
         float wy, wdummy;
@@ -389,47 +404,77 @@ upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo
         if (dy == 0) s_rb[yy] = rb;
     }
     __syncthreads();
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    const int cg = idx % C8, X = idx / C8;
-    if (X >= Wo) return;
+    const int XB = 256 / C8;                            // output columns of this block
+    const int Xb0 = blockIdx.x * XB;
+    const int cg = tid % C8, X = Xb0 + tid / C8;
+    const bool active = X < Wo;
     const int b = blockIdx.z;
-    // horizontal taps of this column: low-resolution columns and weights of X - 1, X, X + 1 (weight 0 outside the image)
+    // low-resolution columns the block touches: taps of columns Xb0 - 1 .. Xb0 + XB
+    int col0, col1, dummy;
+    float wdummy;
+    lin_coord(max(Xb0 - 1, 0), w, Wo, &col0, &dummy, &wdummy);
+    lin_coord(min(Xb0 + XB, Wo - 1), w, Wo, &dummy, &col1, &wdummy);
+    const int ncols = col1 - col0 + 1;                  // <= ncols_max = XB / 2 + 3
+    const int pitch16 = 9 * C8 + 1;                     // column pitch in 16-byte units (+1: bank spread)
+    const int plane16 = ncols_max * pitch16;
+    const int buf16 = (SPLIT ? 2 : 1) * plane16;
+    // horizontal taps of this thread's column: staged column index and weight of X - 1, X, X + 1 (weight 0 outside the image)
     int xo[3][2];
     float xw[3][2];
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
         const int Xt = X + dx - 1;
-        const bool in = Xt >= 0 && Xt < Wo;
+        const bool in = active && Xt >= 0 && Xt < Wo;
         int x0, x1;
         float wx;
-        lin_coord(in ? Xt : X, w, Wo, &x0, &x1, &wx);
-        xo[dx][0] = x0; xo[dx][1] = x1;
+        lin_coord(in ? Xt : min(X, Wo - 1), w, Wo, &x0, &x1, &wx);
+        xo[dx][0] = in ? x0 - col0 : 0; xo[dx][1] = in ? x1 - col0 : 0;
         xw[dx][0] = in ? 1.f - wx : 0.f; xw[dx][1] = in ? wx : 0.f;
     }
-    const size_t img = (size_t)b * h * w * C9 + (size_t)cg * 8;
     float bv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) bv[e] = __ldg(bias + cg * 8 + e);
-    int rb = s_rb[0];
+    const int r_first = s_rb[0];
+    const int n_rows = 3 + s_rb[Y1 - Y0 - 1] - r_first;          // low-resolution rows this block folds, in order
+    const int per_col = 9 * C8;
+    auto load_row = [&](int n) {                                   // row n of the sequence -> ring slot n & 1
+        const int r = min(r_first + n, h - 1);
+        uint4* dst = upb_stage + (n & 1) * buf16;
+        const size_t src = (((size_t)b * h + r) * w + col0) * (size_t)C9;
+        for (int i = tid; i < ncols * per_col; i += 256) {
+            const int col = i / per_col, e = i - col * per_col;
+            cp_async16(dst + col * pitch16 + e, q_hi + src + (size_t)col * C9 + e * 8);
+            if (SPLIT) cp_async16(dst + plane16 + col * pitch16 + e, q_lo + src + (size_t)col * C9 + e * 8);
+        }
+        cp_async_commit();
+    };
     float H[3][3][8];          // [dy][window row k = low-resolution row rb + k][channel]
+    int n_done = 0;            // rows folded so far
+    auto fold_next = [&](int k) {                                  // fold row n_done into window slot k (block-uniform call sequence)
+        if (n_done + 1 < n_rows) load_row(n_done + 1); else cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint4* st = upb_stage + (n_done & 1) * buf16;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const size_t rbase = img + (size_t)min(rb + k, h - 1) * w * C9;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) upconv_fold_row<SPLIT>(q_hi, q_lo, rbase, C9, dy * 3, C, xo, xw, f16, H[dy][k]);
-    }
-    size_t oo = (((size_t)b * Ho + Y0) * Wo + X) * C + cg * 8;
+        for (int dy = 0; dy < 3; ++dy) upconv_fold_row<SPLIT>(st, st + plane16, pitch16, dy * 3, C8, cg, xo, xw, f16, H[dy][k]);
+        __syncthreads();                                           // the slot may be refilled by the load issued in the next call
+        ++n_done;
+    };
+    load_row(0);
+    fold_next(0);
+    fold_next(1);
+    fold_next(2);
+    int rb = r_first;
+    size_t oo = (((size_t)b * Ho + Y0) * Wo + (active ? X : 0)) * C + cg * 8;
     const size_t ostep = (size_t)Wo * C;
     for (int yy = 0; yy < Y1 - Y0; ++yy, oo += ostep) {
         if (s_rb[yy] != rb) {        // the window moves down by one low-resolution row
             rb = s_rb[yy];
-            const size_t rbase = img + (size_t)min(rb + 2, h - 1) * w * C9;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
+            for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { H[dy][0][e] = H[dy][1][e]; H[dy][1][e] = H[dy][2][e]; }
-                upconv_fold_row<SPLIT>(q_hi, q_lo, rbase, C9, dy * 3, C, xo, xw, f16, H[dy][2]);
-            }
+            fold_next(2);
         }
         float acc[8];
 #pragma unroll
@@ -445,22 +490,38 @@ upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = acc[e] >= 0.f ? acc[e] : slope * acc[e];
-        st8(out_hi, out_lo, oo, acc, f16);
-        if (out_q8) *reinterpret_cast<uint2*>(out_q8 + oo) = pack8_q8(acc);
+        if (active) {
+            st8(out_hi, out_lo, oo, acc, f16);
+            if (out_q8) *reinterpret_cast<uint2*>(out_q8 + oo) = pack8_q8(acc);
+        }
     }
+    cp_async_wait<0>();
 }
 
 int upconv_blend(const Act& q, const Act& out, const float* bias, float slope, int batch, cudaStream_t stream) {
     ADP_CHECK_ARG(q.C == 9 * out.C && out.H == 2 * q.H && out.W == 2 * q.W && out.C % 8 == 0 && q.f16 == out.f16, "upconv_blend shapes");
     ADP_CHECK_ARG((q.lo != nullptr) == (out.lo != nullptr) || q.f16, "upconv_blend: q and out must use the same plane format");
+    const int C8 = out.C / 8;
+    ADP_CHECK_ARG(256 % C8 == 0, "upconv_blend: C / 8 must divide 256");
     if (batch == 0) return ADP_OK;
-    const int cols = out.W * (out.C / 8);
+    const int XB = 256 / C8;
+    const int ncols_max = XB / 2 + 3;
+    const bool split = q.lo && !q.f16;
+    const int smem = 2 * (split ? 2 : 1) * ncols_max * (9 * C8 + 1) * 16;
     // strips of output rows: long enough to amortise the 3-row window fill, short enough to fill the GPU
     int strip = out.H < UPB_MAX_STRIP ? out.H : UPB_MAX_STRIP;
-    while (strip > 8 && (size_t)batch * ((cols + 255) / 256) * ((out.H + strip - 1) / strip) < 4 * 148) strip = (strip + 1) / 2;
-    const dim3 grid((cols + 255) / 256, (out.H + strip - 1) / strip, batch);
-    if (q.lo && !q.f16) upconv_blend_kernel<true><<<grid, 256, 0, stream>>>(q.hi, q.lo, out.hi, out.lo, nullptr, bias, slope, q.H, q.W, out.C, 0, strip);
-    else upconv_blend_kernel<false><<<grid, 256, 0, stream>>>(q.hi, nullptr, out.hi, out.lo, out.f16 ? out.q8 : nullptr, bias, slope, q.H, q.W, out.C, q.f16, strip);
+    const int xblocks = (out.W + XB - 1) / XB;
+    while (strip > 8 && (size_t)batch * xblocks * ((out.H + strip - 1) / strip) < 4 * 148) strip = (strip + 1) / 2;
+    const dim3 grid(xblocks, (out.H + strip - 1) / strip, batch);
+    static int attr_s[kMaxDevices], attr_h[kMaxDevices];
+    if (split) {
+        ADP_TRY(ensure_dyn_smem(upconv_blend_kernel<true>, smem, attr_s));
+        upconv_blend_kernel<true><<<grid, 256, smem, stream>>>(q.hi, q.lo, out.hi, out.lo, nullptr, bias, slope, q.H, q.W, out.C, 0, strip, ncols_max);
+    } else {
+        ADP_TRY(ensure_dyn_smem(upconv_blend_kernel<false>, smem, attr_h));
+        upconv_blend_kernel<false><<<grid, 256, smem, stream>>>(q.hi, nullptr, out.hi, out.lo, out.f16 ? out.q8 : nullptr, bias, slope, q.H, q.W,
+                                                                out.C, q.f16, strip, ncols_max);
+    }
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }

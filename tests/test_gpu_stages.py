@@ -47,6 +47,7 @@ TC2D_CASES = [
     (1, 224, 224, 64, 64, 3, 1),
     (1, 224, 224, 64, 32, 1, 1),
     (3, 20, 12, 64, 128, 3, 1),
+    (2, 20, 24, 64, 64, 3, 1),          # fp16x2: slab kernel with [W_hi | W_lo] slots, partial tiles in y
 ]
 
 
