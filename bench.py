@@ -327,7 +327,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--num-envs", type=int, default=1024)
     ap.add_argument("--chunk", type=int, default=74,
-                    help="envs per chunk; 74 = num_SMs / 2: 148 frames per backbone launch = whole waves of 128-row tiles on 148 SMs")
+                    help="envs per chunk (= what an auto-sized estimator grows to); 74 = num_SMs / 2: 148 frames per backbone launch = whole "
+                         "waves of 128-row tiles on 148 SMs.  Measured A/B on one box: chunk 148 gives the same device-resident rate "
+                         "(3373-3400 vs 3369-3377) but 5 %% less end to end (3232-3278 vs 3411)")
     ap.add_argument("--precision", default="fp16f8")
     ap.add_argument("--unique", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=16)

@@ -75,6 +75,8 @@ def chunk_bounds(N, max_envs, first=0):
     return bounds
 
 
+AUTO_CHUNK_MAX = 74       # envs per chunk an auto-sized workspace grows to: 148 frames = whole waves of 128-row tiles on 148 SMs, 18 GB
+
 _BOX_SIGNS = np.array([[1, 1, 1], [1, 1, -1], [-1, 1, 1], [-1, 1, -1], [1, -1, 1], [1, -1, -1], [-1, -1, 1], [-1, -1, -1]], np.float64)
 
 
@@ -165,9 +167,12 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             device = devices[0] if isinstance(devices[0], (str, torch.device)) else f"cuda:{int(devices[0])}"
         device = device or cfg.get("device", "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0")
         self.device = torch.device(device)
-        self.estimator = Engine(state_dict, device=self.device, max_envs=int(max_envs or cfg.get("max_envs_per_chunk", 16)),
-                                precision=precision or cfg.get("precision", "fp16f8"), regress_pose=regress,
-                                img_size=int(cfg.get("img_size", 224)), **engine_kw)
+        # chunk capacity: an explicit ``max_envs`` / ``max_envs_per_chunk`` is final; otherwise the workspace starts at 16 environments
+        # and grows with the batches it sees, up to AUTO_CHUNK_MAX per chunk (a drop-in user never sizes anything)
+        self._auto_chunk = max_envs is None and "max_envs_per_chunk" not in cfg
+        self._engine_args = dict(device=self.device, precision=precision or cfg.get("precision", "fp16f8"), regress_pose=regress,
+                                 img_size=int(cfg.get("img_size", 224)), **engine_kw)
+        self.estimator = Engine(state_dict, max_envs=int(max_envs or cfg.get("max_envs_per_chunk", 16)), **self._engine_args)
         self._seed = int(cfg.get("sample_seed", 0))
         self._calls = 0
         self._copy_stream = None
@@ -178,6 +183,20 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         self.h2d_bytes = 0          # bytes copied host -> device so far (bench.py reports the per-step figure)
         self._keep_f64 = bool(cfg.get("keep_float64", False))
         self._first_chunk = int(cfg.get("first_chunk_envs", 16))
+
+    def _ensure_capacity(self, N):
+        """Auto-sized workspace: rebuild the engine with a larger chunk capacity the first time a bigger batch shows up."""
+        eng = self.estimator
+        want = min(max(int(N), 1), AUTO_CHUNK_MAX)
+        if not self._auto_chunk or want <= eng.E:
+            return
+        sd = eng.sd
+        torch.cuda.synchronize(self.device)
+        eng.close()
+        self.estimator = eng = None
+        self._stage_bufs, self._win_state, self._slot_free = {}, {}, [None, None]
+        torch.cuda.empty_cache()
+        self.estimator = Engine(sd, max_envs=want, **self._engine_args)
 
     # -- helpers ---------------------------------------------------------------------------------
     _RGB_OK = (torch.uint8, torch.float32, torch.float64)
@@ -321,6 +340,7 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
             return self._estimate_multi((camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
                                          rgb2_batch, view2_mask_batch, view2_extrinsic_batch), choose, return_tensor, ransac_idx,
                                         env_offset, sample_seed)
+        self._ensure_capacity(len(camera_intrinsic_batch))
         eng = self.estimator
         eng.check_error_flag(wait=False)        # a flag read posted by an earlier tensor-returning call
         batches = tuple(self._as_tensor(a) for a in (camera_intrinsic_batch, rgb1_batch, view1_mask_batch, view1_extrinsic_batch,
@@ -385,6 +405,7 @@ class AdaPoseEstimator_v5(BasePoseEstimator):
         """BASELINE configs[0..1]: one view per environment -> (nocs [N,1024,3] float32, choose [N,1024] int32, valid [N] bool)
         as numpy arrays.  This is the per-view part of the reference forward (preprocessing, PSPNet, ``instance_color`` +
         ``nocs_head``, network_v5.py:432-444); a full pose needs two views (interface_v5.py:256-257)."""
+        self._ensure_capacity(len(camera_intrinsic_batch))
         eng = self.estimator
         K_b, rgb_b, m_b = (self._as_tensor(a) for a in (camera_intrinsic_batch, rgb_batch, mask_batch))
         N = K_b.shape[0]

@@ -195,3 +195,21 @@ def test_window_row_upload_equals_whole_frame_upload():
     np.testing.assert_array_equal(a[5], O.DEFAULT_BBOX)
     assert a_est.h2d_bytes < 0.75 * w_est.h2d_bytes * 2, (a_est.h2d_bytes, w_est.h2d_bytes)     # a_est ran twice as many calls
     a_est.estimator.close(); w_est.estimator.close()
+
+
+def test_auto_sized_workspace_grows_with_the_batch():
+    """Without max_envs / max_envs_per_chunk the estimator sizes itself: 16 environments to start with, grown on demand (up to
+    AUTO_CHUNK_MAX per chunk) when a larger batch arrives; results equal those of an explicitly sized estimator."""
+    from rgbmanip_b200.estimator import AUTO_CHUNK_MAX
+    b = synth.make_batch(20, seed=4, n_unique=5)
+    auto = _make()
+    assert auto._auto_chunk and auto.estimator.E == 16
+    small = auto.estimate(*b.slice(0, 4).args(), sample_seed=3)
+    assert auto.estimator.E == 16
+    boxes = auto.estimate(*b.args(), sample_seed=3)
+    assert auto.estimator.E == 20 <= AUTO_CHUNK_MAX
+    fixed = _make(max_envs=20)
+    assert not fixed._auto_chunk
+    np.testing.assert_array_equal(boxes, fixed.estimate(*b.args(), sample_seed=3))
+    np.testing.assert_array_equal(small, boxes[:4])
+    assert not _make({"max_envs_per_chunk": 8})._auto_chunk
