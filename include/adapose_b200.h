@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ADP_ABI_VERSION 4
+#define ADP_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define ADP_API __attribute__((visibility("default")))
@@ -139,7 +139,8 @@ ADP_API int adp_upconv_blend(const adp_act* q, const adp_act* out, const float* 
 ADP_API int adp_pack_s2d(const float* crops, const adp_act* out, int batch, int S, void* stream);
 
 /* conv0 of the cost-regularisation U-Net (network_v5.py:263,283) as a depth-ring tcgen05 kernel: vol [B,D,H,W,32] ->
- * out [B,D,H,W,16] (8 channels + 8 zero), folded BatchNorm + ReLU.  w: 16-bit [9 (ky,kx)][4 chunks][32 (kz,co)][8].
+ * out [B,D,H,W,16] (8 channels + 8 zero), folded BatchNorm + ReLU.  w: 16-bit [3 kx][4 chunks of 8 channels][80 n][8] with
+ * n = (kz*3+ky)*8 + co (rows 72..79 zero): depth and row taps folded into the MMA's N (rgbmanip_b200.geometry.conv0_ring_weights).
  * flags: bit 0 must be 0 (reserved: planar volume layout); bit 1 (ADP_LAYOUT_S2D) = write the 8 real channels
  * space-to-depth(2): out [B,D/2,H/2,W/2,64], channel = ((d&1)*4 + (y&1)*2 + (x&1))*8 + co.  In that layout the stride-2
  * conv1 and the skip connection of the transposed conv11 (network_v5.py:265,278,283) read it as a stride-1 tensor. */

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libadapose_b200.so")
 
-ADP_ABI_VERSION = 4
+ADP_ABI_VERSION = 5
 DT_U8, DT_F32, DT_F64 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_TANH = 0, 1, 2, 3
 LAYOUT_F16, LAYOUT_S2D = 1, 2          # adp_decode x11_format / adp_conv0_plan_create flags

@@ -2,18 +2,21 @@
 // [24, 224, 224] plane-sweep volume -- 68 % of the U-Net's FLOPs with only 8 output channels.
 //
 // A plain implicit GEMM (M = pixels, N = 8) re-reads the volume 27 times and leaves the MMA N dimension nearly empty.
-// This kernel instead walks the depth axis sequentially and folds the depth taps into N:
+// This kernel instead walks the depth axis sequentially and folds BOTH the depth taps and the row taps into N:
 //
-//   P[d'][pixel, (kz, co)] = sum_{ky,kx,c} In[d', y+ky-1, x+kx-1, c] * W[co, c, kz, ky, kx]      (N = 3 x 8 = 24 of 32)
-//   out[d][pixel, co]      = P[d-1][kz=0] + P[d][kz=1] + P[d+1][kz=2]
+//   P[d'][y'][pixel, (kz, ky, co)] = sum_{kx,c} In[d', y', x+kx-1, c] * W[co, c, kz, ky, kx]          (N = 9 x 8 = 72 of 80)
+//   out[d][y][pixel, co]           = sum_{kz,ky} P[d+kz-1][y+ky-1][pixel, (kz, ky, co)]
 //
-// One work unit = one image row segment of 112 pixels (M = 128 rows of the UMMA tile) for all 24 depths.  For each
+// One work unit = R = 4 image rows x one segment of 112 pixels (M = 128 rows of the UMMA tile) for all 24 depths.  For each
 // input plane d' the rows y-1 .. y+R (with a one-pixel halo in x) are brought in by ONE TMA box in pixel-major
 // 64-byte-swizzled K-major layout ([row][pixel][32 channels]); the swizzle is a function of the absolute shared-memory
-// address, so the (ky, kx) taps are plain row/pixel shifts of the descriptor start address (+64 B per pixel) and every
-// volume row is read (R+2)/R times instead of 27.  P[d'] accumulates in one of four 32-column TMEM slots (a ring over depth); the epilogue warps add the three
-// lane-aligned column groups of three consecutive slots, apply the folded BatchNorm + ReLU and store 16 channels
-// (8 real + 8 zero: conv1 needs Cin = 16 for the K = 16 MMA).
+// address, so the kx taps are plain pixel shifts of the descriptor start address (+64 B per pixel).  An MMA with N <= 64 is
+// bound by the 128 B/clk shared-memory read of its A operand (4 KB per M128 x K16 instruction), not by the tensor pipe: with
+// only kz in N (round 1: N = 24, 72 MMAs per plane step) the kernel sat at 93 % L1/TEX throughput.  With (kz, ky) in N every
+// input row needs 3 (kx) x 2 (K steps) MMAs of N = 80 -- 36 per plane step, half the A bytes.  Each (plane, input row) product
+// lands in one slot of a six-deep 80-column TMEM ring; the epilogue warps pull a slot out once, release it at once, and add its
+// nine 8-column groups into three register accumulators per output row (output planes d'-1, d', d'+1), apply the folded
+// BatchNorm + ReLU when a plane is complete and store 16 channels (8 real + 8 zero: conv1 needs Cin = 16 for the K = 16 MMA).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -22,7 +25,7 @@
 
 namespace adp {
 
-constexpr int C0_THREADS = 192;
+constexpr int C0_THREADS = 320;              // warp 0: TMA, warp 1: MMA, warps 2-5 / 6-9: epilogue of output rows 0-1 / 2-3
 constexpr int C0_SEG = 112;                 // pixels per unit (224 = 2 x 112)
 constexpr int C0_R = 4;                                   // output rows per unit: rows y0-1 .. y0+R are loaded once for R outputs
 constexpr int C0_PIXPITCH = 120;                          // pixels per slab row in smem (112 + halo, padded so that a row is a 128-byte multiple)
@@ -30,8 +33,9 @@ constexpr int C0_ROWPITCH = C0_PIXPITCH * 64;             // 7680 bytes: one sla
 constexpr int C0_BOX_BYTES = (C0_R + 2) * C0_ROWPITCH;    // one depth plane of the unit = ONE TMA box
 constexpr int C0_STAGE_BYTES = C0_BOX_BYTES + 1024;       // + slack: the M = 128 tile overhangs the last slab row by 10 pixels
 constexpr int C0_STAGES = 4;
-constexpr int C0_W_BYTES = 9 * 4 * 32 * 16;               // [tap][chunk][n = 32][8 ch] 16-bit
-constexpr int C0_SLOTS = 4;                               // depth ring; TMEM column = (row * 4 + slot) * 32
+constexpr int C0_N = 80;                                  // MMA N: (kz, ky, co) = 72 columns, padded to a multiple of 16
+constexpr int C0_W_BYTES = 3 * 4 * C0_N * 16;             // [kx][chunk][n = 80][8 ch] 16-bit
+constexpr int C0_SLOTS = C0_R + 2;                        // TMEM ring over (plane, input row) items; column = slot * 80
 constexpr int C0_SMEM = C0_STAGES * C0_STAGE_BYTES + C0_W_BYTES + 1024 + 256;
 
 struct Conv0Params {
@@ -67,8 +71,8 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* wsm = smem + C0_STAGES * C0_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + C0_W_BYTES);
-    // bars: [0,S) full, [S,2S) empty, [2S,2S+4) tmem_full, [2S+4,2S+8) tmem_empty, then the TMEM base
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C0_STAGES + 8);
+    // bars: [0,S) full, [S,2S) empty, [2S,2S+SLOTS) tmem_full, [2S+SLOTS,2S+2 SLOTS) tmem_empty, then the TMEM base
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C0_STAGES + 2 * C0_SLOTS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t w_base = ptx::smem_u32(wsm);
@@ -76,7 +80,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C0_STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C0_STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C0_STAGES + 4 + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C0_STAGES + C0_SLOTS + s); };
 
     // weights -> smem (generic proxy), made visible to the tensor core's async proxy by the fence below
     for (int i = threadIdx.x; i < C0_W_BYTES / 16; i += C0_THREADS)
@@ -88,11 +92,12 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmIn);
         for (int s = 0; s < C0_STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < C0_SLOTS; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+        // slot == input row (C0_SLOTS items per plane); rows 2 and 3 feed output rows of both epilogue groups
+        for (int s = 0; s < C0_SLOTS; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), (s == 2 || s == 3) ? 8 : 4); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 128 * C0_R);
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -123,49 +128,52 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: 9 (ky,kx) taps x 2 K steps per plane into TMEM slot g % 4 =====================
+        // ===================== MMA issuer: per input row 3 kx taps x 2 K steps of N = 80 into the next ring slot =====================
         // warp-convergent: all lanes carry the same descriptors, the elected lane issues (see ptx::umma_bf16_elected)
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t idesc = make_idesc_n(32, p.f16);
+        const uint32_t idesc = make_idesc_n(C0_N, p.f16);
         const uint32_t elected = ptx::elect_one();
         const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-        unsigned g = 0;   // running plane counter (D % 4 == 0 keeps slot == depth % 4)
+        int slot = 0;
+        uint32_t sphase = 0;          // ring phase: flips every C0_SLOTS items
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            for (int d = 0; d < D; ++d, ++g) {
-                const int slot = g & 3;
-                ptx::mbar_wait(tempty_bar(slot), ((g >> 2) & 1) ^ 1, p.err, 12);
+            for (int d = 0; d < D; ++d) {
                 ptx::mbar_wait(full_bar(stage), phase, p.err, 13);
                 ptx::tc_fence_after();
                 const uint32_t sa = smem_base + stage * C0_STAGE_BYTES;
                 const uint64_t a0 = make_desc_sw64(sa);
-                const uint64_t b0 = make_desc_noswz(w_base, 512, 128);
+                const uint64_t b0 = make_desc_noswz(w_base, C0_N * 16, 128);
 #pragma unroll
-                for (int r = 0; r < C0_R; ++r) {
-                    const uint32_t tmem_d = tbase + (uint32_t)((r * C0_SLOTS + slot) * 32);
+                for (int r = 0; r < C0_R + 2; ++r) {
+                    ptx::mbar_wait(tempty_bar(slot), sphase ^ 1, p.err, 12);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tbase + (uint32_t)(slot * C0_N);
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                // start-address field is (addr >> 4): constant offsets are plain adds (no carry out of the 14-bit field below 256 KB)
-                                const uint64_t adesc = a0 + (uint64_t)(((r + ky) * C0_ROWPITCH + kx * 64 + ks * 32) >> 4);
-                                const uint64_t bdesc = b0 + (uint64_t)((((ky * 3 + kx) * 4 + 2 * ks) * 512) >> 4);
-                                ptx::umma_bf16_elected(tmem_d, adesc, bdesc, idesc, (ky | kx | ks) ? 1u : 0u, elected);
-                            }
+                        for (int ks = 0; ks < 2; ++ks) {
+                            // start-address field is (addr >> 4): constant offsets are plain adds (no carry out of the 14-bit field below 256 KB)
+                            const uint64_t adesc = a0 + (uint64_t)((r * C0_ROWPITCH + kx * 64 + ks * 32) >> 4);
+                            const uint64_t bdesc = b0 + (uint64_t)(((kx * 4 + 2 * ks) * C0_N * 16) >> 4);
+                            ptx::umma_bf16_elected(tmem_d, adesc, bdesc, idesc, (kx | ks) ? 1u : 0u, elected);
+                        }
+                    ptx::umma_commit_elected(tfull_bar(slot), elected);
+                    if (++slot == C0_SLOTS) { slot = 0; sphase ^= 1; }
                 }
                 ptx::umma_commit_elected(empty_bar(stage), elected);
-                ptx::umma_commit_elected(tfull_bar(slot), elected);
                 __syncwarp();
                 if (++stage == C0_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue: out[d] = P[d-1][kz=0] + P[d][kz=1] + P[d+1][kz=2] =====================
-        // Each plane's partial sums are pulled out of TMEM exactly once, as soon as the plane completes, and its slot is
-        // released immediately: the three-plane sum lives in registers (two carried accumulators per output row), so the MMA
-        // warp can run the whole ring (3 planes) ahead instead of waiting for the epilogue of the plane before last.
+        // ===================== epilogue: out[d][y] = sum_{kz,ky} P[d+kz-1][y+ky-1][(kz,ky)] =====================
+        // Every (plane, input row) product is pulled out of TMEM as soon as it completes and its slot is released immediately.
+        // Two groups of four warps: group g owns output rows 2g, 2g+1 of the unit (one warp per scheduler leaves every TMEM /
+        // barrier latency exposed; the groups halve the work per warp).  Three accumulators per output row live in registers:
+        // the output planes d'-1 (completed by plane d'), d' and d'+1.
+        constexpr int RG = C0_R / 2;                // output rows per group
+        const int grp = (warp - 2) >> 2;
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -194,46 +202,54 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
                 dst[1] = make_uint4(0, 0, 0, 0);
             }
         };
-        unsigned g = 0;   // running plane counter (matches the MMA warp's)
+        uint32_t sphase = 0;          // slot == input row: one pass over the ring per plane
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int seg = u % segs, y0 = ((u / segs) % ygroups) * C0_R, b = u / (segs * ygroups);
+            const int seg = u % segs, y0 = ((u / segs) % ygroups) * C0_R + grp * RG, b = u / (segs * ygroups);
             const int x = seg * C0_SEG + m;
             const bool valid = m < C0_SEG;
-            float acc_cur[C0_R][8];     // out[d']   so far: P[d'-1][kz=0] (+ P[d'][kz=1] once plane d' is in)
-            float acc_nxt[C0_R][8];     // out[d'+1] so far: P[d'][kz=0]
+            float acc[3][RG][8];        // [0]: out[d'-1], [1]: out[d'], [2]: out[d'+1] while plane d' is being added
 #pragma unroll
-            for (int r = 0; r < C0_R; ++r)
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { acc_cur[r][j] = 0.f; acc_nxt[r][j] = 0.f; }
-            for (int d = 0; d < D; ++d, ++g) {
-                const int slot = g & 3;
-                ptx::mbar_wait(tfull_bar(slot), (g >> 2) & 1, p.err, 14);
-                ptx::tc_fence_after();
-                uint32_t rr[C0_R][3][8];
+                for (int r = 0; r < RG; ++r)
 #pragma unroll
-                for (int r = 0; r < C0_R; ++r)
+                    for (int j = 0; j < 8; ++j) acc[a][r][j] = 0.f;
+            for (int d = 0; d < D; ++d, sphase ^= 1) {
+#pragma unroll
+                for (int rl = 0; rl < RG + 2; ++rl) {       // the group's input rows: unit rows grp * RG + rl  (= slot)
+                    const int slot = grp * RG + rl;
+                    ptx::mbar_wait(tfull_bar(slot), sphase, p.err, 14);
+                    ptx::tc_fence_after();
+                    // input row rl (group-local) feeds the group's output row rl - ky (ky = 0..2); the other column groups belong
+                    // to the other group or to the units above / below and are not read
+                    uint32_t rr[3][3][8];
 #pragma unroll
                     for (int kz = 0; kz < 3; ++kz)
-                        tmem_ld8(lane_addr + (uint32_t)((r * C0_SLOTS + slot) * 32 + kz * 8), rr[r][kz]);
-                ptx::tmem_ld_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar(slot));       // the slot is free as soon as it has been read
 #pragma unroll
-                for (int r = 0; r < C0_R; ++r) {
-                    // plane d contributes kz=2 to out[d-1] (now complete), kz=1 to out[d], kz=0 to out[d+1]
-                    if (d >= 1) {
-                        float prev[8];
+                        for (int ky = 0; ky < 3; ++ky)
+                            if (rl - ky >= 0 && rl - ky < RG)
+                                tmem_ld8(lane_addr + (uint32_t)(slot * C0_N + (kz * 3 + ky) * 8), rr[kz][ky]);
+                    ptx::tmem_ld_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(tempty_bar(slot));       // this warp is done with the slot
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) prev[j] = acc_cur[r][j] + __uint_as_float(rr[r][2][j]);
-                        if (valid) store_row(prev, b, d - 1, y0 + r, x);
-                    }
+                    for (int kz = 0; kz < 3; ++kz)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        acc_cur[r][j] = acc_nxt[r][j] + __uint_as_float(rr[r][1][j]);
-                        acc_nxt[r][j] = __uint_as_float(rr[r][0][j]);
-                    }
-                    if (d == D - 1 && valid) store_row(acc_cur[r], b, d, y0 + r, x);
+                        for (int ky = 0; ky < 3; ++ky)
+                            if (rl - ky >= 0 && rl - ky < RG) {
+                                // plane d' contributes kz = 2 to out[d'-1], kz = 1 to out[d'], kz = 0 to out[d'+1]
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[2 - kz][rl - ky][j] += __uint_as_float(rr[kz][ky][j]);
+                            }
+                }
+                // out[d-1] is complete; rotate the accumulators
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                    if (d >= 1 && valid) store_row(acc[0][r], b, d - 1, y0 + r, x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { acc[0][r][j] = acc[1][r][j]; acc[1][r][j] = acc[2][r][j]; acc[2][r][j] = 0.f; }
+                    if (d == D - 1 && valid) store_row(acc[0][r], b, d, y0 + r, x);
                 }
             }
         }
@@ -242,7 +258,7 @@ conv0_ring_kernel(const __grid_constant__ CUtensorMap tmIn, const Conv0Params p,
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 128 * C0_R);
+        ptx::tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -263,8 +279,8 @@ int conv0_plan(Conv0Plan* pl, const Act& in, const uint16_t* w_packed, const flo
                int flags, int num_sms) {
     const int planar = flags & 1;
     ADP_TRY(tc_conv_init_driver());
-    ADP_CHECK_ARG(in.C == 32 && in.W % C0_SEG == 0 && in.D % 4 == 0 && in.D >= 4 && in.H % C0_R == 0,
-                  "conv0 ring kernel: C = 32, W % 112 == 0, D % 4 == 0, H % 4 == 0");
+    ADP_CHECK_ARG(in.C == 32 && in.W % C0_SEG == 0 && in.D >= 2 && in.H % C0_R == 0,
+                  "conv0 ring kernel: C = 32, W % 112 == 0, D >= 2, H % 4 == 0");
     cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.D, (cuuint64_t)in.B};
     cuuint64_t strides[4] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2,
                              (cuuint64_t)in.D * in.H * in.W * in.C * 2};

@@ -81,14 +81,16 @@ def stem_s2d_weights(w):
 
 
 def conv0_ring_weights(w):
-    """[8,32,3,3,3] torch weights -> [9 (ky,kx)][4 chunks][32 n = kz*8+co][8 ch] for adp_conv0_run (rows 24..31 zero)."""
+    """[8,32,3,3,3] torch weights -> [3 kx][4 chunks of 8 channels][80 n = (kz*3+ky)*8 + co][8 ch] for adp_conv0_run (rows 72..79
+    zero): the depth and row taps are folded into the MMA's N dimension (csrc/conv0_ring.cu)."""
     import torch
-    out = torch.zeros(9, 4, 32, 8)
-    for ky in range(3):
-        for kx in range(3):
-            for kz in range(3):
+    out = torch.zeros(3, 4, 80, 8)
+    for kx in range(3):
+        for kz in range(3):
+            for ky in range(3):
                 blk = w[:, :, kz, ky, kx]                       # [co, c]
-                out[ky * 3 + kx, :, kz * 8:(kz + 1) * 8, :] = blk.reshape(8, 4, 8).permute(1, 0, 2)
+                n0 = (kz * 3 + ky) * 8
+                out[kx, :, n0:n0 + 8, :] = blk.reshape(8, 4, 8).permute(1, 0, 2)
     return out.contiguous()
 
 
