@@ -5,12 +5,14 @@ include/adapose_b200.h; torch is used for device memory, streams and host<->devi
 
 Stage map (reference lines relative to models/pose_estimator/AdaPose):
   preprocess   interface_v5.py:58-170          -> adp_preprocess
-  backbone     lib/pspnet.py:33-158            -> adp_conv_tc_* (tcgen05) / adp_conv_direct / adp_maxpool3x3s2 /
-                                                  adp_psp_priors / adp_psp_concat_up / adp_upsample2x
+  backbone     lib/pspnet.py:33-158            -> adp_conv_tc_* (tcgen05) / adp_pack_s2d / adp_maxpool3x3s2 / adp_psp_priors /
+                                                  adp_psp_fill_priors / adp_upconv_blend (up_1, up_2) / adp_upsample2x (up_3)
   volume       lib/network_v5.py:378-430       -> adp_warp_matrices, adp_build_volume
-  cost reg.    lib/network_v5.py:260-291       -> adp_conv_tc_* (stride 1) / adp_conv_direct (stride 2, transposed)
-  decode       lib/network_v5.py:432-499       -> adp_decode (the `prob` conv is evaluated at the sampled pixels only)
-  fit + box    lib/utils.py:40-119, interface_v5.py:318-374 -> adp_fit
+  cost reg.    lib/network_v5.py:260-291       -> adp_conv0_run (depth ring), adp_tconv_run (conv9), adp_conv_tc_* (everything else)
+  decode       lib/network_v5.py:432-499       -> adp_decode_gather (the `prob` conv is evaluated at the sampled pixels only) +
+                                                  per-point MLPs on adp_conv_tc_* + adp_colsum / adp_pose_gbias / adp_rot_head
+  fit + box    lib/utils.py:40-119, lib/align.py, interface_v5.py:318-374 -> adp_fit / adp_fit_umeyama / adp_nocs_match
+  transformer variant  lib/network_baseline.py:523-669, lib/fusion.py -> adp_view_fusion (arch="baseline")
 """
 from __future__ import annotations
 
