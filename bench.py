@@ -575,6 +575,28 @@ def main():
                                                     f"runs that share on each of the {world} rank(s): add_view (preprocess + backbone of the new frame) + "
                                                     "get_estimation (stereo head on cached features) + get_observation + actor forward (60-96-96-32-12 ELU)")
 
+        # ---- the other fit branches and the transformer variant, 256 envs device-resident, for the record
+        if world == 1:
+            from rgbmanip_b200.estimator import AdaPoseEstimator_baseline
+            n_v = min(256, n_loc)
+            a_v = [devt[k][:n_v] for k in ("K", "rgb1", "mask1", "E1", "rgb2", "mask2", "E2")]
+            variants_fit = {}
+            for label, cls, extra, arch in (("branch_b_ransac_umeyama", AdaPoseEstimator_v5, {"direct_regression": False, "use_depth": True}, "v5"),
+                                            ("branch_c_nocs_matching_pnp", AdaPoseEstimator_v5, {"direct_regression": False, "use_depth": False}, "v5"),
+                                            ("transformer_variant_adapose_baseline", AdaPoseEstimator_baseline, {"name": "adapose_baseline"}, "baseline")):
+                cfg_v = dict(CFG, **extra)
+                sd_v = weights.init_state_dict(0, regress_pose=cfg_v["direct_regression"], arch=arch)
+                est_v = cls(None, cfg_v, None, state_dict=sd_v, device=dev, max_envs=min(args.chunk, n_v), precision=args.precision)
+                f_v = lambda: est_v.estimate(*a_v, return_tensor=True)
+                ms_v, wall_v, _ = timed(f_v, 2, 2)
+                variants_fit[label] = {"value": n_v * 2 / wall_v, "unit": "estimates/s", "num_envs": n_v, "ms_per_step": wall_v * 1e3 / 2}
+                est_v.estimator.close()
+                del est_v
+                torch.cuda.empty_cache()
+            variants_fit["branch_c_nocs_matching_pnp"]["note"] = ("device part (NOCS of both views, matching, triangulation, median scale) + the "
+                                                                  "reference's cv2.solvePnPRansac per environment on a host thread pool (~18 ms per environment and thread), which is the bound")
+            configs["other_branches_n256"] = variants_fit
+
     # ---- per-kernel-class timing of one chunk, live, on the launching stream
     n_chunk = min(eng.E, n_loc)
     E1c = devt["E1"][:n_chunk].contiguous(); E2c = devt["E2"][:n_chunk].contiguous()

@@ -80,41 +80,57 @@ AUTO_CHUNK_MAX = 74       # envs per chunk an auto-sized workspace grows to: 148
 _BOX_SIGNS = np.array([[1, 1, 1], [1, 1, -1], [-1, 1, 1], [-1, 1, -1], [1, -1, 1], [1, -1, -1], [-1, -1, 1], [-1, -1, -1]], np.float64)
 
 
+_PNP_POOL = None
+
+
+def _pnp_one(nocs, pts2d, scale, valid, K, E1):
+    """One environment of :func:`pnp_box_tail` -> [8,3] float64."""
+    import cv2
+    ts = np.float64(scale)
+    if not valid or not np.isfinite(ts):
+        return DEFAULT_BBOX          # NaN scale: the reference's box is NaN too and fails its finite check -> sentinel
+    temp = nocs * ts                                         # float32 array * np.float64 scalar, as in the reference
+    try:
+        ok, rv, tv, _ = cv2.solvePnPRansac(temp, pts2d, K, np.zeros(4), flags=cv2.SOLVEPNP_EPNP, reprojectionError=3.0)
+        if ok:
+            crit = (cv2.TERM_CRITERIA_MAX_ITER + cv2.TERM_CRITERIA_EPS, 20, 1e-6)
+            rv, tv = cv2.solvePnPRefineVVS(temp, pts2d, K, None, rv, tv, criteria=crit)
+        Rm, _ = cv2.Rodrigues(rv)
+    except cv2.error:
+        return DEFAULT_BBOX
+    size = 2 * np.max(np.abs(nocs), axis=0) * ts
+    sRT = np.eye(4).astype(np.float32)                       # float32 matrix, no scale in it (interface_v5.py:359-361)
+    sRT[:3, :3] = Rm
+    sRT[:3, 3] = np.asarray(tv).flatten()
+    cam = sRT @ np.vstack([(_BOX_SIGNS * (size / 2)).T, np.ones((1, 8), np.float32)])
+    cam = cam[:3] / cam[3]
+    with np.errstate(all="ignore"):
+        try:
+            inv = np.linalg.inv(E1)
+        except np.linalg.LinAlgError:
+            return DEFAULT_BBOX
+    if np.isfinite(inv).all() and np.isfinite(cam).all():
+        return (inv[:3, :3] @ cam + inv[:3, 3:4]).T
+    return DEFAULT_BBOX
+
+
 def pnp_box_tail(nocs, pts2d, scale, valid, K, E1):
     """Host tail of branch C, per environment as the reference runs it: ``estimatePnPRansac`` (align.py:104-115) with size = the
     median scale of the triangulated matches, then the box + world transform + finite check of interface_v5.py:350-374.  The
-    PnP is the reference's own OpenCV call (its RANSAC lives inside cv2); everything before it ran on the device.
+    PnP is the reference's own OpenCV call (its RANSAC lives inside cv2 and seeds its generator per call, so the result does not
+    depend on the thread); everything before it ran on the device.  The environments are independent and cv2 releases the GIL:
+    they go through a host thread pool (18 ms per environment on one thread is what bounds this branch).
     nocs [n,P,3] f32, pts2d [n,P,2] f32, scale [n] f64, valid [n], K [n,3,3], E1 [n,4,4] -> [n,8,3] float64."""
-    import cv2
-    out = np.empty((len(scale), 8, 3))
-    crit = (cv2.TERM_CRITERIA_MAX_ITER + cv2.TERM_CRITERIA_EPS, 20, 1e-6)
-    for e in range(len(scale)):
-        out[e] = DEFAULT_BBOX
-        ts = np.float64(scale[e])
-        if not valid[e] or not np.isfinite(ts):
-            continue          # NaN scale: the reference's box is NaN too and fails its finite check -> sentinel
-        temp = nocs[e] * ts                                  # float32 array * np.float64 scalar, as in the reference
-        try:
-            ok, rv, tv, _ = cv2.solvePnPRansac(temp, pts2d[e], K[e], np.zeros(4), flags=cv2.SOLVEPNP_EPNP, reprojectionError=3.0)
-            if ok:
-                rv, tv = cv2.solvePnPRefineVVS(temp, pts2d[e], K[e], None, rv, tv, criteria=crit)
-            Rm, _ = cv2.Rodrigues(rv)
-        except cv2.error:
-            continue
-        size = 2 * np.max(np.abs(nocs[e]), axis=0) * ts
-        sRT = np.eye(4).astype(np.float32)                   # float32 matrix, no scale in it (interface_v5.py:359-361)
-        sRT[:3, :3] = Rm
-        sRT[:3, 3] = np.asarray(tv).flatten()
-        cam = sRT @ np.vstack([(_BOX_SIGNS * (size / 2)).T, np.ones((1, 8), np.float32)])
-        cam = cam[:3] / cam[3]
-        with np.errstate(all="ignore"):
-            try:
-                inv = np.linalg.inv(E1[e])
-            except np.linalg.LinAlgError:
-                continue
-        if np.isfinite(inv).all() and np.isfinite(cam).all():
-            out[e] = (inv[:3, :3] @ cam + inv[:3, 3:4]).T
-    return out
+    global _PNP_POOL
+    n = len(scale)
+    if n <= 1:
+        return np.stack([np.asarray(_pnp_one(nocs[e], pts2d[e], scale[e], valid[e], K[e], E1[e]), np.float64) for e in range(n)]).reshape(n, 8, 3)
+    if _PNP_POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _PNP_POOL = ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1), thread_name_prefix="adapose-pnp")
+    out = list(_PNP_POOL.map(lambda e: _pnp_one(nocs[e], pts2d[e], scale[e], valid[e], K[e], E1[e]), range(n)))
+    return np.stack([np.asarray(o, np.float64) for o in out])
 
 
 class AdaPoseEstimator_v5(BasePoseEstimator):
