@@ -29,7 +29,9 @@ MUG_CORNER_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]      # rl_pose.py:220-221
 class ViewRing:
     def __init__(self, estimator, num_envs: int, max_steps: int, height: int = 480, width: int = 640):
         self.estimator = estimator
-        self.eng = eng = estimator.estimator
+        if hasattr(estimator, "_ensure_capacity"):
+            estimator._ensure_capacity(num_envs)         # an auto-sized estimator grows its chunk capacity to the ring's batch
+        eng = estimator.estimator
         if not eng.regress_pose:
             raise NotImplementedError("the view ring drives the direct-regression fit (every shipped config)")
         self.num_envs, self.max_steps, self.h, self.w = int(num_envs), int(max_steps), int(height), int(width)
@@ -50,6 +52,10 @@ class ViewRing:
         self._hw = torch.tensor([self.h, self.w, self.h, self.w], dtype=torch.float64, device=dev)
         self.accumulate_steps = 0          # advanced by the caller after add_view, as in the reference (rl_pose.py:116)
         self._adds = 0
+
+    @property
+    def eng(self):
+        return self.estimator.estimator          # looked up per call: an auto-sized estimator may rebuild its engine
 
     # ---- queue state in the reference's host format (small arrays: observations / rewards read them) ----
     @property
