@@ -155,6 +155,25 @@ __device__ __forceinline__ float max_nan(float a, float b) {
     return r;
 }
 
+// fp32 accumulator += fp16 x fp16 with no conversion instruction: the sm_100 mixed-precision FMA (PTX ISA 8.6 `fma.rn.f32.f16`,
+// SASS `FHFMA Rd, Ra.H0|H1, Rb.H0|H1, Rc`; the register-pair moves below fold into the operand selectors).  Measured 114 FMA per
+// clock and SM against 53 for the HADD2.F32 (fp16 -> fp32) + FFMA pair it replaces (tools/micro/fhfma_rate.cu).  The product of two
+// halves is exact in fp32, so the only rounding beyond the fp32 path is that of the fp16 multiplier itself.
+// v[0..7] += half(u's 8 channels) * half(w16's low half)
+__device__ __forceinline__ void fhfma8(const uint4& u, uint32_t w16, float* v) {
+    const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+    unsigned short wl, wh;
+    asm("mov.b32 {%0,%1}, %2;" : "=h"(wl), "=h"(wh) : "r"(w16));
+    (void)wh;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned short lo, hi;
+        asm("mov.b32 {%0,%1}, %2;" : "=h"(lo), "=h"(hi) : "r"(q[k]));
+        asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(v[2 * k]) : "h"(lo), "h"(wl));
+        asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(v[2 * k + 1]) : "h"(hi), "h"(wl));
+    }
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of a kernel: one engine per GPU in the

@@ -1,13 +1,13 @@
 """CUDA-event time of every stereo stage (volume, cost-reg ops, decode pieces, fit) for one chunk.
-usage: python tools/time_stereo_tail.py [chunk_envs] [decode_tc 0|1]"""
+usage: python tools/time_stereo_tail.py [chunk_envs]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rgbmanip_b200 import synth, weights
 from rgbmanip_b200.engine import Engine
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-tc = bool(int(sys.argv[2])) if len(sys.argv) > 2 else True
-eng = Engine(weights.init_state_dict(0), max_envs=E, decode_tc=tc)
+tc = True
+eng = Engine(weights.init_state_dict(0), max_envs=E)
 b = synth.make_batch(E, seed=1, special=False, n_unique=8)
 dev = eng.device
 t = lambda a, dt=None: (torch.from_numpy(np.ascontiguousarray(a)).to(dt) if dt else torch.from_numpy(np.ascontiguousarray(a))).to(dev)
@@ -35,4 +35,4 @@ tot = 0.0
 for k, v in acc.items():
     m = float(np.median(v)); tot += m
     print(f"{k:18s} {m:8.3f} ms  ({m / E * 1e3:7.2f} us/env)")
-print(f"total {tot:.3f} ms for {E} envs, decode_tc={tc}")
+print(f"total {tot:.3f} ms for {E} envs")
