@@ -174,6 +174,12 @@ __device__ __forceinline__ void fhfma8(const uint4& u, uint32_t w16, float* v) {
     }
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, through L1) and the wait for all copies of this thread
+__device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of a kernel: one engine per GPU in the

@@ -163,14 +163,15 @@ build_volume_tile_kernel(const __half* __restrict__ f_ref, const __half* __restr
         const int bx1 = some ? min(box[2], W - 1) : -1, by1 = some ? min(box[3], H - 1) : -1;
         const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
         const bool staged = bw > 0 && bh > 0 && bw * bh <= VT_MAXPX;       // uniform over the block
-        if (staged) {           // a warp per footprint row: bw x 64 contiguous bytes, lane -> (pixel, 16-byte chunk)
+        if (staged) {           // a warp per footprint row (bw x 64 contiguous bytes, lane -> (pixel, 16-byte chunk)), every copy in flight at once;
+                                // through L1: neighbouring planes and tiles re-read most of the footprint (.ca 1.51 ms, .cg 1.65 ms per chunk)
             const int rowq = bw * 4;
             for (int r = warp; r < bh; r += 8) {
                 const uint4* g = reinterpret_cast<const uint4*>(src + ((size_t)(by0 + r) * W + bx0) * C);
                 uint4* st = &stage[lane & 3][r * bw + (lane >> 2)];
-#pragma unroll 4
-                for (int i = lane; i < rowq; i += 32, st += 8) *st = __ldg(g + i);
+                for (int i = lane; i < rowq; i += 32, st += 8) cp_async16_ca(st, g + i);
             }
+            cp_async_wait_all();
         }
         __syncthreads();                         // B: the footprint is staged
         // the other parity's box was last read before B of the previous plane: reset it for the next plane
