@@ -167,6 +167,11 @@ int adp_conv_tc_plan(adp_conv_plan** plan, const adp_act* in, const void* w_hi, 
         p.coalesce = (!off && !ep->out_lo && cout % ch == 0 && ((cout | p.out_cs | p.out_coff) & 7) == 0) ? 1 : 0;
     }
     pl->num_sms = num_sms > 0 ? num_sms : 148;
+    r = tc_conv_finish_epilogue(&pl->layer);
+    if (r != ADP_OK) {
+        delete pl;
+        return r;
+    }
     *plan = pl;
     return ADP_OK;
 }

@@ -631,22 +631,32 @@ struct SlabCfg {
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
     static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : 256;
     static constexpr int EPI_BYTES = 4 * 2048;
+    static constexpr int TILE_BYTES = 128 * BN * 2;               // BULK epilogue: one residual / output tile (16-bit channels)
+    static constexpr int BULK_BYTES = 3 * TILE_BYTES;             // two residual tiles + the output staging tile
     static constexpr int MAX_STAGES = 6;
 };
 
-template <int BN, int KC, int CTAS>
+// BULK (the full-resolution U-Net layer conv11: 64 fp16 channels out, 64-channel skip tensor, one 128-byte row per pixel): the
+// epilogue moves no global memory through registers.  The residual tile (128 rows x 128 B) arrives by TMA into a buffer tied to
+// the accumulator stage, issued by a second producer lane as soon as the epilogue has released that stage, and the result tile
+// leaves through a 128-byte-swizzled staging buffer with one TMA store per epilogue warp (32 rows = a {64 ch, 8 x, 4 y} box).
+// With per-lane loads the kernel sat at 2.6 TB/s on the latency of the residual loads at 8 epilogue warps per SM (ncu: long
+// scoreboard 42 % of the stall samples, 18.75 % occupancy at 168 registers).
+template <int BN, int KC, int CTAS, bool BULK = false>
 __global__ void __launch_bounds__(kTcThreads, CTAS)
-slab_conv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant__ CUtensorMap tmW, const TcConvParams p, int batch) {
+slab_conv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmRes,
+                 const __grid_constant__ CUtensorMap tmOut, const TcConvParams p, int batch) {
     using Cfg = SlabCfg<BN, KC>;
     const int STAGES = p.slab_stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
     uint8_t* wsm = smem + STAGES * stage_bytes;
-    uint4* epi_buf = reinterpret_cast<uint4*>(wsm + p.ntaps * Cfg::W_SLOT);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_buf) + Cfg::EPI_BYTES);
-    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4] weights, then the TMEM base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::MAX_STAGES + 5);
+    uint4* epi_buf = reinterpret_cast<uint4*>(wsm + p.ntaps * Cfg::W_SLOT);       // BULK: [residual tile x 2][output tile], 1 KB aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_buf) + (BULK ? Cfg::BULK_BYTES : Cfg::EPI_BYTES));
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4] weights, [2S+5..2S+7) residual full,
+    // then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::MAX_STAGES + 7);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -658,10 +668,19 @@ slab_conv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_consta
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + 2 + s); };
     const uint32_t w_bar = bar_base + 8u * (2 * Cfg::MAX_STAGES + 4);
+    auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + 5 + s); };
+    const uint32_t res_base = ptx::smem_u32(epi_buf);                 // BULK: residual tile of accumulator stage s at + s * 16 KB
+    const uint32_t obuf_base = res_base + 2u * Cfg::TILE_BYTES;       // BULK: output staging, 4 KB per epilogue warp
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmSlab);
         ptx::prefetch_tmap(&tmW);
+        if (BULK) {
+            ptx::prefetch_tmap(&tmRes);
+            ptx::prefetch_tmap(&tmOut);
+            ptx::mbar_init(rfull_bar(0), 1);
+            ptx::mbar_init(rfull_bar(1), 1);
+        }
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
@@ -704,6 +723,22 @@ slab_conv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_consta
                                  d + p.sloz, b);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+        } else if (BULK && lane == 1) {
+            // second producer: the residual tile of a tile goes to the buffer of its accumulator stage once the epilogue has
+            // released that stage (two tiles of residual in flight per CTA, independent of the slab ring)
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int tx = t % p.tiles_x; t /= p.tiles_x;
+                const int ty = t % p.tiles_y; t /= p.tiles_y;
+                const int d = t % p.D;
+                const int b = t / p.D;
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1, p.err, 36);
+                ptx::mbar_arrive_expect_tx(rfull_bar(as), (uint32_t)Cfg::TILE_BYTES);
+                ptx::tma_load_5d(&tmRes, rfull_bar(as), res_base + (uint32_t)(as * Cfg::TILE_BYTES), 0, tx * p.TW, ty * p.TH, d, b);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-convergent, elected lane) =====================
@@ -745,6 +780,58 @@ slab_conv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_consta
         constexpr bool RES_PREFETCH = BN <= 64;          // residual of the whole tile fits in registers (<= 8 x 16 B per lane)
         const bool res_co = p.coalesce && p.res_hi && !p.res_lo && (p.res_cs & 7) == 0;
         uint4* wbuf = epi_buf + q * 128;
+        if (BULK) {
+            // a lane owns tile row m: 128 bytes at m * 128 of a 128-byte-swizzled tile (16-byte chunk c sits at c ^ (m & 7))
+            const uint32_t rrow = (uint32_t)(m * 128), sw = (uint32_t)(m & 7);
+            const uint32_t orow = obuf_base + rrow;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int tx = t % p.tiles_x; t /= p.tiles_x;
+                const int ty = t % p.tiles_y; t /= p.tiles_y;
+                const int d = t % p.D;
+                const int b = t / p.D;
+                ptx::mbar_wait(tfull_bar(as), aphase, p.err, 35);
+                ptx::mbar_wait(rfull_bar(as), aphase, p.err, 37);
+                ptx::tc_fence_after();
+                if (lane == 0) ptx::bulk_wait_read0();         // the previous tile's store has read this warp's staging rows
+                __syncwarp();
+                const uint32_t rsrc = res_base + (uint32_t)(as * Cfg::TILE_BYTES) + rrow;
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::ACC_STRIDE + c0);
+                    ptx::tmem_ld16(taddr, r);
+                    ptx::tmem_ld16(taddr + 16, r + 16);
+                    float res[32], v[32];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        const uint32_t a = rsrc + ((((uint32_t)(c0 >> 3) + j) ^ sw) << 4);
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a));
+                        tc_unpack8(u, 1, res + 8 * j);
+                    }
+                    ptx::tmem_ld_wait();
+                    tc_epilogue_math<32, true>(p, r, 0, c0, b, v, res);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 o = tc_pack8(v + 8 * j, 1);
+                        const uint32_t a = orow + ((((uint32_t)(c0 >> 3) + j) ^ sw) << 4);
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                    }
+                }
+                // accumulator and residual stage are free again; the staged rows become visible to the TMA unit, one store per warp
+                ptx::tc_fence_before();
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive(tempty_bar(as));
+                    ptx::tma_store_5d(&tmOut, obuf_base + (uint32_t)(q * 4096), 0, tx * p.TW, ty * p.TH + 4 * q, d, b);
+                    ptx::bulk_commit();
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (lane == 0) ptx::bulk_wait0();
+        } else
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int t = tile;
             const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -998,6 +1085,40 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     return ADP_OK;
 }
 
+int tc_conv_finish_epilogue(TcConvLayer* L) {
+    TcConvParams& p = L->p;
+    L->bulk_epi = false;
+    static const bool off = getenv("ADP_NO_BULK_EPI") != nullptr;
+    if (off || !L->slab || L->BN != 64 || L->KC != 16 || p.Cout != 64 || !p.f16 || !p.coalesce) return ADP_OK;
+    if (!p.res_hi || p.res_lo || p.res_cs != 64 || !p.out_hi || p.out_lo || p.out_cs != 64 || p.out_coff != 0) return ADP_OK;
+    if (p.out_f32 || p.out_h16 || p.out_q8 || p.bias_per_batch || p.TW != 8 || p.TH != 16) return ADP_OK;
+    if (((uintptr_t)p.res_hi | (uintptr_t)p.out_hi) & 15) return ADP_OK;
+    // shared memory: the residual / output tiles take the place of the transpose buffers; give up slab stages to stay at 2 CTAs per SM
+    using Cfg = SlabCfg<64, 16>;
+    const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
+    const int fixed = p.ntaps * Cfg::W_SLOT + Cfg::BULK_BYTES + 1024 + 512;
+    int stages = p.slab_stages;
+    while (stages >= 2 && stages * stage_bytes + fixed > 111 * 1024) --stages;
+    if (stages < 2) return ADP_OK;
+    cuuint64_t dims[5] = {64, (cuuint64_t)p.oW, (cuuint64_t)p.oH, (cuuint64_t)p.oD, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {128, (cuuint64_t)p.oW * 128, (cuuint64_t)p.oH * p.oW * 128, (cuuint64_t)p.oD * p.oH * p.oW * 128};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box_r[5] = {64, 8, 16, 1, 1}, box_o[5] = {64, 8, 4, 1, 1};
+    CUresult r = g_encode(&L->tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<bf16*>(p.res_hi), dims, strides, box_r, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+        r = g_encode(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, p.out_hi, dims, strides, box_o, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(residual / output tiles %dx%dx%d) failed: %d", p.oW, p.oH, p.oD, (int)r);
+        return ADP_ERR_CUDA;
+    }
+    p.slab_stages = stages;
+    L->bulk_epi = true;
+    return ADP_OK;
+}
+
 template <int BN, int KC, int FUSED = 0, bool NCAT_EN = false>
 static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
     using Cfg = TcCfg<BN, KC, FUSED, NCAT_EN>;
@@ -1013,19 +1134,20 @@ static int launch_impl(const TcConvLayer* L, int batch, int num_sms, cudaStream_
     return ADP_OK;
 }
 
-template <int BN, int KC, int CTAS>
+template <int BN, int KC, int CTAS, bool BULK = false>
 static int launch_slab(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream) {
     using Cfg = SlabCfg<BN, KC>;
     const TcConvParams& p = L->p;
     const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
-    const int smem = p.slab_stages * stage_bytes + p.ntaps * Cfg::W_SLOT + Cfg::EPI_BYTES + 1024 + 512;
+    const int smem = p.slab_stages * stage_bytes + p.ntaps * Cfg::W_SLOT + (BULK ? Cfg::BULK_BYTES : Cfg::EPI_BYTES) + 1024 + 512;
     static int attr[kMaxDevices];
-    ADP_TRY(ensure_dyn_smem(slab_conv_kernel<BN, KC, CTAS>, smem, attr));
+    ADP_TRY(ensure_dyn_smem(slab_conv_kernel<BN, KC, CTAS, BULK>, smem, attr));
     const long long total = (long long)batch * p.D * p.tiles_y * p.tiles_x;
     const long long slots = (long long)num_sms * CTAS;
     const int grid = (int)(total < slots ? total : slots);
     if (grid <= 0) return ADP_OK;
-    slab_conv_kernel<BN, KC, CTAS><<<grid, kTcThreads, smem, stream>>>(L->tmSlab, L->tmW_hi, p, batch);
+    slab_conv_kernel<BN, KC, CTAS, BULK><<<grid, kTcThreads, smem, stream>>>(L->tmSlab, L->tmW_hi, BULK ? L->tmRes : L->tmSlab,
+                                                                             BULK ? L->tmOut : L->tmSlab, p, batch);
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
 }
@@ -1036,6 +1158,7 @@ int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t st
     if (L->slab) {
         if (L->BN == 16 && L->KC == 16) return launch_slab<16, 16, 2>(L, batch, num_sms, stream);
         if (L->BN == 16 && L->KC == 64) return launch_slab<16, 64, 2>(L, batch, num_sms, stream);
+        if (L->BN == 64 && L->KC == 16 && L->bulk_epi) return launch_slab<64, 16, 2, true>(L, batch, num_sms, stream);
         if (L->BN == 64 && L->KC == 16) return launch_slab<64, 16, 2>(L, batch, num_sms, stream);   // (3 CTAs per SM spill: 1.5 -> 1.9 ms)
         if (L->BN == 32 && L->KC == 32) return launch_slab<32, 32, 2>(L, batch, num_sms, stream);
         set_last_error("no slab conv instantiation for BN=%d KC=%d", L->BN, L->KC);

@@ -67,6 +67,9 @@ struct TcConvLayer {
     bool fused = false;      // split precision with hi and lo operands sharing a pipeline stage
     bool slab = false;       // one halo slab per tile, taps by descriptor offsets, weights resident (slab_conv_kernel)
     CUtensorMap tmSlab;
+    bool bulk_epi = false;   // slab mode, 64 fp16 channels in and out with a 64-channel residual: residual tiles arrive by TMA, results
+                             // leave by TMA store (tc_conv_finish_epilogue decides)
+    CUtensorMap tmRes, tmOut;
     bool ready = false;
 };
 
@@ -83,6 +86,8 @@ struct TcGeom {             // non-standard geometries (NULL = stride-1 "same" c
 
 int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_lo, int Cout, int kd, int ks,
                  int dil, int npass, const TcGeom* geom, int f16);
+// after the epilogue fields of L->p are set: picks the TMA epilogue where it applies and encodes its tensor maps
+int tc_conv_finish_epilogue(TcConvLayer* L);
 int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t stream);
 
 }  // namespace adp

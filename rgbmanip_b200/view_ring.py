@@ -32,8 +32,9 @@ class ViewRing:
         if hasattr(estimator, "_ensure_capacity"):
             estimator._ensure_capacity(num_envs)         # an auto-sized estimator grows its chunk capacity to the ring's batch
         eng = estimator.estimator
-        if not eng.regress_pose:
-            raise NotImplementedError("the view ring drives the direct-regression fit (every shipped config)")
+        if getattr(eng, "branch_c", False) or getattr(eng, "arch", "v5") != "v5":
+            raise NotImplementedError("the view ring drives the cost-volume head with the direct-regression fit (every shipped config) "
+                                      "or the RANSAC + Umeyama fit (direct_regression=False, use_depth=True)")
         self.num_envs, self.max_steps, self.h, self.w = int(num_envs), int(max_steps), int(height), int(width)
         self.device = eng.device
         T, N, S, P = self.max_steps, self.num_envs, eng.S, eng.P
@@ -141,8 +142,10 @@ class ViewRing:
             out.append(torch.where(m, ring, torch.full_like(ring, -1)).max(0).values)
         return torch.stack(out)
 
-    def get_estimation(self, return_tensor: bool = False):
-        """rl_pose.py:189-223 -> [N,8,3] float64 world-frame boxes (sentinel where an env has no valid view pair)."""
+    def get_estimation(self, return_tensor: bool = False, ransac_idx=None):
+        """rl_pose.py:189-223 -> [N,8,3] float64 world-frame boxes (sentinel where an env has no valid view pair).
+        ``ransac_idx`` ([N,128,5] int32, optional) replays given RANSAC draws of the Umeyama fit (direct_regression=False);
+        by default they come from the device hash, as in ``estimate()``."""
         eng, N = self.eng, self.num_envs
         E = eng.E
         out = torch.empty((N, 8, 3), dtype=torch.float64, device=self.device)
@@ -165,7 +168,10 @@ class ViewRing:
                     eng.choose[o:o + n].copy_(self.choose[sc, idx])
                     eng.valid[o:o + n].copy_(self.valid[sc, idx] * have.to(torch.uint8))
                     ext.append(self.extrinsic[sc, idx].contiguous())
-                eng.stereo(n, ext[0], ext[1])
+                ridx = None
+                if ransac_idx is not None and not eng.regress_pose:
+                    ridx = torch.as_tensor(np.ascontiguousarray(ransac_idx[lo:hi])).to(torch.int32).to(self.device)
+                eng.stereo(n, ext[0], ext[1], ransac_idx=ridx, seed=7919 * self._adds + lo)
                 out[lo:hi].copy_(eng.bbox[:n])
             if self.estimator.cfg.get("task_name") == "mugs":
                 out = out[:, MUG_CORNER_ORDER]

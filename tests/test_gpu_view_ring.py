@@ -14,11 +14,11 @@ from rgbmanip_b200 import synth, weights
 pytestmark = [pytest.mark.gpu, pytest.mark.filterwarnings("ignore")]
 
 
-def _estimator(max_envs, task="one_drawer_cabinet"):
+def _estimator(max_envs, task="one_drawer_cabinet", direct=True):
     from rgbmanip_b200.estimator import AdaPoseEstimator_v5
     cfg = {"name": "adapose_v5", "task_name": task, "load": False, "img_size": 224, "use_depth": True, "n_pts": 1024,
-           "direct_regression": True, "real_world": False}
-    return AdaPoseEstimator_v5(None, cfg, None, state_dict=weights.init_state_dict(0), max_envs=max_envs)
+           "direct_regression": direct, "real_world": False}
+    return AdaPoseEstimator_v5(None, cfg, None, state_dict=weights.init_state_dict(0, regress_pose=direct), max_envs=max_envs)
 
 
 def test_queue_state_matches_reference_controller(golden_dir):
@@ -85,6 +85,29 @@ def test_ring_estimation_equals_estimator_on_paired_frames():
                 np.testing.assert_array_equal(want[e], O.DEFAULT_BBOX)
             else:
                 np.testing.assert_allclose(got[e], want[e], rtol=0, atol=2e-5)     # same kernels, same inputs (atomics order only)
+    est.estimator.close()
+
+
+def test_ring_branch_b_equals_estimator_on_paired_frames():
+    """The ring with the RANSAC + Umeyama fit (direct_regression=False, use_depth=True; interface_v5.py:322-338): the same
+    boxes as estimate() on the paired frames, given the same pixel subsets and the same RANSAC draws."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbmanip_b200.view_ring import ViewRing
+    N = 3
+    est = _estimator(2, direct=False)                     # chunk of 2 < 3 envs
+    ring = ViewRing(est, N, 4)
+    b = synth.make_batch(N, seed=31, special=False)
+    for rgb, m, E in ((b.rgb1, b.mask1, b.E1), (b.rgb2, b.mask2, b.E2)):
+        ring.add_view({"camera0": {"Color": rgb, "Mask": m, "Intrinsic": b.K, "Extrinsic": E}}, np.zeros((N, 7)))
+        ring.accumulate_steps += 1
+    ridx = np.random.default_rng(3).integers(0, 1024, size=(N, 128, 5)).astype(np.int32)
+    got = ring.get_estimation(ransac_idx=ridx)
+    ch = ring.choose.cpu().numpy()
+    want = est.estimate(b.K, b.rgb1, b.mask1, b.E1, b.rgb2, b.mask2, b.E2, choose=(ch[0], ch[1]), ransac_idx=ridx)
+    assert not np.array_equal(want[0], O.DEFAULT_BBOX)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+    assert ring.get_estimation().shape == (N, 8, 3)       # device-drawn samples
     est.estimator.close()
 
 
