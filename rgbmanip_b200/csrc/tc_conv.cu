@@ -287,6 +287,21 @@ __device__ __forceinline__ void tc_epilogue_store_warp(const TcConvParams& p, co
         for (int j = 0; j < NP16; ++j) pc[j] = tc_pack8(v + 8 * j, p.f16);
         tc_store_rows<NP16>(wbuf, lane, pc, pix, validmask, reinterpret_cast<uint8_t*>(p.out_hi), (size_t)p.out_cs * 2,
                             (size_t)(p.out_coff + nbase) * 2);
+        if (p.out_lo && !p.f16) {     // bf16 split precision: lo = bf16(v - hi), the same pitch and offset (the per-point MLPs)
+#pragma unroll
+            for (int j = 0; j < NP16; ++j) {
+                const uint32_t hw[4] = {pc[j].x, pc[j].y, pc[j].z, pc[j].w};
+                float l[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    l[2 * q] = v[8 * j + 2 * q] - __uint_as_float(hw[q] << 16);
+                    l[2 * q + 1] = v[8 * j + 2 * q + 1] - __uint_as_float(hw[q] & 0xffff0000u);
+                }
+                pc[j] = tc_pack8(l, 0);
+            }
+            tc_store_rows<NP16>(wbuf, lane, pc, pix, validmask, reinterpret_cast<uint8_t*>(p.out_lo), (size_t)p.out_cs * 2,
+                                (size_t)(p.out_coff + nbase) * 2);
+        }
     }
     if (CH == 32 && p.out_q8) {       // fp8 twin (value / 2, e4m3) for the low-order pass of the consuming layer: 32 bytes per row
         uint4 pc[2];
