@@ -341,11 +341,23 @@ int upsample2x(const Act& in, const Act& out, int batch, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // One low-resolution row of q, columns [col0, col0 + ncols), staged in shared memory: [col][9 C channels] 16-bit, column pitch padded
 // by 16 bytes (9 C * 2 is a multiple of 128: without the pad the columns of different threads would share banks).
-template <bool SPLIT>
+template <bool SPLIT, bool F16>
 __device__ __forceinline__ void upconv_fold_row(const uint4* __restrict__ st_hi, const uint4* __restrict__ st_lo, int pitch16, int tap0, int C8,
-                                                int cg, const int (&xo)[3][2], const float (&xw)[3][2], int f16, float* H) {
+                                                int cg, const int (&xo)[3][2], const float (&xw)[3][2], const uint32_t (&xn)[3][2], int f16,
+                                                float* H) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) H[j] = 0.f;
+    if (F16) {
+        // fp16 plane: the mixed-precision FMA takes the stored halves as they are (no conversions: half the instructions of this
+        // loop).  Its multiplier is fp16 too, so the weights are the integer numerators of k / (Wo - 1) (exact in fp16, exact
+        // products, fp32 accumulation); the common denominator is folded into the vertical coefficients.
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) fhfma8(st_hi[xo[dx][j] * pitch16 + (tap0 + dx) * C8 + cg], xn[dx][j], H);
+        }
+        return;
+    }
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
@@ -378,7 +390,7 @@ constexpr int UPB_MAX_STRIP = 64;      // output rows a block walks at most (sha
 // Block = 256 threads = (256 / (C/8)) consecutive output columns x C/8 channel groups; it walks a strip of output rows.  The q rows
 // it needs come through a two-deep shared-memory ring filled with cp.async: every q element is fetched once per block (the
 // direct version had each of them fetched by ~4 threads of different warps: 7 TB/s of L2 traffic, the kernel's bound).
-template <bool SPLIT>
+template <bool SPLIT, bool F16>
 __global__ void __launch_bounds__(256, 2)
 upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
                     uint8_t* __restrict__ out_q8, const float* __restrict__ bias, float slope, int h, int w, int C, int f16, int strip,
@@ -400,7 +412,9 @@ upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo
         const bool in = Yt >= 0 && Yt < Ho;
         lin_coord(in ? Yt : Y, h, Ho, &y0, &y1, &wy);
         const int k0 = y0 - rb, k1 = y1 - rb;          // k0 in {0, 1}, k1 in {k0, k0 + 1}: rows Y - 1 .. Y + 1 span < 1 low-resolution row
-        for (int k = 0; k < 3; ++k) s_cf[yy][dy * 3 + k] = in ? ((k == k0 ? 1.f - wy : 0.f) + (k == k1 ? wy : 0.f)) : 0.f;
+        // (fp16 plane: the horizontal fold works with integer numerators over Wo - 1, see upconv_fold_row)
+        const float hs = (F16 && Wo > 1) ? 1.f / (float)(Wo - 1) : 1.f;
+        for (int k = 0; k < 3; ++k) s_cf[yy][dy * 3 + k] = in ? hs * ((k == k0 ? 1.f - wy : 0.f) + (k == k1 ? wy : 0.f)) : 0.f;
         if (dy == 0) s_rb[yy] = rb;
     }
     __syncthreads();
@@ -421,6 +435,7 @@ upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo
     // horizontal taps of this thread's column: staged column index and weight of X - 1, X, X + 1 (weight 0 outside the image)
     int xo[3][2];
     float xw[3][2];
+    uint32_t xn[3][2];
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
         const int Xt = X + dx - 1;
@@ -430,6 +445,10 @@ upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo
         lin_coord(in ? Xt : min(X, Wo - 1), w, Wo, &x0, &x1, &wx);
         xo[dx][0] = in ? x0 - col0 : 0; xo[dx][1] = in ? x1 - col0 : 0;
         xw[dx][0] = in ? 1.f - wx : 0.f; xw[dx][1] = in ? wx : 0.f;
+        // wx = k / (Wo - 1) up to float rounding: the integer numerators as fp16 multipliers
+        const int n1 = __float2int_rn(wx * (float)(Wo - 1));
+        xn[dx][0] = in ? (uint32_t)__half_as_ushort(__int2half_rn(Wo - 1 - n1)) : 0u;
+        xn[dx][1] = in ? (uint32_t)__half_as_ushort(__int2half_rn(n1)) : 0u;
     }
     float bv[8];
 #pragma unroll
@@ -456,7 +475,7 @@ upconv_blend_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo
         __syncthreads();
         const uint4* st = upb_stage + (n_done & 1) * buf16;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) upconv_fold_row<SPLIT>(st, st + plane16, pitch16, dy * 3, C8, cg, xo, xw, f16, H[dy][k]);
+        for (int dy = 0; dy < 3; ++dy) upconv_fold_row<SPLIT, F16>(st, st + plane16, pitch16, dy * 3, C8, cg, xo, xw, xn, f16, H[dy][k]);
         __syncthreads();                                           // the slot may be refilled by the load issued in the next call
         ++n_done;
     };
@@ -513,14 +532,18 @@ int upconv_blend(const Act& q, const Act& out, const float* bias, float slope, i
     const int xblocks = (out.W + XB - 1) / XB;
     while (strip > 8 && (size_t)batch * xblocks * ((out.H + strip - 1) / strip) < 4 * 148) strip = (strip + 1) / 2;
     const dim3 grid(xblocks, (out.H + strip - 1) / strip, batch);
-    static int attr_s[kMaxDevices], attr_h[kMaxDevices];
+    static int attr_s[kMaxDevices], attr_h[kMaxDevices], attr_f[kMaxDevices];
     if (split) {
-        ADP_TRY(ensure_dyn_smem(upconv_blend_kernel<true>, smem, attr_s));
-        upconv_blend_kernel<true><<<grid, 256, smem, stream>>>(q.hi, q.lo, out.hi, out.lo, nullptr, bias, slope, q.H, q.W, out.C, 0, strip, ncols_max);
+        ADP_TRY(ensure_dyn_smem(upconv_blend_kernel<true, false>, smem, attr_s));
+        upconv_blend_kernel<true, false><<<grid, 256, smem, stream>>>(q.hi, q.lo, out.hi, out.lo, nullptr, bias, slope, q.H, q.W, out.C, 0, strip, ncols_max);
+    } else if (q.f16) {
+        ADP_TRY(ensure_dyn_smem(upconv_blend_kernel<false, true>, smem, attr_f));
+        upconv_blend_kernel<false, true><<<grid, 256, smem, stream>>>(q.hi, nullptr, out.hi, out.lo, out.q8, bias, slope, q.H, q.W, out.C, 1, strip,
+                                                                      ncols_max);
     } else {
-        ADP_TRY(ensure_dyn_smem(upconv_blend_kernel<false>, smem, attr_h));
-        upconv_blend_kernel<false><<<grid, 256, smem, stream>>>(q.hi, nullptr, out.hi, out.lo, out.f16 ? out.q8 : nullptr, bias, slope, q.H, q.W,
-                                                                out.C, q.f16, strip, ncols_max);
+        ADP_TRY(ensure_dyn_smem(upconv_blend_kernel<false, false>, smem, attr_h));
+        upconv_blend_kernel<false, false><<<grid, 256, smem, stream>>>(q.hi, nullptr, out.hi, out.lo, nullptr, bias, slope, q.H, q.W, out.C, 0, strip,
+                                                                       ncols_max);
     }
     ADP_CUDA(cudaGetLastError());
     return ADP_OK;
