@@ -55,7 +55,7 @@ typedef struct adp_act {      /* channels-last activation [B, D, H, W, C]; D == 
 } adp_act;
 
 typedef struct adp_tc_geom {  /* non-default geometry of a tcgen05 conv: explicit tap table and grid mapping */
-    int32_t ntaps;            /* <= 28 */
+    int32_t ntaps;            /* <= 32 */
     int8_t dz[32], dy[32], dx[32], wt[32];   /* input offset of each tap (after in_mul scaling) and its weight slab */
     int32_t in_mul;           /* input coord = tile coord * in_mul + offset: 2 for stride-2 convs */
     int32_t out_mul, out_oz, out_oy, out_ox; /* output coord = tile coord * out_mul + offset: 2 / parity for transposed convs */

@@ -1042,7 +1042,7 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
     }
     L->fused = (npass >= 2) && (BN <= g_fuse_max_bn) && KC >= 16;
     ADP_CHECK_ARG(npass != 4 || (BN == 256 || BN == 128 || BN == 64), "fp16 + fp8 low-order pass: Cout tile of 64, 128 or 256");
-    // slab mode: single K chunk, single pass, small N, unit strides, a tap window of at most 3 per axis, 8 | W
+    // slab mode: single K chunk, single pass, small N, unit strides, a tap window of at most 3 planes x 4 x 4, 8 | W
     L->slab = false;
     {
         static const bool off = getenv("ADP_NO_SLAB") != nullptr;
@@ -1052,9 +1052,10 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
             for (int a = 0; a < 3; ++a) { lo[a] = o[a] < lo[a] ? o[a] : lo[a]; hi[a] = o[a] > hi[a] ? o[a] : hi[a]; }
         }
         const bool shape_ok = (BN == 16 && (KC == 16 || KC == 64)) || (BN == 64 && KC == 16) || (BN == 32 && KC == 32);
-        if (!off && in.D > 1 && p.kchunks == 1 && npass == 1 && coutPad == BN && shape_ok && p.in_mul == 1 && p.out_mul == 1 &&
+        // (2-D maps qualify too: the s2d stem runs here as 2 x 16 taps - hi and lo weight slabs of the same 4 x 4 window)
+        if (!off && p.kchunks == 1 && npass == 1 && coutPad == BN && shape_ok && p.in_mul == 1 && p.out_mul == 1 &&
             p.out_oz == 0 && p.out_oy == 0 && p.out_ox == 0 && p.W % 8 == 0 && p.ntaps >= 4 &&
-            hi[0] - lo[0] <= 2 && hi[1] - lo[1] <= 2 && hi[2] - lo[2] <= 2) {
+            hi[0] - lo[0] <= 2 && hi[1] - lo[1] <= 3 && hi[2] - lo[2] <= 3) {
             p.TW = 8; p.TH = 16;
             p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
             p.sSX = 8 + hi[2] - lo[2]; p.sSY = 16 + hi[1] - lo[1]; p.sSZ = 1 + hi[0] - lo[0];

@@ -17,7 +17,7 @@
 
 namespace adp {
 
-constexpr int kTcMaxTaps = 28;
+constexpr int kTcMaxTaps = 32;
 
 struct TcConvParams {
     int B, D, H, W;          // tile-space extent: the grid the M tiles walk over (output grid for convs, input grid for

@@ -252,8 +252,16 @@ class Engine:
         s2d = self._act(F, S // 2, S // 2, 16)
         ops.append(("pack_s2d", lambda b, o=s2d: L.check(
             self.lib.adp_pack_s2d(L.ptr(self.crops), C.byref(o.c), b, S, self.stream), "pack_s2d")))
-        ops.append(("conv1", self._tc_plans(s2d, G.stem_s2d_weights(w), 64, 1, 4, 1, self.npass,
-                                            self._epilogue(c1, act=L.ACT_RELU), [G.stem_s2d(S)])))
+        wst = G.stem_s2d_weights(w)
+        if s2d.f16 and self.npass == 2 and S % 32 == 0:
+            # fp16 hi + lo weights as 2 x 16 taps of a single pass on the slab kernel (geometry.stem_s2d_split)
+            w_hi = wst.to(torch.float16).float()
+            w_lo = (wst - w_hi).to(torch.float16).float()
+            ops.append(("conv1", self._tc_plans(s2d, torch.cat([w_hi, w_lo], 0), 64, 1, 4, 1, 1,
+                                                self._epilogue(c1, act=L.ACT_RELU), [G.stem_s2d_split(S)])))
+        else:
+            ops.append(("conv1", self._tc_plans(s2d, wst, 64, 1, 4, 1, self.npass,
+                                                self._epilogue(c1, act=L.ACT_RELU), [G.stem_s2d(S)])))
         mp = self._act(F, S // 4, S // 4, 64)
         ops.append(("maxpool", lambda b, a=c1, o=mp: L.check(
             self.lib.adp_maxpool3x3s2(C.byref(a.c), C.byref(o.c), b, self.stream), "maxpool")))

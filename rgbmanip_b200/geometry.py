@@ -6,7 +6,7 @@ from . import _lib as L
 
 def _fill(g, taps):
     g.ntaps = len(taps)
-    assert g.ntaps <= 28
+    assert g.ntaps <= 32
     for i, (dz, dy, dx, wt) in enumerate(taps):
         g.dz[i], g.dy[i], g.dx[i], g.wt[i] = dz, dy, dx, wt
     return g
@@ -61,6 +61,18 @@ def stem_s2d(S):
     g.gD, g.gH, g.gW = 1, S // 2, S // 2
     g.oD, g.oH, g.oW = 1, S // 2, S // 2
     g.w_taps = 16
+    return g
+
+
+def stem_s2d_split(S):
+    """stem_s2d with the fp16 weight split unrolled into the tap table: taps 0..15 read the hi slabs, taps 16..31 the lo slabs of
+    the same window, so that the single-pass slab kernel (one halo slab per tile, all 32 weight slabs resident) computes
+    A W_hi + A W_lo in one accumulator.  The generic kernel moves 16 x 128 rows of 32 bytes per tile and pass and is bound by the
+    TMA unit's rows per cycle (0.40 ms per 148 frames); the slab is 209 rows."""
+    g = stem_s2d(S)
+    taps = [(0, ty - 2, tx - 2, h * 16 + ty * 4 + tx) for h in range(2) for ty in range(4) for tx in range(4)]
+    _fill(g, taps)
+    g.w_taps = 32
     return g
 
 
