@@ -1064,11 +1064,16 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
             const int stage_bytes = (p.slab_bytes + 1023) & ~1023;
             const int w_slot = (BN * KC * 2 + 1023) / 1024 * 1024;
             const int fixed = p.ntaps * w_slot + 8192 + 1024 + 512;
-            const int ctas = 2;                                       // CTAs per SM (see tc_conv_launch)
+            int ctas = 2;                                             // CTAs per SM (see tc_conv_launch)
             int stages = (220 * 1024 / ctas - fixed) / stage_bytes;
+            if (stages < 2 && BN == 32 && KC == 32) {                 // conv4 (32 -> 32, 35 KB slabs + 54 KB of weights): one CTA per SM
+                ctas = 1;
+                stages = (220 * 1024 - fixed) / stage_bytes;
+            }
             stages = stages > 6 ? 6 : stages;
             if (stages >= 2) {
                 p.slab_stages = stages;
+                L->slab_ctas = ctas;
                 cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.D, (cuuint64_t)in.B};
                 cuuint64_t strides[4] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2,
                                          (cuuint64_t)in.D * in.H * in.W * in.C * 2};
@@ -1176,6 +1181,7 @@ int tc_conv_launch(const TcConvLayer* L, int batch, int num_sms, cudaStream_t st
         if (L->BN == 16 && L->KC == 64) return launch_slab<16, 64, 2>(L, batch, num_sms, stream);
         if (L->BN == 64 && L->KC == 16 && L->bulk_epi) return launch_slab<64, 16, 2, true>(L, batch, num_sms, stream);
         if (L->BN == 64 && L->KC == 16) return launch_slab<64, 16, 2>(L, batch, num_sms, stream);   // (3 CTAs per SM spill: 1.5 -> 1.9 ms)
+        if (L->BN == 32 && L->KC == 32 && L->slab_ctas == 1) return launch_slab<32, 32, 1>(L, batch, num_sms, stream);
         if (L->BN == 32 && L->KC == 32) return launch_slab<32, 32, 2>(L, batch, num_sms, stream);
         set_last_error("no slab conv instantiation for BN=%d KC=%d", L->BN, L->KC);
         return ADP_ERR_ARG;

@@ -67,6 +67,7 @@ struct TcConvLayer {
     bool fused = false;      // split precision with hi and lo operands sharing a pipeline stage
     bool slab = false;       // one halo slab per tile, taps by descriptor offsets, weights resident (slab_conv_kernel)
     CUtensorMap tmSlab;
+    int slab_ctas = 2;       // CTAs per SM the slab stages were sized for
     bool bulk_epi = false;   // slab mode, 64 fp16 channels in and out with a 64-channel residual: residual tiles arrive by TMA, results
                              // leave by TMA store (tc_conv_finish_epilogue decides)
     CUtensorMap tmRes, tmOut;
