@@ -50,7 +50,7 @@ GF_COSTREG_PER_VIEW = 24.4506e9
 BYTES_VOLUME_COSTREG_PER_ENV = 302.7e6
 BYTES_DECODE_GATHER_PER_ENV = 1024 * (3 * 3 * 26 * 16 + 24 * 4 * 128 + 128 + 4 + 4 + 2 * 128 * 2)
 # "profile constants": figures of an ncu capture of one chunk (not of this run); the launch list they come from is committed
-NCU_PROFILE = {"fp16f8": {"dram_bytes_per_frame": 13287.2e6 / 148, "tensor_pipe_active": 0.643, "src": "profiles/r02c_chunk_by_kernel.csv"},
+NCU_PROFILE = {"fp16f8": {"dram_bytes_per_frame": 13312.8e6 / 148, "tensor_pipe_active": 0.660, "src": "profiles/r02d_chunk_launches.csv"},
                "fp16x2": {"dram_bytes_per_frame": 11141.8e6 / 148, "tensor_pipe_active": 0.720, "src": "profiles/r01_chunk_by_kernel.csv"},
                "bf16x3": {"dram_bytes_per_frame": 18958.8e6 / 128, "tensor_pipe_active": 0.712, "src": "profiles/r01_bf16x3_backbone_tc_summary.csv"}}
 CFG = {"name": "adapose_v5", "task_name": "one_drawer_cabinet", "load": False, "img_size": 224, "use_depth": True,
