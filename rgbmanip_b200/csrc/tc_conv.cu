@@ -1109,7 +1109,7 @@ int tc_conv_plan(TcConvLayer* L, const Act& in, const bf16* w_hi, const bf16* w_
 int tc_conv_finish_epilogue(TcConvLayer* L) {
     TcConvParams& p = L->p;
     L->bulk_epi = false;
-    static const bool off = getenv("ADP_NO_BULK_EPI") != nullptr;
+    const bool off = getenv("ADP_NO_BULK_EPI") != nullptr;        // read per plan: the A/B test builds one engine each way
     if (off || !L->slab || L->BN != 64 || L->KC != 16 || p.Cout != 64 || !p.f16 || !p.coalesce) return ADP_OK;
     if (!p.res_hi || p.res_lo || p.res_cs != 64 || !p.out_hi || p.out_lo || p.out_cs != 64 || p.out_coff != 0) return ADP_OK;
     if (p.out_f32 || p.out_h16 || p.out_q8 || p.bias_per_batch || p.TW != 8 || p.TH != 16) return ADP_OK;

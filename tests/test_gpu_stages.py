@@ -595,6 +595,38 @@ def test_volume_tiled_fp16_features(G, case):
         assert float(diff.max()) < 0.02 and float(diff.mean()) < 1e-3, (d, float(diff.max()), float(diff.mean()))   # fp16 storage of O(1..5) values
 
 
+def test_conv11_tma_epilogue_is_bit_identical(G, monkeypatch):
+    """conv11 on the slab kernel with the TMA epilogue (residual tiles by TMA load, results by TMA store through a swizzled
+    staging tile) against the per-lane epilogue it replaces (ADP_NO_BULK_EPI): the same arithmetic per element, so the
+    s2d output tensor must agree bit for bit, and with it every later stage."""
+    from rgbmanip_b200.engine import Engine
+    sd = weights.init_state_dict(0)
+    batch, views = _stereo_inputs(3)
+    outs = []
+    for bulk in (True, False):
+        if bulk:
+            monkeypatch.delenv("ADP_NO_BULK_EPI", raising=False)
+        else:
+            monkeypatch.setenv("ADP_NO_BULK_EPI", "1")
+        eng = Engine(sd, device=G.DEV, max_envs=2, debug=True)
+        g = torch.Generator().manual_seed(5)
+        feat = torch.randn((4, 224, 224, 32), generator=g) * 0.5
+        eng.feat.copy_(feat)
+        eng.feat16.copy_(eng.feat)
+        eng.choose[:2].copy_(torch.from_numpy(np.stack([v[0][1] for v in views])).to(torch.int32))
+        eng.Kp[:2].copy_(torch.from_numpy(np.stack([v[0][3] for v in views]).reshape(2, 9)))
+        eng.Kp[2:4].copy_(torch.from_numpy(np.stack([v[1][3] for v in views]).reshape(2, 9)))
+        eng.valid.fill_(1)
+        eng.stereo(2, torch.from_numpy(batch.E1).to(G.DEV), torch.from_numpy(batch.E2).to(G.DEV))
+        torch.cuda.synchronize()
+        eng.check_error_flag()
+        outs.append((eng.cr_taps["conv11"].value().cpu().clone(), eng.bbox.cpu().clone()))
+        eng.close()
+    assert float(outs[0][0].abs().max()) > 0
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 def _run_costreg_decode(G, sd, eng_kw):
     from rgbmanip_b200.engine import Engine
     eng = Engine(sd, device=G.DEV, max_envs=2, debug=True, **eng_kw)
