@@ -278,6 +278,12 @@ upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo
     float wx;
     lin_coord(X, W, Wo, &x0, &x1, &wx);
     const int cx0 = (x0 - ix0) * 8 + g, cx1 = (x1 - ix0) * 8 + g;
+    // fp16 plane: the x interpolation runs on the mixed-precision FMA (no conversions).  Its weights are k / (Wo - 1): the integer
+    // numerators are exact fp16 multipliers, the denominator is folded into the y weights (see upconv_fold_row).
+    const bool fast = !SPLIT && f16;
+    const int n1x = __float2int_rn(wx * (float)(Wo - 1));
+    const uint32_t xn0 = __half_as_ushort(__int2half_rn(Wo - 1 - n1x)), xn1 = __half_as_ushort(__int2half_rn(n1x));
+    const float xs = 1.f / (float)(Wo - 1);
 #pragma unroll 2
     for (int r = r0; r < UP_T; r += 2) {
         const int Y = Y0 + r;
@@ -286,6 +292,20 @@ upsample2x_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo
         float wy;
         lin_coord(Y, H, Ho, &y0, &y1, &wy);
         const int ry0 = (y0 - iy0) * UP_IN * 8, ry1 = (y1 - iy0) * UP_IN * 8;
+        if (fast) {
+            float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, u[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[8];
+            fhfma8(tile[ry0 + cx0], xn0, t);
+            fhfma8(tile[ry0 + cx1], xn1, t);
+            fhfma8(tile[ry1 + cx0], xn0, u);
+            fhfma8(tile[ry1 + cx1], xn1, u);
+            const float w0 = (1.f - wy) * xs, w1 = wy * xs;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(w1, u[j], w0 * t[j]);
+            const size_t oo = (((size_t)b * Ho + Y) * Wo + X) * C + c0 + g * 8;
+            st8(out_hi, out_lo, oo, o, f16);
+            if (out_q8) *reinterpret_cast<uint2*>(out_q8 + oo) = pack8_q8(o);
+            continue;
+        }
         float a[8], bq[8], c[8], d[8], o[8];
         up_unpack8(tile[ry0 + cx0], a, !SPLIT && f16);
         up_unpack8(tile[ry0 + cx1], bq, !SPLIT && f16);
