@@ -49,6 +49,30 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in_hi, const bf16* 
         const int ox = (int)(t % Wo); t /= Wo;
         const int oy = (int)(t % Ho);
         const int b = (int)(t / Ho);
+        if (f16) {        // a single fp16 plane: the maximum is exact on packed halves (max.NaN.f16x2), no conversions
+            __half2 hm[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hm[j] = __half2half2(__ushort_as_half((unsigned short)0xfc00u));      // -inf
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = oy * 2 - 1 + ky;
+                if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ox * 2 - 1 + kx;
+                    if (ix < 0 || ix >= Wi) continue;
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in_hi + (((size_t)b * Hi + iy) * Wi + ix) * C + c));
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hm[j] = __hmax2_nan(hm[j], *reinterpret_cast<const __half2*>(&w[j]));
+                }
+            }
+            uint4 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&hm[0]); o.y = *reinterpret_cast<const uint32_t*>(&hm[1]);
+            o.z = *reinterpret_cast<const uint32_t*>(&hm[2]); o.w = *reinterpret_cast<const uint32_t*>(&hm[3]);
+            *reinterpret_cast<uint4*>(out_hi + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
+            continue;
+        }
         float m[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
