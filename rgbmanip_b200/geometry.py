@@ -65,12 +65,13 @@ def stem_s2d(S):
 
 
 def stem_s2d_split(S):
-    """stem_s2d with the fp16 weight split unrolled into the tap table: taps 0..15 read the hi slabs, taps 16..31 the lo slabs of
-    the same window, so that the single-pass slab kernel (one halo slab per tile, all 32 weight slabs resident) computes
-    A W_hi + A W_lo in one accumulator.  The generic kernel moves 16 x 128 rows of 32 bytes per tile and pass and is bound by the
-    TMA unit's rows per cycle (0.40 ms per 148 frames); the slab is 209 rows."""
+    """stem_s2d with the fp16 weight split unrolled into the tap table: every window position appears twice, reading weight slab t
+    (hi) and then 16 + t (lo), so that the single-pass slab kernel (one halo slab per tile, all 32 weight slabs resident) computes
+    A W_hi + A W_lo in one accumulator IN THE ORDER of the two-pass generic kernel (per K step: hi, then lo).  The generic kernel
+    moves 16 x 128 rows of 32 bytes per tile and pass and is bound by the TMA unit's rows per cycle (0.40 ms per 148 frames); the
+    slab is 209 rows."""
     g = stem_s2d(S)
-    taps = [(0, ty - 2, tx - 2, h * 16 + ty * 4 + tx) for h in range(2) for ty in range(4) for tx in range(4)]
+    taps = [(0, ty - 2, tx - 2, h * 16 + ty * 4 + tx) for ty in range(4) for tx in range(4) for h in range(2)]
     _fill(g, taps)
     g.w_taps = 32
     return g
