@@ -12,10 +12,11 @@ namespace adp {
 // The plane-sweep gather reads every source pixel ~4 times (once per bilinear footprint that covers it); done per voxel
 // from global memory that is 256 B of L2 traffic per 64 B written, and the kernel is L2-bandwidth bound.  Here the
 // source footprint of the tile at one depth (the bounding box of its 256 sample cells, found with a block min/max) is
-// staged in shared memory once and the four corners are read from there; the reference features stay in registers
-// across the depth loop.  A footprint larger than the staging buffer (strong rotation / scale between the views) falls
-// back to the direct gather for that (tile, depth).
-// The kernel is bound by instruction issue, so the inner loop is kept lean: the bilinear blend runs on the mixed-precision
+// staged in shared memory once (cp.async, every copy in flight) and the four corners are read from there; the reference
+// features are re-read per plane (L1 / L2 hits) rather than held in 16 registers.  A footprint larger than the staging
+// buffer (strong rotation / scale between the views) falls back to the direct gather for that (tile, depth).
+// The kernel was bound by instruction issue (529 warp instructions per voxel and plane, now 286), so the inner loop is kept
+// lean: the bilinear blend runs on the mixed-precision
 // FMA (fhfma8: the fp16 feature times the fp16-rounded bilinear weight, exact product, fp32 accumulation - the weight rounding
 // of <= 2^-12 relative per corner sits below the fp16 storage rounding of the result), the per-voxel projection uses one
 // reciprocal instead of four divisions (sample positions agree with the reference's expression to ~5e-5 px), and the footprint
